@@ -1,0 +1,401 @@
+"""diffeq_b200 — host-side mirror of mattsse/diffeq's problem/solver surface over libdiffeq_b200.so.
+
+The reference API for this path (all /root/reference/src/ode/):
+    OdeProblem::builder().fun(f).init(y0).tspan(ts) / .tspan_linspace(a, b, n).build()?   problem.rs:60-131
+    problem.solve(Ode::X, OdeOptionMap) / .ode45(opts) / .ode4() ...                      problem.rs:133-190
+    OdeSolution { tout, yout }                                                            solution.rs:22-29
+    Ode enum + FromStr                                                                    mod.rs:14-46
+    option newtypes Reltol/Abstol/Minstep/Maxstep/Initstep/Points, OdeOptionMap           options.rs
+    OdeError                                                                              error.rs:4-23
+Differences forced by the device: `fun` takes a device functor (`Rhs.builtin(...)` or `Rhs.from_source(...)`),
+its captured constants are passed with `.params(...)`, and `init` may be one state or an [ntraj, n] ensemble.
+
+Everything numeric happens in the CUDA library behind the C ABI (include/diffeq_b200.h).  There is no CPU
+fallback: importing works without a GPU (so the ABI can be inspected), but any solve without the extension or
+without a CUDA device raises.
+"""
+import ctypes as C
+import enum
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libdiffeq_b200.so")
+_lib = None
+
+
+class OdeError(Exception):
+    """Mirrors `OdeError` (error.rs:4-23); `.status` is the deq_status code, `.kind` the variant name."""
+    KINDS = {1: "Uninitialized", 2: "InvalidButcherTableauWeightType", 3: "NAN", 4: "ZeroTimeSpan",
+             5: "InvalidInitstep", 6: "InvalidMatrix", 7: "Cuda", 8: "Nvrtc", 9: "Unsupported", 10: "InvalidArg"}
+
+    def __init__(self, status, msg):
+        self.status = status
+        self.kind = self.KINDS.get(status, "Unknown")
+        super().__init__(f"{self.kind}: {msg}")
+
+
+class Ode(enum.IntEnum):
+    """`enum Ode` (mod.rs:14-26), same order; Ode21 is the `.ode21()` method (problem.rs:164-166)."""
+    Feuler = 0
+    Heun = 1
+    Midpoint = 2
+    Ode23 = 3
+    Ode23s = 4
+    Ode4 = 5
+    Ode45 = 6
+    Ode45fe = 7
+    Ode4skr = 8
+    Ode4ss = 9
+    Ode78 = 10
+    Ode21 = 11
+
+    @staticmethod
+    def from_str(s):
+        """`impl FromStr for Ode` (mod.rs:28-46) — including its quirks: no name for Ode45fe, "ode4s" -> Ode4ss."""
+        table = {"feuler": Ode.Feuler, "heun": Ode.Heun, "midpoint": Ode.Midpoint, "ode23": Ode.Ode23,
+                 "ode23s": Ode.Ode23s, "ode4": Ode.Ode4, "ode45": Ode.Ode45, "ode4skr": Ode.Ode4skr,
+                 "ode4s": Ode.Ode4ss, "ode78": Ode.Ode78}
+        if s not in table:
+            raise ValueError(f"{s} is not a valid Ode identifier")
+        return table[s]
+
+
+class TableauSet(enum.IntEnum):
+    Reference = 0
+    Textbook = 1
+
+
+class Points(enum.IntEnum):
+    """`Points` (options.rs:120-137)."""
+    All = 0
+    Specified = 1
+
+
+class Output(enum.IntEnum):
+    Final = 0
+    Tspan = 1
+
+
+class System(enum.IntEnum):
+    Lorenz = 0
+    VanDerPol = 1
+    Pendulum = 2
+
+
+class _Options(C.Structure):
+    _fields_ = [("reltol", C.c_double), ("abstol", C.c_double), ("has_minstep", C.c_int), ("minstep", C.c_double),
+                ("has_maxstep", C.c_int), ("maxstep", C.c_double), ("initstep", C.c_double), ("points", C.c_int),
+                ("output", C.c_int), ("max_steps", C.c_uint64), ("refill", C.c_int), ("async_", C.c_int)]
+
+
+# The symbols include/diffeq_b200.h declares (checked by tests/test_abi.py).
+ABI_SYMBOLS = [
+    "deq_last_error_message", "deq_version", "deq_rhs_builtin", "deq_rhs_from_source", "deq_rhs_dim",
+    "deq_rhs_nparams", "deq_rhs_destroy", "deq_tspan_linspace", "deq_ensemble_create", "deq_ensemble_create_device",
+    "deq_ensemble_destroy", "deq_ensemble_ntraj", "deq_set_stream", "deq_options_default", "deq_solve",
+    "deq_result_final", "deq_result_counts", "deq_result_totals", "deq_result_dense", "deq_result_device_ptrs",
+    "deq_result_trajectory", "deq_result_kernel_ms", "deq_result_destroy", "deq_tableau_get", "deq_host_alloc",
+    "deq_host_free", "deq_test_pow", "deq_test_log10", "deq_measure_fp64_peak",
+]
+
+
+def lib():
+    """Loads the CUDA extension; fails loudly if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError(f"{_LIB_PATH} is missing: build it with `python -m diffeq_b200.build` "
+                              "(diffeq_b200 has no CPU fallback)")
+        L = C.CDLL(_LIB_PATH)
+        L.deq_last_error_message.restype = C.c_char_p
+        L.deq_version.restype = C.c_char_p
+        L.deq_options_default.restype = _Options
+        L.deq_ensemble_ntraj.restype = C.c_size_t
+        for name in ABI_SYMBOLS:
+            getattr(L, name)
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise OdeError(rc, lib().deq_last_error_message().decode())
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _ptr(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def set_stream(cuda_stream_ptr):
+    """Enqueue this thread's subsequent library work on the given cudaStream_t (int), e.g. torch's current stream."""
+    _check(lib().deq_set_stream(C.c_void_p(cuda_stream_ptr or 0)))
+
+
+def linspace(a, b, n):
+    """`tspan_linspace` (problem.rs:84-87)."""
+    out = np.empty(n, dtype=np.float64)
+    _check(lib().deq_tspan_linspace(C.c_double(a), C.c_double(b), C.c_size_t(n), _ptr(out)))
+    return out
+
+
+def tableau(method, tableau_set=TableauSet.Reference):
+    S = C.c_int(); ad = C.c_int(); om = C.c_int(); fs = C.c_int()
+    a = np.zeros(169); b = np.zeros(26); c = np.zeros(13)
+    _check(lib().deq_tableau_get(int(method), int(tableau_set), C.byref(S), _ptr(a), _ptr(b), _ptr(c), C.byref(ad),
+                                 C.byref(om), C.byref(fs)))
+    s = S.value
+    return dict(S=s, a=a[:s * s].reshape(s, s).copy(), b=b[:2 * s].reshape(s, 2).copy(), c=c[:s].copy(),
+                adaptive=bool(ad.value), order_min=om.value, fsal=bool(fs.value))
+
+
+def measure_fp64_peak():
+    tf = C.c_double(); mhz = C.c_double()
+    _check(lib().deq_measure_fp64_peak(C.byref(tf), C.byref(mhz)))
+    return tf.value, mhz.value
+
+
+def device_pow(x, y):
+    x, y = _f64(x), _f64(y)
+    out = np.empty_like(x)
+    _check(lib().deq_test_pow(_ptr(x), _ptr(y), _ptr(out), C.c_size_t(x.size)))
+    return out
+
+
+def device_log10(x):
+    x = _f64(x)
+    out = np.empty_like(x)
+    _check(lib().deq_test_log10(_ptr(x), _ptr(out), C.c_size_t(x.size)))
+    return out
+
+
+class Rhs:
+    """Device right-hand side: replaces the closure `F: Fn(f64,&Y)->Y` (problem.rs:32-36)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def builtin(system):
+        h = C.c_void_p()
+        _check(lib().deq_rhs_builtin(int(system), C.byref(h)))
+        return Rhs(h)
+
+    @staticmethod
+    def from_source(cuda_src, n, nparams):
+        h = C.c_void_p()
+        _check(lib().deq_rhs_from_source(cuda_src.encode(), int(n), int(nparams), C.byref(h)))
+        return Rhs(h)
+
+    @property
+    def dim(self):
+        return lib().deq_rhs_dim(self._h)
+
+    @property
+    def nparams(self):
+        return lib().deq_rhs_nparams(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.deq_rhs_destroy(self._h)
+            self._h = None
+
+
+# ---- option newtypes (options.rs:258-281) ----
+class _Opt:
+    name = None
+
+    def __init__(self, v):
+        self.v = v
+
+
+class Reltol(_Opt): name = "Reltol"
+class Abstol(_Opt): name = "Abstol"
+class Minstep(_Opt): name = "Minstep"
+class Maxstep(_Opt): name = "Maxstep"
+class Initstep(_Opt): name = "Initstep"
+class MaxSteps(_Opt): name = "MaxSteps"      # extension (guard; the reference has none)
+class Refill(_Opt): name = "Refill"          # extension (scheduling only; results do not depend on it)
+class OutputOpt(_Opt): name = "Output"       # extension (what to materialise)
+
+
+class OdeOptionMap(dict):
+    """`OdeOptionMap` (options.rs:8-25): a map keyed by option name.  Unknown/unused reference options
+    (Norm, StepTimeout, Retries) are accepted and ignored exactly like the reference ignores them."""
+
+    def insert(self, *opts):
+        for o in opts:
+            if isinstance(o, Points):
+                self["Points"] = o
+            elif isinstance(o, Output):
+                self["Output"] = o
+            else:
+                self[o.name] = o.v
+        return self
+
+    def to_c(self):
+        o = lib().deq_options_default()
+        if "Reltol" in self: o.reltol = float(self["Reltol"])
+        if "Abstol" in self: o.abstol = float(self["Abstol"])
+        if "Minstep" in self: o.has_minstep, o.minstep = 1, float(self["Minstep"])
+        if "Maxstep" in self: o.has_maxstep, o.maxstep = 1, float(self["Maxstep"])
+        if "Initstep" in self: o.initstep = float(self["Initstep"])
+        if "Points" in self: o.points = int(self["Points"])
+        if "Output" in self: o.output = int(self["Output"])
+        if "MaxSteps" in self: o.max_steps = int(self["MaxSteps"])
+        if "Refill" in self: o.refill = int(self["Refill"])
+        return o
+
+
+class OdeSolution:
+    """`OdeSolution{tout, yout}` (solution.rs:22-29) for an ensemble, plus the diagnostics the reference drops.
+
+    final      [ntraj, n]  last element of each trajectory's yout
+    accepted / rejected / nfe / status / t_reached   per trajectory (adaptive methods)
+    tout, yout  tspan and [ntraj, ntspan, n] values when solved with Output.Tspan (rows >= nvalid[i] except the
+                last are NaN: the reference never emitted them)
+    """
+
+    def __init__(self):
+        self.final = None
+        self.accepted = self.rejected = self.nfe = self.status = self.t_reached = None
+        self.tout = self.yout = self.nvalid = None
+        self.kernel_ms = None
+        self.totals = None
+
+    def zipped(self, traj=0):
+        """`OdeSolution::zipped` (solution.rs:33-36) for one trajectory."""
+        return list(zip(self.tout, self.yout[traj]))
+
+
+class OdeProblem:
+    """`OdeProblem` (problem.rs:32-47) over an ensemble of initial states / parameter sets."""
+
+    def __init__(self, rhs, y0, tspan, params, single):
+        self._rhs = rhs
+        self._single = single
+        self.ntraj, self.n = y0.shape
+        self.tspan = tspan
+        h = C.c_void_p()
+        per = int(params is not None and params.ndim == 2)
+        _check(lib().deq_ensemble_create(rhs._h, C.c_size_t(self.ntraj), _ptr(y0), _ptr(params), per, _ptr(tspan),
+                                         C.c_size_t(len(tspan)), C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def builder():
+        return OdeBuilder()
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.deq_ensemble_destroy(self._h)
+            self._h = None
+
+    # -- solve + per-method wrappers (problem.rs:133-190) --
+    def solve(self, ode, opts=None, tableau_set=TableauSet.Reference, fetch=True):
+        opts = opts if opts is not None else OdeOptionMap()
+        o = opts.to_c()
+        res = C.c_void_p()
+        L = lib()
+        _check(L.deq_solve(self._h, int(ode), int(tableau_set), C.byref(o), C.byref(res)))
+        try:
+            return self._collect(res, o, fetch, tableau(ode, tableau_set)["adaptive"])
+        finally:
+            L.deq_result_destroy(res)
+
+    def _collect(self, res, o, fetch, adaptive):
+        L = lib()
+        sol = OdeSolution()
+        ms = C.c_float()
+        _check(L.deq_result_kernel_ms(res, C.byref(ms)))
+        sol.kernel_ms = ms.value
+        a = C.c_uint64(); r = C.c_uint64(); f = C.c_uint64()
+        _check(L.deq_result_totals(res, C.byref(a), C.byref(r), C.byref(f)))
+        sol.totals = dict(accepted=a.value, rejected=r.value, nfe=f.value)
+        if not fetch:
+            return sol
+        nt = len(self.tspan)
+        sol.final = np.empty((self.ntraj, self.n))
+        if self.ntraj and not (nt == 0):
+            _check(L.deq_result_final(res, _ptr(sol.final)))
+        if adaptive and nt > 0:
+            sol.accepted = np.empty(self.ntraj, np.uint32); sol.rejected = np.empty(self.ntraj, np.uint32)
+            sol.nfe = np.empty(self.ntraj, np.uint32); sol.status = np.empty(self.ntraj, np.uint8)
+            sol.t_reached = np.empty(self.ntraj)
+            _check(L.deq_result_counts(res, _ptr(sol.accepted, C.c_uint32), _ptr(sol.rejected, C.c_uint32),
+                                       _ptr(sol.nfe, C.c_uint32), _ptr(sol.status, C.c_uint8), _ptr(sol.t_reached)))
+        if o.output == Output.Tspan and nt > 0:
+            dense = np.full((self.n, nt, self.ntraj), np.nan)
+            nv = np.empty(self.ntraj, np.uint32)
+            _check(L.deq_result_dense(res, C.c_size_t(0), C.c_size_t(self.ntraj), _ptr(dense), _ptr(nv, C.c_uint32)))
+            idx = np.arange(nt)[:, None]
+            invalid = (idx >= nv[None, :]) & (idx != nt - 1)
+            dense[:, invalid] = np.nan
+            sol.tout = self.tspan.copy()
+            sol.yout = np.ascontiguousarray(dense.transpose(2, 1, 0))
+            sol.nvalid = nv
+        return sol
+
+    def feuler(self): return self.solve(Ode.Feuler)
+    def heun(self): return self.solve(Ode.Heun)
+    def midpoint(self): return self.solve(Ode.Midpoint)
+    def ode4(self): return self.solve(Ode.Ode4)
+    def ode21(self, opts=None, **kw): return self.solve(Ode.Ode21, opts, **kw)
+    def ode23(self, opts=None, **kw): return self.solve(Ode.Ode23, opts, **kw)
+    def ode45(self, opts=None, **kw): return self.solve(Ode.Ode45, opts, **kw)
+    def ode45_dp(self, opts=None, **kw): return self.solve(Ode.Ode45, opts, **kw)
+    def ode45_fe(self, opts=None, **kw): return self.solve(Ode.Ode45fe, opts, **kw)
+    def ode78(self, opts=None, **kw): return self.solve(Ode.Ode78, opts, **kw)
+
+
+class OdeBuilder:
+    """`OdeBuilder` (problem.rs:49-119): fun / init / tspan / tspan_linspace / build."""
+
+    def __init__(self):
+        self._f = None
+        self._y0 = None
+        self._tspan = None
+        self._params = None
+
+    def fun(self, rhs):
+        self._f = rhs
+        return self
+
+    def params(self, p):
+        self._params = _f64(p)
+        return self
+
+    def init(self, y0):
+        self._y0 = _f64(y0)
+        return self
+
+    def tspan(self, ts):
+        self._tspan = _f64(ts)
+        return self
+
+    def tspan_linspace(self, a, b, n):
+        self._tspan = linspace(a, b, n)
+        return self
+
+    def build(self):
+        # problem.rs:92-104
+        if self._f is None:
+            raise OdeError(1, "Required problem must be initialized")
+        if self._y0 is None:
+            raise OdeError(1, "Initial starting point must be initialized")
+        if self._tspan is None:
+            raise OdeError(1, "Time span must be initialized")
+        y0 = self._y0
+        single = y0.ndim == 1
+        if single:
+            y0 = y0[None, :]
+        if y0.shape[1] != self._f.dim:
+            raise OdeError(10, f"state has {y0.shape[1]} components, the right-hand side expects {self._f.dim}")
+        if self._f.nparams and self._params is None:
+            raise OdeError(1, "Required problem parameters must be initialized")
+        return OdeProblem(self._f, np.ascontiguousarray(y0), self._tspan, self._params, single)

@@ -1,0 +1,532 @@
+// capi.cu — implementation of the C ABI declared in include/diffeq_b200.h.
+//
+// Host-side logic of the reference that lives here (file:line under /root/reference/src/ode/):
+//   solve dispatch Ode -> tableau -> loop        problem.rs:133-190
+//   option defaults / minstep / maxstep           options.rs:283-299, problem.rs:219-225
+//   initstep sign check -> InvalidInitstep        problem.rs:232-240
+//   empty tspan handling                          problem.rs:211-214 (adaptive: empty Ok), :377 (fixed: panics)
+// Device memory is owned by the handles; all work goes to the calling thread's stream (deq_set_stream).
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/diffeq_b200.h"
+#include "launch.h"
+#include "nvrtc_rhs.h"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local cudaStream_t g_stream = nullptr;
+
+deq_status fail(deq_status s, const std::string& msg) { g_err = msg; return s; }
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(DEQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+    } while (0)
+
+const deql::TbEntry g_tb[deql::TB_COUNT] = {
+#define E(ID) {deql::launch_adapt_##ID, deql::launch_fixed_##ID, deql::info_##ID}
+    E(0), E(1), E(2), E(3), E(4), E(5), E(6), E(7), E(8), E(9), E(10), E(11), E(12)
+#undef E
+};
+
+// (method, set) -> tableau id; -1 unsupported, -2 invalid
+int tb_of(int method, int set) {
+    const bool t = set == DEQ_TABLEAU_TEXTBOOK;
+    switch (method) {
+        case DEQ_FEULER: return deql::TB_FEULER;
+        case DEQ_MIDPOINT: return deql::TB_MIDPOINT;
+        case DEQ_HEUN: return deql::TB_HEUN;
+        case DEQ_ODE4: return deql::TB_RK4;
+        case DEQ_ODE21: return t ? deql::TB_RK21_TXT : deql::TB_RK21_REF;
+        case DEQ_ODE23: return t ? deql::TB_RK23_TXT : deql::TB_RK23_REF;
+        case DEQ_ODE45FE: return deql::TB_RK45;
+        case DEQ_ODE45: return t ? deql::TB_DOPRI5_TXT : deql::TB_DOPRI5_REF;
+        case DEQ_ODE78: return t ? deql::TB_FEH78_TXT : deql::TB_FEH78_REF;
+        case DEQ_ODE23S: case DEQ_ODE4SKR: case DEQ_ODE4SS: return -1;
+        default: return -2;
+    }
+}
+
+double signum(double x) { return std::isnan(x) ? x : std::copysign(1.0, x); }  // f64::signum
+
+}  // namespace
+
+namespace deql {
+const TbEntry& tb_entry(int tb) { return g_tb[tb]; }
+}
+
+struct deq_rhs {
+    int kind;  // 0 builtin, 1 nvrtc
+    int sys;
+    int n, np;
+    deqn::Program* prog;  // nvrtc only (shared, ref-counted)
+};
+
+struct deq_ensemble {
+    deq_rhs rhs;
+    size_t ntraj = 0, nt = 0;
+    int per_traj = 0;
+    double* d_y0 = nullptr;      // SoA [n][ntraj]
+    bool own_y0 = true;
+    double* d_params = nullptr;  // SoA [np][ntraj]
+    bool own_params = true;
+    deqk::SharedParams shared{};
+    std::vector<double> tspan;
+    double* d_tspan = nullptr;
+    bool has_tspan = false;
+};
+
+struct deq_result {
+    size_t ntraj = 0, nt = 0;
+    int n = 0;
+    bool fixed = false, dense = false;
+    cudaStream_t stream = nullptr;
+    double* d_yfinal = nullptr;
+    uint32_t *d_acc = nullptr, *d_rej = nullptr, *d_nfe = nullptr, *d_nvalid = nullptr;
+    uint8_t* d_status = nullptr;
+    double* d_treached = nullptr;
+    double* d_dense = nullptr;
+    double *d_f0 = nullptr, *d_h0 = nullptr;
+    unsigned long long* d_scalars = nullptr;  // [0] work counter, [1..3] totals
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t fixed_nfe_per_traj = 0;
+};
+
+namespace {
+
+template <class T>
+cudaError_t dalloc(T** p, size_t count, cudaStream_t st) {
+    *p = nullptr;
+    if (count == 0) return cudaSuccess;
+    return cudaMallocAsync((void**)p, count * sizeof(T), st);
+}
+void dfree(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+
+deq_status upload_soa(const double* h_aos, size_t ntraj, int n, double** d_soa, cudaStream_t st) {
+    double* d_aos = nullptr;
+    CK(dalloc(&d_aos, ntraj * n, st));
+    CK(dalloc(d_soa, ntraj * n, st));
+    CK(cudaMemcpyAsync(d_aos, h_aos, ntraj * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(deql::launch_transpose_to_soa(d_aos, *d_soa, ntraj, n, st));
+    dfree(d_aos, st);
+    return DEQ_OK;
+}
+
+deq_status ensemble_common(const deq_rhs* rhs, size_t ntraj, const double* params, int per_traj, const double* tspan,
+                           size_t ntspan, bool params_on_device, deq_ensemble* e) {
+    e->rhs = *rhs;
+    if (rhs->prog) deqn::retain(rhs->prog);
+    e->ntraj = ntraj;
+    e->per_traj = per_traj ? 1 : 0;
+    cudaStream_t st = g_stream;
+    if (rhs->np > 0) {
+        if (!params) return fail(DEQ_ERR_UNINITIALIZED, "Required problem parameters must be initialized");
+        if (per_traj) {
+            if (params_on_device) { e->d_params = const_cast<double*>(params); e->own_params = false; }
+            else { deq_status s = upload_soa(params, ntraj, rhs->np, &e->d_params, st); if (s) return s; }
+        } else {
+            for (int j = 0; j < rhs->np; ++j) e->shared.v[j] = params[j];
+        }
+    }
+    if (tspan) {
+        e->has_tspan = true;
+        e->nt = ntspan;
+        e->tspan.assign(tspan, tspan + ntspan);
+        CK(dalloc(&e->d_tspan, ntspan, st));
+        if (ntspan) CK(cudaMemcpyAsync(e->d_tspan, e->tspan.data(), ntspan * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return DEQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* deq_last_error_message(void) { return g_err.c_str(); }
+const char* deq_version(void) { return "diffeq_b200 0.1 (sm_100a)"; }
+
+deq_status deq_rhs_builtin(int system, deq_rhs** out) {
+    if (!out) return fail(DEQ_ERR_INVALID_ARG, "out is NULL");
+    int n, np;
+    switch (system) {
+        case DEQ_SYS_LORENZ: n = 3; np = 3; break;
+        case DEQ_SYS_VANDERPOL: n = 2; np = 1; break;
+        case DEQ_SYS_PENDULUM: n = 2; np = 3; break;
+        default: return fail(DEQ_ERR_INVALID_ARG, "unknown built-in system");
+    }
+    *out = new deq_rhs{0, system, n, np, nullptr};
+    return DEQ_OK;
+}
+
+deq_status deq_rhs_from_source(const char* cuda_src, int n, int nparams, deq_rhs** out) {
+    if (!out || !cuda_src) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
+    if (n < 1 || n > 16 || nparams < 0 || nparams > deqk::MAX_NP)
+        return fail(DEQ_ERR_INVALID_ARG, "need 1 <= n <= 16 and 0 <= nparams <= 8");
+    std::string err;
+    deqn::Program* p = deqn::create(cuda_src, n, nparams, &err);
+    if (!p) return fail(DEQ_ERR_NVRTC, err);
+    *out = new deq_rhs{1, -1, n, nparams, p};
+    return DEQ_OK;
+}
+
+int deq_rhs_dim(const deq_rhs* rhs) { return rhs ? rhs->n : -1; }
+int deq_rhs_nparams(const deq_rhs* rhs) { return rhs ? rhs->np : -1; }
+void deq_rhs_destroy(deq_rhs* rhs) {
+    if (!rhs) return;
+    if (rhs->prog) deqn::release(rhs->prog);
+    delete rhs;
+}
+
+deq_status deq_tspan_linspace(double from, double to, size_t n, double* out) {
+    if (n && !out) return fail(DEQ_ERR_INVALID_ARG, "out is NULL");
+    const double step = n > 1 ? (to - from) / (double)(n - 1) : 0.0;
+    for (size_t i = 0; i < n; ++i) out[i] = from + step * (double)i;
+    return DEQ_OK;
+}
+
+deq_status deq_set_stream(void* s) { g_stream = (cudaStream_t)s; return DEQ_OK; }
+
+deq_status deq_ensemble_create(const deq_rhs* rhs, size_t ntraj, const double* y0, const double* params,
+                               int params_per_traj, const double* tspan, size_t ntspan, deq_ensemble** out) {
+    if (!out) return fail(DEQ_ERR_INVALID_ARG, "out is NULL");
+    if (!rhs) return fail(DEQ_ERR_UNINITIALIZED, "Required problem must be initialized");
+    if (!y0 && ntraj) return fail(DEQ_ERR_UNINITIALIZED, "Initial starting point must be initialized");
+    if (!tspan) return fail(DEQ_ERR_UNINITIALIZED, "Time span must be initialized");
+    deq_ensemble* e = new deq_ensemble();
+    deq_status s = upload_soa(y0, ntraj, rhs->n, &e->d_y0, g_stream);
+    if (!s) s = ensemble_common(rhs, ntraj, params, params_per_traj, tspan, ntspan, false, e);
+    if (s) { deq_ensemble_destroy(e); return s; }
+    *out = e;
+    return DEQ_OK;
+}
+
+deq_status deq_ensemble_create_device(const deq_rhs* rhs, size_t ntraj, const double* d_y0_soa, const double* params,
+                                      int params_per_traj, const double* tspan, size_t ntspan, deq_ensemble** out) {
+    if (!out) return fail(DEQ_ERR_INVALID_ARG, "out is NULL");
+    if (!rhs) return fail(DEQ_ERR_UNINITIALIZED, "Required problem must be initialized");
+    if (!d_y0_soa && ntraj) return fail(DEQ_ERR_UNINITIALIZED, "Initial starting point must be initialized");
+    if (!tspan) return fail(DEQ_ERR_UNINITIALIZED, "Time span must be initialized");
+    deq_ensemble* e = new deq_ensemble();
+    e->d_y0 = const_cast<double*>(d_y0_soa);
+    e->own_y0 = false;
+    deq_status s = ensemble_common(rhs, ntraj, params, params_per_traj, tspan, ntspan, true, e);
+    if (s) { deq_ensemble_destroy(e); return s; }
+    *out = e;
+    return DEQ_OK;
+}
+
+void deq_ensemble_destroy(deq_ensemble* e) {
+    if (!e) return;
+    if (e->own_y0) dfree(e->d_y0, g_stream);
+    if (e->own_params) dfree(e->d_params, g_stream);
+    dfree(e->d_tspan, g_stream);
+    if (e->rhs.prog) deqn::release(e->rhs.prog);
+    delete e;
+}
+
+size_t deq_ensemble_ntraj(const deq_ensemble* e) { return e ? e->ntraj : 0; }
+
+deq_options deq_options_default(void) {
+    deq_options o;
+    std::memset(&o, 0, sizeof(o));
+    o.reltol = 1e-5;   // options.rs:283-287
+    o.abstol = 1e-8;   // options.rs:289-293
+    o.points = DEQ_POINTS_ALL;
+    o.output = DEQ_OUT_FINAL;
+    o.refill = 1;
+    return o;
+}
+
+deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_options* opts_in, deq_result** out) {
+    if (!e || !out) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
+    if (tableau_set != DEQ_TABLEAU_REFERENCE && tableau_set != DEQ_TABLEAU_TEXTBOOK)
+        return fail(DEQ_ERR_INVALID_ARG, "unknown tableau set");
+    const int tb = tb_of(method, tableau_set);
+    if (tb == -1) return fail(DEQ_ERR_UNSUPPORTED, "stiff (Rosenbrock) methods are not part of the RK hot path");
+    if (tb < 0) return fail(DEQ_ERR_INVALID_ARG, "unknown method");
+    const deq_options o = opts_in ? *opts_in : deq_options_default();
+    deql::TableauInfo info;
+    g_tb[tb].info(&info);
+    cudaStream_t st = g_stream;
+    const int n = e->rhs.n;
+    const size_t ntraj = e->ntraj, nt = e->nt;
+    const bool want_dense = o.output == DEQ_OUT_TSPAN;
+
+    deq_result* r = new deq_result();
+    r->ntraj = ntraj; r->nt = nt; r->n = n; r->stream = st; r->fixed = !info.adaptive; r->dense = want_dense;
+    auto bail = [&](deq_status s) { deq_result_destroy(r); return s; };
+#define CKR(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return bail(fail(DEQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)));       \
+    } while (0)
+
+    CKR(cudaEventCreate(&r->ev0));
+    CKR(cudaEventCreate(&r->ev1));
+    CKR(dalloc(&r->d_scalars, 4, st));
+    CKR(cudaMemsetAsync(r->d_scalars, 0, 4 * sizeof(unsigned long long), st));
+
+    if (!info.adaptive) {
+        // ---- oderk_fixed ----
+        if (nt == 0) return bail(fail(DEQ_ERR_INVALID_ARG, "fixed-step methods need a non-empty tspan (the reference panics, problem.rs:377)"));
+        CKR(dalloc(&r->d_yfinal, ntraj * n, st));
+        if (want_dense) CKR(dalloc(&r->d_dense, ntraj * n * nt, st));
+        deqk::FixedParams P{};
+        P.y0 = e->d_y0; P.params = e->d_params; P.shared = e->shared; P.tspan = e->d_tspan; P.nt = nt; P.ntraj = ntraj;
+        P.yfinal = r->d_yfinal; P.yall = r->d_dense;
+        r->fixed_nfe_per_traj = (uint64_t)info.S * (nt - 1);
+        CKR(cudaEventRecord(r->ev0, st));
+        if (ntraj) {
+            if (e->rhs.kind == 0) CKR(g_tb[tb].fixed(e->rhs.sys, e->per_traj, want_dense ? 1 : 0, P, st));
+            else {
+                std::string err;
+                if (!deqn::launch_fixed(e->rhs.prog, tb, e->per_traj, want_dense ? 1 : 0, P, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
+            }
+        }
+        CKR(cudaEventRecord(r->ev1, st));
+    } else {
+        // ---- oderk_adapt ----
+        if (o.points != DEQ_POINTS_ALL)
+            return bail(fail(DEQ_ERR_UNSUPPORTED, "Points::Specified re-reads y from the output vector in the reference (problem.rs:262) and yields wrong trajectories; use DEQ_POINTS_ALL with output = DEQ_OUT_TSPAN"));
+        if (nt == 0) { *out = r; r->ntraj = 0; return DEQ_OK; }  // problem.rs:211-214: nothing to solve
+        if (want_dense && nt < 2) return bail(fail(DEQ_ERR_INVALID_ARG, "DEQ_OUT_TSPAN needs at least 2 tspan points"));
+        const double t0 = e->tspan[0], tend = e->tspan[nt - 1];
+        const double tdir = signum(tend - t0);
+        if (tdir == 0.) return bail(fail(DEQ_ERR_ZERO_TIMESPAN, "Zero time span is not allowed"));
+        if (o.initstep != 0. && !(std::fabs(signum(o.initstep) - tdir) < DBL_EPSILON))
+            return bail(fail(DEQ_ERR_INVALID_INITSTEP, "Initial step has wrong sign"));
+        CKR(dalloc(&r->d_yfinal, ntraj * n, st));
+        CKR(dalloc(&r->d_acc, ntraj, st)); CKR(dalloc(&r->d_rej, ntraj, st)); CKR(dalloc(&r->d_nfe, ntraj, st));
+        CKR(dalloc(&r->d_status, ntraj, st)); CKR(dalloc(&r->d_treached, ntraj, st));
+        CKR(dalloc(&r->d_f0, ntraj * n, st)); CKR(dalloc(&r->d_h0, ntraj, st));
+        if (want_dense) { CKR(dalloc(&r->d_dense, ntraj * n * nt, st)); CKR(dalloc(&r->d_nvalid, ntraj, st)); }
+        deqk::HinitParams H{};
+        H.y0 = e->d_y0; H.params = e->d_params; H.shared = e->shared; H.ntraj = ntraj; H.t0 = t0; H.tend = tend;
+        H.reltol = o.reltol; H.abstol = o.abstol; H.order = info.order_min; H.f0 = r->d_f0; H.h0 = r->d_h0;
+        deqk::AdaptParams P{};
+        P.y0 = e->d_y0; P.f0 = r->d_f0; P.h0 = r->d_h0; P.params = e->d_params; P.shared = e->shared;
+        P.tspan = e->d_tspan; P.nt = nt; P.ntraj = ntraj; P.t0 = t0; P.tend = tend; P.tdir = tdir;
+        P.minstep = o.has_minstep ? o.minstep : std::fabs(tend - t0) / 1e18;   // problem.rs:219-221
+        P.maxstep = o.has_maxstep ? o.maxstep : std::fabs(tend - t0) / 2.5;    // problem.rs:223-225
+        P.reltol = o.reltol; P.abstol = o.abstol; P.initstep = o.initstep; P.use_initstep = o.initstep != 0.;
+        P.refill = o.refill; P.max_steps = o.max_steps;
+        P.yfinal = r->d_yfinal; P.accepted = r->d_acc; P.rejected = r->d_rej; P.nfe = r->d_nfe; P.status = r->d_status;
+        P.t_reached = r->d_treached; P.dense = r->d_dense; P.nvalid = r->d_nvalid;
+        P.work_counter = r->d_scalars; P.totals = r->d_scalars + 1;
+        const int mode = want_dense ? deqk::MODE_DENSE : deqk::MODE_FINAL;
+        if (ntraj) {
+            if (e->rhs.kind == 0) {
+                CKR(deql::launch_hinit(e->rhs.sys, e->per_traj, H, st));
+                CKR(cudaEventRecord(r->ev0, st));
+                CKR(g_tb[tb].adapt(e->rhs.sys, e->per_traj, mode, P, 0, st));
+            } else {
+                std::string err;
+                if (!deqn::launch_hinit(e->rhs.prog, e->per_traj, H, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
+                CKR(cudaEventRecord(r->ev0, st));
+                if (!deqn::launch_adapt(e->rhs.prog, tb, e->per_traj, mode, P, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
+            }
+        } else {
+            CKR(cudaEventRecord(r->ev0, st));
+        }
+        CKR(cudaEventRecord(r->ev1, st));
+    }
+    if (!o.async) CKR(cudaStreamSynchronize(st));
+#undef CKR
+    *out = r;
+    return DEQ_OK;
+}
+
+deq_status deq_result_final(deq_result* r, double* y) {
+    if (!r || !y) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
+    if (r->ntraj == 0) return DEQ_OK;
+    double* d_aos = nullptr;
+    CK(dalloc(&d_aos, r->ntraj * r->n, r->stream));
+    CK(deql::launch_transpose_to_aos(r->d_yfinal, d_aos, r->ntraj, r->n, r->stream));
+    CK(cudaMemcpyAsync(y, d_aos, r->ntraj * r->n * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+    dfree(d_aos, r->stream);
+    CK(cudaStreamSynchronize(r->stream));
+    return DEQ_OK;
+}
+
+deq_status deq_result_counts(deq_result* r, uint32_t* accepted, uint32_t* rejected, uint32_t* nfe, uint8_t* status,
+                             double* t_reached) {
+    if (!r) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
+    if (r->fixed) return fail(DEQ_ERR_INVALID_ARG, "fixed-step solves carry no per-trajectory counters");
+    if (r->ntraj == 0) return DEQ_OK;
+    const size_t n = r->ntraj;
+    if (accepted) CK(cudaMemcpyAsync(accepted, r->d_acc, n * 4, cudaMemcpyDeviceToHost, r->stream));
+    if (rejected) CK(cudaMemcpyAsync(rejected, r->d_rej, n * 4, cudaMemcpyDeviceToHost, r->stream));
+    if (nfe) CK(cudaMemcpyAsync(nfe, r->d_nfe, n * 4, cudaMemcpyDeviceToHost, r->stream));
+    if (status) CK(cudaMemcpyAsync(status, r->d_status, n, cudaMemcpyDeviceToHost, r->stream));
+    if (t_reached) CK(cudaMemcpyAsync(t_reached, r->d_treached, n * 8, cudaMemcpyDeviceToHost, r->stream));
+    CK(cudaStreamSynchronize(r->stream));
+    return DEQ_OK;
+}
+
+deq_status deq_result_totals(deq_result* r, uint64_t* accepted, uint64_t* rejected, uint64_t* nfe) {
+    if (!r) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if (r->d_scalars) {
+        CK(cudaMemcpyAsync(h, r->d_scalars, sizeof(h), cudaMemcpyDeviceToHost, r->stream));
+        CK(cudaStreamSynchronize(r->stream));
+    }
+    if (r->fixed) {  // every trajectory takes nt-1 steps of S evaluations
+        h[1] = (unsigned long long)r->ntraj * (r->nt ? r->nt - 1 : 0); h[2] = 0; h[3] = r->fixed_nfe_per_traj * r->ntraj;
+    }
+    if (accepted) *accepted = h[1];
+    if (rejected) *rejected = h[2];
+    if (nfe) *nfe = h[3];
+    return DEQ_OK;
+}
+
+deq_status deq_result_dense(deq_result* r, size_t b, size_t e, double* out, uint32_t* nvalid) {
+    if (!r || !out) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
+    if (!r->dense || !r->d_dense) return fail(DEQ_ERR_INVALID_ARG, "solve was not run with output = DEQ_OUT_TSPAN");
+    if (b > e || e > r->ntraj) return fail(DEQ_ERR_INVALID_ARG, "trajectory range out of bounds");
+    const size_t w = e - b;
+    if (w == 0) return DEQ_OK;
+    // rows of [n*nt][ntraj] restricted to columns [b,e)
+    CK(cudaMemcpy2DAsync(out, w * sizeof(double), r->d_dense + b, r->ntraj * sizeof(double), w * sizeof(double),
+                         (size_t)r->n * r->nt, cudaMemcpyDeviceToHost, r->stream));
+    if (nvalid) {
+        if (r->fixed) { CK(cudaStreamSynchronize(r->stream)); for (size_t i = 0; i < w; ++i) nvalid[i] = (uint32_t)r->nt; }
+        else CK(cudaMemcpyAsync(nvalid, r->d_nvalid + b, w * 4, cudaMemcpyDeviceToHost, r->stream));
+    }
+    CK(cudaStreamSynchronize(r->stream));
+    return DEQ_OK;
+}
+
+deq_status deq_result_device_ptrs(deq_result* r, const double** yf, const double** dn) {
+    if (!r) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
+    if (yf) *yf = r->d_yfinal;
+    if (dn) *dn = r->d_dense;
+    return DEQ_OK;
+}
+
+deq_status deq_result_trajectory(deq_result* r, size_t traj, double* yout) {
+    if (!r || !yout) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
+    if (!r->dense || !r->d_dense) return fail(DEQ_ERR_INVALID_ARG, "solve was not run with output = DEQ_OUT_TSPAN");
+    if (traj >= r->ntraj) return fail(DEQ_ERR_INVALID_ARG, "trajectory index out of bounds");
+    std::vector<double> tmp((size_t)r->n * r->nt);
+    CK(cudaMemcpy2DAsync(tmp.data(), sizeof(double), r->d_dense + traj, r->ntraj * sizeof(double), sizeof(double),
+                         (size_t)r->n * r->nt, cudaMemcpyDeviceToHost, r->stream));
+    CK(cudaStreamSynchronize(r->stream));
+    for (size_t i = 0; i < r->nt; ++i)
+        for (int d = 0; d < r->n; ++d) yout[i * r->n + d] = tmp[(size_t)d * r->nt + i];
+    return DEQ_OK;
+}
+
+deq_status deq_result_kernel_ms(deq_result* r, float* ms) {
+    if (!r || !ms) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
+    *ms = 0.f;
+    if (!r->ev0 || !r->ev1) return DEQ_OK;
+    CK(cudaEventSynchronize(r->ev1));
+    CK(cudaEventElapsedTime(ms, r->ev0, r->ev1));
+    return DEQ_OK;
+}
+
+void deq_result_destroy(deq_result* r) {
+    if (!r) return;
+    cudaStream_t st = r->stream;
+    dfree(r->d_yfinal, st); dfree(r->d_acc, st); dfree(r->d_rej, st); dfree(r->d_nfe, st); dfree(r->d_nvalid, st);
+    dfree(r->d_status, st); dfree(r->d_treached, st); dfree(r->d_dense, st); dfree(r->d_f0, st); dfree(r->d_h0, st);
+    dfree(r->d_scalars, st);
+    if (r->ev0) cudaEventDestroy(r->ev0);
+    if (r->ev1) cudaEventDestroy(r->ev1);
+    delete r;
+}
+
+deq_status deq_tableau_get(int method, int set, int* stages, double* a, double* b, double* c, int* adaptive,
+                           int* order_min, int* fsal) {
+    const int tb = tb_of(method, set);
+    if (tb == -1) return fail(DEQ_ERR_UNSUPPORTED, "stiff (Rosenbrock) methods are not part of the RK hot path");
+    if (tb < 0) return fail(DEQ_ERR_INVALID_ARG, "unknown method");
+    deql::TableauInfo info;
+    g_tb[tb].info(&info);
+    if (stages) *stages = info.S;
+    if (adaptive) *adaptive = info.adaptive;
+    if (order_min) *order_min = info.order_min;
+    if (fsal) *fsal = info.fsal;
+    if (a) std::memcpy(a, info.a, sizeof(double) * info.S * info.S);
+    if (b) std::memcpy(b, info.b, sizeof(double) * info.S * 2);
+    if (c) std::memcpy(c, info.c, sizeof(double) * info.S);
+    return DEQ_OK;
+}
+
+deq_status deq_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(DEQ_ERR_INVALID_ARG, "out is NULL");
+    CK(cudaMallocHost(out, bytes ? bytes : 1));
+    return DEQ_OK;
+}
+void deq_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+deq_status deq_test_pow(const double* x, const double* y, double* out, size_t n) {
+    if (n == 0) return DEQ_OK;
+    cudaStream_t st = g_stream;
+    double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    CK(dalloc(&dx, n, st)); CK(dalloc(&dy, n, st)); CK(dalloc(&dout, n, st));
+    CK(cudaMemcpyAsync(dx, x, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dy, y, n * 8, cudaMemcpyHostToDevice, st));
+    CK(deql::launch_test_pow(dx, dy, dout, n, st));
+    CK(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, st));
+    dfree(dx, st); dfree(dy, st); dfree(dout, st);
+    CK(cudaStreamSynchronize(st));
+    return DEQ_OK;
+}
+
+deq_status deq_test_log10(const double* x, double* out, size_t n) {
+    if (n == 0) return DEQ_OK;
+    cudaStream_t st = g_stream;
+    double *dx = nullptr, *dout = nullptr;
+    CK(dalloc(&dx, n, st)); CK(dalloc(&dout, n, st));
+    CK(cudaMemcpyAsync(dx, x, n * 8, cudaMemcpyHostToDevice, st));
+    CK(deql::launch_test_log10(dx, dout, n, st));
+    CK(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, st));
+    dfree(dx, st); dfree(dout, st);
+    CK(cudaStreamSynchronize(st));
+    return DEQ_OK;
+}
+
+deq_status deq_measure_fp64_peak(double* tflops, double* sm_clock_mhz_hint) {
+    if (!tflops) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
+    cudaStream_t st = g_stream;
+    int dev = 0, sms = 0, khz = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    const int blocks = sms * 8, iters = 4096;
+    double* sink = nullptr;
+    CK(dalloc(&sink, (size_t)blocks * 256, st));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(a, st));
+        CK(deql::launch_dfma_peak(sink, iters, blocks, st));
+        CK(cudaEventRecord(b, st));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        const double fl = (double)blocks * 256.0 * iters * 64.0 * 2.0;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    dfree(sink, st);
+    CK(cudaStreamSynchronize(st));
+    *tflops = best;
+    if (sm_clock_mhz_hint) *sm_clock_mhz_hint = khz / 1000.0;
+    return DEQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// kernels_common.cu — tableau-independent kernels: hinit pre-pass, AoS<->SoA transposes, device self-tests for the
+// libm replicas and the DFMA-rate microbenchmark that provides the FP64 roofline denominator.
+// Compiled with -fmad=false like every parity translation unit.
+#include "stepper.cuh"
+#include "launch.h"
+
+namespace deql {
+
+template <class F>
+static cudaError_t launch_hinit_f(int pt, const deqk::HinitParams& P, cudaStream_t st) {
+    const unsigned long long grid = (P.ntraj + deqk::BLOCK - 1) / deqk::BLOCK;
+    if (pt) deqk::hinit_kernel<F, true><<<(unsigned)grid, deqk::BLOCK, 0, st>>>(P);
+    else deqk::hinit_kernel<F, false><<<(unsigned)grid, deqk::BLOCK, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hinit(int sys, int pt, const deqk::HinitParams& P, cudaStream_t st) {
+    switch (sys) {
+        case 0: return launch_hinit_f<deqr::Lorenz>(pt, P, st);
+        case 1: return launch_hinit_f<deqr::VanDerPol>(pt, P, st);
+        case 2: return launch_hinit_f<deqr::Pendulum>(pt, P, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// [ntraj][n] -> [n][ntraj].  n is small (2..16): each thread moves one trajectory; the strided side stays within
+// a few cache lines per warp, so both sides run at full sector efficiency out of L1/L2.
+__global__ void to_soa_kernel(const double* __restrict__ aos, double* __restrict__ soa, unsigned long long ntraj, int n) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntraj) return;
+    for (int d = 0; d < n; ++d) soa[(unsigned long long)d * ntraj + i] = aos[i * n + d];
+}
+__global__ void to_aos_kernel(const double* __restrict__ soa, double* __restrict__ aos, unsigned long long ntraj, int n) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntraj) return;
+    for (int d = 0; d < n; ++d) aos[i * n + d] = soa[(unsigned long long)d * ntraj + i];
+}
+cudaError_t launch_transpose_to_soa(const double* a, double* s, unsigned long long ntraj, int n, cudaStream_t st) {
+    if (ntraj == 0) return cudaSuccess;
+    to_soa_kernel<<<(unsigned)((ntraj + 255) / 256), 256, 0, st>>>(a, s, ntraj, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_transpose_to_aos(const double* s, double* a, unsigned long long ntraj, int n, cudaStream_t st) {
+    if (ntraj == 0) return cudaSuccess;
+    to_aos_kernel<<<(unsigned)((ntraj + 255) / 256), 256, 0, st>>>(s, a, ntraj, n);
+    return cudaGetLastError();
+}
+
+__global__ void test_pow_kernel(const double* x, const double* y, double* out, unsigned long long n) {
+    __shared__ uint64_t s_exp[256];
+    __shared__ double s_powlog[384];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_exp[i] = deqk::g_exp_tab[i];
+    for (int i = threadIdx.x; i < 384; i += blockDim.x) s_powlog[i] = deqk::g_powlog_tab[i];
+    __syncthreads();
+    const deqm::Tables T{s_exp, s_powlog, nullptr};
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = deqm::pow_glibc(x[i], y[i], T);
+}
+__global__ void test_log10_kernel(const double* x, double* out, unsigned long long n) {
+    const deqm::Tables T{deqk::g_exp_tab, deqk::g_powlog_tab, deqk::g_log_tab};
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = deqm::log10_glibc(x[i], T);
+}
+cudaError_t launch_test_pow(const double* x, const double* y, double* out, unsigned long long n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    test_pow_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(x, y, out, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_test_log10(const double* x, double* out, unsigned long long n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    test_log10_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(x, out, n);
+    return cudaGetLastError();
+}
+
+// DFMA stream: 8 independent accumulator chains per thread, 2 flop per FMA.  The result is written so the loop
+// cannot be removed.  Used to measure the chip's sustained FP64 rate (MEASURED_PEAKS.json has no FP64 figure).
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* sink, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3., a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+            a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+        }
+    }
+    sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+cudaError_t launch_dfma_peak(double* sink, int iters, int blocks, cudaStream_t st) {
+    dfma_peak_kernel<<<blocks, 256, 0, st>>>(sink, iters);
+    return cudaGetLastError();
+}
+
+}  // namespace deql

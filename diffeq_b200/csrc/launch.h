@@ -1,0 +1,46 @@
+// launch.h — host-side entry points of the per-tableau kernel translation units (kernels_inst.cu is compiled once
+// per tableau with -DDEQ_TB=<id>; see build.py).  capi.cu dispatches a (method, tableau set) pair to one of these.
+#pragma once
+#include <cuda_runtime.h>
+#include "params.h"
+
+namespace deql {
+
+// Tableau ids (one object file each).
+enum TbId : int {
+    TB_FEULER = 0, TB_MIDPOINT, TB_HEUN, TB_RK4,                 // fixed step
+    TB_RK21_REF, TB_RK21_TXT, TB_RK23_REF, TB_RK23_TXT, TB_RK45,  // adaptive
+    TB_DOPRI5_REF, TB_DOPRI5_TXT, TB_FEH78_REF, TB_FEH78_TXT,
+    TB_COUNT
+};
+
+struct TableauInfo { int S; int adaptive; int order_min; int fsal; double a[13 * 13]; double b[13 * 2]; double c[13]; };
+
+// Launch the adaptive kernel of tableau `tb` for built-in system `sys` (deq_system).  `grid_blocks` <= 0 lets the
+// launcher size a persistent grid (SM count x resident CTAs per SM).  Returns the CUDA error of the launch.
+typedef cudaError_t (*AdaptLaunchFn)(int sys, int per_traj_params, int mode, const deqk::AdaptParams& P,
+                                     int grid_blocks, cudaStream_t st);
+typedef cudaError_t (*FixedLaunchFn)(int sys, int per_traj_params, int all, const deqk::FixedParams& P,
+                                     cudaStream_t st);
+typedef void (*InfoFn)(TableauInfo* out);
+
+struct TbEntry { AdaptLaunchFn adapt; FixedLaunchFn fixed; InfoFn info; };
+const TbEntry& tb_entry(int tb);  // defined in capi.cu from the per-TU registrars below
+
+#define DEQ_DECL_TB(ID) \
+    cudaError_t launch_adapt_##ID(int, int, int, const deqk::AdaptParams&, int, cudaStream_t); \
+    cudaError_t launch_fixed_##ID(int, int, int, const deqk::FixedParams&, cudaStream_t);      \
+    void info_##ID(TableauInfo*);
+DEQ_DECL_TB(0) DEQ_DECL_TB(1) DEQ_DECL_TB(2) DEQ_DECL_TB(3) DEQ_DECL_TB(4) DEQ_DECL_TB(5) DEQ_DECL_TB(6)
+DEQ_DECL_TB(7) DEQ_DECL_TB(8) DEQ_DECL_TB(9) DEQ_DECL_TB(10) DEQ_DECL_TB(11) DEQ_DECL_TB(12)
+#undef DEQ_DECL_TB
+
+// hinit pre-pass and small helpers live in kernels_common.cu
+cudaError_t launch_hinit(int sys, int per_traj_params, const deqk::HinitParams& P, cudaStream_t st);
+cudaError_t launch_transpose_to_soa(const double* d_aos, double* d_soa, unsigned long long ntraj, int n, cudaStream_t st);
+cudaError_t launch_transpose_to_aos(const double* d_soa, double* d_aos, unsigned long long ntraj, int n, cudaStream_t st);
+cudaError_t launch_test_pow(const double* x, const double* y, double* out, unsigned long long n, cudaStream_t st);
+cudaError_t launch_test_log10(const double* x, double* out, unsigned long long n, cudaStream_t st);
+cudaError_t launch_dfma_peak(double* sink, int iters, int blocks, cudaStream_t st);
+
+}  // namespace deql

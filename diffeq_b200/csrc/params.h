@@ -1,0 +1,55 @@
+// params.h — plain-old-data launch descriptors shared by the kernels (stepper.cuh), the per-tableau launchers
+// (kernels_inst.cu) and the C ABI implementation (capi.cu).  All pointers are DEVICE pointers; ensemble arrays are
+// structure-of-arrays over trajectories ([component][trajectory]) so that a warp's loads and stores coalesce.
+#pragma once
+#include <stdint.h>
+
+namespace deqk {
+
+enum : int { MODE_FINAL = 0, MODE_DENSE = 1 };
+enum : uint8_t { ST_DONE = 0, ST_MINSTEP_BREAK = 1, ST_MAX_STEPS = 2 };
+
+constexpr int BLOCK = 128;
+constexpr int MAX_NP = 8;
+
+struct SharedParams { double v[MAX_NP]; };
+
+struct AdaptParams {
+    // inputs (device, SoA over trajectories)
+    const double* y0;      // [N][ntraj]
+    const double* f0;      // [N][ntraj]   f(t0, y0) from hinit_kernel (k0 of the first step)
+    const double* h0;      // [ntraj]      first step from hinit_kernel (ignored if use_initstep)
+    const double* params;  // [NP][ntraj]  when per-trajectory, else unused
+    SharedParams shared;   // parameters shared by the whole ensemble
+    const double* tspan;   // [nt]
+    unsigned long long nt;
+    unsigned long long ntraj;
+    double t0, tend, tdir, minstep, maxstep, reltol, abstol, initstep;
+    int use_initstep;
+    int refill;            // 1: persistent lanes re-filled individually; 0: a warp takes 32 trajectories at a time
+    unsigned long long max_steps;  // guard (extension; the reference loops forever); 0 = none
+    // outputs
+    double* yfinal;        // [N][ntraj]
+    uint32_t* accepted; uint32_t* rejected; uint32_t* nfe; uint8_t* status; double* t_reached;
+    double* dense;         // MODE_DENSE: [N][nt][ntraj]
+    uint32_t* nvalid;      // MODE_DENSE: number of leading tspan rows written (reference quirk)
+    unsigned long long* work_counter;  // zeroed before launch
+    unsigned long long* totals;        // [3] += accepted, rejected, nfe over the ensemble
+};
+
+struct HinitParams {
+    const double* y0; const double* params; SharedParams shared;
+    unsigned long long ntraj;
+    double t0, tend, reltol, abstol;
+    int order;
+    double* f0; double* h0;
+};
+
+struct FixedParams {
+    const double* y0; const double* params; SharedParams shared;
+    const double* tspan; unsigned long long nt; unsigned long long ntraj;
+    double* yfinal;   // [N][ntraj]
+    double* yall;     // [N][nt][ntraj] or nullptr
+};
+
+}  // namespace deqk

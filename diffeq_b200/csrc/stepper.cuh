@@ -1,0 +1,338 @@
+// stepper.cuh — sm_100a kernels for the Runge–Kutta hot path: one trajectory per thread, stage vectors and
+// controller state in registers, tableau coefficients as immediates / constant-bank operands.
+//
+// Replaces (reference file:line, /root/reference/src/ode/problem.rs):
+//   oderk_fixed :361-406            -> fixed_kernel
+//   hinit :850-899                  -> hinit_kernel          (pre-pass, once per trajectory)
+//   oderk_adapt :193-358            -> adapt_kernel          (calc_coefficients :702-737, embedded_step :740-780,
+//                                                             stepsize_hw92 :801-845, hermite_interp :783-798 inlined)
+// PARITY CONTRACT: every + - * / below is one IEEE f64 operation in the reference's evaluation order (SURVEY.md
+// App. A); this translation unit must be compiled with -fmad=false so nvcc never contracts, and pow/log10 come
+// from deq_math.cuh (glibc's algorithm).  Zero tableau entries are multiplied through like the reference does
+// (they matter for NaN/Inf propagation and the sign of zero).
+//
+// Execution model (B200): 148 SMs x 4 resident CTAs x 128 threads.  Trajectories of an adaptive ensemble need
+// different numbers of steps, so the adaptive kernel is PERSISTENT: lanes whose trajectory finished are re-filled
+// from a global work counter (one warp-aggregated atomicAdd per refill, lanes ranked with a ballot), which keeps
+// the FP64 pipe busy instead of idling until the slowest lane of the warp finishes.  HBM traffic is
+// (2N + NP + 1) doubles in and N doubles + 21 bytes of counters out per trajectory for ~10^3 steps: the kernel
+// is bound by the FP64 pipe, not by memory.  Dense output (MODE_DENSE) writes SoA [N][ntspan][ntraj] so that lanes
+// that are at the same output index store to consecutive addresses.
+#pragma once
+#include <stdint.h>
+#include <float.h>
+#include "deq_math.cuh"
+#include "tableaus.cuh"
+#include "rhs.cuh"
+#include "params.h"
+
+namespace deqk {
+
+__device__ const uint64_t g_exp_tab[256] = {DEQ_EXP_TAB_INIT};
+__device__ const double g_powlog_tab[384] = {DEQ_POWLOG_TAB_INIT};
+__device__ const double g_log_tab[256] = {DEQ_LOG_TAB_INIT};
+
+template <class F, bool PT>
+__device__ __forceinline__ void load_params(double* prm, const double* params, const SharedParams& sh,
+                                            unsigned long long traj, unsigned long long ntraj) {
+#pragma unroll
+    for (int j = 0; j < F::NP; ++j) prm[j] = PT ? params[(unsigned long long)j * ntraj + traj] : sh.v[j];
+}
+
+// calc_coefficients (problem.rs:702-737): k[0] holds k0; fills k[1..S-1].
+template <class TB, class F>
+__device__ __forceinline__ void stages(double t, const double (&y)[F::N], double dt, double (&k)[TB::S][F::N],
+                                       const double* prm) {
+    constexpr auto tb = TB::data();
+#pragma unroll
+    for (int row = 1; row < TB::S; ++row) {
+        double yi[F::N];
+#pragma unroll
+        for (int d = 0; d < F::N; ++d) yi[d] = y[d];
+#pragma unroll
+        for (int col = 0; col < row; ++col) {
+            const double w = tb.a[row][col] * dt;
+#pragma unroll
+            for (int d = 0; d < F::N; ++d) yi[d] = yi[d] + k[col][d] * w;
+        }
+        const double tn = t + tb.c[row] * dt;
+        F::eval(tn, yi, k[row], prm);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// oderk_fixed (problem.rs:361-406): every trajectory walks the same tspan grid, dt = tspan[i+1] - tspan[i].
+// ---------------------------------------------------------------------------------------------------------------
+template <class TB, class F, bool PT, bool ALL>
+__global__ void __launch_bounds__(BLOCK) fixed_kernel(const FixedParams P) {
+    constexpr int N = F::N, S = TB::S;
+    constexpr auto tb = TB::data();
+    const unsigned long long traj = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (traj >= P.ntraj) return;
+    double prm[F::NP];
+    load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
+    double y[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) y[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
+    if (ALL) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) P.yall[((unsigned long long)d * P.nt) * P.ntraj + traj] = y[d];
+    }
+    double tcur = P.nt ? __ldg(P.tspan) : 0.0;
+    for (unsigned long long i = 0; i + 1 < P.nt; ++i) {
+        const double tnext = __ldg(P.tspan + i + 1);
+        const double dt = tnext - tcur;
+        double k[S][N];
+        F::eval(tcur, y, k[0], prm);
+        stages<TB, F>(tcur, y, dt, k, prm);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+#pragma unroll
+            for (int d = 0; d < N; ++d) y[d] = y[d] + (k[s][d] * tb.b[s][0]) * dt;
+        }
+        if (ALL) {
+#pragma unroll
+            for (int d = 0; d < N; ++d) P.yall[((unsigned long long)d * P.nt + (i + 1)) * P.ntraj + traj] = y[d];
+        }
+        tcur = tnext;
+    }
+#pragma unroll
+    for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = y[d];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// hinit (problem.rs:850-899), one thread per trajectory; writes f0 = f(t0,y0) and the first step h.
+// ---------------------------------------------------------------------------------------------------------------
+template <class F, bool PT>
+__global__ void __launch_bounds__(BLOCK) hinit_kernel(const HinitParams P) {
+    constexpr int N = F::N;
+    __shared__ uint64_t s_exp[256];
+    __shared__ double s_powlog[384];
+    __shared__ double s_log[256];
+    for (int i = threadIdx.x; i < 256; i += BLOCK) { s_exp[i] = g_exp_tab[i]; s_log[i] = g_log_tab[i]; }
+    for (int i = threadIdx.x; i < 384; i += BLOCK) s_powlog[i] = g_powlog_tab[i];
+    __syncthreads();
+    const deqm::Tables T{s_exp, s_powlog, s_log};
+    const unsigned long long traj = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (traj >= P.ntraj) return;
+    double prm[F::NP];
+    load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
+    double x0[N], f0[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) x0[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
+    const double t0 = P.t0, tend = P.tend, reltol = P.reltol, abstol = P.abstol;
+    const double diff = tend - t0;
+    const double tdir = (diff != diff) ? diff : copysign(1.0, diff);  // f64::signum
+    double norm = 0.0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) { const double a = fabs(x0[d]); if (a > norm) norm = a; }
+    const double tau = fmax(norm * reltol, 1.0 * abstol);
+    const double d0 = norm / tau;
+    F::eval(t0, x0, f0, prm);
+    double nf0 = 0.0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) { const double a = fabs(f0[d]); if (a > nf0) nf0 = a; }
+    const double d1 = nf0 / tau;
+    const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1.0e-6 : 0.01 * (d0 / d1);
+    double x1[N], f1[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) x1[d] = x0[d] + (f0[d] * h0) * tdir;
+    F::eval(t0 + tdir * h0, x1, f1, prm);
+    double nf1 = 0.0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) { const double a = fabs(f1[d] - f0[d]); if (a > nf1) nf1 = a; }
+    const double d2 = nf1 / (tau * h0);
+    const double m = fmax(d1, d2);
+    double h1;
+    if (m < 1e-15) {
+        h1 = fmax(1.0e-6, 1.0e-3 * h0);
+    } else {
+        const double pw = (-(2. + deqm::log10_glibc(m, T))) / (double)(P.order + 1);
+        h1 = deqm::pow_glibc(10.0, pw, T);
+    }
+    const double h = tdir * fmin(fmin(h1, 100. * h0), tdir * (tend - t0));
+    P.h0[traj] = h;
+#pragma unroll
+    for (int d = 0; d < N; ++d) P.f0[(unsigned long long)d * P.ntraj + traj] = f0[d];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// oderk_adapt (problem.rs:193-358), Points::All semantics.
+// ---------------------------------------------------------------------------------------------------------------
+template <class TB, class F, bool PT, int MODE>
+__global__ void __launch_bounds__(BLOCK, 4) adapt_kernel(const AdaptParams P) {
+    constexpr int N = F::N, S = TB::S;
+    constexpr auto tb = TB::data();
+    constexpr bool FSAL = deqt::fsal_of(tb);
+    constexpr double PW = 1. / (double)(TB::ORDER_MIN + 1);
+
+    __shared__ uint64_t s_exp[256];
+    __shared__ double s_powlog[384];
+    for (int i = threadIdx.x; i < 256; i += BLOCK) s_exp[i] = g_exp_tab[i];
+    for (int i = threadIdx.x; i < 384; i += BLOCK) s_powlog[i] = g_powlog_tab[i];
+    __syncthreads();
+    const deqm::Tables T{s_exp, s_powlog, nullptr};
+
+    const unsigned lane = threadIdx.x & 31u;
+    const double tdir = P.tdir, tend = P.tend, reltol = P.reltol, abstol = P.abstol;
+
+    bool active = false;
+    bool pool_empty = false;
+    unsigned long long traj = 0;
+    double t = 0.0, dt = 0.0;
+    double cy[N], ck[N], prm[F::NP];
+    unsigned timeout = 0;
+    bool last_step = false;
+    uint32_t acc = 0, rej = 0;
+    unsigned long long attempts = 0, it = 1;
+    unsigned long long tot_acc = 0, tot_rej = 0, tot_nfe = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) { cy[d] = 0.0; ck[d] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < F::NP; ++j) prm[j] = 0.0;
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle != 0u && !pool_empty && (P.refill || idle == 0xffffffffu)) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + (unsigned long long)__popc(idle) >= P.ntraj) pool_empty = true;
+            if (!active) {
+                const unsigned long long my = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
+                if (my < P.ntraj) {
+                    traj = my;
+                    active = true;
+                    load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
+#pragma unroll
+                    for (int d = 0; d < N; ++d) {
+                        cy[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
+                        ck[d] = P.f0[(unsigned long long)d * P.ntraj + traj];
+                    }
+                    t = P.t0;
+                    dt = P.use_initstep ? P.initstep : P.h0[traj];
+                    timeout = 0;
+                    last_step = fabs((t + dt) - tend) <= DBL_EPSILON;
+                    acc = 0; rej = 0; attempts = 0; it = 1;
+                    if (MODE == MODE_DENSE) {
+#pragma unroll
+                        for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt) * P.ntraj + traj] = cy[d];
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) break;
+        if (!active) continue;
+
+        // ---- one step attempt (loop body of problem.rs:260-352) ----
+        uint8_t fin = 0xff;  // 0xff: keep going
+        if (P.max_steps != 0ull && attempts >= P.max_steps) {
+            fin = ST_MAX_STEPS;
+        } else {
+            ++attempts;
+            double k[S][N];
+#pragma unroll
+            for (int d = 0; d < N; ++d) k[0][d] = ck[d];
+            stages<TB, F>(t, cy, dt, k, prm);
+            // embedded_step :761-771  (y == cy under Points::All)
+            double ytrial[N], yerr[N];
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                double p = 0.0, q = 0.0;
+#pragma unroll
+                for (int s = 0; s < S; ++s) { p = p + k[s][d] * tb.b[s][0]; q = q + k[s][d] * tb.b[s][1]; }
+                yerr[d] = (p - q) * dt;
+                ytrial[d] = cy[d] + (p * dt);
+            }
+            // stepsize_hw92 :801-845
+            double err, ndt;
+            bool isnan_trial = false;
+#pragma unroll
+            for (int d = 0; d < N; ++d) isnan_trial = isnan_trial || (ytrial[d] != ytrial[d]);
+            if (isnan_trial) {
+                err = 10.; ndt = 0.2 * dt; timeout = 5;
+            } else {
+                double ssum = 0.0;
+#pragma unroll
+                for (int d = 0; d < N; ++d) {
+                    const double e = yerr[d] / (fmax(fabs(cy[d]), fabs(ytrial[d])) * reltol + abstol);
+                    const double a = fabs(e);
+                    ssum = ssum + a * a;
+                }
+                err = deqm::pow_glibc(ssum, 0.5, T);
+                double nd = fmin(P.maxstep, (fmax(0.2, deqm::pow_glibc(1.0 / err, PW, T) * 0.8) * tdir) * dt);
+                if (timeout > 0) { nd = fmin(nd, dt); timeout -= 1; }
+                ndt = tdir * nd;
+            }
+            if (err < 1.) {
+                acc += 1;
+                double f1[N];
+                if (FSAL) {
+#pragma unroll
+                    for (int d = 0; d < N; ++d) f1[d] = k[S - 1][d];
+                } else {
+                    F::eval(t + dt, ytrial, f1, prm);
+                }
+                if (MODE == MODE_DENSE) {
+                    // Points::All :303-319 — Hermite values at tspan points strictly inside (t, t+dt)
+                    const double tn = t + dt;
+                    while (it < P.nt) {
+                        const double tq = __ldg(P.tspan + it);
+                        if (!(tdir * t < tdir * tq && tdir * tq < tdir * tn)) break;
+                        const double theta = (tq - t) / dt;
+#pragma unroll
+                        for (int d = 0; d < N; ++d) {
+                            const double v = (cy[d] * (1. - theta) + ytrial[d] * theta) +
+                                             ((ytrial[d] - cy[d]) * (1. - 2. * theta) + k[0][d] * (theta - 1.) * dt +
+                                              f1[d] * theta * dt) * theta * (theta - 1.);
+                            P.dense[((unsigned long long)d * P.nt + it) * P.ntraj + traj] = v;
+                        }
+                        ++it;
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < N; ++d) { ck[d] = f1[d]; cy[d] = ytrial[d]; }
+                if (last_step) {
+                    fin = ST_DONE;
+                    t = t + dt;  // t_reached
+                } else {
+                    t = t + dt;
+                    dt = ndt;
+                    if (tdir * ((t + dt) + dt / 100.) >= tdir * tend) { dt = tend - t; last_step = true; }
+                }
+            } else if (fabs(ndt) < P.minstep) {
+                fin = ST_MINSTEP_BREAK;
+            } else {
+                rej += 1;
+                last_step = false;
+                dt = ndt;
+                timeout = 5;
+            }
+        }
+        if (fin != 0xff) {
+            const uint32_t nfe = 2u + (uint32_t)attempts * (uint32_t)(S - 1) + (FSAL ? 0u : acc);
+#pragma unroll
+            for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = cy[d];
+            P.accepted[traj] = acc; P.rejected[traj] = rej; P.nfe[traj] = nfe; P.status[traj] = fin; P.t_reached[traj] = t;
+            if (MODE == MODE_DENSE) {
+#pragma unroll
+                for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt + (P.nt - 1)) * P.ntraj + traj] = cy[d];
+                P.nvalid[traj] = (uint32_t)it;
+            }
+            tot_acc += acc; tot_rej += rej; tot_nfe += nfe;
+            active = false;
+        }
+    }
+    // ensemble totals: warp reduce, one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tot_acc += __shfl_down_sync(0xffffffffu, tot_acc, o);
+        tot_rej += __shfl_down_sync(0xffffffffu, tot_rej, o);
+        tot_nfe += __shfl_down_sync(0xffffffffu, tot_nfe, o);
+    }
+    if (lane == 0) {
+        atomicAdd(P.totals + 0, tot_acc); atomicAdd(P.totals + 1, tot_rej); atomicAdd(P.totals + 2, tot_nfe);
+    }
+}
+
+}  // namespace deqk

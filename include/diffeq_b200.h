@@ -1,0 +1,164 @@
+/* diffeq_b200.h — C ABI of libdiffeq_b200.so: B200-native ensemble Runge–Kutta integration behind the
+ * problem/solver surface of the Rust crate mattsse/diffeq.
+ *
+ * The reference has no FFI of its own; its boundary for this path is the Rust API
+ *     OdeProblem::builder().fun(f).init(y0).tspan(ts).build()?      src/ode/problem.rs:60-131
+ *     problem.solve(Ode::X, OdeOptionMap) -> Result<OdeSolution, OdeError>   src/ode/problem.rs:133-147
+ * Every entry point below names the reference item it replaces.  A Rust `-sys` crate binds these symbols
+ * one-to-one (see INTEGRATION.md and rust/); everything is `extern "C"`, plain pointers and sizes.
+ *
+ * Conventions: all calls return deq_status (DEQ_OK == 0); deq_last_error_message() gives a thread-local detail
+ * string.  The caller owns every buffer it passes; inputs are copied during *_create, outputs are copied into
+ * caller-provided buffers.  Handles are not internally synchronised (one thread per handle at a time).  One
+ * handle lives on one GPU (the current CUDA device at creation); an ensemble is sharded over GPUs by creating one
+ * handle per device/process over a contiguous slice of the trajectories (no inter-GPU traffic is needed: every
+ * trajectory is an independent OdeProblem, problem.rs:32-47).
+ */
+#ifndef DIFFEQ_B200_H
+#define DIFFEQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors OdeError (src/error.rs:4-23) + backend codes. */
+typedef enum deq_status {
+    DEQ_OK = 0,
+    DEQ_ERR_UNINITIALIZED = 1,     /* OdeError::Uninitialized (problem.rs:92-104) */
+    DEQ_ERR_WEIGHT_TYPE = 2,       /* OdeError::InvalidButcherTableauWeightType (problem.rs:204-209) */
+    DEQ_ERR_NAN = 3,               /* OdeError::NAN (never produced by the RK path) */
+    DEQ_ERR_ZERO_TIMESPAN = 4,     /* OdeError::ZeroTimeSpan (unreachable for f64: signum(0) == 1) */
+    DEQ_ERR_INVALID_INITSTEP = 5,  /* OdeError::InvalidInitstep (problem.rs:232-237) */
+    DEQ_ERR_INVALID_MATRIX = 6,    /* OdeError::InvalidMatrix (Rosenbrock only) */
+    DEQ_ERR_CUDA = 7,
+    DEQ_ERR_NVRTC = 8,
+    DEQ_ERR_UNSUPPORTED = 9,       /* Ode23s / Ode4skr / Ode4ss: stiff path, not built yet */
+    DEQ_ERR_INVALID_ARG = 10
+} deq_status;
+
+/* Same variants and order as `enum Ode` (src/ode/mod.rs:14-26); DEQ_ODE21 exposes `.ode21()` (problem.rs:164). */
+typedef enum deq_method {
+    DEQ_FEULER = 0, DEQ_HEUN = 1, DEQ_MIDPOINT = 2, DEQ_ODE23 = 3, DEQ_ODE23S = 4, DEQ_ODE4 = 5, DEQ_ODE45 = 6,
+    DEQ_ODE45FE = 7, DEQ_ODE4SKR = 8, DEQ_ODE4SS = 9, DEQ_ODE78 = 10, DEQ_ODE21 = 11
+} deq_method;
+
+/* Which coefficients the adaptive tableaus use: REFERENCE = bug-for-bug runge_kutta.rs:231-817,
+ * TEXTBOOK = corrected rk21 / rk23 / dopri5 c[3] / feh78. */
+typedef enum deq_tableau_set { DEQ_TABLEAU_REFERENCE = 0, DEQ_TABLEAU_TEXTBOOK = 1 } deq_tableau_set;
+
+typedef enum deq_system { DEQ_SYS_LORENZ = 0, DEQ_SYS_VANDERPOL = 1, DEQ_SYS_PENDULUM = 2 } deq_system;
+
+/* `Points` (src/ode/options.rs:120-137).  Only Points::All is reference-valid (Specified re-reads y from the
+ * output vector, problem.rs:262).  DEQ_POINTS_TSPAN is Points::All filtered to the tspan times. */
+typedef enum deq_points { DEQ_POINTS_ALL = 0, DEQ_POINTS_SPECIFIED = 1 } deq_points;
+
+/* What deq_solve materialises. */
+typedef enum deq_output {
+    DEQ_OUT_FINAL = 0,  /* last element of yout + per-trajectory counters */
+    DEQ_OUT_TSPAN = 1   /* additionally the rows of (tout,yout) that fall on tspan times, SoA [n][ntspan][ntraj] */
+} deq_output;
+
+/* Per-trajectory completion code (the reference returns Ok(partial) silently in the first two cases). */
+typedef enum deq_traj_status {
+    DEQ_TRAJ_DONE = 0,
+    DEQ_TRAJ_MINSTEP_BREAK = 1,  /* |dt| < minstep: problem.rs:342-344 */
+    DEQ_TRAJ_MAX_STEPS = 2       /* extension: options.max_steps reached */
+} deq_traj_status;
+
+/* AdaptiveOptions (src/ode/options.rs:49-70); defaults from options.rs:283-299 and problem.rs:219-225.
+ * `norm`, `step_timeout` and `retries` are accepted by the reference but never used and are
+ * therefore absent. */
+typedef struct deq_options {
+    double reltol;       /* Reltol, default 1e-5 */
+    double abstol;       /* Abstol, default 1e-8 */
+    int has_minstep;     /* Minstep: None -> |tend - t0| / 1e18 */
+    double minstep;
+    int has_maxstep;     /* Maxstep: None -> |tend - t0| / 2.5 */
+    double maxstep;
+    double initstep;     /* Initstep, 0 = estimate with hinit (problem.rs:232-240) */
+    int points;          /* deq_points, default DEQ_POINTS_ALL */
+    int output;          /* deq_output, default DEQ_OUT_FINAL */
+    uint64_t max_steps;  /* extension: stop a trajectory after this many step attempts (0 = unlimited) */
+    int refill;          /* 1 (default): persistent lanes refilled individually; 0: static warp assignment */
+    int async;           /* 0 (default): deq_solve returns after the GPU finished; 1: returns after enqueueing */
+} deq_options;
+
+typedef struct deq_rhs deq_rhs;
+typedef struct deq_ensemble deq_ensemble;
+typedef struct deq_result deq_result;
+
+const char* deq_last_error_message(void);
+const char* deq_version(void);
+
+/* ---- right-hand side: replaces the closure `F: Fn(f64,&Y)->Y` (problem.rs:32-36) ---- */
+deq_status deq_rhs_builtin(int system /* deq_system */, deq_rhs** out);
+/* User CUDA source defining
+ *     __device__ void rhs(double t, const double* y, double* dy, const double* p);
+ * for an n-dimensional state and nparams parameters, compiled with NVRTC for sm_100a. */
+deq_status deq_rhs_from_source(const char* cuda_src, int n, int nparams, deq_rhs** out);
+int deq_rhs_dim(const deq_rhs* rhs);
+int deq_rhs_nparams(const deq_rhs* rhs);
+void deq_rhs_destroy(deq_rhs* rhs);
+
+/* OdeBuilder::tspan_linspace (problem.rs:84-87; itertools_num::linspace): out[i] = from + ((to-from)/(n-1))*i */
+deq_status deq_tspan_linspace(double from, double to, size_t n, double* out);
+
+/* ---- problem: replaces OdeProblem / OdeBuilder (problem.rs:32-119), one problem per trajectory ----
+ * y0     host, [ntraj][n] row-major (one `Y` per trajectory, like the reference's Vec<f64> state)
+ * params host, [ntraj][nparams] if params_per_traj else [nparams] (may be NULL if nparams == 0)
+ * tspan  host, [ntspan], shared by all trajectories (may be NULL -> DEQ_ERR_UNINITIALIZED like build()) */
+deq_status deq_ensemble_create(const deq_rhs* rhs, size_t ntraj, const double* y0, const double* params,
+                               int params_per_traj, const double* tspan, size_t ntspan, deq_ensemble** out);
+/* Same, with inputs already resident on the current device in the library's layout:
+ * y0_soa [n][ntraj], params_soa [nparams][ntraj] (or host [nparams] shared values if !params_per_traj). */
+deq_status deq_ensemble_create_device(const deq_rhs* rhs, size_t ntraj, const double* d_y0_soa,
+                                      const double* params, int params_per_traj, const double* tspan,
+                                      size_t ntspan, deq_ensemble** out);
+void deq_ensemble_destroy(deq_ensemble* ens);
+size_t deq_ensemble_ntraj(const deq_ensemble* ens);
+
+/* CUDA stream (cudaStream_t as void*) all work of this thread's subsequent calls is enqueued on; NULL = default. */
+deq_status deq_set_stream(void* cuda_stream);
+
+/* ---- solve: replaces OdeProblem::solve(Ode, OdeOptionMap) (problem.rs:133-147) ---- */
+deq_options deq_options_default(void);
+deq_status deq_solve(deq_ensemble* ens, int method /* deq_method */, int tableau_set /* deq_tableau_set */,
+                     const deq_options* opts, deq_result** out);
+
+/* ---- result: replaces OdeSolution{tout,yout} (src/ode/solution.rs:22-29) + the Diagnostics the reference
+ * counts but drops (problem.rs:957-970).  All getters synchronise with the solve first. ---- */
+deq_status deq_result_final(deq_result* res, double* y /* host [ntraj][n] */);
+deq_status deq_result_counts(deq_result* res, uint32_t* accepted, uint32_t* rejected, uint32_t* nfe,
+                             uint8_t* status, double* t_reached /* each host [ntraj], any may be NULL */);
+deq_status deq_result_totals(deq_result* res, uint64_t* accepted, uint64_t* rejected, uint64_t* nfe);
+/* DEQ_OUT_TSPAN: rows of trajectories [traj_begin, traj_end) into host out[n][ntspan][traj_end-traj_begin];
+ * nvalid (may be NULL) receives, per trajectory, how many leading tspan rows the reference would have emitted. */
+deq_status deq_result_dense(deq_result* res, size_t traj_begin, size_t traj_end, double* out, uint32_t* nvalid);
+/* Device views (library layout, valid until deq_result_destroy): yfinal [n][ntraj], dense [n][ntspan][ntraj]. */
+deq_status deq_result_device_ptrs(deq_result* res, const double** d_yfinal_soa, const double** d_dense_soa);
+/* Fixed-step methods with DEQ_OUT_TSPAN: the full OdeSolution of one trajectory, yout host [ntspan][n]. */
+deq_status deq_result_trajectory(deq_result* res, size_t traj, double* yout);
+/* Milliseconds the main stepping kernel took on the device (CUDA events around that launch). */
+deq_status deq_result_kernel_ms(deq_result* res, float* ms);
+void deq_result_destroy(deq_result* res);
+
+/* ---- utilities ---- */
+/* Tableau introspection (runge_kutta.rs:87-100): a[S*S] row-major, b[S*2] (stepping, error), c[S]. */
+deq_status deq_tableau_get(int method, int tableau_set, int* stages, double* a, double* b, double* c,
+                           int* adaptive, int* order_min, int* fsal);
+/* Pinned host memory for fast H2D / D2H of caller buffers. */
+deq_status deq_host_alloc(size_t bytes, void** out);
+void deq_host_free(void* p);
+/* Device self-tests used by the parity suite: evaluate the library's pow / log10 on the GPU. */
+deq_status deq_test_pow(const double* x, const double* y, double* out, size_t n);
+deq_status deq_test_log10(const double* x, double* out, size_t n);
+/* FP64 roofline denominator: sustained DFMA rate of this GPU in TFLOP/s (FMA = 2 flop). */
+deq_status deq_measure_fp64_peak(double* tflops, double* sm_clock_mhz_hint);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFEQ_B200_H */

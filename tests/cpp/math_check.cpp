@@ -1,0 +1,43 @@
+// Host-side check of diffeq_b200/csrc/deq_math.cuh against the running glibc (the libm the reference calls).
+// Build: g++ -O2 -ffp-contract=off -mfma tests/cpp/math_check.cpp -o /tmp/math_check -lm ; run: math_check <n>
+// Prints "MISMATCHES <k>" (k must be 0).
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include "../../diffeq_b200/csrc/deq_math.cuh"
+static uint64_t s = 88172645463325252ULL;
+static inline uint64_t rnd() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
+static inline double u01() { return (rnd() >> 11) * 0x1p-53; }
+static inline bool same(double a, double b) { return deqm::asu64(a) == deqm::asu64(b) || (a != a && b != b); }
+int main(int argc, char** argv) {
+    const long n = argc > 1 ? atol(argv[1]) : 2000000;
+    const deqm::Tables T = deqm::host();
+    long bad = 0;
+    const double ys[] = {0.5, 0.2, 0.125, 1.0 / 3.0, 0.5, 1.0 / 6.0, 0.25, 1.0 / 8.0};
+    for (long i = 0; i < n; ++i) {
+        double x = exp((u01() * 2 - 1) * (i % 4 == 0 ? 700.0 : 46.0));
+        if (i % 7 == 0) x = 1.0 + (u01() * 2 - 1) * 0.5 * pow(2.0, -(double)(i % 50));
+        const double y = ys[i % 8];
+        volatile double vx = x, vy = y;
+        if (!same(pow(vx, vy), deqm::pow_glibc(x, y, T))) { if (bad < 5) printf("pow x=%a y=%a\n", x, y); ++bad; }
+        double p = (u01() * 2 - 1) * (i % 3 == 0 ? 330.0 : 30.0);
+        volatile double v10 = 10.0, vp = p;
+        if (!same(pow(v10, vp), deqm::pow_glibc(10.0, p, T))) { if (bad < 5) printf("pow10 p=%a\n", p); ++bad; }
+        if (!same(log10(vx), deqm::log10_glibc(x, T))) { if (bad < 5) printf("log10 x=%a\n", x); ++bad; }
+        if (!same(log(vx), deqm::log_glibc(x, T))) { if (bad < 5) printf("log x=%a\n", x); ++bad; }
+    }
+    const double sp[] = {0.0, INFINITY, NAN, 1.0, 0x1p-1074, 0x1p-1030, 0x1p-1022, 1e300, 1e-300, 2.0, 4.0, 1e308, 0.5, 0x1.fffffffffffffp-1, 0x1.0000000000001p0};
+    const double spy[] = {0.5, 0.2, 0.125, 1.0 / 3.0, -0.5, 0.0, 1.0, 2.0, 1e-70, 1e70, -1e70, INFINITY, -INFINITY, NAN, 700.0, -700.0};
+    for (double x : sp) {
+        for (double y : spy) {
+            volatile double vx = x, vy = y;
+            if (!same(pow(vx, vy), deqm::pow_glibc(x, y, T))) { printf("special pow x=%a y=%a glibc=%a mine=%a\n", x, y, pow(vx, vy), deqm::pow_glibc(x, y, T)); ++bad; }
+        }
+        volatile double vx = x;
+        if (!same(log10(vx), deqm::log10_glibc(x, T))) { printf("special log10 x=%a\n", x); ++bad; }
+        volatile double nx = -x;
+        if (!same(log10(nx), deqm::log10_glibc(-x, T))) { printf("special log10 x=%a\n", -x); ++bad; }
+    }
+    printf("MISMATCHES %ld\n", bad);
+    return bad != 0;
+}

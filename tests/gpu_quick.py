@@ -1,0 +1,17 @@
+"""Quick GPU timing probe (not a test): config 2 at 1M trajectories, device-resident, plus the FP64 peak."""
+import sys, time
+import numpy as np
+sys.path.insert(0, ".")
+import diffeq_b200 as D
+from diffeq_b200 import synth
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+T = float(sys.argv[2]) if len(sys.argv) > 2 else 10.0
+print("fp64 peak TFLOP/s, MHz:", D.measure_fp64_peak())
+y0 = synth.lorenz_ics(0, N)
+p = D.OdeProblem.builder().fun(D.Rhs.builtin(0)).params(synth.LORENZ_PARAMS).init(y0).tspan([0.0, T]).build()
+for refill in (1, 0, 1, 0):
+    o = D.OdeOptionMap().insert(D.Reltol(1e-8), D.Abstol(1e-8), D.Refill(refill))
+    t = time.time(); s = p.solve(D.Ode.Ode45, o, fetch=False); w = time.time() - t
+    steps = s.totals["accepted"] + s.totals["rejected"]
+    print(f"refill={refill} kernel_ms={s.kernel_ms:.3f} wall_ms={w*1e3:.1f} steps={steps} steps/s={steps/(s.kernel_ms*1e-3):.4e} TFLOP/s(314/step)={steps*314/(s.kernel_ms*1e-3)/1e12:.2f}")
