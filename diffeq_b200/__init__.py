@@ -399,3 +399,41 @@ class OdeBuilder:
         if self._f.nparams and self._params is None:
             raise OdeError(1, "Required problem parameters must be initialized")
         return OdeProblem(self._f, np.ascontiguousarray(y0), self._tspan, self._params, single)
+
+
+def solve_host(rhs, y0, params, tspan, ode, opts=None, out_final=None, out_accepted=None, out_rejected=None,
+               tableau_set=TableauSet.Reference):
+    """End-to-end call on HOST buffers (the drop-in shape of `OdeProblem::solve` for an ensemble): uploads y0 / params /
+    tspan, integrates on the GPU, and copies the final states and step counters back into the given (ideally pinned)
+    buffers.  Returns (final, accepted, rejected)."""
+    L = lib()
+    y0 = _f64(y0)
+    if y0.ndim == 1:
+        y0 = y0[None, :]
+    ntraj, n = y0.shape
+    params = _f64(params) if params is not None else None
+    tspan = _f64(tspan)
+    o = (opts if opts is not None else OdeOptionMap()).to_c()
+    per = int(params is not None and params.ndim == 2)
+    ens = C.c_void_p(); res = C.c_void_p()
+    _check(L.deq_ensemble_create(rhs._h, C.c_size_t(ntraj), _ptr(y0), _ptr(params), per, _ptr(tspan),
+                                 C.c_size_t(len(tspan)), C.byref(ens)))
+    try:
+        o.async_ = 1
+        _check(L.deq_solve(ens, int(ode), int(tableau_set), C.byref(o), C.byref(res)))
+        try:
+            if out_final is None:
+                out_final = np.empty((ntraj, n))
+            _check(L.deq_result_final(res, _ptr(out_final)))
+            if tableau(ode, tableau_set)["adaptive"]:
+                if out_accepted is None:
+                    out_accepted = np.empty(ntraj, np.uint32)
+                if out_rejected is None:
+                    out_rejected = np.empty(ntraj, np.uint32)
+                _check(L.deq_result_counts(res, _ptr(out_accepted, C.c_uint32), _ptr(out_rejected, C.c_uint32), None,
+                                           None, None))
+        finally:
+            L.deq_result_destroy(res)
+    finally:
+        L.deq_ensemble_destroy(ens)
+    return out_final, out_accepted, out_rejected
