@@ -21,7 +21,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libdiffeq_b200.so")
+_LIB_PATH = os.environ.get("DEQ_LIB", os.path.join(_HERE, "libdiffeq_b200.so"))  # DEQ_LIB: experiment variants
 _lib = None
 
 

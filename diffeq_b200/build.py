@@ -46,12 +46,25 @@ def _run(cmd):
     return r.stderr
 
 
-def build(force=False, verbose=False):
-    os.makedirs(OBJ, exist_ok=True)
-    stamp = os.path.join(OBJ, "fingerprint")
-    fp = _fingerprint()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == fp:
-        return LIB
+def build(force=False, verbose=False, extra_flags=(), lib_path=None, obj_dir=None):
+    """extra_flags / lib_path / obj_dir build an experiment variant next to the product library."""
+    global NVCC_FLAGS
+    base_flags = NVCC_FLAGS
+    OBJ_ = obj_dir or OBJ
+    LIB_ = lib_path or LIB
+    os.makedirs(OBJ_, exist_ok=True)
+    stamp = os.path.join(OBJ_, "fingerprint")
+    fp = _fingerprint() + " ".join(extra_flags)
+    if not force and os.path.exists(LIB_) and os.path.exists(stamp) and open(stamp).read() == fp:
+        return LIB_
+    NVCC_FLAGS = list(base_flags) + list(extra_flags)
+    try:
+        return _build(OBJ_, LIB_, stamp, fp, verbose)
+    finally:
+        NVCC_FLAGS = base_flags
+
+
+def _build(OBJ, LIB, stamp, fp, verbose):
     jobs = []
     for tb in range(N_TB):
         o = os.path.join(OBJ, "kernels_tb%d.o" % tb)
@@ -73,4 +86,10 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    extra = [a[len("--flag="):] for a in sys.argv if a.startswith("--flag=")]
+    name = [a[len("--variant="):] for a in sys.argv if a.startswith("--variant=")]
+    if name:
+        print(build(force=True, verbose=False, extra_flags=extra,
+                    lib_path=os.path.join(HERE, "libdiffeq_b200_%s.so" % name[0]), obj_dir=os.path.join(HERE, "_build_" + name[0])))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True, extra_flags=extra))

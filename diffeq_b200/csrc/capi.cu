@@ -110,6 +110,20 @@ cudaError_t dalloc(T** p, size_t count, cudaStream_t st) {
 }
 void dfree(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
 
+// Keep freed blocks cached in the stream-ordered pool (default release threshold is 0: every synchronize would hand
+// the memory back to the driver and the next solve would pay cudaMalloc-class latencies again).
+void ensure_pool() {
+    static thread_local int done_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_dev) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done_dev = dev;
+}
+
 deq_status upload_soa(const double* h_aos, size_t ntraj, int n, double** d_soa, cudaStream_t st) {
     double* d_aos = nullptr;
     CK(dalloc(&d_aos, ntraj * n, st));
@@ -201,6 +215,7 @@ deq_status deq_ensemble_create(const deq_rhs* rhs, size_t ntraj, const double* y
     if (!rhs) return fail(DEQ_ERR_UNINITIALIZED, "Required problem must be initialized");
     if (!y0 && ntraj) return fail(DEQ_ERR_UNINITIALIZED, "Initial starting point must be initialized");
     if (!tspan) return fail(DEQ_ERR_UNINITIALIZED, "Time span must be initialized");
+    ensure_pool();
     deq_ensemble* e = new deq_ensemble();
     deq_status s = upload_soa(y0, ntraj, rhs->n, &e->d_y0, g_stream);
     if (!s) s = ensemble_common(rhs, ntraj, params, params_per_traj, tspan, ntspan, false, e);
@@ -243,6 +258,7 @@ deq_options deq_options_default(void) {
     o.points = DEQ_POINTS_ALL;
     o.output = DEQ_OUT_FINAL;
     o.refill = 1;
+    o.max_steps = 10000000ull;  // guard (extension): the reference can loop forever
     return o;
 }
 
@@ -254,6 +270,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
     if (tb == -1) return fail(DEQ_ERR_UNSUPPORTED, "stiff (Rosenbrock) methods are not part of the RK hot path");
     if (tb < 0) return fail(DEQ_ERR_INVALID_ARG, "unknown method");
     const deq_options o = opts_in ? *opts_in : deq_options_default();
+    ensure_pool();
     deql::TableauInfo info;
     g_tb[tb].info(&info);
     cudaStream_t st = g_stream;

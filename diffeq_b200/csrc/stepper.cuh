@@ -32,6 +32,23 @@ __device__ const uint64_t g_exp_tab[256] = {DEQ_EXP_TAB_INIT};
 __device__ const double g_powlog_tab[384] = {DEQ_POWLOG_TAB_INIT};
 __device__ const double g_log_tab[256] = {DEQ_LOG_TAB_INIT};
 
+// Tableau coefficients live in the constant bank: a DMUL/DADD takes `c[0x3][offset]` as an operand for free, whereas
+// 64-bit immediates cost two UMOV issue slots each (r1 profile: ~100 UMOV per step attempt).  Not `const` on
+// purpose, so the front end does not fold the values back into immediates.
+template <class TB>
+__constant__ deqt::Data<TB::S> c_tab = TB::data();
+#ifndef DEQ_TAB_CONST
+#define DEQ_TAB_CONST 1
+#endif
+#if DEQ_TAB_CONST
+#define DEQ_TAB(TB) const auto& tb = c_tab<TB>
+#else
+#define DEQ_TAB(TB) constexpr auto tb = TB::data()
+#endif
+#ifndef DEQ_MIN_BLOCKS
+#define DEQ_MIN_BLOCKS 4
+#endif
+
 template <class F, bool PT>
 __device__ __forceinline__ void load_params(double* prm, const double* params, const SharedParams& sh,
                                             unsigned long long traj, unsigned long long ntraj) {
@@ -43,7 +60,7 @@ __device__ __forceinline__ void load_params(double* prm, const double* params, c
 template <class TB, class F>
 __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double dt, double (&k)[TB::S][F::N],
                                        const double* prm) {
-    constexpr auto tb = TB::data();
+    DEQ_TAB(TB);
 #pragma unroll
     for (int row = 1; row < TB::S; ++row) {
         double yi[F::N];
@@ -66,7 +83,7 @@ __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double
 template <class TB, class F, bool PT, bool ALL>
 __global__ void __launch_bounds__(BLOCK) fixed_kernel(const FixedParams P) {
     constexpr int N = F::N, S = TB::S;
-    constexpr auto tb = TB::data();
+    DEQ_TAB(TB);
     const unsigned long long traj = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;
     if (traj >= P.ntraj) return;
     double prm[F::NP];
@@ -160,10 +177,10 @@ __global__ void __launch_bounds__(BLOCK) hinit_kernel(const HinitParams P) {
 // oderk_adapt (problem.rs:193-358), Points::All semantics.
 // ---------------------------------------------------------------------------------------------------------------
 template <class TB, class F, bool PT, int MODE>
-__global__ void __launch_bounds__(BLOCK, 4) adapt_kernel(const AdaptParams P) {
+__global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const AdaptParams P) {
     constexpr int N = F::N, S = TB::S;
-    constexpr auto tb = TB::data();
-    constexpr bool FSAL = deqt::fsal_of(tb);
+    constexpr bool FSAL = deqt::fsal_of(TB::data());
+    DEQ_TAB(TB);
     constexpr double PW = 1. / (double)(TB::ORDER_MIN + 1);
 
     __shared__ uint64_t s_exp[256];

@@ -52,7 +52,7 @@ typedef enum deq_tableau_set { DEQ_TABLEAU_REFERENCE = 0, DEQ_TABLEAU_TEXTBOOK =
 typedef enum deq_system { DEQ_SYS_LORENZ = 0, DEQ_SYS_VANDERPOL = 1, DEQ_SYS_PENDULUM = 2 } deq_system;
 
 /* `Points` (src/ode/options.rs:120-137).  Only Points::All is reference-valid (Specified re-reads y from the
- * output vector, problem.rs:262).  DEQ_POINTS_TSPAN is Points::All filtered to the tspan times. */
+ * output vector, problem.rs:262) and is rejected with DEQ_ERR_UNSUPPORTED; use deq_output for tspan-only rows. */
 typedef enum deq_points { DEQ_POINTS_ALL = 0, DEQ_POINTS_SPECIFIED = 1 } deq_points;
 
 /* What deq_solve materialises. */
@@ -81,7 +81,8 @@ typedef struct deq_options {
     double initstep;     /* Initstep, 0 = estimate with hinit (problem.rs:232-240) */
     int points;          /* deq_points, default DEQ_POINTS_ALL */
     int output;          /* deq_output, default DEQ_OUT_FINAL */
-    uint64_t max_steps;  /* extension: stop a trajectory after this many step attempts (0 = unlimited) */
+    uint64_t max_steps;  /* extension: stop a trajectory after this many step attempts; default 10^7, 0 = unlimited
+                          (the reference has no guard and can loop forever: broken tableaus, backward runs) */
     int refill;          /* 1 (default): persistent lanes refilled individually; 0: static warp assignment */
     int async;           /* 0 (default): deq_solve returns after the GPU finished; 1: returns after enqueueing */
 } deq_options;

@@ -1,0 +1,127 @@
+"""CPU: host-side logic, the C ABI surface and the libm replicas (no GPU needed, no compute calls)."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def test_abi_exports_every_declared_symbol(deq):
+    """libdiffeq_b200.so loads and exports exactly the functions include/diffeq_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "diffeq_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(deq_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(deq.ABI_SYMBOLS)
+    L = ctypes.CDLL(os.path.join(ROOT, "diffeq_b200", "libdiffeq_b200.so"))
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in deq.lib().deq_version()
+
+
+def test_product_does_not_touch_the_oracle():
+    """The product path must not import / link the oracle (it is test infrastructure)."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "diffeq_b200")):
+        if "_build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"(import\s+oracle|from\s+oracle|#include[^\n]*oracle|liboracle|oracle_[a-z]+\s*\()", txt), \
+                    f"{f} uses the oracle"
+    out = subprocess.run(["ldd", os.path.join(ROOT, "diffeq_b200", "libdiffeq_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def test_product_tableaus_match_reference_source(deq):
+    tabs = json.load(open(os.path.join(HERE, "golden", "tableaus.json")))
+    name2tab = {"Feuler": "feuler", "Heun": "heun", "Midpoint": "midpoint", "Ode4": "rk4", "Ode21": "rk21", "Ode23": "rk23",
+                "Ode45": "dopri5", "Ode45fe": "rk45", "Ode78": "feh78"}
+    fh = lambda v: [fh(x) for x in v] if isinstance(v, list) else float.fromhex(v)  # noqa: E731
+    for tset, key in ((deq.TableauSet.Reference, "reference"), (deq.TableauSet.Textbook, "textbook")):
+        for m, tn in name2tab.items():
+            g = tabs[key][tn]
+            t = deq.tableau(getattr(deq.Ode, m), tset)
+            assert (t["S"], t["adaptive"], t["order_min"], t["fsal"]) == (g["S"], g["adaptive"], g["order_min"], g["fsal"]), (m, key)
+            assert np.array_equal(t["a"], np.array(fh(g["a"]))) and np.array_equal(t["c"], np.array(fh(g["c"])))
+            gb = np.array(fh(g["b"]))
+            assert np.array_equal(t["b"] if g["adaptive"] else t["b"][:, 0], gb if g["adaptive"] else gb[:, 0])
+
+
+def test_ode_enum_and_from_str(deq):
+    """mod.rs:14-46: variant order and the FromStr table (no name for Ode45fe; "ode4s" -> Ode4ss)."""
+    assert [e.name for e in deq.Ode][:11] == ["Feuler", "Heun", "Midpoint", "Ode23", "Ode23s", "Ode4", "Ode45", "Ode45fe",
+                                               "Ode4skr", "Ode4ss", "Ode78"]
+    assert deq.Ode.from_str("ode45") is deq.Ode.Ode45 and deq.Ode.from_str("ode4s") is deq.Ode.Ode4ss
+    for bad in ("ode45fe", "rk4", ""):
+        with pytest.raises(ValueError):
+            deq.Ode.from_str(bad)
+
+
+def test_option_defaults_and_map(deq):
+    """options.rs:283-299 defaults; unknown reference options (Norm, StepTimeout, Retries) are ignored."""
+    o = deq.lib().deq_options_default()
+    assert (o.reltol, o.abstol, o.initstep, o.has_minstep, o.has_maxstep, o.points) == (1e-5, 1e-8, 0.0, 0, 0, 0)
+    m = deq.OdeOptionMap().insert(deq.Reltol(1e-3), deq.Maxstep(0.5), deq.Points.All)
+    m["StepTimeout"] = 7
+    c = m.to_c()
+    assert (c.reltol, c.abstol, c.has_maxstep, c.maxstep, c.has_minstep) == (1e-3, 1e-8, 1, 0.5, 0)
+
+
+def test_builder_uninitialized_errors(deq):
+    """problem.rs:92-104: build() fails with Uninitialized for every missing field (checked before any CUDA call)."""
+    rhs = deq.Rhs.builtin(deq.System.Lorenz)
+    assert rhs.dim == 3 and rhs.nparams == 3
+    for b in (deq.OdeProblem.builder().init([1, 2, 3]).tspan([0, 1]),
+              deq.OdeProblem.builder().fun(rhs).params([10, 28, 8 / 3]).tspan([0, 1]),
+              deq.OdeProblem.builder().fun(rhs).params([10, 28, 8 / 3]).init([1, 2, 3]),
+              deq.OdeProblem.builder().fun(rhs).init([1, 2, 3]).tspan([0, 1])):
+        with pytest.raises(deq.OdeError) as e:
+            b.build()
+        assert e.value.kind == "Uninitialized"
+    with pytest.raises(deq.OdeError):
+        deq.Rhs.builtin(99)
+
+
+def test_linspace_and_synth_are_deterministic(deq, oracle):
+    ts = deq.linspace(0.0, 100.0, 100001)
+    assert np.array_equal(ts, oracle.linspace(0.0, 100.0, 100001))
+    assert ts[0] == 0.0 and len(set(np.diff(ts).tolist())) == 16   # 16 distinct dt values on this grid
+    from diffeq_b200 import synth
+    a = synth.lorenz_ics(0, 1000)
+    b = np.concatenate([synth.lorenz_ics(0, 333), synth.lorenz_ics(333, 1000)])
+    assert np.array_equal(a, b)                      # counter RNG: shards generate the same inputs
+    assert a[:, :2].min() >= -20 and a[:, :2].max() < 20 and a[:, 2].min() >= 0 and a[:, 2].max() < 50
+    assert synth.splitmix64(np.array([0], dtype=np.uint64))[0] == np.uint64(0xE220A8397B1DCDAF)
+
+
+def test_device_math_header_matches_libm_on_host():
+    """deq_math.cuh compiled for the host (explicit FMAs, -ffp-contract=off) == the running glibc, bit for bit."""
+    exe = "/tmp/deq_math_check"
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma",
+                           os.path.join(HERE, "cpp", "math_check.cpp"), "-o", exe, "-lm"])
+    out = subprocess.run([exe, "1000000"], capture_output=True, text=True)
+    assert out.returncode == 0 and "MISMATCHES 0" in out.stdout, out.stdout[-500:]
+
+
+def test_shard_ranges():
+    from diffeq_b200 import sharding
+    for total, world in ((10, 3), (1 << 20, 8), (7, 8), (0, 2)):
+        r = [sharding.shard_range(total, k, world) for k in range(world)]
+        assert r[0][0] == 0 and r[-1][1] == total and all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+        assert max(e - b for b, e in r) - min(e - b for b, e in r) <= 1
+    assert sharding.weak_range(100, 3) == (300, 400)
+
+
+def test_bench_reference_arm_prints_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300)
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "trajectory-steps/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
