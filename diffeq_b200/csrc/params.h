@@ -2,7 +2,7 @@
 // (kernels_inst.cu) and the C ABI implementation (capi.cu).  All pointers are DEVICE pointers; ensemble arrays are
 // structure-of-arrays over trajectories ([component][trajectory]) so that a warp's loads and stores coalesce.
 #pragma once
-#include <stdint.h>
+#include "deq_rtc_compat.h"
 
 namespace deqk {
 

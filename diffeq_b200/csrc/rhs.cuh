@@ -6,7 +6,7 @@
 // (shared by the ensemble or one row per trajectory).  User systems come in as CUDA source through NVRTC with the
 // same signature (see nvrtc_rhs.cpp).
 #pragma once
-#include <math.h>
+#include "deq_rtc_compat.h"
 #if defined(__CUDACC__)
 #define DEQ_RHS_HD __host__ __device__ __forceinline__
 #else

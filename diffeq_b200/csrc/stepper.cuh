@@ -19,8 +19,7 @@
 // is bound by the FP64 pipe, not by memory.  Dense output (MODE_DENSE) writes SoA [N][ntspan][ntraj] so that lanes
 // that are at the same output index store to consecutive addresses.
 #pragma once
-#include <stdint.h>
-#include <float.h>
+#include "deq_rtc_compat.h"
 #include "deq_math.cuh"
 #include "tableaus.cuh"
 #include "rhs.cuh"
@@ -86,7 +85,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_kernel(const FixedParams P) {
     DEQ_TAB(TB);
     const unsigned long long traj = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;
     if (traj >= P.ntraj) return;
-    double prm[F::NP];
+    double prm[F::NP ? F::NP : 1];
     load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
     double y[N];
 #pragma unroll
@@ -132,7 +131,7 @@ __global__ void __launch_bounds__(BLOCK) hinit_kernel(const HinitParams P) {
     const deqm::Tables T{s_exp, s_powlog, s_log};
     const unsigned long long traj = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;
     if (traj >= P.ntraj) return;
-    double prm[F::NP];
+    double prm[F::NP ? F::NP : 1];
     load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
     double x0[N], f0[N];
 #pragma unroll
@@ -197,7 +196,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     bool pool_empty = false;
     unsigned long long traj = 0;
     double t = 0.0, dt = 0.0;
-    double cy[N], ck[N], prm[F::NP];
+    double cy[N], ck[N], prm[F::NP ? F::NP : 1];
     unsigned timeout = 0;
     bool last_step = false;
     uint32_t acc = 0, rej = 0;
@@ -206,7 +205,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
 #pragma unroll
     for (int d = 0; d < N; ++d) { cy[d] = 0.0; ck[d] = 0.0; }
 #pragma unroll
-    for (int j = 0; j < F::NP; ++j) prm[j] = 0.0;
+    for (int j = 0; j < (F::NP ? F::NP : 1); ++j) prm[j] = 0.0;
 
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !active);

@@ -203,3 +203,65 @@ def test_error_behaviour(deq):
     # zero time span: one accepted zero-length step
     sol = _problem(deq, deq.System.Lorenz, LOR, [0.1, 0.0, 0.0], [1.0, 1.0]).solve(deq.Ode.Ode45)
     assert int(sol.accepted[0]) == 1
+
+
+USER_LORENZ = r'''
+// same operation order as the reference fixture (problem.rs:989-1000)
+__device__ void rhs(double t, const double* v, double* d, const double* p) {
+    double x = v[0], y = v[1], z = v[2];
+    d[0] = p[0] * (y - x);
+    d[1] = x * (p[1] - z) - y;
+    d[2] = x * y - p[2] * z;
+}
+'''
+USER_VDP = r'''
+__device__ void rhs(double t, const double* v, double* d, const double* p) {
+    d[0] = v[1];
+    d[1] = p[0] * (1.0 - v[0] * v[0]) * v[1] - v[0];
+}
+'''
+
+
+def test_nvrtc_user_rhs_matches_oracle(deq, oracle):
+    """User CUDA source through NVRTC runs the same stepper templates: bit-exact vs the oracle, all output modes."""
+    from diffeq_b200 import synth
+    rhs = deq.Rhs.from_source(USER_LORENZ, 3, 3)
+    assert (rhs.dim, rhs.nparams) == (3, 3)
+    y0 = synth.lorenz_ics(0, 700)
+    o = deq.OdeOptionMap().insert(deq.Reltol(1e-8), deq.Abstol(1e-8))
+    sol = deq.OdeProblem.builder().fun(rhs).params(LOR).init(y0).tspan([0.0, 3.0]).build().solve(deq.Ode.Ode45, o)
+    ref = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, y0, [0.0, 3.0], oracle.opts(1e-8, 1e-8))
+    assert np.array_equal(sol.final, ref["yfinal"]) and np.array_equal(sol.accepted, ref["accepted"])
+    # fixed step, full solution of one trajectory
+    ts = deq.linspace(0.0, 1.0, 1001)
+    fx = deq.OdeProblem.builder().fun(rhs).params(LOR).init([0.1, 0.0, 0.0]).tspan(ts).build().solve(
+        deq.Ode.Ode4, deq.OdeOptionMap().insert(deq.Output.Tspan))
+    rf = oracle.solve_fixed(oracle.ODE4, oracle.LORENZ, LOR, [0.1, 0.0, 0.0], ts)
+    assert np.array_equal(fx.yout[0], rf["yout"])
+    # per-trajectory parameters + dense output
+    vd = deq.Rhs.from_source(USER_VDP, 2, 1)
+    y0v, mu = synth.vdp_sweep(0, 200, 200)
+    tsd = deq.linspace(0.0, 20.0, 300)
+    od = deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8), deq.Output.Tspan)
+    sd = deq.OdeProblem.builder().fun(vd).params(mu).init(y0v).tspan(tsd).build().solve(deq.Ode.Ode45fe, od)
+    rd = oracle.ensemble_dense(oracle.ODE45FE, oracle.VANDERPOL, mu, y0v, tsd, oracle.opts(1e-6, 1e-8))
+    want = rd["out"].transpose(2, 1, 0)
+    m = ~np.isnan(want)
+    assert np.array_equal(sd.nvalid, rd["nvalid"]) and np.array_equal(sd.yout[m], want[m])
+
+
+def test_nvrtc_compile_error_is_reported(deq):
+    with pytest.raises(deq.OdeError) as e:
+        deq.Rhs.from_source("__device__ void rhs(double t, const double* y, double* dy, const double* p) { dy[0] = undefined_symbol; }", 1, 0)
+    assert e.value.kind == "Nvrtc" and "undefined_symbol" in str(e.value)
+
+
+def test_nvrtc_generic_dimension_converges(deq):
+    """A 4-dimensional user system with no parameters (two uncoupled harmonic oscillators): exact solution known."""
+    src = "__device__ void rhs(double t, const double* y, double* dy, const double* p) { dy[0] = y[1]; dy[1] = -y[0]; dy[2] = 2.0 * y[3]; dy[3] = -2.0 * y[2]; }"
+    rhs = deq.Rhs.from_source(src, 4, 0)
+    y0 = np.tile(np.array([1.0, 0.0, 0.0, 1.0]), (33, 1))
+    o = deq.OdeOptionMap().insert(deq.Reltol(1e-10), deq.Abstol(1e-10))
+    sol = deq.OdeProblem.builder().fun(rhs).init(y0).tspan([0.0, 2.0]).build().solve(deq.Ode.Ode45, o, tableau_set=deq.TableauSet.Textbook)
+    want = np.array([np.cos(2.0), -np.sin(2.0), np.sin(4.0), np.cos(4.0)])
+    np.testing.assert_allclose(sol.final, np.tile(want, (33, 1)), rtol=0, atol=1e-8)
