@@ -78,6 +78,12 @@ class Output(enum.IntEnum):
     Tspan = 1
 
 
+class Mode(enum.IntEnum):
+    """Arithmetic mode (deq_mode): Parity = bit-identical to the reference restatement, Fast = FMA / zero-skipping."""
+    Parity = 0
+    Fast = 1
+
+
 class System(enum.IntEnum):
     Lorenz = 0
     VanDerPol = 1
@@ -87,7 +93,8 @@ class System(enum.IntEnum):
 class _Options(C.Structure):
     _fields_ = [("reltol", C.c_double), ("abstol", C.c_double), ("has_minstep", C.c_int), ("minstep", C.c_double),
                 ("has_maxstep", C.c_int), ("maxstep", C.c_double), ("initstep", C.c_double), ("points", C.c_int),
-                ("output", C.c_int), ("max_steps", C.c_uint64), ("refill", C.c_int), ("async_", C.c_int)]
+                ("output", C.c_int), ("max_steps", C.c_uint64), ("refill", C.c_int), ("async_", C.c_int),
+                ("mode", C.c_int)]
 
 
 # The symbols include/diffeq_b200.h declares (checked by tests/test_abi.py).
@@ -234,6 +241,8 @@ class OdeOptionMap(dict):
                 self["Points"] = o
             elif isinstance(o, Output):
                 self["Output"] = o
+            elif isinstance(o, Mode):
+                self["Mode"] = o
             else:
                 self[o.name] = o.v
         return self
@@ -249,6 +258,7 @@ class OdeOptionMap(dict):
         if "Output" in self: o.output = int(self["Output"])
         if "MaxSteps" in self: o.max_steps = int(self["MaxSteps"])
         if "Refill" in self: o.refill = int(self["Refill"])
+        if "Mode" in self: o.mode = int(self["Mode"])
         return o
 
 

@@ -32,9 +32,11 @@ deq_status fail(deq_status s, const std::string& msg) { g_err = msg; return s; }
     } while (0)
 
 const deql::TbEntry g_tb[deql::TB_COUNT] = {
-#define E(ID) {deql::launch_adapt_##ID, deql::launch_fixed_##ID, deql::info_##ID}
-    E(0), E(1), E(2), E(3), E(4), E(5), E(6), E(7), E(8), E(9), E(10), E(11), E(12)
+#define EF(ID) {deql::launch_adapt_##ID, nullptr, deql::launch_fixed_##ID, deql::info_##ID}  // fixed-step tableaus
+#define E(ID) {deql::launch_adapt_##ID, deql::launch_adapt_fast_##ID, deql::launch_fixed_##ID, deql::info_##ID}
+    EF(0), EF(1), EF(2), EF(3), E(4), E(5), E(6), E(7), E(8), E(9), E(10), E(11), E(12)
 #undef E
+#undef EF
 };
 
 // (method, set) -> tableau id; -1 unsupported, -2 invalid
@@ -97,6 +99,7 @@ struct deq_result {
     double *d_f0 = nullptr, *d_h0 = nullptr;
     unsigned long long* d_scalars = nullptr;  // [0] work counter, [1..3] totals
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;  // both events were recorded
     uint64_t fixed_nfe_per_traj = 0;
 };
 
@@ -270,6 +273,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
     if (tb == -1) return fail(DEQ_ERR_UNSUPPORTED, "stiff (Rosenbrock) methods are not part of the RK hot path");
     if (tb < 0) return fail(DEQ_ERR_INVALID_ARG, "unknown method");
     const deq_options o = opts_in ? *opts_in : deq_options_default();
+    if (o.mode != DEQ_MODE_PARITY && o.mode != DEQ_MODE_FAST) return fail(DEQ_ERR_INVALID_ARG, "unknown arithmetic mode");
     ensure_pool();
     deql::TableauInfo info;
     g_tb[tb].info(&info);
@@ -345,18 +349,19 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
             if (e->rhs.kind == 0) {
                 CKR(deql::launch_hinit(e->rhs.sys, e->per_traj, H, st));
                 CKR(cudaEventRecord(r->ev0, st));
-                CKR(g_tb[tb].adapt(e->rhs.sys, e->per_traj, mode, P, 0, st));
+                CKR((o.mode == DEQ_MODE_FAST ? g_tb[tb].adapt_fast : g_tb[tb].adapt)(e->rhs.sys, e->per_traj, mode, P, 0, st));
             } else {
                 std::string err;
                 if (!deqn::launch_hinit(e->rhs.prog, e->per_traj, H, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
                 CKR(cudaEventRecord(r->ev0, st));
-                if (!deqn::launch_adapt(e->rhs.prog, tb, e->per_traj, mode, P, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
+                if (!deqn::launch_adapt(e->rhs.prog, tb, e->per_traj, mode, o.mode == DEQ_MODE_FAST, P, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
             }
         } else {
             CKR(cudaEventRecord(r->ev0, st));
         }
         CKR(cudaEventRecord(r->ev1, st));
     }
+    r->timed = true;
     if (!o.async) CKR(cudaStreamSynchronize(st));
 #undef CKR
     *out = r;
@@ -446,7 +451,7 @@ deq_status deq_result_trajectory(deq_result* r, size_t traj, double* yout) {
 deq_status deq_result_kernel_ms(deq_result* r, float* ms) {
     if (!r || !ms) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
     *ms = 0.f;
-    if (!r->ev0 || !r->ev1) return DEQ_OK;
+    if (!r->timed || !r->ev0 || !r->ev1) return DEQ_OK;
     CK(cudaEventSynchronize(r->ev1));
     CK(cudaEventElapsedTime(ms, r->ev0, r->ev1));
     return DEQ_OK;

@@ -52,10 +52,18 @@ static int persistent_grid(K kernel, unsigned long long ntraj) {
     return (int)(want < cap ? (want ? want : 1) : cap);
 }
 
+#ifdef DEQ_FAST_TU
+constexpr bool kFast = true;    // this object is compiled with -fmad=true: FMA contraction everywhere
+#define DEQ_LAUNCH_ADAPT DEQ_CAT(launch_adapt_fast_, DEQ_TB)
+#else
+constexpr bool kFast = false;   // parity object, -fmad=false
+#define DEQ_LAUNCH_ADAPT DEQ_CAT(launch_adapt_, DEQ_TB)
+#endif
+
 template <class F, bool PT, int MODE>
 static cudaError_t launch_adapt_t(const deqk::AdaptParams& P, int grid_blocks, cudaStream_t st) {
     if constexpr (TB::ADAPTIVE) {
-        auto kernel = deqk::adapt_kernel<TB, F, PT, MODE>;
+        auto kernel = deqk::adapt_kernel<TB, F, PT, MODE, kFast>;
         const int grid = grid_blocks > 0 ? grid_blocks : persistent_grid(kernel, P.ntraj);
         kernel<<<grid, deqk::BLOCK, 0, st>>>(P);
         return cudaGetLastError();
@@ -73,8 +81,7 @@ static cudaError_t launch_adapt_f(int pt, int mode, const deqk::AdaptParams& P, 
                                     : launch_adapt_t<F, false, deqk::MODE_FINAL>(P, grid_blocks, st);
 }
 
-cudaError_t DEQ_CAT(launch_adapt_, DEQ_TB)(int sys, int pt, int mode, const deqk::AdaptParams& P, int grid_blocks,
-                                           cudaStream_t st) {
+cudaError_t DEQ_LAUNCH_ADAPT(int sys, int pt, int mode, const deqk::AdaptParams& P, int grid_blocks, cudaStream_t st) {
     switch (sys) {
         case 0: return launch_adapt_f<deqr::Lorenz>(pt, mode, P, grid_blocks, st);
         case 1: return launch_adapt_f<deqr::VanDerPol>(pt, mode, P, grid_blocks, st);
@@ -83,6 +90,7 @@ cudaError_t DEQ_CAT(launch_adapt_, DEQ_TB)(int sys, int pt, int mode, const deqk
     }
 }
 
+#ifndef DEQ_FAST_TU
 template <class F, bool PT, bool ALL>
 static cudaError_t launch_fixed_t(const deqk::FixedParams& P, cudaStream_t st) {
     if constexpr (!TB::ADAPTIVE) {
@@ -119,5 +127,7 @@ void DEQ_CAT(info_, DEQ_TB)(TableauInfo* out) {
         out->b[2 * r] = tb.b[r][0]; out->b[2 * r + 1] = tb.b[r][1]; out->c[r] = tb.c[r];
     }
 }
+
+#endif  // !DEQ_FAST_TU
 
 }  // namespace deql

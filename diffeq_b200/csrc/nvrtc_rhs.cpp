@@ -82,7 +82,7 @@ struct Program {
     ~Program() { for (auto& kv : cache) if (kv.second.lib) cudaLibraryUnload(kv.second.lib); }
 };
 
-static bool compile(Program* p, const std::string& name_expr, Kernel* out, std::string* err) {
+static bool compile(Program* p, const std::string& name_expr, bool fmad, Kernel* out, std::string* err) {
     Nvrtc* rt = nvrtc(err);
     if (!rt) return false;
     std::ostringstream src;
@@ -96,8 +96,8 @@ static bool compile(Program* p, const std::string& name_expr, Kernel* out, std::
     nvrtcResult rc = rt->CreateProgram(&prog, src.str().c_str(), "deq_user_program.cu", kNumSrc, kSrcTexts, kSrcNames);
     if (rc) { if (err) *err = std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc); return false; }
     rt->AddNameExpression(prog, name_expr.c_str());
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-default-device", "-lineinfo",
-                          "-DDEQ_NVRTC=1"};
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", fmad ? "--fmad=true" : "--fmad=false", "-default-device",
+                          "-lineinfo", "-DDEQ_NVRTC=1"};
     rc = rt->CompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
     if (rc) {
         size_t n = 0;
@@ -138,10 +138,11 @@ static bool get_kernel(Program* p, int kind, int tb, int pt, int mode, Kernel* o
     std::ostringstream ne;
     const char* b = pt ? "true" : "false";
     if (kind == 0) ne << "&deqk::hinit_kernel<DeqUserRhs, " << b << ">";
-    else if (kind == 1) ne << "&deqk::adapt_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << mode << ">";
+    else if (kind == 1) ne << "&deqk::adapt_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode & 1) << ", "
+                           << ((mode & 2) ? "true" : "false") << ">";
     else ne << "&deqk::fixed_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode ? "true" : "false") << ">";
     Kernel k;
-    if (!compile(p, ne.str(), &k, err)) return false;
+    if (!compile(p, ne.str(), kind == 1 && (mode & 2), &k, err)) return false;
     p->cache[key] = k;
     *out = k;
     return true;
@@ -174,9 +175,10 @@ bool launch_hinit(Program* p, int pt, const deqk::HinitParams& P, cudaStream_t s
     return launch(k, (unsigned)((P.ntraj + deqk::BLOCK - 1) / deqk::BLOCK), P, st, err);
 }
 
-bool launch_adapt(Program* p, int tb, int pt, int mode, const deqk::AdaptParams& P, cudaStream_t st, std::string* err) {
+bool launch_adapt(Program* p, int tb, int pt, int mode, bool fast, const deqk::AdaptParams& P, cudaStream_t st,
+                  std::string* err) {
     Kernel k;
-    if (!get_kernel(p, 1, tb, pt ? 1 : 0, mode, &k, err)) return false;
+    if (!get_kernel(p, 1, tb, pt ? 1 : 0, (mode & 1) | (fast ? 2 : 0), &k, err)) return false;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -16,8 +16,8 @@ void retain(Program* p);
 void release(Program* p);
 
 bool launch_hinit(Program* p, int per_traj_params, const deqk::HinitParams& P, cudaStream_t st, std::string* err);
-bool launch_adapt(Program* p, int tb, int per_traj_params, int mode, const deqk::AdaptParams& P, cudaStream_t st,
-                  std::string* err);
+bool launch_adapt(Program* p, int tb, int per_traj_params, int mode, bool fast, const deqk::AdaptParams& P,
+                  cudaStream_t st, std::string* err);
 bool launch_fixed(Program* p, int tb, int per_traj_params, int all, const deqk::FixedParams& P, cudaStream_t st,
                   std::string* err);
 

@@ -56,10 +56,13 @@ __device__ __forceinline__ void load_params(double* prm, const double* params, c
 }
 
 // calc_coefficients (problem.rs:702-737): k[0] holds k0; fills k[1..S-1].
-template <class TB, class F>
+// FAST = false: the reference's operation order, one rounding per * and +, zero coefficients multiplied through.
+// FAST = true : fused multiply-adds, structurally-zero coefficients skipped (results differ in the last bits).
+template <class TB, class F, bool FAST>
 __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double dt, double (&k)[TB::S][F::N],
                                        const double* prm) {
     DEQ_TAB(TB);
+    constexpr auto tbc = TB::data();
 #pragma unroll
     for (int row = 1; row < TB::S; ++row) {
         double yi[F::N];
@@ -67,13 +70,34 @@ __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double
         for (int d = 0; d < F::N; ++d) yi[d] = y[d];
 #pragma unroll
         for (int col = 0; col < row; ++col) {
-            const double w = tb.a[row][col] * dt;
+            if (FAST) {
+                if (tbc.a[row][col] != 0.0) {
+                    const double w = tb.a[row][col] * dt;
 #pragma unroll
-            for (int d = 0; d < F::N; ++d) yi[d] = yi[d] + k[col][d] * w;
+                    for (int d = 0; d < F::N; ++d) yi[d] = __fma_rn(k[col][d], w, yi[d]);
+                }
+            } else {
+                const double w = tb.a[row][col] * dt;
+#pragma unroll
+                for (int d = 0; d < F::N; ++d) yi[d] = yi[d] + k[col][d] * w;
+            }
         }
-        const double tn = t + tb.c[row] * dt;
+        const double tn = FAST ? __fma_rn(tb.c[row], dt, t) : t + tb.c[row] * dt;
         F::eval(tn, yi, k[row], prm);
     }
+}
+
+// 1/x to full double precision without the IEEE corner-case handling (x is a positive, normal error scale):
+// MUFU.RCP64H seed + Newton steps.  FAST mode only.
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = __fma_rn(-x, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-x, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-x, r, 1.0);
+    return __fma_rn(r, e, r);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -100,7 +124,7 @@ __global__ void __launch_bounds__(BLOCK) fixed_kernel(const FixedParams P) {
         const double dt = tnext - tcur;
         double k[S][N];
         F::eval(tcur, y, k[0], prm);
-        stages<TB, F>(tcur, y, dt, k, prm);
+        stages<TB, F, false>(tcur, y, dt, k, prm);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
 #pragma unroll
@@ -175,7 +199,7 @@ __global__ void __launch_bounds__(BLOCK) hinit_kernel(const HinitParams P) {
 // ---------------------------------------------------------------------------------------------------------------
 // oderk_adapt (problem.rs:193-358), Points::All semantics.
 // ---------------------------------------------------------------------------------------------------------------
-template <class TB, class F, bool PT, int MODE>
+template <class TB, class F, bool PT, int MODE, bool FAST>
 __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const AdaptParams P) {
     constexpr int N = F::N, S = TB::S;
     constexpr bool FSAL = deqt::fsal_of(TB::data());
@@ -249,36 +273,67 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
             double k[S][N];
 #pragma unroll
             for (int d = 0; d < N; ++d) k[0][d] = ck[d];
-            stages<TB, F>(t, cy, dt, k, prm);
-            // embedded_step :761-771  (y == cy under Points::All)
+            stages<TB, F, FAST>(t, cy, dt, k, prm);
             double ytrial[N], yerr[N];
-#pragma unroll
-            for (int d = 0; d < N; ++d) {
-                double p = 0.0, q = 0.0;
-#pragma unroll
-                for (int s = 0; s < S; ++s) { p = p + k[s][d] * tb.b[s][0]; q = q + k[s][d] * tb.b[s][1]; }
-                yerr[d] = (p - q) * dt;
-                ytrial[d] = cy[d] + (p * dt);
-            }
-            // stepsize_hw92 :801-845
             double err, ndt;
-            bool isnan_trial = false;
+            if (!FAST) {
+                // embedded_step :761-771  (y == cy under Points::All)
 #pragma unroll
-            for (int d = 0; d < N; ++d) isnan_trial = isnan_trial || (ytrial[d] != ytrial[d]);
-            if (isnan_trial) {
-                err = 10.; ndt = 0.2 * dt; timeout = 5;
+                for (int d = 0; d < N; ++d) {
+                    double p = 0.0, q = 0.0;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) { p = p + k[s][d] * tb.b[s][0]; q = q + k[s][d] * tb.b[s][1]; }
+                    yerr[d] = (p - q) * dt;
+                    ytrial[d] = cy[d] + (p * dt);
+                }
+                // stepsize_hw92 :801-845
+                bool isnan_trial = false;
+#pragma unroll
+                for (int d = 0; d < N; ++d) isnan_trial = isnan_trial || (ytrial[d] != ytrial[d]);
+                if (isnan_trial) {
+                    err = 10.; ndt = 0.2 * dt; timeout = 5;
+                } else {
+                    double ssum = 0.0;
+#pragma unroll
+                    for (int d = 0; d < N; ++d) {
+                        const double e = yerr[d] / (fmax(fabs(cy[d]), fabs(ytrial[d])) * reltol + abstol);
+                        const double a = fabs(e);
+                        ssum = ssum + a * a;
+                    }
+                    err = deqm::pow_glibc(ssum, 0.5, T);
+                    double nd = fmin(P.maxstep, (fmax(0.2, deqm::pow_glibc(1.0 / err, PW, T) * 0.8) * tdir) * dt);
+                    if (timeout > 0) { nd = fmin(nd, dt); timeout -= 1; }
+                    ndt = tdir * nd;
+                }
             } else {
+                // FAST: same formulas with fused multiply-adds; zero weights skipped; error weights b - b* combined;
+                // err < 1 decided on the squared norm; one pow for the step factor: (1/err)^PW = ssum^(-PW/2).
+                constexpr auto tbc = TB::data();
+#pragma unroll
+                for (int d = 0; d < N; ++d) {
+                    double p = 0.0, e = 0.0;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        if (tbc.b[s][0] != 0.0) p = __fma_rn(k[s][d], tb.b[s][0], p);
+                        if (tbc.b[s][0] - tbc.b[s][1] != 0.0) e = __fma_rn(k[s][d], tbc.b[s][0] - tbc.b[s][1], e);
+                    }
+                    yerr[d] = e * dt;
+                    ytrial[d] = __fma_rn(p, dt, cy[d]);
+                }
                 double ssum = 0.0;
 #pragma unroll
                 for (int d = 0; d < N; ++d) {
-                    const double e = yerr[d] / (fmax(fabs(cy[d]), fabs(ytrial[d])) * reltol + abstol);
-                    const double a = fabs(e);
-                    ssum = ssum + a * a;
+                    const double e = yerr[d] * rcp_fast(__fma_rn(fmax(fabs(cy[d]), fabs(ytrial[d])), reltol, abstol));
+                    ssum = __fma_rn(e, e, ssum);
                 }
-                err = deqm::pow_glibc(ssum, 0.5, T);
-                double nd = fmin(P.maxstep, (fmax(0.2, deqm::pow_glibc(1.0 / err, PW, T) * 0.8) * tdir) * dt);
-                if (timeout > 0) { nd = fmin(nd, dt); timeout -= 1; }
-                ndt = tdir * nd;
+                if (ssum != ssum) {
+                    err = 10.; ndt = 0.2 * dt; timeout = 5;
+                } else {
+                    err = ssum;  // compared against 1 below: sqrt(ssum) < 1  <=>  ssum < 1
+                    double nd = fmin(P.maxstep, (fmax(0.2, deqm::pow_glibc(ssum, -0.5 * PW, T) * 0.8) * tdir) * dt);
+                    if (timeout > 0) { nd = fmin(nd, dt); timeout -= 1; }
+                    ndt = tdir * nd;
+                }
             }
             if (err < 1.) {
                 acc += 1;
@@ -314,7 +369,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                 } else {
                     t = t + dt;
                     dt = ndt;
-                    if (tdir * ((t + dt) + dt / 100.) >= tdir * tend) { dt = tend - t; last_step = true; }
+                    if (tdir * ((t + dt) + (FAST ? dt * 0.01 : dt / 100.)) >= tdir * tend) { dt = tend - t; last_step = true; }
                 }
             } else if (fabs(ndt) < P.minstep) {
                 fin = ST_MINSTEP_BREAK;

@@ -61,6 +61,12 @@ typedef enum deq_output {
     DEQ_OUT_TSPAN = 1   /* additionally the rows of (tout,yout) that fall on tspan times, SoA [n][ntspan][ntraj] */
 } deq_output;
 
+/* Arithmetic of the adaptive kernels.  PARITY (default): every operation rounded and ordered as in the reference,
+ * glibc-exact pow — results are bit-identical to the CPU restatement of the crate.  FAST: fused multiply-adds,
+ * structurally-zero tableau entries skipped, one pow per step — identical accepted-step counts and final states
+ * within 10 x rtol of PARITY on the BASELINE ensembles (tests/test_gpu_parity.py), ~2x the throughput. */
+typedef enum deq_mode { DEQ_MODE_PARITY = 0, DEQ_MODE_FAST = 1 } deq_mode;
+
 /* Per-trajectory completion code (the reference returns Ok(partial) silently in the first two cases). */
 typedef enum deq_traj_status {
     DEQ_TRAJ_DONE = 0,
@@ -85,6 +91,7 @@ typedef struct deq_options {
                           (the reference has no guard and can loop forever: broken tableaus, backward runs) */
     int refill;          /* 1 (default): persistent lanes refilled individually; 0: static warp assignment */
     int async;           /* 0 (default): deq_solve returns after the GPU finished; 1: returns after enqueueing */
+    int mode;            /* deq_mode, default DEQ_MODE_PARITY (adaptive methods only; fixed-step is always parity) */
 } deq_options;
 
 typedef struct deq_rhs deq_rhs;

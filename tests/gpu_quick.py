@@ -10,8 +10,8 @@ T = float(sys.argv[2]) if len(sys.argv) > 2 else 10.0
 print("fp64 peak TFLOP/s, MHz:", D.measure_fp64_peak())
 y0 = synth.lorenz_ics(0, N)
 p = D.OdeProblem.builder().fun(D.Rhs.builtin(0)).params(synth.LORENZ_PARAMS).init(y0).tspan([0.0, T]).build()
-for refill in (1, 0, 1, 0):
-    o = D.OdeOptionMap().insert(D.Reltol(1e-8), D.Abstol(1e-8), D.Refill(refill))
+for refill, mode in ((1, 0), (0, 0), (1, 0), (1, 1), (0, 1), (1, 1)):
+    o = D.OdeOptionMap().insert(D.Reltol(1e-8), D.Abstol(1e-8), D.Refill(refill), D.Mode(mode))
     t = time.time(); s = p.solve(D.Ode.Ode45, o, fetch=False); w = time.time() - t
     steps = s.totals["accepted"] + s.totals["rejected"]
-    print(f"refill={refill} kernel_ms={s.kernel_ms:.3f} wall_ms={w*1e3:.1f} steps={steps} steps/s={steps/(s.kernel_ms*1e-3):.4e} TFLOP/s(314/step)={steps*314/(s.kernel_ms*1e-3)/1e12:.2f}")
+    print(f"mode={mode} refill={refill} kernel_ms={s.kernel_ms:.3f} wall_ms={w*1e3:.1f} steps={steps} steps/s={steps/(s.kernel_ms*1e-3):.4e} TFLOP/s(314/step)={steps*314/(s.kernel_ms*1e-3)/1e12:.2f}")
