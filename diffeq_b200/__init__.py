@@ -101,7 +101,7 @@ class _Options(C.Structure):
 ABI_SYMBOLS = [
     "deq_last_error_message", "deq_version", "deq_rhs_builtin", "deq_rhs_from_source", "deq_rhs_dim",
     "deq_rhs_nparams", "deq_rhs_destroy", "deq_tspan_linspace", "deq_ensemble_create", "deq_ensemble_create_device",
-    "deq_ensemble_destroy", "deq_ensemble_ntraj", "deq_set_stream", "deq_options_default", "deq_solve",
+    "deq_ensemble_destroy", "deq_ensemble_ntraj", "deq_set_stream", "deq_set_device", "deq_get_device", "deq_options_default", "deq_solve",
     "deq_result_final", "deq_result_counts", "deq_result_totals", "deq_result_dense", "deq_result_device_ptrs",
     "deq_result_trajectory", "deq_result_kernel_ms", "deq_result_destroy", "deq_tableau_get", "deq_host_alloc",
     "deq_host_free", "deq_test_pow", "deq_test_log10", "deq_measure_fp64_peak",
@@ -137,6 +137,11 @@ def _f64(a):
 
 def _ptr(a, t=C.c_double):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def set_device(device):
+    """Select the GPU for this thread's subsequent library calls (mirror torch.cuda.set_device here)."""
+    _check(lib().deq_set_device(int(device)))
 
 
 def set_stream(cuda_stream_ptr):

@@ -211,6 +211,8 @@ deq_status deq_tspan_linspace(double from, double to, size_t n, double* out) {
 }
 
 deq_status deq_set_stream(void* s) { g_stream = (cudaStream_t)s; return DEQ_OK; }
+deq_status deq_set_device(int device) { CK(cudaSetDevice(device)); return DEQ_OK; }
+deq_status deq_get_device(int* device) { if (!device) return fail(DEQ_ERR_INVALID_ARG, "NULL argument"); CK(cudaGetDevice(device)); return DEQ_OK; }
 
 deq_status deq_ensemble_create(const deq_rhs* rhs, size_t ntraj, const double* y0, const double* params,
                                int params_per_traj, const double* tspan, size_t ntspan, deq_ensemble** out) {

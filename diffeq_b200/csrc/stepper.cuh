@@ -87,17 +87,29 @@ __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double
     }
 }
 
+// max(|a|, |b|) and min/max for operands that are known not to be NaN at the call site (a NaN trial state takes the
+// reject branch before the error scale is formed; accepted states are never NaN).  fmax()/fmin() lower to a DSETP plus
+// ~7 integer/select instructions on sm_100a because of their NaN rules; these compare-selects are 3 and return the same
+// value for every non-NaN input (f64::max / f64::min of the reference, problem.rs:827,833,836).
+__device__ __forceinline__ double max_abs_nonan(double a, double b) {
+    const double fa = fabs(a), fb = fabs(b);
+    return fa > fb ? fa : fb;
+}
+// sel_max(c, x) == f64::max(c, x) when c is not NaN: a NaN x yields c, like the NaN-ignoring reference call.
+__device__ __forceinline__ double sel_max(double c, double x) { return x > c ? x : c; }
+__device__ __forceinline__ double sel_min(double c, double x) { return x < c ? x : c; }
+
+constexpr int BURST_ATTEMPTS = 8;
+
 // 1/x to full double precision without the IEEE corner-case handling (x is a positive, normal error scale):
 // MUFU.RCP64H seed + Newton steps.  FAST mode only.
 __device__ __forceinline__ double rcp_fast(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = __fma_rn(-x, r, 1.0);
-    r = __fma_rn(r, e, r);
+    double e = __fma_rn(-x, r, 1.0);   // seed is good to ~2^-20
+    r = __fma_rn(r, e, r);             // ~2^-40
     e = __fma_rn(-x, r, 1.0);
-    r = __fma_rn(r, e, r);
-    e = __fma_rn(-x, r, 1.0);
-    return __fma_rn(r, e, r);
+    return __fma_rn(r, e, r);          // ~2^-80 -> rounded double
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -211,10 +223,11 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     for (int i = threadIdx.x; i < 256; i += BLOCK) s_exp[i] = g_exp_tab[i];
     for (int i = threadIdx.x; i < 384; i += BLOCK) s_powlog[i] = g_powlog_tab[i];
     __syncthreads();
-    const deqm::Tables T{s_exp, s_powlog, nullptr};
+    const deqm::SmemTables T{(unsigned)__cvta_generic_to_shared(s_exp), (unsigned)__cvta_generic_to_shared(s_powlog), 0u};
 
     const unsigned lane = threadIdx.x & 31u;
     const double tdir = P.tdir, tend = P.tend, reltol = P.reltol, abstol = P.abstol;
+    const uint32_t max_steps = P.max_steps == 0ull || P.max_steps > 0xffffffffull ? 0xffffffffu : (uint32_t)P.max_steps;
 
     bool active = false;
     bool pool_empty = false;
@@ -223,8 +236,8 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     double cy[N], ck[N], prm[F::NP ? F::NP : 1];
     unsigned timeout = 0;
     bool last_step = false;
-    uint32_t acc = 0, rej = 0;
-    unsigned long long attempts = 0, it = 1;
+    uint32_t acc = 0, rej = 0, attempts = 0;
+    unsigned long long it = 1;
     unsigned long long tot_acc = 0, tot_rej = 0, tot_nfe = 0;
 #pragma unroll
     for (int d = 0; d < N; ++d) { cy[d] = 0.0; ck[d] = 0.0; }
@@ -232,6 +245,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     for (int j = 0; j < (F::NP ? F::NP : 1); ++j) prm[j] = 0.0;
 
     for (;;) {
+        // ---- refill idle lanes from the global work counter (warp-aggregated) ----
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
         if (idle != 0u && !pool_empty && (P.refill || idle == 0xffffffffu)) {
             unsigned long long base = 0;
@@ -262,136 +276,145 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
             }
         }
         if (__ballot_sync(0xffffffffu, active) == 0u) break;
-        if (!active) continue;
 
-        // ---- one step attempt (loop body of problem.rs:260-352) ----
-        uint8_t fin = 0xff;  // 0xff: keep going
-        if (P.max_steps != 0ull && attempts >= P.max_steps) {
-            fin = ST_MAX_STEPS;
-        } else {
-            ++attempts;
-            double k[S][N];
+        // ---- a burst of step attempts without any warp-level synchronisation: the refill check above costs ~20
+        // issue slots, which at one check per attempt was ~3 % of the kernel (FP64 instructions hold the issue port
+        // for two cycles on B200 and nothing co-issues, so every non-FP64 instruction is paid in full).  A lane that
+        // finishes inside a burst idles for at most BURST-1 attempts out of the ~10^3 its trajectory took. ----
+#pragma unroll 1
+        for (int burst = 0; burst < BURST_ATTEMPTS && active; ++burst) {
+            // one step attempt (loop body of problem.rs:260-352)
+            uint8_t fin = 0xff;  // 0xff: keep going
+            if (attempts >= max_steps) {
+                fin = ST_MAX_STEPS;
+            } else {
+                ++attempts;
+                double k[S][N];
 #pragma unroll
-            for (int d = 0; d < N; ++d) k[0][d] = ck[d];
-            stages<TB, F, FAST>(t, cy, dt, k, prm);
-            double ytrial[N], yerr[N];
-            double err, ndt;
-            if (!FAST) {
-                // embedded_step :761-771  (y == cy under Points::All)
+                for (int d = 0; d < N; ++d) k[0][d] = ck[d];
+                stages<TB, F, FAST>(t, cy, dt, k, prm);
+                double ytrial[N], yerr[N];
+                double ndt;
+                bool accept;
+                if (!FAST) {
+                    // embedded_step :761-771  (y == cy under Points::All)
 #pragma unroll
-                for (int d = 0; d < N; ++d) {
-                    double p = 0.0, q = 0.0;
+                    for (int d = 0; d < N; ++d) {
+                        double p = 0.0, q = 0.0;
 #pragma unroll
-                    for (int s = 0; s < S; ++s) { p = p + k[s][d] * tb.b[s][0]; q = q + k[s][d] * tb.b[s][1]; }
-                    yerr[d] = (p - q) * dt;
-                    ytrial[d] = cy[d] + (p * dt);
-                }
-                // stepsize_hw92 :801-845
-                bool isnan_trial = false;
+                        for (int s = 0; s < S; ++s) { p = p + k[s][d] * tb.b[s][0]; q = q + k[s][d] * tb.b[s][1]; }
+                        yerr[d] = (p - q) * dt;
+                        ytrial[d] = cy[d] + (p * dt);
+                    }
+                    // stepsize_hw92 :801-845
+                    bool isnan_trial = false;
 #pragma unroll
-                for (int d = 0; d < N; ++d) isnan_trial = isnan_trial || (ytrial[d] != ytrial[d]);
-                if (isnan_trial) {
-                    err = 10.; ndt = 0.2 * dt; timeout = 5;
+                    for (int d = 0; d < N; ++d) isnan_trial = isnan_trial || (ytrial[d] != ytrial[d]);
+                    if (isnan_trial) {
+                        accept = false; ndt = 0.2 * dt; timeout = 5;   // err = 10
+                    } else {
+                        double ssum = 0.0;
+#pragma unroll
+                        for (int d = 0; d < N; ++d) {
+                            const double e = yerr[d] / (max_abs_nonan(cy[d], ytrial[d]) * reltol + abstol);
+                            const double a = fabs(e);
+                            ssum = ssum + a * a;
+                        }
+                        const double err = deqm::pow_glibc(ssum, 0.5, T);
+                        const double g = deqm::pow_glibc(1.0 / err, PW, T) * 0.8;
+                        double nd = sel_min(P.maxstep, (sel_max(0.2, g) * tdir) * dt);
+                        if (timeout > 0) { nd = sel_min(nd, dt); timeout -= 1; }
+                        ndt = tdir * nd;
+                        accept = err < 1.;
+                    }
                 } else {
+                    // FAST: same formulas with fused multiply-adds; zero weights skipped; error weights b - b* combined;
+                    // err < 1 decided on the squared norm; one pow for the step factor: (1/err)^PW = ssum^(-PW/2).
+                    constexpr auto tbc = TB::data();
+#pragma unroll
+                    for (int d = 0; d < N; ++d) {
+                        double p = 0.0, e = 0.0;
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            if (tbc.b[s][0] != 0.0) p = __fma_rn(k[s][d], tb.b[s][0], p);
+                            if (tbc.b[s][0] - tbc.b[s][1] != 0.0) e = __fma_rn(k[s][d], tbc.b[s][0] - tbc.b[s][1], e);
+                        }
+                        yerr[d] = e * dt;
+                        ytrial[d] = __fma_rn(p, dt, cy[d]);
+                    }
                     double ssum = 0.0;
 #pragma unroll
                     for (int d = 0; d < N; ++d) {
-                        const double e = yerr[d] / (fmax(fabs(cy[d]), fabs(ytrial[d])) * reltol + abstol);
-                        const double a = fabs(e);
-                        ssum = ssum + a * a;
+                        const double e = yerr[d] * rcp_fast(__fma_rn(max_abs_nonan(cy[d], ytrial[d]), reltol, abstol));
+                        ssum = __fma_rn(e, e, ssum);
                     }
-                    err = deqm::pow_glibc(ssum, 0.5, T);
-                    double nd = fmin(P.maxstep, (fmax(0.2, deqm::pow_glibc(1.0 / err, PW, T) * 0.8) * tdir) * dt);
-                    if (timeout > 0) { nd = fmin(nd, dt); timeout -= 1; }
-                    ndt = tdir * nd;
-                }
-            } else {
-                // FAST: same formulas with fused multiply-adds; zero weights skipped; error weights b - b* combined;
-                // err < 1 decided on the squared norm; one pow for the step factor: (1/err)^PW = ssum^(-PW/2).
-                constexpr auto tbc = TB::data();
-#pragma unroll
-                for (int d = 0; d < N; ++d) {
-                    double p = 0.0, e = 0.0;
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        if (tbc.b[s][0] != 0.0) p = __fma_rn(k[s][d], tb.b[s][0], p);
-                        if (tbc.b[s][0] - tbc.b[s][1] != 0.0) e = __fma_rn(k[s][d], tbc.b[s][0] - tbc.b[s][1], e);
+                    if (ssum != ssum) {
+                        accept = false; ndt = 0.2 * dt; timeout = 5;
+                    } else {
+                        const double g = deqm::pow_glibc(ssum, -0.5 * PW, T) * 0.8;
+                        double nd = sel_min(P.maxstep, (sel_max(0.2, g) * tdir) * dt);
+                        if (timeout > 0) { nd = sel_min(nd, dt); timeout -= 1; }
+                        ndt = tdir * nd;
+                        accept = ssum < 1.;   // sqrt(ssum) < 1  <=>  ssum < 1
                     }
-                    yerr[d] = e * dt;
-                    ytrial[d] = __fma_rn(p, dt, cy[d]);
                 }
-                double ssum = 0.0;
+                if (accept) {
+                    acc += 1;
+                    double f1[N];
+                    if (FSAL) {
 #pragma unroll
-                for (int d = 0; d < N; ++d) {
-                    const double e = yerr[d] * rcp_fast(__fma_rn(fmax(fabs(cy[d]), fabs(ytrial[d])), reltol, abstol));
-                    ssum = __fma_rn(e, e, ssum);
-                }
-                if (ssum != ssum) {
-                    err = 10.; ndt = 0.2 * dt; timeout = 5;
-                } else {
-                    err = ssum;  // compared against 1 below: sqrt(ssum) < 1  <=>  ssum < 1
-                    double nd = fmin(P.maxstep, (fmax(0.2, deqm::pow_glibc(ssum, -0.5 * PW, T) * 0.8) * tdir) * dt);
-                    if (timeout > 0) { nd = fmin(nd, dt); timeout -= 1; }
-                    ndt = tdir * nd;
-                }
-            }
-            if (err < 1.) {
-                acc += 1;
-                double f1[N];
-                if (FSAL) {
+                        for (int d = 0; d < N; ++d) f1[d] = k[S - 1][d];
+                    } else {
+                        F::eval(t + dt, ytrial, f1, prm);
+                    }
+                    if (MODE == MODE_DENSE) {
+                        // Points::All :303-319 — Hermite values at tspan points strictly inside (t, t+dt)
+                        const double tn = t + dt;
+                        while (it < P.nt) {
+                            const double tq = __ldg(P.tspan + it);
+                            if (!(tdir * t < tdir * tq && tdir * tq < tdir * tn)) break;
+                            const double theta = (tq - t) / dt;
 #pragma unroll
-                    for (int d = 0; d < N; ++d) f1[d] = k[S - 1][d];
-                } else {
-                    F::eval(t + dt, ytrial, f1, prm);
-                }
-                if (MODE == MODE_DENSE) {
-                    // Points::All :303-319 — Hermite values at tspan points strictly inside (t, t+dt)
-                    const double tn = t + dt;
-                    while (it < P.nt) {
-                        const double tq = __ldg(P.tspan + it);
-                        if (!(tdir * t < tdir * tq && tdir * tq < tdir * tn)) break;
-                        const double theta = (tq - t) / dt;
-#pragma unroll
-                        for (int d = 0; d < N; ++d) {
-                            const double v = (cy[d] * (1. - theta) + ytrial[d] * theta) +
-                                             ((ytrial[d] - cy[d]) * (1. - 2. * theta) + k[0][d] * (theta - 1.) * dt +
-                                              f1[d] * theta * dt) * theta * (theta - 1.);
-                            P.dense[((unsigned long long)d * P.nt + it) * P.ntraj + traj] = v;
+                            for (int d = 0; d < N; ++d) {
+                                const double v = (cy[d] * (1. - theta) + ytrial[d] * theta) +
+                                                 ((ytrial[d] - cy[d]) * (1. - 2. * theta) + k[0][d] * (theta - 1.) * dt +
+                                                  f1[d] * theta * dt) * theta * (theta - 1.);
+                                P.dense[((unsigned long long)d * P.nt + it) * P.ntraj + traj] = v;
+                            }
+                            ++it;
                         }
-                        ++it;
                     }
-                }
 #pragma unroll
-                for (int d = 0; d < N; ++d) { ck[d] = f1[d]; cy[d] = ytrial[d]; }
-                if (last_step) {
-                    fin = ST_DONE;
-                    t = t + dt;  // t_reached
-                } else {
+                    for (int d = 0; d < N; ++d) { ck[d] = f1[d]; cy[d] = ytrial[d]; }
                     t = t + dt;
+                    if (last_step) {
+                        fin = ST_DONE;   // t is t_reached
+                    } else {
+                        dt = ndt;
+                        if (tdir * ((t + dt) + (FAST ? dt * 0.01 : dt / 100.)) >= tdir * tend) { dt = tend - t; last_step = true; }
+                    }
+                } else if (fabs(ndt) < P.minstep) {
+                    fin = ST_MINSTEP_BREAK;
+                } else {
+                    rej += 1;
+                    last_step = false;
                     dt = ndt;
-                    if (tdir * ((t + dt) + (FAST ? dt * 0.01 : dt / 100.)) >= tdir * tend) { dt = tend - t; last_step = true; }
+                    timeout = 5;
                 }
-            } else if (fabs(ndt) < P.minstep) {
-                fin = ST_MINSTEP_BREAK;
-            } else {
-                rej += 1;
-                last_step = false;
-                dt = ndt;
-                timeout = 5;
             }
-        }
-        if (fin != 0xff) {
-            const uint32_t nfe = 2u + (uint32_t)attempts * (uint32_t)(S - 1) + (FSAL ? 0u : acc);
+            if (fin != 0xff) {
+                const uint32_t nfe = 2u + attempts * (uint32_t)(S - 1) + (FSAL ? 0u : acc);
 #pragma unroll
-            for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = cy[d];
-            P.accepted[traj] = acc; P.rejected[traj] = rej; P.nfe[traj] = nfe; P.status[traj] = fin; P.t_reached[traj] = t;
-            if (MODE == MODE_DENSE) {
+                for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = cy[d];
+                P.accepted[traj] = acc; P.rejected[traj] = rej; P.nfe[traj] = nfe; P.status[traj] = fin; P.t_reached[traj] = t;
+                if (MODE == MODE_DENSE) {
 #pragma unroll
-                for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt + (P.nt - 1)) * P.ntraj + traj] = cy[d];
-                P.nvalid[traj] = (uint32_t)it;
+                    for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt + (P.nt - 1)) * P.ntraj + traj] = cy[d];
+                    P.nvalid[traj] = (uint32_t)it;
+                }
+                tot_acc += acc; tot_rej += rej; tot_nfe += nfe;
+                active = false;
             }
-            tot_acc += acc; tot_rej += rej; tot_nfe += nfe;
-            active = false;
         }
     }
     // ensemble totals: warp reduce, one atomic per warp

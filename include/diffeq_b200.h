@@ -128,6 +128,10 @@ deq_status deq_ensemble_create_device(const deq_rhs* rhs, size_t ntraj, const do
 void deq_ensemble_destroy(deq_ensemble* ens);
 size_t deq_ensemble_ntraj(const deq_ensemble* ens);
 
+/* Select the GPU this thread's subsequent calls use (the library links its own CUDA runtime, so a caller that picked a
+ * device with another runtime instance — e.g. torch.cuda.set_device — must tell the library too). */
+deq_status deq_set_device(int device);
+deq_status deq_get_device(int* device);
 /* CUDA stream (cudaStream_t as void*) all work of this thread's subsequent calls is enqueued on; NULL = default. */
 deq_status deq_set_stream(void* cuda_stream);
 
