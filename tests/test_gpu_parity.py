@@ -292,3 +292,15 @@ def test_fast_mode_within_north_star_tolerance(deq, oracle, method, system, T, t
     assert same.mean() >= 0.999
     assert err.max() <= 10.0
     assert np.array_equal(sol.status, ref["status"])
+
+
+def test_cpp_host_mirror_on_gpu(deq, oracle):
+    """The header-only C++ mirror (include/diffeq_b200.hpp) drives the same C ABI: result equals the oracle's."""
+    import subprocess, os
+    from tests.test_host_cpu import _build_hpp_smoke
+    out = subprocess.run([_build_hpp_smoke()], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    tok = out.stdout.split()
+    ref = oracle.solve_adaptive(oracle.ODE45, oracle.LORENZ, LOR, [0.1, 0.0, 0.0], [0.0, 1.0], oracle.opts(1e-8, 1e-8))
+    assert tok[0] == "HPP_OK" and int(tok[1]) == 1000 and int(tok[2]) == ref["accepted"] and float(tok[3]) == ref["yfinal"][0]
+    assert "HPP_ERR 1" in out.stdout   # Uninitialized, like OdeBuilder::build (problem.rs:92-104)

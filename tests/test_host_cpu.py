@@ -125,3 +125,21 @@ def test_bench_reference_arm_prints_contract_line():
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["unit"] == "trajectory-steps/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def _build_hpp_smoke():
+    exe = "/tmp/deq_hpp_smoke"
+    libdir = os.path.join(ROOT, "diffeq_b200")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", os.path.join(HERE, "cpp", "hpp_smoke.cpp"), "-o", exe,
+                           "-L" + libdir, "-ldiffeq_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(deq):
+    """include/diffeq_b200.hpp (C++ mirror of the reference API) builds against the C ABI; without a CUDA device the
+    solve must fail with a CUDA error — never fall back to a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    out = subprocess.run([_build_hpp_smoke()], capture_output=True, text=True)
+    assert out.returncode == 1 and "HPP_FAIL 7" in out.stdout
