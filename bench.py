@@ -93,16 +93,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the OS, not OpenMP)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_run(ntraj, nthreads=0, offset=0):
     """The reference's CPU path (C++ restatement, OpenMP over trajectories) on trajectories [offset, offset+ntraj)."""
     from oracle import oracle as O
     from diffeq_b200 import synth
+    nthreads = nthreads or host_threads()
     y0 = synth.lorenz_ics(offset, offset + ntraj)
     t = time.perf_counter()
     r = O.ensemble_adaptive(O.ODE45, O.LORENZ, synth.LORENZ_PARAMS, y0, TSPAN, O.opts(RTOL, ATOL), nthreads=nthreads)
     dt = time.perf_counter() - t
     steps = int(r["accepted"].sum()) + int(r["rejected"].sum())
-    return steps, dt, O.num_threads()
+    return steps, dt, nthreads
 
 
 def run_reference(args, rank, world):
@@ -235,6 +244,20 @@ def main():
     h2d = y0.nbytes + 8 * len(TSPAN) + 8 * 3
     d2h = h_final.numel() * 8 + h_acc.numel() * 4 + h_rej.numel() * 4
 
+    # ---------------- final gather of the sharded final states (the only inter-GPU traffic the path needs) ----------------
+    gather_ms = None
+    if distributed:
+        from diffeq_b200 import sharding
+        loc = torch.from_numpy(f_par).cuda()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        parts = sharding.gather_final(dist, loc, device="cuda")
+        g1.record(stream)
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+        assert sum(p.shape[0] for p in parts) == ntraj * world and torch.equal(parts[rank], loc)
+
     # ---------------- reduce over ranks ----------------
     t = torch.tensor([dev_ms, e2e_s, wall, fast_ms, e2e_fast_s], dtype=torch.float64, device="cuda")
     c = torch.tensor([steps_done, e2e_steps, fast_steps, e2e_fast_steps], dtype=torch.float64, device="cuda")
@@ -274,6 +297,7 @@ def main():
                           "roofline": roofline(fast_kernel_ms, fast_steps, "deqk::adapt_kernel<Dopri5<false>, Lorenz, false, MODE_FINAL, FAST=true>",
                                                "FMA counted as 2 flop; algorithmic flop per step attempt from SURVEY.md 8(d)")},
             "mode_check": mode_check,
+            "final_gather_ms": gather_ms,
             "clocks": clocks, "wall_s_timed_region": wall_max,
         }
         if not args.no_cpu_baseline:

@@ -223,7 +223,12 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     for (int i = threadIdx.x; i < 256; i += BLOCK) s_exp[i] = g_exp_tab[i];
     for (int i = threadIdx.x; i < 384; i += BLOCK) s_powlog[i] = g_powlog_tab[i];
     __syncthreads();
-    const deqm::SmemTables T{(unsigned)__cvta_generic_to_shared(s_exp), (unsigned)__cvta_generic_to_shared(s_powlog), 0u};
+    // Shared-window base addresses, computed once and made opaque (volatile asm) so the compiler keeps them in registers
+    // instead of re-deriving them from SR_CgaCtaId in front of every table lookup.
+    unsigned exp_base = (unsigned)__cvta_generic_to_shared(s_exp), powlog_base = (unsigned)__cvta_generic_to_shared(s_powlog);
+    asm volatile("mov.u32 %0, %0;" : "+r"(exp_base));
+    asm volatile("mov.u32 %0, %0;" : "+r"(powlog_base));
+    const deqm::SmemTables T{exp_base, powlog_base, 0u};
 
     const unsigned lane = threadIdx.x & 31u;
     const double tdir = P.tdir, tend = P.tend, reltol = P.reltol, abstol = P.abstol;
