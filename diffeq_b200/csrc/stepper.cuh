@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     if (ssum != ssum) {
                         accept = false; ndt = 0.2 * dt; timeout = 5;
                     } else {
-                        const double g = deqm::pow_glibc(ssum, -0.5 * PW, T) * 0.8;
+                        const double g = deqm::pow_fast_pos(ssum, -0.5 * PW, T) * 0.8;
                         double nd = sel_min(P.maxstep, (sel_max(0.2, g) * tdir) * dt);
                         if (timeout > 0) { nd = sel_min(nd, dt); timeout -= 1; }
                         ndt = tdir * nd;

@@ -38,6 +38,18 @@ int main(int argc, char** argv) {
         volatile double nx = -x;
         if (!same(log10(nx), deqm::log10_glibc(-x, T))) { printf("special log10 x=%a\n", -x); ++bad; }
     }
+    // FAST-mode step factor: relative error of pow_fast_pos against libm (not bit-exact by design)
+    double worst = 0.0;
+    for (long i = 0; i < n; ++i) {
+        const double x = exp((u01() * 2 - 1) * (i % 4 == 0 ? 700.0 : 40.0));
+        const double y = -0.5 / (double)(2 + i % 7);
+        const double a = pow(x, y), b = deqm::pow_fast_pos(x, y, T);
+        const double rel = fabs(a - b) / a;
+        if (rel > worst) worst = rel;
+    }
+    printf("POW_FAST_MAX_REL %.3e\n", worst);
+    if (!(worst < 1e-12)) ++bad;
+    if (deqm::pow_fast_pos(0.0, -0.1, T) != INFINITY || deqm::pow_fast_pos(INFINITY, -0.1, T) != 0.0) { printf("pow_fast specials\n"); ++bad; }
     printf("MISMATCHES %ld\n", bad);
     return bad != 0;
 }
