@@ -88,16 +88,18 @@ static bool compile(Program* p, const std::string& name_expr, bool fmad, Kernel*
     std::ostringstream src;
     src << "#define DEQ_USER_N " << p->n << "\n#define DEQ_USER_NP " << p->np << "\n"
         << "__device__ void rhs(double t, const double* y, double* dy, const double* p);\n"
+        << "#include \"rhs.cuh\"\n"
         << "#line 1 \"user_rhs.cu\"\n" << p->user_src << "\n#line 1 \"deq_user_glue.cu\"\n"
         << "#include \"stepper.cuh\"\n"
         << "struct DeqUserRhs {\n  static constexpr int N = DEQ_USER_N, NP = DEQ_USER_NP;\n"
+        << "  static constexpr bool USES_SINCOS = true;  // user code may call deq_sin / deq_cos (3.5 KB of shared memory)\n"
         << "  __device__ __forceinline__ static void eval(double t, const double* y, double* dy, const double* p) { rhs(t, y, dy, p); }\n};\n";
     nvrtcProgram prog = nullptr;
     nvrtcResult rc = rt->CreateProgram(&prog, src.str().c_str(), "deq_user_program.cu", kNumSrc, kSrcTexts, kSrcNames);
     if (rc) { if (err) *err = std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc); return false; }
     rt->AddNameExpression(prog, name_expr.c_str());
     const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", fmad ? "--fmad=true" : "--fmad=false", "-default-device",
-                          "-lineinfo", "-DDEQ_NVRTC=1"};
+                          "-lineinfo", "-DDEQ_NVRTC=1", fmad ? "-DDEQ_FAST_TU=1" : "-DDEQ_PARITY_TU=1"};
     rc = rt->CompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
     if (rc) {
         size_t n = 0;

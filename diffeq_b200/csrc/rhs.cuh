@@ -7,17 +7,50 @@
 // same signature (see nvrtc_rhs.cpp).
 #pragma once
 #include "deq_rtc_compat.h"
+#include "deq_sincos.cuh"
 #if defined(__CUDACC__)
 #define DEQ_RHS_HD __host__ __device__ __forceinline__
 #else
 #define DEQ_RHS_HD inline
 #endif
 
+// sin / cos with glibc's bits (what `f64::sin` / `f64::cos` in a reference closure evaluate to); user NVRTC sources
+// may call these too when they need bit parity with a Rust right-hand side.
+// In a FAST-mode translation unit (DEQ_FAST_TU) they are the platform's sin / cos instead.  Not inlined on the device:
+// a 13-stage tableau would otherwise carry 26 copies of the four-way range dispatch (~300 KB of SASS) and thrash the
+// instruction cache (measured 3x slower than one shared copy behind a call).
+#if defined(__CUDACC__) && defined(DEQ_FAST_TU)
+#define DEQ_TRIG_HD static __host__ __device__ __forceinline__
+#elif defined(__CUDACC__)
+#define DEQ_TRIG_HD static __host__ __device__ __noinline__
+#else
+#define DEQ_TRIG_HD inline
+#endif
+DEQ_TRIG_HD double deq_sin(double x) {
+#if defined(__CUDA_ARCH__) && defined(DEQ_FAST_TU)
+    return sin(x);
+#elif defined(__CUDA_ARCH__)
+    return deqm::sin_glibc(x, deqm::SinCosShared());
+#else
+    return deqm::sin_glibc(x, deqm::SinCosHost());
+#endif
+}
+DEQ_TRIG_HD double deq_cos(double x) {
+#if defined(__CUDA_ARCH__) && defined(DEQ_FAST_TU)
+    return cos(x);
+#elif defined(__CUDA_ARCH__)
+    return deqm::cos_glibc(x, deqm::SinCosShared());
+#else
+    return deqm::cos_glibc(x, deqm::SinCosHost());
+#endif
+}
+
 namespace deqr {
 
 // Lorenz-63, operation order of the reference's test fixture (problem.rs:989-1000); p = {sigma, rho, beta}.
 struct Lorenz {
     static constexpr int N = 3, NP = 3;
+    static constexpr bool USES_SINCOS = false;
     DEQ_RHS_HD static void eval(double, const double* v, double* d, const double* p) {
         const double x = v[0], y = v[1], z = v[2];
         d[0] = p[0] * (y - x);
@@ -29,6 +62,7 @@ struct Lorenz {
 // Van der Pol  x' = y, y' = mu (1 - x^2) y - x ; p = {mu}.
 struct VanDerPol {
     static constexpr int N = 2, NP = 1;
+    static constexpr bool USES_SINCOS = false;
     DEQ_RHS_HD static void eval(double, const double* v, double* d, const double* p) {
         const double x = v[0], y = v[1];
         d[0] = y;
@@ -39,10 +73,11 @@ struct VanDerPol {
 // Damped driven pendulum  th' = w, w' = -gamma w - sin th + A cos(Omega t) ; p = {gamma, A, Omega}.
 struct Pendulum {
     static constexpr int N = 2, NP = 3;
+    static constexpr bool USES_SINCOS = true;
     DEQ_RHS_HD static void eval(double t, const double* v, double* d, const double* p) {
         const double th = v[0], w = v[1];
         d[0] = w;
-        d[1] = -p[0] * w - sin(th) + p[1] * cos(p[2] * t);
+        d[1] = -p[0] * w - deq_sin(th) + p[1] * deq_cos(p[2] * t);
     }
 };
 

@@ -119,6 +119,7 @@ template <class TB, class F, bool PT, bool ALL>
 __global__ void __launch_bounds__(BLOCK) fixed_kernel(const FixedParams P) {
     constexpr int N = F::N, S = TB::S;
     DEQ_TAB(TB);
+    if (F::USES_SINCOS) { deqm::sincos_stage(); __syncthreads(); }
     const unsigned long long traj = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;
     if (traj >= P.ntraj) return;
     double prm[F::NP ? F::NP : 1];
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(BLOCK) hinit_kernel(const HinitParams P) {
     __shared__ double s_log[256];
     for (int i = threadIdx.x; i < 256; i += BLOCK) { s_exp[i] = g_exp_tab[i]; s_log[i] = g_log_tab[i]; }
     for (int i = threadIdx.x; i < 384; i += BLOCK) s_powlog[i] = g_powlog_tab[i];
+    if (F::USES_SINCOS) deqm::sincos_stage();
     __syncthreads();
     const deqm::Tables T{s_exp, s_powlog, s_log};
     const unsigned long long traj = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;
@@ -222,6 +224,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     __shared__ double s_powlog[384];
     for (int i = threadIdx.x; i < 256; i += BLOCK) s_exp[i] = g_exp_tab[i];
     for (int i = threadIdx.x; i < 384; i += BLOCK) s_powlog[i] = g_powlog_tab[i];
+    if (F::USES_SINCOS) deqm::sincos_stage();
     __syncthreads();
     // Shared-window base addresses, computed once and made opaque (volatile asm) so the compiler keeps them in registers
     // instead of re-deriving them from SR_CgaCtaId in front of every table lookup.

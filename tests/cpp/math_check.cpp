@@ -4,7 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
+#include <initializer_list>
 #include "../../diffeq_b200/csrc/deq_math.cuh"
+#include "../../diffeq_b200/csrc/deq_sincos.cuh"
 static uint64_t s = 88172645463325252ULL;
 static inline uint64_t rnd() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
 static inline double u01() { return (rnd() >> 11) * 0x1p-53; }
@@ -37,6 +39,21 @@ int main(int argc, char** argv) {
         if (!same(log10(vx), deqm::log10_glibc(x, T))) { printf("special log10 x=%a\n", x); ++bad; }
         volatile double nx = -x;
         if (!same(log10(nx), deqm::log10_glibc(-x, T))) { printf("special log10 x=%a\n", -x); ++bad; }
+    }
+    // sin / cos replicas (pendulum right-hand side)
+    const deqm::SinCosHost ST;
+    for (long i = 0; i < n; ++i) {
+        double x; const int mm = (int)(i % 7);
+        if (mm == 0) x = (u01() * 2 - 1) * 0.9; else if (mm == 1) x = (u01() * 2 - 1) * 2.5; else if (mm == 2) x = (u01() * 2 - 1) * 100;
+        else if (mm == 3) x = (u01() * 2 - 1) * 1e6; else if (mm == 4) x = (u01() * 2 - 1) * pow(2.0, -(double)(i % 60));
+        else if (mm == 5) x = (u01() * 2 - 1) * 8; else x = (u01() * 2 - 1) * 1e8;
+        volatile double vx = x;
+        if (!same(sin(vx), deqm::sin_glibc(x, ST))) { if (bad < 5) printf("sin x=%a\n", x); ++bad; }
+        if (!same(cos(vx), deqm::cos_glibc(x, ST))) { if (bad < 5) printf("cos x=%a\n", x); ++bad; }
+    }
+    for (double x : {0.0, -0.0, 0.126, -0.126, 0.855469, 2.426265, 105414349.0, 1e-300, 3.141592653589793, 1.5707963267948966, (double)INFINITY}) {
+        volatile double vx = x;
+        if (!same(sin(vx), deqm::sin_glibc(x, ST)) || !same(cos(vx), deqm::cos_glibc(x, ST))) { printf("sincos special x=%a\n", x); ++bad; }
     }
     // FAST-mode step factor: relative error of pow_fast_pos against libm (not bit-exact by design)
     double worst = 0.0;
