@@ -76,6 +76,7 @@ class Points(enum.IntEnum):
 class Output(enum.IntEnum):
     Final = 0
     Tspan = 1
+    All = 2
 
 
 class Mode(enum.IntEnum):
@@ -102,7 +103,8 @@ ABI_SYMBOLS = [
     "deq_last_error_message", "deq_version", "deq_rhs_builtin", "deq_rhs_from_source", "deq_rhs_dim",
     "deq_rhs_nparams", "deq_rhs_destroy", "deq_tspan_linspace", "deq_ensemble_create", "deq_ensemble_create_device",
     "deq_ensemble_destroy", "deq_ensemble_ntraj", "deq_set_stream", "deq_set_device", "deq_get_device", "deq_options_default", "deq_solve",
-    "deq_result_final", "deq_result_counts", "deq_result_totals", "deq_result_dense", "deq_result_device_ptrs",
+    "deq_result_final", "deq_result_counts", "deq_result_totals", "deq_result_dense", "deq_result_all_offsets",
+    "deq_result_all_copy", "deq_result_device_ptrs",
     "deq_result_trajectory", "deq_result_kernel_ms", "deq_result_destroy", "deq_tableau_get", "deq_host_alloc",
     "deq_host_free", "deq_test_pow", "deq_test_log10", "deq_measure_fp64_peak",
 ]
@@ -282,6 +284,12 @@ class OdeSolution:
         self.tout = self.yout = self.nvalid = None
         self.kernel_ms = None
         self.totals = None
+        self.offsets = self.tout_flat = self.yout_flat = None   # Output.All: ragged Points::All streams
+
+    def trajectory(self, i):
+        """Output.All: the reference-shaped (tout, yout) of trajectory i (problem.rs:354-357)."""
+        a, b = int(self.offsets[i]), int(self.offsets[i + 1])
+        return self.tout_flat[a:b], self.yout_flat[a:b]
 
     def zipped(self, traj=0):
         """`OdeSolution::zipped` (solution.rs:33-36) for one trajectory."""
@@ -344,6 +352,13 @@ class OdeProblem:
             sol.t_reached = np.empty(self.ntraj)
             _check(L.deq_result_counts(res, _ptr(sol.accepted, C.c_uint32), _ptr(sol.rejected, C.c_uint32),
                                        _ptr(sol.nfe, C.c_uint32), _ptr(sol.status, C.c_uint8), _ptr(sol.t_reached)))
+        if o.output == Output.All and nt > 0 and adaptive:
+            sol.offsets = np.zeros(self.ntraj + 1, np.uint64)
+            _check(L.deq_result_all_offsets(res, _ptr(sol.offsets, C.c_uint64)))
+            rows = int(sol.offsets[-1])
+            sol.tout_flat = np.empty(rows)
+            sol.yout_flat = np.empty((rows, self.n))
+            _check(L.deq_result_all_copy(res, C.c_size_t(0), C.c_size_t(self.ntraj), _ptr(sol.tout_flat), _ptr(sol.yout_flat)))
         if o.output == Output.Tspan and nt > 0:
             dense = np.full((self.n, nt, self.ntraj), np.nan)
             nv = np.empty(self.ntraj, np.uint32)

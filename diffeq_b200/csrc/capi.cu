@@ -97,6 +97,12 @@ struct deq_result {
     double* d_treached = nullptr;
     double* d_dense = nullptr;
     double *d_f0 = nullptr, *d_h0 = nullptr;
+    // DEQ_OUT_ALL: the reference's ragged (tout, yout) per trajectory
+    bool all = false;
+    uint32_t* d_rec_counts = nullptr;
+    unsigned long long* d_rec_offsets = nullptr;
+    double *d_rec_t = nullptr, *d_rec_y = nullptr;
+    std::vector<unsigned long long> rec_offsets;  // [ntraj + 1], host
     unsigned long long* d_scalars = nullptr;  // [0] work counter, [1..3] totals
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;  // both events were recorded
@@ -283,6 +289,8 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
     const int n = e->rhs.n;
     const size_t ntraj = e->ntraj, nt = e->nt;
     const bool want_dense = o.output == DEQ_OUT_TSPAN;
+    const bool want_all = o.output == DEQ_OUT_ALL;
+    if (o.output != DEQ_OUT_FINAL && !want_dense && !want_all) return fail(DEQ_ERR_INVALID_ARG, "unknown output kind");
 
     deq_result* r = new deq_result();
     r->ntraj = ntraj; r->nt = nt; r->n = n; r->stream = st; r->fixed = !info.adaptive; r->dense = want_dense;
@@ -299,6 +307,8 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
     CKR(dalloc(&r->d_scalars, 4, st));
     CKR(cudaMemsetAsync(r->d_scalars, 0, 4 * sizeof(unsigned long long), st));
 
+    if (!info.adaptive && want_all)
+        return bail(fail(DEQ_ERR_INVALID_ARG, "fixed-step methods output exactly the tspan rows: use DEQ_OUT_TSPAN"));
     if (!info.adaptive) {
         // ---- oderk_fixed ----
         if (nt == 0) return bail(fail(DEQ_ERR_INVALID_ARG, "fixed-step methods need a non-empty tspan (the reference panics, problem.rs:377)"));
@@ -323,6 +333,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
             return bail(fail(DEQ_ERR_UNSUPPORTED, "Points::Specified re-reads y from the output vector in the reference (problem.rs:262) and yields wrong trajectories; use DEQ_POINTS_ALL with output = DEQ_OUT_TSPAN"));
         if (nt == 0) { *out = r; r->ntraj = 0; return DEQ_OK; }  // problem.rs:211-214: nothing to solve
         if (want_dense && nt < 2) return bail(fail(DEQ_ERR_INVALID_ARG, "DEQ_OUT_TSPAN needs at least 2 tspan points"));
+        r->all = want_all;
         const double t0 = e->tspan[0], tend = e->tspan[nt - 1];
         const double tdir = signum(tend - t0);
         if (tdir == 0.) return bail(fail(DEQ_ERR_ZERO_TIMESPAN, "Zero time span is not allowed"));
@@ -333,6 +344,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         CKR(dalloc(&r->d_status, ntraj, st)); CKR(dalloc(&r->d_treached, ntraj, st));
         CKR(dalloc(&r->d_f0, ntraj * n, st)); CKR(dalloc(&r->d_h0, ntraj, st));
         if (want_dense) { CKR(dalloc(&r->d_dense, ntraj * n * nt, st)); CKR(dalloc(&r->d_nvalid, ntraj, st)); }
+        if (want_all) { CKR(dalloc(&r->d_nvalid, ntraj, st)); CKR(dalloc(&r->d_rec_counts, ntraj, st)); CKR(dalloc(&r->d_rec_offsets, ntraj + 1, st)); }
         deqk::HinitParams H{};
         H.y0 = e->d_y0; H.params = e->d_params; H.shared = e->shared; H.ntraj = ntraj; H.t0 = t0; H.tend = tend;
         H.reltol = o.reltol; H.abstol = o.abstol; H.order = info.order_min; H.f0 = r->d_f0; H.h0 = r->d_h0;
@@ -346,8 +358,42 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         P.yfinal = r->d_yfinal; P.accepted = r->d_acc; P.rejected = r->d_rej; P.nfe = r->d_nfe; P.status = r->d_status;
         P.t_reached = r->d_treached; P.dense = r->d_dense; P.nvalid = r->d_nvalid;
         P.work_counter = r->d_scalars; P.totals = r->d_scalars + 1;
-        const int mode = want_dense ? deqk::MODE_DENSE : deqk::MODE_FINAL;
-        if (ntraj) {
+        const int mode = (want_dense || want_all) ? deqk::MODE_DENSE : deqk::MODE_FINAL;
+        P.rec_mode = want_all ? deqk::REC_COUNT : deqk::REC_TSPAN;
+        P.rec_counts = r->d_rec_counts;
+        auto launch_adapt = [&](std::string* err) -> int {  // 0 ok, 1 cuda error (g_err set), 2 nvrtc error
+            if (e->rhs.kind == 0) {
+                cudaError_t ce = (o.mode == DEQ_MODE_FAST ? g_tb[tb].adapt_fast : g_tb[tb].adapt)(e->rhs.sys, e->per_traj, mode, P, 0, st);
+                if (ce != cudaSuccess) { fail(DEQ_ERR_CUDA, std::string("adaptive kernel launch: ") + cudaGetErrorString(ce)); return 1; }
+                return 0;
+            }
+            return deqn::launch_adapt(e->rhs.prog, tb, e->per_traj, mode, o.mode == DEQ_MODE_FAST, P, st, err) ? 0 : 2;
+        };
+        if (ntraj && want_all) {
+            // two passes: count the rows each trajectory emits, prefix-sum, then re-run writing them.  The
+            // solver is deterministic, so both passes take identical steps.
+            std::string err;
+            if (e->rhs.kind == 0) CKR(deql::launch_hinit(e->rhs.sys, e->per_traj, H, st));
+            else if (!deqn::launch_hinit(e->rhs.prog, e->per_traj, H, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
+            int rc = launch_adapt(&err);
+            if (rc == 1) return bail(DEQ_ERR_CUDA);
+            if (rc == 2) return bail(fail(DEQ_ERR_NVRTC, err));
+            std::vector<uint32_t> counts(ntraj);
+            CKR(cudaMemcpyAsync(counts.data(), r->d_rec_counts, ntraj * 4, cudaMemcpyDeviceToHost, st));
+            CKR(cudaStreamSynchronize(st));
+            r->rec_offsets.assign(ntraj + 1, 0ull);
+            for (size_t i = 0; i < ntraj; ++i) r->rec_offsets[i + 1] = r->rec_offsets[i] + counts[i];
+            const unsigned long long total = r->rec_offsets[ntraj];
+            CKR(cudaMemcpyAsync(r->d_rec_offsets, r->rec_offsets.data(), (ntraj + 1) * 8, cudaMemcpyHostToDevice, st));
+            CKR(dalloc(&r->d_rec_t, total, st));
+            CKR(dalloc(&r->d_rec_y, total * n, st));
+            CKR(cudaMemsetAsync(r->d_scalars, 0, 4 * sizeof(unsigned long long), st));
+            P.rec_mode = deqk::REC_WRITE; P.rec_offsets = r->d_rec_offsets; P.rec_t = r->d_rec_t; P.rec_y = r->d_rec_y;
+            CKR(cudaEventRecord(r->ev0, st));
+            rc = launch_adapt(&err);
+            if (rc == 1) return bail(DEQ_ERR_CUDA);
+            if (rc == 2) return bail(fail(DEQ_ERR_NVRTC, err));
+        } else if (ntraj) {
             if (e->rhs.kind == 0) {
                 CKR(deql::launch_hinit(e->rhs.sys, e->per_traj, H, st));
                 CKR(cudaEventRecord(r->ev0, st));
@@ -430,6 +476,26 @@ deq_status deq_result_dense(deq_result* r, size_t b, size_t e, double* out, uint
     return DEQ_OK;
 }
 
+deq_status deq_result_all_offsets(deq_result* r, uint64_t* offsets) {
+    if (!r || !offsets) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
+    if (!r->all) return fail(DEQ_ERR_INVALID_ARG, "solve was not run with output = DEQ_OUT_ALL");
+    for (size_t i = 0; i < r->rec_offsets.size(); ++i) offsets[i] = r->rec_offsets[i];
+    return DEQ_OK;
+}
+
+deq_status deq_result_all_copy(deq_result* r, size_t b, size_t e, double* tout, double* yout) {
+    if (!r || !tout || !yout) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
+    if (!r->all) return fail(DEQ_ERR_INVALID_ARG, "solve was not run with output = DEQ_OUT_ALL");
+    if (b > e || e > r->ntraj) return fail(DEQ_ERR_INVALID_ARG, "trajectory range out of bounds");
+    const unsigned long long r0 = r->rec_offsets[b], r1 = r->rec_offsets[e];
+    if (r1 > r0) {
+        CK(cudaMemcpyAsync(tout, r->d_rec_t + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, r->stream));
+        CK(cudaMemcpyAsync(yout, r->d_rec_y + r0 * r->n, (r1 - r0) * r->n * 8, cudaMemcpyDeviceToHost, r->stream));
+    }
+    CK(cudaStreamSynchronize(r->stream));
+    return DEQ_OK;
+}
+
 deq_status deq_result_device_ptrs(deq_result* r, const double** yf, const double** dn) {
     if (!r) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
     if (yf) *yf = r->d_yfinal;
@@ -464,7 +530,7 @@ void deq_result_destroy(deq_result* r) {
     cudaStream_t st = r->stream;
     dfree(r->d_yfinal, st); dfree(r->d_acc, st); dfree(r->d_rej, st); dfree(r->d_nfe, st); dfree(r->d_nvalid, st);
     dfree(r->d_status, st); dfree(r->d_treached, st); dfree(r->d_dense, st); dfree(r->d_f0, st); dfree(r->d_h0, st);
-    dfree(r->d_scalars, st);
+    dfree(r->d_scalars, st); dfree(r->d_rec_counts, st); dfree(r->d_rec_offsets, st); dfree(r->d_rec_t, st); dfree(r->d_rec_y, st);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
     delete r;

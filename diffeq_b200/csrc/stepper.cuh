@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     unsigned timeout = 0;
     bool last_step = false;
     uint32_t acc = 0, rej = 0, attempts = 0;
-    unsigned long long it = 1;
+    unsigned long long it = 1, wpos = 0, wbase = 0;
     unsigned long long tot_acc = 0, tot_rej = 0, tot_nfe = 0;
 #pragma unroll
     for (int d = 0; d < N; ++d) { cy[d] = 0.0; ck[d] = 0.0; }
@@ -277,8 +277,19 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     last_step = fabs((t + dt) - tend) <= DBL_EPSILON;
                     acc = 0; rej = 0; attempts = 0; it = 1;
                     if (MODE == MODE_DENSE) {
+                        if (P.rec_mode == REC_TSPAN) {
 #pragma unroll
-                        for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt) * P.ntraj + traj] = cy[d];
+                            for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt) * P.ntraj + traj] = cy[d];
+                        } else {  // ragged Points::All stream: row 0 = (t0, y0)
+                            wpos = P.rec_mode == REC_WRITE ? P.rec_offsets[traj] : 0ull;
+                            wbase = wpos;
+                            if (P.rec_mode == REC_WRITE) {
+                                P.rec_t[wpos] = t;
+#pragma unroll
+                                for (int d = 0; d < N; ++d) P.rec_y[wpos * N + d] = cy[d];
+                            }
+                            ++wpos;
+                        }
                     }
                 }
             }
@@ -387,9 +398,22 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                                 const double v = (cy[d] * (1. - theta) + ytrial[d] * theta) +
                                                  ((ytrial[d] - cy[d]) * (1. - 2. * theta) + k[0][d] * (theta - 1.) * dt +
                                                   f1[d] * theta * dt) * theta * (theta - 1.);
-                                P.dense[((unsigned long long)d * P.nt + it) * P.ntraj + traj] = v;
+                                if (P.rec_mode == REC_TSPAN) P.dense[((unsigned long long)d * P.nt + it) * P.ntraj + traj] = v;
+                                else if (P.rec_mode == REC_WRITE) P.rec_y[wpos * N + d] = v;
+                            }
+                            if (P.rec_mode != REC_TSPAN) {
+                                if (P.rec_mode == REC_WRITE) P.rec_t[wpos] = tq;
+                                ++wpos;
                             }
                             ++it;
+                        }
+                        if (P.rec_mode != REC_TSPAN) {  // "also store every step taken" (problem.rs:320-322)
+                            if (P.rec_mode == REC_WRITE) {
+                                P.rec_t[wpos] = tn;
+#pragma unroll
+                                for (int d = 0; d < N; ++d) P.rec_y[wpos * N + d] = ytrial[d];
+                            }
+                            ++wpos;
                         }
                     }
 #pragma unroll
@@ -416,8 +440,12 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                 for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = cy[d];
                 P.accepted[traj] = acc; P.rejected[traj] = rej; P.nfe[traj] = nfe; P.status[traj] = fin; P.t_reached[traj] = t;
                 if (MODE == MODE_DENSE) {
+                    if (P.rec_mode == REC_TSPAN) {
 #pragma unroll
-                    for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt + (P.nt - 1)) * P.ntraj + traj] = cy[d];
+                        for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt + (P.nt - 1)) * P.ntraj + traj] = cy[d];
+                    } else if (P.rec_mode == REC_COUNT) {
+                        P.rec_counts[traj] = (uint32_t)(wpos - wbase);
+                    }
                     P.nvalid[traj] = (uint32_t)it;
                 }
                 tot_acc += acc; tot_rej += rej; tot_nfe += nfe;

@@ -58,7 +58,9 @@ typedef enum deq_points { DEQ_POINTS_ALL = 0, DEQ_POINTS_SPECIFIED = 1 } deq_poi
 /* What deq_solve materialises. */
 typedef enum deq_output {
     DEQ_OUT_FINAL = 0,  /* last element of yout + per-trajectory counters */
-    DEQ_OUT_TSPAN = 1   /* additionally the rows of (tout,yout) that fall on tspan times, SoA [n][ntspan][ntraj] */
+    DEQ_OUT_TSPAN = 1,  /* additionally the rows of (tout,yout) that fall on tspan times, SoA [n][ntspan][ntraj] */
+    DEQ_OUT_ALL = 2     /* the reference's complete Points::All output per trajectory (problem.rs:301-323): y0, every
+                           Hermite value at a tspan point inside a step, every step end point — ragged, two passes */
 } deq_output;
 
 /* Arithmetic of the adaptive kernels.  PARITY (default): every operation rounded and ordered as in the reference,
@@ -149,6 +151,10 @@ deq_status deq_result_totals(deq_result* res, uint64_t* accepted, uint64_t* reje
 /* DEQ_OUT_TSPAN: rows of trajectories [traj_begin, traj_end) into host out[n][ntspan][traj_end-traj_begin];
  * nvalid (may be NULL) receives, per trajectory, how many leading tspan rows the reference would have emitted. */
 deq_status deq_result_dense(deq_result* res, size_t traj_begin, size_t traj_end, double* out, uint32_t* nvalid);
+/* DEQ_OUT_ALL: offsets[ntraj+1] — trajectory i owns rows [offsets[i], offsets[i+1]) of the ragged (tout, yout). */
+deq_status deq_result_all_offsets(deq_result* res, uint64_t* offsets);
+/* DEQ_OUT_ALL: rows of trajectories [traj_begin, traj_end): tout[rows], yout[rows][n] (one `Y` per row like Vec<Y>). */
+deq_status deq_result_all_copy(deq_result* res, size_t traj_begin, size_t traj_end, double* tout, double* yout);
 /* Device views (library layout, valid until deq_result_destroy): yfinal [n][ntraj], dense [n][ntspan][ntraj]. */
 deq_status deq_result_device_ptrs(deq_result* res, const double** d_yfinal_soa, const double** d_dense_soa);
 /* Fixed-step methods with DEQ_OUT_TSPAN: the full OdeSolution of one trajectory, yout host [ntspan][n]. */

@@ -303,3 +303,25 @@ def test_cpp_host_mirror_on_gpu(deq, oracle):
     ref = oracle.solve_adaptive(oracle.ODE45, oracle.LORENZ, LOR, [0.1, 0.0, 0.0], [0.0, 1.0], oracle.opts(1e-8, 1e-8))
     assert tok[0] == "HPP_OK" and int(tok[1]) == 1000 and int(tok[2]) == ref["accepted"] and float(tok[3]) == ref["yfinal"][0]
     assert "HPP_ERR 1" in out.stdout   # Uninitialized, like OdeBuilder::build (problem.rs:92-104)
+
+
+def test_ragged_points_all_output_matches_reference_shape(deq, oracle):
+    """Output.All = the reference's complete Points::All result per trajectory (y0, Hermite values at tspan points inside
+    each step, every step end point; problem.rs:301-323), ragged, bit-exact vs the oracle's (tout, yout)."""
+    from diffeq_b200 import synth
+    n = 257
+    y0, mu = synth.vdp_sweep(0, n, n)
+    ts = deq.linspace(0.0, 20.0, 100)
+    o = deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8), deq.Output.All)
+    sol = _problem(deq, deq.System.VanDerPol, mu, y0, ts).solve(deq.Ode.Ode45fe, o)
+    for i in (0, 1, 100, 256):
+        ref = oracle.solve_adaptive(oracle.ODE45FE, oracle.VANDERPOL, mu[i], y0[i], ts, oracle.opts(1e-6, 1e-8))
+        tout, yout = sol.trajectory(i)
+        assert len(tout) == ref["nout"] == 1 + int(sol.accepted[i]) + (int(sol.offsets[i + 1] - sol.offsets[i]) - 1 - int(sol.accepted[i]))
+        assert np.array_equal(tout, ref["tout"]) and np.array_equal(yout, ref["yout"])
+    # single Lorenz trajectory with a 2-point tspan: tout.len() == 1 + accepted (SURVEY §5 "observable proxy")
+    s1 = _problem(deq, deq.System.Lorenz, LOR, [0.1, 0.0, 0.0], [0.0, 10.0]).solve(
+        deq.Ode.Ode45, deq.OdeOptionMap().insert(deq.Reltol(1e-8), deq.Abstol(1e-8), deq.Output.All))
+    r1 = oracle.solve_adaptive(oracle.ODE45, oracle.LORENZ, LOR, [0.1, 0.0, 0.0], [0.0, 10.0], oracle.opts(1e-8, 1e-8))
+    t1, y1 = s1.trajectory(0)
+    assert len(t1) == 947 and np.array_equal(t1, r1["tout"]) and np.array_equal(y1, r1["yout"])
