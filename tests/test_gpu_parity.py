@@ -325,3 +325,23 @@ def test_ragged_points_all_output_matches_reference_shape(deq, oracle):
     r1 = oracle.solve_adaptive(oracle.ODE45, oracle.LORENZ, LOR, [0.1, 0.0, 0.0], [0.0, 10.0], oracle.opts(1e-8, 1e-8))
     t1, y1 = s1.trajectory(0)
     assert len(t1) == 947 and np.array_equal(t1, r1["tout"]) and np.array_equal(y1, r1["yout"])
+
+
+def test_demo_json_entry_point(deq, oracle):
+    """diffeq-example-wasm's `solve_lorenz_attractor` (lib.rs:38-65) on the GPU backend: same JSON in, serde-shaped
+    OdeSolution out, values equal to the oracle's for an adaptive and a fixed-step method."""
+    import json
+    from diffeq_b200 import demo
+    cfg = {"ode": "ode45", "init": [0.1, 0.0, 0.0], "start_time": 0.0, "end_time": 5.0, "num_times": 101}
+    out = json.loads(demo.solve_lorenz_attractor(json.dumps(cfg)))
+    ts = oracle.linspace(0.0, 5.0, 101)
+    ref = oracle.solve_adaptive(oracle.ODE45, oracle.LORENZ, LOR, cfg["init"], ts)
+    assert list(out) == ["tout", "yout"] and out["tout"] == ref["tout"].tolist() and out["yout"] == ref["yout"].tolist()
+    cfg["ode"] = "ode4"
+    out = json.loads(demo.solve_lorenz_attractor(json.dumps(cfg)))
+    rf = oracle.solve_fixed(oracle.ODE4, oracle.LORENZ, LOR, cfg["init"], ts)
+    assert out["tout"] == ts.tolist() and out["yout"] == rf["yout"].tolist()
+    with pytest.raises(ValueError, match="not a valid Ode identifier"):
+        demo.solve_lorenz_attractor(json.dumps(dict(cfg, ode="rk99")))
+    with pytest.raises(ValueError, match="Can't solve for 2 dimensional type"):
+        demo.solve_lorenz_attractor(json.dumps(dict(cfg, init=[1.0, 2.0])))
