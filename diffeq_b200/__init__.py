@@ -432,10 +432,10 @@ class OdeBuilder:
 
 
 def solve_host(rhs, y0, params, tspan, ode, opts=None, out_final=None, out_accepted=None, out_rejected=None,
-               tableau_set=TableauSet.Reference):
+               tableau_set=TableauSet.Reference, return_totals=False):
     """End-to-end call on HOST buffers (the drop-in shape of `OdeProblem::solve` for an ensemble): uploads y0 / params /
     tspan, integrates on the GPU, and copies the final states and step counters back into the given (ideally pinned)
-    buffers.  Returns (final, accepted, rejected)."""
+    buffers.  Returns (final, accepted, rejected) — plus the device-reduced totals dict when return_totals is set."""
     L = lib()
     y0 = _f64(y0)
     if y0.ndim == 1:
@@ -445,9 +445,11 @@ def solve_host(rhs, y0, params, tspan, ode, opts=None, out_final=None, out_accep
     tspan = _f64(tspan)
     o = (opts if opts is not None else OdeOptionMap()).to_c()
     per = int(params is not None and params.ndim == 2)
+    adaptive = tableau(ode, tableau_set)["adaptive"]
     ens = C.c_void_p(); res = C.c_void_p()
     _check(L.deq_ensemble_create(rhs._h, C.c_size_t(ntraj), _ptr(y0), _ptr(params), per, _ptr(tspan),
                                  C.c_size_t(len(tspan)), C.byref(ens)))
+    totals = None
     try:
         o.async_ = 1
         _check(L.deq_solve(ens, int(ode), int(tableau_set), C.byref(o), C.byref(res)))
@@ -455,15 +457,21 @@ def solve_host(rhs, y0, params, tspan, ode, opts=None, out_final=None, out_accep
             if out_final is None:
                 out_final = np.empty((ntraj, n))
             _check(L.deq_result_final(res, _ptr(out_final)))
-            if tableau(ode, tableau_set)["adaptive"]:
+            if adaptive:
                 if out_accepted is None:
                     out_accepted = np.empty(ntraj, np.uint32)
                 if out_rejected is None:
                     out_rejected = np.empty(ntraj, np.uint32)
                 _check(L.deq_result_counts(res, _ptr(out_accepted, C.c_uint32), _ptr(out_rejected, C.c_uint32), None,
                                            None, None))
+            if return_totals:
+                a = C.c_uint64(); r = C.c_uint64(); f = C.c_uint64()
+                _check(L.deq_result_totals(res, C.byref(a), C.byref(r), C.byref(f)))
+                totals = dict(accepted=a.value, rejected=r.value, nfe=f.value)
         finally:
             L.deq_result_destroy(res)
     finally:
         L.deq_ensemble_destroy(ens)
+    if return_totals:
+        return out_final, out_accepted, out_rejected, totals
     return out_final, out_accepted, out_rejected
