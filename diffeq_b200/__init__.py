@@ -85,6 +85,11 @@ class Mode(enum.IntEnum):
     Fast = 1
 
 
+class Precision(enum.IntEnum):
+    F64 = 0
+    F32 = 1
+
+
 class System(enum.IntEnum):
     Lorenz = 0
     VanDerPol = 1
@@ -95,7 +100,7 @@ class _Options(C.Structure):
     _fields_ = [("reltol", C.c_double), ("abstol", C.c_double), ("has_minstep", C.c_int), ("minstep", C.c_double),
                 ("has_maxstep", C.c_int), ("maxstep", C.c_double), ("initstep", C.c_double), ("points", C.c_int),
                 ("output", C.c_int), ("max_steps", C.c_uint64), ("refill", C.c_int), ("async_", C.c_int),
-                ("mode", C.c_int)]
+                ("mode", C.c_int), ("precision", C.c_int)]
 
 
 # The symbols include/diffeq_b200.h declares (checked by tests/test_abi.py).
@@ -250,6 +255,8 @@ class OdeOptionMap(dict):
                 self["Output"] = o
             elif isinstance(o, Mode):
                 self["Mode"] = o
+            elif isinstance(o, Precision):
+                self["Precision"] = o
             else:
                 self[o.name] = o.v
         return self
@@ -266,6 +273,7 @@ class OdeOptionMap(dict):
         if "MaxSteps" in self: o.max_steps = int(self["MaxSteps"])
         if "Refill" in self: o.refill = int(self["Refill"])
         if "Mode" in self: o.mode = int(self["Mode"])
+        if "Precision" in self: o.precision = int(self["Precision"])
         return o
 
 

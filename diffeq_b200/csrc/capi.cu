@@ -32,8 +32,8 @@ deq_status fail(deq_status s, const std::string& msg) { g_err = msg; return s; }
     } while (0)
 
 const deql::TbEntry g_tb[deql::TB_COUNT] = {
-#define EF(ID) {deql::launch_adapt_##ID, nullptr, deql::launch_fixed_##ID, deql::info_##ID}  // fixed-step tableaus
-#define E(ID) {deql::launch_adapt_##ID, deql::launch_adapt_fast_##ID, deql::launch_fixed_##ID, deql::info_##ID}
+#define EF(ID) {deql::launch_adapt_##ID, nullptr, nullptr, deql::launch_fixed_##ID, deql::info_##ID}  // fixed-step tableaus
+#define E(ID) {deql::launch_adapt_##ID, deql::launch_adapt_fast_##ID, deql::launch_adapt_f32_##ID, deql::launch_fixed_##ID, deql::info_##ID}
     EF(0), EF(1), EF(2), EF(3), E(4), E(5), E(6), E(7), E(8), E(9), E(10), E(11), E(12)
 #undef E
 #undef EF
@@ -282,6 +282,9 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
     if (tb < 0) return fail(DEQ_ERR_INVALID_ARG, "unknown method");
     const deq_options o = opts_in ? *opts_in : deq_options_default();
     if (o.mode != DEQ_MODE_PARITY && o.mode != DEQ_MODE_FAST) return fail(DEQ_ERR_INVALID_ARG, "unknown arithmetic mode");
+    if (o.precision != DEQ_PRECISION_F64 && o.precision != DEQ_PRECISION_F32) return fail(DEQ_ERR_INVALID_ARG, "unknown precision");
+    if (o.precision == DEQ_PRECISION_F32 && (e->rhs.kind != 0 || o.output == DEQ_OUT_ALL))
+        return fail(DEQ_ERR_UNSUPPORTED, "the f32 mode covers the built-in systems with FINAL / TSPAN output");
     ensure_pool();
     deql::TableauInfo info;
     g_tb[tb].info(&info);
@@ -363,7 +366,8 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         P.rec_counts = r->d_rec_counts;
         auto launch_adapt = [&](std::string* err) -> int {  // 0 ok, 1 cuda error (g_err set), 2 nvrtc error
             if (e->rhs.kind == 0) {
-                cudaError_t ce = (o.mode == DEQ_MODE_FAST ? g_tb[tb].adapt_fast : g_tb[tb].adapt)(e->rhs.sys, e->per_traj, mode, P, 0, st);
+                deql::AdaptLaunchFn fn = o.precision == DEQ_PRECISION_F32 ? g_tb[tb].adapt_f32 : o.mode == DEQ_MODE_FAST ? g_tb[tb].adapt_fast : g_tb[tb].adapt;
+                cudaError_t ce = fn(e->rhs.sys, e->per_traj, mode, P, 0, st);
                 if (ce != cudaSuccess) { fail(DEQ_ERR_CUDA, std::string("adaptive kernel launch: ") + cudaGetErrorString(ce)); return 1; }
                 return 0;
             }
@@ -397,7 +401,8 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
             if (e->rhs.kind == 0) {
                 CKR(deql::launch_hinit(e->rhs.sys, e->per_traj, H, st));
                 CKR(cudaEventRecord(r->ev0, st));
-                CKR((o.mode == DEQ_MODE_FAST ? g_tb[tb].adapt_fast : g_tb[tb].adapt)(e->rhs.sys, e->per_traj, mode, P, 0, st));
+                deql::AdaptLaunchFn fn = o.precision == DEQ_PRECISION_F32 ? g_tb[tb].adapt_f32 : o.mode == DEQ_MODE_FAST ? g_tb[tb].adapt_fast : g_tb[tb].adapt;
+                CKR(fn(e->rhs.sys, e->per_traj, mode, P, 0, st));
             } else {
                 std::string err;
                 if (!deqn::launch_hinit(e->rhs.prog, e->per_traj, H, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));

@@ -1,6 +1,9 @@
 // kernels_inst.cu — instantiates the steppers of ONE Butcher tableau (selected with -DDEQ_TB=<deql::TbId>) for the
 // built-in systems and exposes host launchers.  Compiled with -fmad=false (parity contract, see stepper.cuh).
 #include "stepper.cuh"
+#ifdef DEQ_FAST_TU
+#include "stepper_f32.cuh"
+#endif
 #include "launch.h"
 
 #ifndef DEQ_TB
@@ -89,6 +92,37 @@ cudaError_t DEQ_LAUNCH_ADAPT(int sys, int pt, int mode, const deqk::AdaptParams&
         default: return cudaErrorInvalidValue;
     }
 }
+
+#ifdef DEQ_FAST_TU
+// optional single-precision variant (stepper_f32.cuh), built-in systems only
+template <class F, bool PT, int MODE>
+static cudaError_t launch_adapt_f32_t(const deqk::AdaptParams& P, int grid_blocks, cudaStream_t st) {
+    if constexpr (TB::ADAPTIVE) {
+        auto kernel = deqk::adapt_kernel_f32<TB, F, PT, MODE>;
+        const int grid = grid_blocks > 0 ? grid_blocks : persistent_grid(kernel, P.ntraj);
+        kernel<<<grid, deqk::BLOCK, 0, st>>>(P);
+        return cudaGetLastError();
+    } else {
+        (void)P; (void)grid_blocks; (void)st;
+        return cudaErrorInvalidValue;
+    }
+}
+template <class F>
+static cudaError_t launch_adapt_f32_f(int pt, int mode, const deqk::AdaptParams& P, int grid_blocks, cudaStream_t st) {
+    if (pt) return mode == deqk::MODE_DENSE ? launch_adapt_f32_t<F, true, deqk::MODE_DENSE>(P, grid_blocks, st)
+                                            : launch_adapt_f32_t<F, true, deqk::MODE_FINAL>(P, grid_blocks, st);
+    return mode == deqk::MODE_DENSE ? launch_adapt_f32_t<F, false, deqk::MODE_DENSE>(P, grid_blocks, st)
+                                    : launch_adapt_f32_t<F, false, deqk::MODE_FINAL>(P, grid_blocks, st);
+}
+cudaError_t DEQ_CAT(launch_adapt_f32_, DEQ_TB)(int sys, int pt, int mode, const deqk::AdaptParams& P, int grid_blocks, cudaStream_t st) {
+    switch (sys) {
+        case 0: return launch_adapt_f32_f<deqr::Lorenz>(pt, mode, P, grid_blocks, st);
+        case 1: return launch_adapt_f32_f<deqr::VanDerPol>(pt, mode, P, grid_blocks, st);
+        case 2: return launch_adapt_f32_f<deqr::Pendulum>(pt, mode, P, grid_blocks, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+#endif
 
 #ifndef DEQ_FAST_TU
 template <class F, bool PT, bool ALL>

@@ -24,12 +24,13 @@ typedef cudaError_t (*FixedLaunchFn)(int sys, int per_traj_params, int all, cons
                                      cudaStream_t st);
 typedef void (*InfoFn)(TableauInfo* out);
 
-struct TbEntry { AdaptLaunchFn adapt; AdaptLaunchFn adapt_fast; FixedLaunchFn fixed; InfoFn info; };
+struct TbEntry { AdaptLaunchFn adapt; AdaptLaunchFn adapt_fast; AdaptLaunchFn adapt_f32; FixedLaunchFn fixed; InfoFn info; };
 const TbEntry& tb_entry(int tb);  // defined in capi.cu from the per-TU registrars below
 
 #define DEQ_DECL_TB(ID) \
     cudaError_t launch_adapt_##ID(int, int, int, const deqk::AdaptParams&, int, cudaStream_t); \
     cudaError_t launch_adapt_fast_##ID(int, int, int, const deqk::AdaptParams&, int, cudaStream_t); \
+    cudaError_t launch_adapt_f32_##ID(int, int, int, const deqk::AdaptParams&, int, cudaStream_t);  \
     cudaError_t launch_fixed_##ID(int, int, int, const deqk::FixedParams&, cudaStream_t);      \
     void info_##ID(TableauInfo*);
 DEQ_DECL_TB(0) DEQ_DECL_TB(1) DEQ_DECL_TB(2) DEQ_DECL_TB(3) DEQ_DECL_TB(4) DEQ_DECL_TB(5) DEQ_DECL_TB(6)

@@ -57,6 +57,13 @@ struct Lorenz {
         d[1] = x * (p[1] - z) - y;
         d[2] = x * y - p[2] * z;
     }
+    template <class R>  // generic-precision form for the optional f32 mode
+    DEQ_RHS_HD static void eval_r(R, const R* v, R* d, const R* p) {
+        const R x = v[0], y = v[1], z = v[2];
+        d[0] = p[0] * (y - x);
+        d[1] = x * (p[1] - z) - y;
+        d[2] = x * y - p[2] * z;
+    }
 };
 
 // Van der Pol  x' = y, y' = mu (1 - x^2) y - x ; p = {mu}.
@@ -68,6 +75,12 @@ struct VanDerPol {
         d[0] = y;
         d[1] = p[0] * (1.0 - x * x) * y - x;
     }
+    template <class R>
+    DEQ_RHS_HD static void eval_r(R, const R* v, R* d, const R* p) {
+        const R x = v[0], y = v[1];
+        d[0] = y;
+        d[1] = p[0] * (R(1) - x * x) * y - x;
+    }
 };
 
 // Damped driven pendulum  th' = w, w' = -gamma w - sin th + A cos(Omega t) ; p = {gamma, A, Omega}.
@@ -78,6 +91,11 @@ struct Pendulum {
         const double th = v[0], w = v[1];
         d[0] = w;
         d[1] = -p[0] * w - deq_sin(th) + p[1] * deq_cos(p[2] * t);
+    }
+    DEQ_RHS_HD static void eval_r(float t, const float* v, float* d, const float* p) {
+        const float th = v[0], w = v[1];
+        d[0] = w;
+        d[1] = -p[0] * w - sinf(th) + p[1] * cosf(p[2] * t);
     }
 };
 

@@ -69,6 +69,11 @@ typedef enum deq_output {
  * within 10 x rtol of PARITY on the BASELINE ensembles (tests/test_gpu_parity.py), ~2x the throughput. */
 typedef enum deq_mode { DEQ_MODE_PARITY = 0, DEQ_MODE_FAST = 1 } deq_mode;
 
+/* Optional single-precision state (north_star "optional f32 mode").  The reference cannot instantiate f32 (types.rs:262-278),
+ * so F32 has no reference result to match; it runs the FAST formulas in float (time stays f64) and is validated against
+ * the f64 path at f32 tolerances.  Adaptive methods, built-in systems, FINAL / TSPAN output. */
+typedef enum deq_precision { DEQ_PRECISION_F64 = 0, DEQ_PRECISION_F32 = 1 } deq_precision;
+
 /* Per-trajectory completion code (the reference returns Ok(partial) silently in the first two cases). */
 typedef enum deq_traj_status {
     DEQ_TRAJ_DONE = 0,
@@ -94,6 +99,7 @@ typedef struct deq_options {
     int refill;          /* 1 (default): persistent lanes refilled individually; 0: static warp assignment */
     int async;           /* 0 (default): deq_solve returns after the GPU finished; 1: returns after enqueueing */
     int mode;            /* deq_mode, default DEQ_MODE_PARITY (adaptive methods only; fixed-step is always parity) */
+    int precision;       /* deq_precision, default DEQ_PRECISION_F64 */
 } deq_options;
 
 typedef struct deq_rhs deq_rhs;

@@ -31,6 +31,7 @@ pub struct deq_options {
     pub refill: c_int,
     pub r#async: c_int,
     pub mode: c_int,
+    pub precision: c_int,
 }
 
 #[repr(C)] pub struct deq_rhs { _p: [u8; 0] }
@@ -66,6 +67,9 @@ extern "C" {
     pub fn deq_result_totals(res: *mut deq_result, accepted: *mut u64, rejected: *mut u64, nfe: *mut u64) -> deq_status;
     pub fn deq_result_dense(res: *mut deq_result, traj_begin: usize, traj_end: usize, out: *mut c_double,
                             nvalid: *mut u32) -> deq_status;
+    pub fn deq_result_all_offsets(res: *mut deq_result, offsets: *mut u64) -> deq_status;
+    pub fn deq_result_all_copy(res: *mut deq_result, traj_begin: usize, traj_end: usize, tout: *mut c_double,
+                               yout: *mut c_double) -> deq_status;
     pub fn deq_result_device_ptrs(res: *mut deq_result, d_yfinal_soa: *mut *const c_double,
                                   d_dense_soa: *mut *const c_double) -> deq_status;
     pub fn deq_result_trajectory(res: *mut deq_result, traj: usize, yout: *mut c_double) -> deq_status;

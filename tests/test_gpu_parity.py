@@ -345,3 +345,22 @@ def test_demo_json_entry_point(deq, oracle):
         demo.solve_lorenz_attractor(json.dumps(dict(cfg, ode="rk99")))
     with pytest.raises(ValueError, match="Can't solve for 2 dimensional type"):
         demo.solve_lorenz_attractor(json.dumps(dict(cfg, init=[1.0, 2.0])))
+
+
+def test_f32_mode_tracks_f64(deq, oracle):
+    """Optional f32 mode (no reference counterpart: the crate cannot instantiate f32): final states track the f64 oracle
+    at single-precision tolerances on a non-chaotic horizon; dense rows likewise."""
+    from diffeq_b200 import synth
+    y0, mu = synth.vdp_sweep(0, 2048, 2048)
+    ref = oracle.ensemble_adaptive(oracle.ODE45FE, oracle.VANDERPOL, mu, y0, [0.0, 5.0], oracle.opts(1e-5, 1e-6))
+    o = deq.OdeOptionMap().insert(deq.Reltol(1e-5), deq.Abstol(1e-6), deq.Precision.F32)
+    sol = _problem(deq, deq.System.VanDerPol, mu, y0, [0.0, 5.0]).solve(deq.Ode.Ode45fe, o)
+    assert np.all(sol.status == 0)
+    np.testing.assert_allclose(sol.final, ref["yfinal"], rtol=2e-3, atol=2e-3)
+    assert abs(int(sol.accepted.sum()) - int(ref["accepted"].sum())) < 0.05 * ref["accepted"].sum()
+    yl = synth.lorenz_ics(0, 1024)
+    rl = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, yl, [0.0, 0.5], oracle.opts(1e-5, 1e-6))
+    sl = _problem(deq, deq.System.Lorenz, LOR, yl, [0.0, 0.5]).solve(deq.Ode.Ode45, o)
+    np.testing.assert_allclose(sl.final, rl["yfinal"], rtol=5e-3, atol=5e-3)
+    with pytest.raises(deq.OdeError):
+        _problem(deq, deq.System.Lorenz, LOR, yl, [0.0, 0.5]).solve(deq.Ode.Ode45, deq.OdeOptionMap().insert(deq.Precision.F32, deq.Output.All))
