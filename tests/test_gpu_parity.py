@@ -364,3 +364,73 @@ def test_f32_mode_tracks_f64(deq, oracle):
     np.testing.assert_allclose(sl.final, rl["yfinal"], rtol=5e-3, atol=5e-3)
     with pytest.raises(deq.OdeError):
         _problem(deq, deq.System.Lorenz, LOR, yl, [0.0, 0.5]).solve(deq.Ode.Ode45, deq.OdeOptionMap().insert(deq.Precision.F32, deq.Output.All))
+
+
+def test_nan_and_overflow_paths_match_oracle(deq, oracle):
+    """Trial states that overflow to inf/NaN take the reference's `err = 10, dt *= 0.2, timeout = 5` branch
+    (problem.rs:819-825) or its natural inf arithmetic; every counter and state must still equal the oracle's
+    (NaN-aware comparison)."""
+    y0 = np.array([[1e200, -1e200, 1e150], [1e308, 1e308, 1e308], [0.0, 0.0, 0.0], [-0.0, 1e-320, 5e-324],
+                   [1e154, 1e154, 1e154], [3.0, 4.0, np.inf], [np.nan, 1.0, 1.0], [1e100, 1.0, -1e100]])
+    for ts, kw in (([0.0, 1.0], dict()), ([0.0, 1e-3], dict(initstep=1e-4)), ([0.0, 10.0], dict(maxstep=5.0))):
+        ref = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, y0, ts, oracle.opts(1e-6, 1e-8, max_steps=400, **kw))
+        o = deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8), deq.MaxSteps(400))
+        if "initstep" in kw: o.insert(deq.Initstep(kw["initstep"]))
+        if "maxstep" in kw: o.insert(deq.Maxstep(kw["maxstep"]))
+        sol = _problem(deq, deq.System.Lorenz, LOR, y0, ts).solve(deq.Ode.Ode45, o)
+        assert np.array_equal(sol.accepted, ref["accepted"]) and np.array_equal(sol.rejected, ref["rejected"]), (ts, kw)
+        assert np.array_equal(sol.status, ref["status"]), (ts, kw)
+        assert np.array_equal(sol.final, ref["yfinal"], equal_nan=True), (ts, kw)
+        assert np.array_equal(sol.t_reached, ref["t_reached"], equal_nan=True), (ts, kw)
+
+
+def test_degenerate_sizes(deq, oracle):
+    """Empty and single-element inputs: zero trajectories, one trajectory, one-point tspan."""
+    e = _problem(deq, deq.System.Lorenz, LOR, np.zeros((0, 3)), [0.0, 1.0]).solve(deq.Ode.Ode45)
+    assert e.final.shape == (0, 3) and e.totals["accepted"] == 0
+    e = _problem(deq, deq.System.Lorenz, LOR, np.zeros((0, 3)), [0.0, 1.0]).solve(deq.Ode.Ode4)
+    assert e.final.shape == (0, 3)
+    # one-point tspan: fixed step takes no step (yout = [y0]); adaptive does one zero-length step (t0 == tend)
+    f = _problem(deq, deq.System.Lorenz, LOR, [1.0, 2.0, 3.0], [0.5]).solve(deq.Ode.Ode4, deq.OdeOptionMap().insert(deq.Output.Tspan))
+    assert f.final.tolist() == [[1.0, 2.0, 3.0]] and f.yout.shape == (1, 1, 3)
+    a = _problem(deq, deq.System.Lorenz, LOR, [1.0, 2.0, 3.0], [0.5]).solve(deq.Ode.Ode45)
+    r = oracle.solve_adaptive(oracle.ODE45, oracle.LORENZ, LOR, [1.0, 2.0, 3.0], [0.5])
+    assert int(a.accepted[0]) == r["accepted"] == 1 and np.array_equal(a.final[0], r["yfinal"])
+
+
+def test_randomised_option_sweep_bit_exact(deq, oracle):
+    """Seeded fuzz over methods, tableau sets, systems, tolerances, horizons, directions and step bounds: every case must
+    be bit-identical to the oracle (guarded by max_steps so the reference's runaway cases terminate)."""
+    from diffeq_b200 import synth
+    rng = np.random.default_rng(20261020)
+    methods = [("Ode45", 0), ("Ode45", 1), ("Ode45fe", 0), ("Ode23", 1), ("Ode23", 0), ("Ode21", 1), ("Ode21", 0), ("Ode78", 1), ("Ode78", 0)]
+    for case in range(24):
+        method, tset = methods[case % len(methods)]
+        system = ["Lorenz", "VanDerPol", "Pendulum"][int(rng.integers(0, 3))]
+        n = int(rng.integers(1, 200))
+        if system == "Lorenz":
+            y0, params = synth.lorenz_ics(case * 1000, case * 1000 + n), np.array(LOR)
+        elif system == "VanDerPol":
+            y0, params = synth.vdp_sweep(0, n, max(n, 2))
+        else:
+            y0, params = synth.pendulum_ics(case * 1000, case * 1000 + n), synth.PENDULUM_PARAMS
+        rtol = 10.0 ** rng.uniform(-9, -3)
+        atol = 10.0 ** rng.uniform(-10, -4)
+        t0 = float(rng.uniform(-1, 1))
+        span = float(10.0 ** rng.uniform(-2, 0.7))
+        ts = [t0, t0 + span] if rng.random() < 0.8 else [t0 + span, t0]
+        kw = dict(max_steps=1500)
+        o = deq.OdeOptionMap().insert(deq.Reltol(rtol), deq.Abstol(atol), deq.MaxSteps(1500))
+        if rng.random() < 0.3:
+            kw["maxstep"] = span / float(rng.integers(3, 30)); o.insert(deq.Maxstep(kw["maxstep"]))
+        if rng.random() < 0.3:
+            kw["initstep"] = float(np.sign(ts[1] - ts[0]) * span * 10.0 ** rng.uniform(-5, -1)); o.insert(deq.Initstep(kw["initstep"]))
+        if rng.random() < 0.2:
+            kw["minstep"] = span * 1e-4; o.insert(deq.Minstep(kw["minstep"]))
+        ref = oracle.ensemble_adaptive(getattr(oracle, method.upper()), getattr(oracle, system.upper()), params, y0, ts,
+                                       oracle.opts(rtol, atol, **kw), tset)
+        sol = _problem(deq, getattr(deq.System, system), params, y0, ts).solve(getattr(deq.Ode, method), o, tableau_set=tset)
+        tag = (case, method, tset, system, n, rtol, atol, ts, kw)
+        assert np.array_equal(sol.accepted, ref["accepted"]) and np.array_equal(sol.rejected, ref["rejected"]), tag
+        assert np.array_equal(sol.status, ref["status"]) and np.array_equal(sol.nfe, ref["nfe"]), tag
+        assert np.array_equal(sol.final, ref["yfinal"], equal_nan=True) and np.array_equal(sol.t_reached, ref["t_reached"]), tag
