@@ -143,3 +143,13 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(deq):
         pytest.skip("CPU-only check")
     out = subprocess.run([_build_hpp_smoke()], capture_output=True, text=True)
     assert out.returncode == 1 and "HPP_FAIL 7" in out.stdout
+
+
+def test_c_abi_is_c99_clean_and_links_from_c(deq):
+    """include/diffeq_b200.h compiles as strict C99 and the library links from a C program (no C++ types in the ABI)."""
+    exe = "/tmp/deq_abi_smoke"
+    libdir = os.path.join(ROOT, "diffeq_b200")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", os.path.join(HERE, "cpp", "abi_smoke.c"),
+                           "-L" + libdir, "-ldiffeq_b200", "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "ABI_VERSION" in out.stdout and ("ABI_OK" in out.stdout or "ABI_NO_GPU" in out.stdout), out.stdout
