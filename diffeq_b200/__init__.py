@@ -85,6 +85,12 @@ class Mode(enum.IntEnum):
     Fast = 1
 
 
+class Libm(enum.IntEnum):
+    """deq_libm: the libm calls as written in the source, or as LLVM folds them in an optimised build (sqrt / exp10)."""
+    AsWritten = 0
+    LlvmFolded = 1
+
+
 class Precision(enum.IntEnum):
     F64 = 0
     F32 = 1
@@ -100,7 +106,7 @@ class _Options(C.Structure):
     _fields_ = [("reltol", C.c_double), ("abstol", C.c_double), ("has_minstep", C.c_int), ("minstep", C.c_double),
                 ("has_maxstep", C.c_int), ("maxstep", C.c_double), ("initstep", C.c_double), ("points", C.c_int),
                 ("output", C.c_int), ("max_steps", C.c_uint64), ("refill", C.c_int), ("async_", C.c_int),
-                ("mode", C.c_int), ("precision", C.c_int)]
+                ("mode", C.c_int), ("precision", C.c_int), ("libm", C.c_int)]
 
 
 # The symbols include/diffeq_b200.h declares (checked by tests/test_abi.py).
@@ -257,6 +263,8 @@ class OdeOptionMap(dict):
                 self["Mode"] = o
             elif isinstance(o, Precision):
                 self["Precision"] = o
+            elif isinstance(o, Libm):
+                self["Libm"] = o
             else:
                 self[o.name] = o.v
         return self
@@ -274,6 +282,7 @@ class OdeOptionMap(dict):
         if "Refill" in self: o.refill = int(self["Refill"])
         if "Mode" in self: o.mode = int(self["Mode"])
         if "Precision" in self: o.precision = int(self["Precision"])
+        if "Libm" in self: o.libm = int(self["Libm"])
         return o
 
 

@@ -283,6 +283,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
     const deq_options o = opts_in ? *opts_in : deq_options_default();
     if (o.mode != DEQ_MODE_PARITY && o.mode != DEQ_MODE_FAST) return fail(DEQ_ERR_INVALID_ARG, "unknown arithmetic mode");
     if (o.precision != DEQ_PRECISION_F64 && o.precision != DEQ_PRECISION_F32) return fail(DEQ_ERR_INVALID_ARG, "unknown precision");
+    if (o.libm != DEQ_LIBM_AS_WRITTEN && o.libm != DEQ_LIBM_LLVM_FOLDED) return fail(DEQ_ERR_INVALID_ARG, "unknown libm flavour");
     if (o.precision == DEQ_PRECISION_F32 && (e->rhs.kind != 0 || o.output == DEQ_OUT_ALL))
         return fail(DEQ_ERR_UNSUPPORTED, "the f32 mode covers the built-in systems with FINAL / TSPAN output");
     ensure_pool();
@@ -351,13 +352,14 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         deqk::HinitParams H{};
         H.y0 = e->d_y0; H.params = e->d_params; H.shared = e->shared; H.ntraj = ntraj; H.t0 = t0; H.tend = tend;
         H.reltol = o.reltol; H.abstol = o.abstol; H.order = info.order_min; H.f0 = r->d_f0; H.h0 = r->d_h0;
+        H.libm_folded = o.libm == DEQ_LIBM_LLVM_FOLDED;
         deqk::AdaptParams P{};
         P.y0 = e->d_y0; P.f0 = r->d_f0; P.h0 = r->d_h0; P.params = e->d_params; P.shared = e->shared;
         P.tspan = e->d_tspan; P.nt = nt; P.ntraj = ntraj; P.t0 = t0; P.tend = tend; P.tdir = tdir;
         P.minstep = o.has_minstep ? o.minstep : std::fabs(tend - t0) / 1e18;   // problem.rs:219-221
         P.maxstep = o.has_maxstep ? o.maxstep : std::fabs(tend - t0) / 2.5;    // problem.rs:223-225
         P.reltol = o.reltol; P.abstol = o.abstol; P.initstep = o.initstep; P.use_initstep = o.initstep != 0.;
-        P.refill = o.refill; P.max_steps = o.max_steps;
+        P.refill = o.refill; P.max_steps = o.max_steps; P.libm_folded = o.libm == DEQ_LIBM_LLVM_FOLDED;
         P.yfinal = r->d_yfinal; P.accepted = r->d_acc; P.rejected = r->d_rej; P.nfe = r->d_nfe; P.status = r->d_status;
         P.t_reached = r->d_treached; P.dense = r->d_dense; P.nvalid = r->d_nvalid;
         P.work_counter = r->d_scalars; P.totals = r->d_scalars + 1;

@@ -28,6 +28,7 @@ struct AdaptParams {
     unsigned long long ntraj;
     double t0, tend, tdir, minstep, maxstep, reltol, abstol, initstep;
     int use_initstep;
+    int libm_folded;       // 0: pow(s, 0.5) as written (types.rs:115); 1: sqrt(s), what LLVM folds pow(x, 0.5) to
     int refill;            // 1: persistent lanes re-filled individually; 0: a warp takes 32 trajectories at a time
     unsigned long long max_steps;  // guard (extension; the reference loops forever); 0 = none
     // outputs
@@ -49,6 +50,7 @@ struct HinitParams {
     unsigned long long ntraj;
     double t0, tend, reltol, abstol;
     int order;
+    int libm_folded;       // 0: pow(10, p) as written (problem.rs:893); 1: exp10(p), what LLVM folds pow(10.0, x) to
     double* f0; double* h0;
 };
 

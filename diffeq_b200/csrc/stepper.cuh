@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(BLOCK) hinit_kernel(const HinitParams P) {
         h1 = fmax(1.0e-6, 1.0e-3 * h0);
     } else {
         const double pw = (-(2. + deqm::log10_glibc(m, T))) / (double)(P.order + 1);
-        h1 = deqm::pow_glibc(10.0, pw, T);
+        h1 = P.libm_folded ? deqm::exp10_glibc(pw, T) : deqm::pow_glibc(10.0, pw, T);
     }
     const double h = tdir * fmin(fmin(h1, 100. * h0), tdir * (tend - t0));
     P.h0[traj] = h;
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                             const double a = fabs(e);
                             ssum = ssum + a * a;
                         }
-                        const double err = deqm::pow_glibc(ssum, 0.5, T);
+                        const double err = P.libm_folded ? sqrt(ssum) : deqm::pow_glibc(ssum, 0.5, T);
                         const double g = deqm::pow_glibc(1.0 / err, PW, T) * 0.8;
                         double nd = sel_min(P.maxstep, (sel_max(0.2, g) * tdir) * dt);
                         if (timeout > 0) { nd = sel_min(nd, dt); timeout -= 1; }

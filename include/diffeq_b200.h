@@ -74,6 +74,14 @@ typedef enum deq_mode { DEQ_MODE_PARITY = 0, DEQ_MODE_FAST = 1 } deq_mode;
  * the f64 path at f32 tolerances.  Adaptive methods, built-in systems, FINAL / TSPAN output. */
 typedef enum deq_precision { DEQ_PRECISION_F64 = 0, DEQ_PRECISION_F32 = 1 } deq_precision;
 
+/* Which libm calls the PARITY arithmetic reproduces.  The source calls `powf(1/p)` with p = 2 for the error norm
+ * (types.rs:115) and `10f64.powf(x)` in hinit (problem.rs:893).  AS_WRITTEN evaluates exactly those (glibc pow).
+ * LLVM_FOLDED evaluates what an optimised rustc build runs after LLVM's libcall simplification: pow(x, 0.5) -> sqrt(x)
+ * (the exponent folds to the constant 0.5 once pnorm(PNorm::default()) is inlined) and pow(10.0, x) -> exp10(x).  The two
+ * differ by one ulp in roughly 1 of 2000 norm evaluations; which one a given build of the crate contains cannot be
+ * determined without a Rust toolchain, so both are provided, each bit-exact against the oracle in the same flavour. */
+typedef enum deq_libm { DEQ_LIBM_AS_WRITTEN = 0, DEQ_LIBM_LLVM_FOLDED = 1 } deq_libm;
+
 /* Per-trajectory completion code (the reference returns Ok(partial) silently in the first two cases). */
 typedef enum deq_traj_status {
     DEQ_TRAJ_DONE = 0,
@@ -100,6 +108,7 @@ typedef struct deq_options {
     int async;           /* 0 (default): deq_solve returns after the GPU finished; 1: returns after enqueueing */
     int mode;            /* deq_mode, default DEQ_MODE_PARITY (adaptive methods only; fixed-step is always parity) */
     int precision;       /* deq_precision, default DEQ_PRECISION_F64 */
+    int libm;            /* deq_libm, default DEQ_LIBM_AS_WRITTEN (PARITY mode only) */
 } deq_options;
 
 typedef struct deq_rhs deq_rhs;

@@ -206,6 +206,12 @@ struct Opts {
     double initstep;
     int points;  // 0 = All, 1 = Specified (reference semantics, including its lagging-y defect)
     uint64_t max_steps;  // oracle guard (the reference has none); 0 = unlimited
+    // 0: libm calls as written in the source — pow(s, 0.5) (types.rs:115) and pow(10, p) (problem.rs:893).
+    // 1: what an optimised rustc/LLVM build evaluates instead: LLVM's SimplifyLibCalls rewrites pow(x, 0.5) with a
+    //    constant exponent to sqrt(x) (the exponent 1/p folds to 0.5 once pnorm(PNorm::default()) is inlined) and
+    //    pow(10.0, x) to exp10(x).  Which of the two a given build of the crate runs cannot be established without a
+    //    Rust toolchain; both are provided and pinned.
+    int libm_folded;
 };
 
 enum Status { ST_DONE = 0, ST_MINSTEP_BREAK = 1, ST_MAX_STEPS = 2 };
@@ -257,7 +263,7 @@ void solve_fixed(const Tableau& tb, const double* y0, const double* tspan, size_
 // hinit, problem.rs:850-899
 template <int N, class F>
 inline void hinit(const double* x0, double t0, double tend, int order, double reltol, double abstol,
-                  const double* p, double& h, double& tdir, double* f0) {
+                  const double* p, double& h, double& tdir, double* f0, int libm_folded = 0) {
     tdir = signum(tend - t0);
     double norm = 0.0;
     for (int d = 0; d < N; ++d) { double a = std::fabs(x0[d]); if (a > norm) norm = a; }
@@ -282,7 +288,7 @@ inline void hinit(const double* x0, double t0, double tend, int order, double re
         h1 = fmax_rs(1.0e-6, 1.0e-3 * h0);
     } else {
         const double pw = -(2. + std::log10(m)) / (double)(order + 1);
-        h1 = std::pow(10.0, pw);
+        h1 = libm_folded ? exp10(pw) : std::pow(10.0, pw);
     }
     h = tdir * fmin_rs(fmin_rs(h1, 100. * h0), tdir * (tend - t0));
 }
@@ -291,7 +297,7 @@ inline void hinit(const double* x0, double t0, double tend, int order, double re
 template <int N>
 inline void stepsize_hw92(double dt, double tdir, const double* x0, const double* xtrial, double* xerr, int order,
                           unsigned timeout, double abstol, double reltol, double maxstep, double& err, double& newdt,
-                          unsigned& timeout_out) {
+                          unsigned& timeout_out, int libm_folded = 0) {
     const double fac = 0.8, facmin = 0.2;
     for (int d = 0; d < N; ++d) {
         if (std::isnan(xtrial[d])) { err = 10.; newdt = facmin * dt; timeout_out = 5; return; }
@@ -299,7 +305,7 @@ inline void stepsize_hw92(double dt, double tdir, const double* x0, const double
     }
     double s = 0.0;
     for (int d = 0; d < N; ++d) { const double a = std::fabs(xerr[d]); s = s + a * a; }
-    err = std::pow(s, 1.0 * (1. / 2.0));
+    err = libm_folded ? std::sqrt(s) : std::pow(s, 1.0 * (1. / 2.0));
     const double pw = 1. / (double)(order + 1);
     double nd = fmin_rs(maxstep, fmax_rs(facmin, std::pow(1.0 / err, pw) * fac) * tdir * dt);
     if (timeout > 0) { nd = fmin_rs(nd, dt); timeout -= 1; }
@@ -344,7 +350,7 @@ int solve_adapt(const Tableau& tb, const double* y0, const double* tspan, size_t
     const double reltol = o.reltol, abstol = o.abstol;
     const int order = tb.order_min;
     double h, tdir, ck[N], cy[N];
-    hinit<N, F>(y0, t, tend, order, reltol, abstol, p, h, tdir, ck);
+    hinit<N, F>(y0, t, tend, order, reltol, abstol, p, h, tdir, ck, o.libm_folded);
     cnt.nfe += 2;
     if (tdir == 0.) return ERR_ZERO_TIMESPAN;        // unreachable for f64 (signum(0)=1)
     double dt;
@@ -375,7 +381,7 @@ int solve_adapt(const Tableau& tb, const double* y0, const double* tspan, size_t
             for (int d = 0; d < N; ++d) { ytrial[d] += k[s][d] * tb.b[s][0]; yerr[d] += k[s][d] * tb.b[s][1]; }
         for (int d = 0; d < N; ++d) { yerr[d] = (ytrial[d] - yerr[d]) * dt; ytrial[d] = y[d] + (ytrial[d] * dt); }
         double err, ndt; unsigned tmo;
-        stepsize_hw92<N>(dt, tdir, y, ytrial, yerr, order, timeout, abstol, reltol, maxstep, err, ndt, tmo);
+        stepsize_hw92<N>(dt, tdir, y, ytrial, yerr, order, timeout, abstol, reltol, maxstep, err, ndt, tmo, o.libm_folded);
         timeout = tmo;
         if (err < 1.) {
             cnt.accepted += 1;
@@ -443,6 +449,7 @@ struct oracle_opts {
     double initstep;
     int points;
     uint64_t max_steps;
+    int libm_folded;
 };
 
 int oracle_rhs_dim(int rhs) { return rhs == LORENZ ? 3 : (rhs == VANDERPOL || rhs == PENDULUM) ? 2 : -1; }
@@ -480,7 +487,7 @@ int oracle_solve_adaptive(int method, int set, int rhs, const double* params, co
                           double* yfinal, uint32_t* counts, uint8_t* status, double* t_reached) {
     if (!is_adapt(method)) return is_fixed(method) ? ERR_WEIGHT_TYPE : ERR_UNSUPPORTED;
     Tableau tb; make_tableau(method, set, tb);
-    Opts op{o->reltol, o->abstol, o->has_minstep, o->minstep, o->has_maxstep, o->maxstep, o->initstep, o->points, o->max_steps};
+    Opts op{o->reltol, o->abstol, o->has_minstep, o->minstep, o->has_maxstep, o->maxstep, o->initstep, o->points, o->max_steps, o->libm_folded};
     return dispatch_rhs(rhs, [&](auto f) {
         using F = decltype(f);
         Sink sink; sink.tout = tout; sink.yout = yout; sink.cap = cap; sink.N = F::N;
@@ -503,7 +510,7 @@ int oracle_ensemble_adaptive(int method, int set, int rhs, size_t ntraj, const d
                              double* t_reached) {
     if (!is_adapt(method)) return is_fixed(method) ? ERR_WEIGHT_TYPE : ERR_UNSUPPORTED;
     Tableau tb; make_tableau(method, set, tb);
-    Opts op{o->reltol, o->abstol, o->has_minstep, o->minstep, o->has_maxstep, o->maxstep, o->initstep, o->points, o->max_steps};
+    Opts op{o->reltol, o->abstol, o->has_minstep, o->minstep, o->has_maxstep, o->maxstep, o->initstep, o->points, o->max_steps, o->libm_folded};
     const int np = oracle_rhs_nparams(rhs);
     return dispatch_rhs(rhs, [&](auto f) {
         using F = decltype(f);
@@ -544,7 +551,7 @@ int oracle_ensemble_dense(int method, int set, int rhs, size_t ntraj, const doub
     if (!is_adapt(method)) return is_fixed(method) ? ERR_WEIGHT_TYPE : ERR_UNSUPPORTED;
     if (nt < 2) return ERR_INVALID_ARG;
     Tableau tb; make_tableau(method, set, tb);
-    Opts op{o->reltol, o->abstol, o->has_minstep, o->minstep, o->has_maxstep, o->maxstep, o->initstep, 0, o->max_steps};
+    Opts op{o->reltol, o->abstol, o->has_minstep, o->minstep, o->has_maxstep, o->maxstep, o->initstep, 0, o->max_steps, o->libm_folded};
     const int np = oracle_rhs_nparams(rhs);
     return dispatch_rhs(rhs, [&](auto f) {
         using F = decltype(f);
@@ -602,5 +609,8 @@ int oracle_num_threads(void) {
 // libm hooks so the tests can compare the product's device pow/log10 against what the oracle (and Rust) call.
 double oracle_pow(double x, double y) { return std::pow(x, y); }
 double oracle_log10(double x) { return std::log10(x); }
+double oracle_exp10(double x) { return exp10(x); }
+double oracle_sin(double x) { return std::sin(x); }
+double oracle_cos(double x) { return std::cos(x); }
 
 }  // extern "C"

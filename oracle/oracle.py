@@ -27,13 +27,14 @@ ST_DONE, ST_MINSTEP_BREAK, ST_MAX_STEPS = 0, 1, 2
 class Opts(C.Structure):
     _fields_ = [("reltol", C.c_double), ("abstol", C.c_double), ("has_minstep", C.c_int), ("minstep", C.c_double),
                 ("has_maxstep", C.c_int), ("maxstep", C.c_double), ("initstep", C.c_double), ("points", C.c_int),
-                ("max_steps", C.c_uint64)]
+                ("max_steps", C.c_uint64), ("libm_folded", C.c_int)]
 
 
-def opts(reltol=1e-5, abstol=1e-8, minstep=None, maxstep=None, initstep=0.0, points=POINTS_ALL, max_steps=0):
-    """Defaults follow options.rs:283-299 (Reltol 1e-5, Abstol 1e-8, Initstep 0, Points::All)."""
+def opts(reltol=1e-5, abstol=1e-8, minstep=None, maxstep=None, initstep=0.0, points=POINTS_ALL, max_steps=0, libm_folded=0):
+    """Defaults follow options.rs:283-299 (Reltol 1e-5, Abstol 1e-8, Initstep 0, Points::All).  libm_folded=1 selects what
+    an LLVM-optimised build evaluates (sqrt / exp10 instead of pow(.,0.5) / pow(10,.)); see diffeq_oracle.cpp."""
     return Opts(reltol, abstol, int(minstep is not None), minstep or 0.0, int(maxstep is not None), maxstep or 0.0,
-                initstep, points, max_steps)
+                initstep, points, max_steps, libm_folded)
 
 
 def build(force=False):
@@ -55,6 +56,9 @@ def lib():
         _LIB.oracle_pow.argtypes = [C.c_double, C.c_double]
         _LIB.oracle_log10.restype = C.c_double
         _LIB.oracle_log10.argtypes = [C.c_double]
+        for fn in ("oracle_exp10", "oracle_sin", "oracle_cos"):
+            getattr(_LIB, fn).restype = C.c_double
+            getattr(_LIB, fn).argtypes = [C.c_double]
     return _LIB
 
 

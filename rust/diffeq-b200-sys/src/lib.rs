@@ -32,6 +32,7 @@ pub struct deq_options {
     pub r#async: c_int,
     pub mode: c_int,
     pub precision: c_int,
+    pub libm: c_int,
 }
 
 #[repr(C)] pub struct deq_rhs { _p: [u8; 0] }

@@ -40,6 +40,16 @@ int main(int argc, char** argv) {
         volatile double nx = -x;
         if (!same(log10(nx), deqm::log10_glibc(-x, T))) { printf("special log10 x=%a\n", -x); ++bad; }
     }
+    // exp10 replica ("LLVM-folded" libm flavour of hinit)
+    for (long i = 0; i < n; ++i) {
+        const double p = (u01() * 2 - 1) * (i % 3 ? 30.0 : 320.0);
+        volatile double vp = p;
+        if (!same(exp10(vp), deqm::exp10_glibc(p, T))) { if (bad < 5) printf("exp10 p=%a\n", p); ++bad; }
+    }
+    for (double p : {0.0, -0.0, 1e-300, 308.0, 308.3, 309.0, -307.0, -308.0, -320.0, -324.0, -400.0, (double)INFINITY, -(double)INFINITY}) {
+        volatile double vp = p;
+        if (!same(exp10(vp), deqm::exp10_glibc(p, T))) { printf("exp10 special p=%a glibc=%a mine=%a\n", p, exp10(vp), deqm::exp10_glibc(p, T)); ++bad; }
+    }
     // sin / cos replicas (pendulum right-hand side)
     const deqm::SinCosHost ST;
     for (long i = 0; i < n; ++i) {

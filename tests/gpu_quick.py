@@ -16,6 +16,11 @@ for refill, mode in ((1, 0), (0, 0), (1, 0), (1, 1), (0, 1), (1, 1)):
     steps = s.totals["accepted"] + s.totals["rejected"]
     print(f"mode={mode} refill={refill} kernel_ms={s.kernel_ms:.3f} wall_ms={w*1e3:.1f} steps={steps} steps/s={steps/(s.kernel_ms*1e-3):.4e} TFLOP/s(314/step)={steps*314/(s.kernel_ms*1e-3)/1e12:.2f}")
 
+o = D.OdeOptionMap().insert(D.Reltol(1e-8), D.Abstol(1e-8), D.Libm.LlvmFolded)
+for rep in range(2):
+    s = p.solve(D.Ode.Ode45, o, fetch=False)
+steps = s.totals["accepted"] + s.totals["rejected"]
+print(f"parity, libm LLVM-folded (sqrt) kernel_ms={s.kernel_ms:.3f} steps={steps} steps/s={steps/(s.kernel_ms*1e-3):.4e}")
 o = D.OdeOptionMap().insert(D.Reltol(1e-5), D.Abstol(1e-6), D.Precision.F32)
 for rep in range(2):
     s = p.solve(D.Ode.Ode45, o, fetch=False)

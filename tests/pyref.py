@@ -9,7 +9,12 @@ math.log10 call the same glibc the Rust crate would.
 
 Follows /root/reference/src/ode/problem.rs:193-406 (loops), :702-899 (helpers), types.rs:91-116 (pnorm).
 """
+import ctypes
 import math
+
+_libm = ctypes.CDLL("libm.so.6")
+_libm.exp10.restype = ctypes.c_double
+_libm.exp10.argtypes = [ctypes.c_double]
 
 EPS = 2.220446049250313e-16
 
@@ -87,7 +92,7 @@ def oderk_fixed(f, tb, y0, tspan):
     return list(tspan), ys
 
 
-def hinit(f, x0, t0, tend, order, reltol, abstol):
+def hinit(f, x0, t0, tend, order, reltol, abstol, libm_folded=False):
     """problem.rs:850-899"""
     tdir = signum(tend - t0)
     norm = 0.0
@@ -116,12 +121,12 @@ def hinit(f, x0, t0, tend, order, reltol, abstol):
         h1 = fmax(1.0e-6, 1.0e-3 * h0)
     else:
         pw = -(2.0 + math.log10(m)) / float(order + 1)
-        h1 = math.pow(10.0, pw)
+        h1 = _libm.exp10(pw) if libm_folded else math.pow(10.0, pw)
     h = tdir * fmin(fmin(h1, 100.0 * h0), tdir * (tend - t0))
     return h, tdir, f0
 
 
-def stepsize_hw92(dt, tdir, x0, xtrial, xerr, order, timeout, abstol, reltol, maxstep):
+def stepsize_hw92(dt, tdir, x0, xtrial, xerr, order, timeout, abstol, reltol, maxstep, libm_folded=False):
     """problem.rs:801-845 with pnorm P(2) (types.rs:109-115)"""
     xerr = list(xerr)
     for d in range(len(x0)):
@@ -132,7 +137,7 @@ def stepsize_hw92(dt, tdir, x0, xtrial, xerr, order, timeout, abstol, reltol, ma
     for v in xerr:
         s = s + abs(v) * abs(v)
     try:
-        err = math.pow(s, 1.0 * (1.0 / 2.0))
+        err = math.sqrt(s) if libm_folded else math.pow(s, 1.0 * (1.0 / 2.0))   # LLVM: pow(x, 0.5) -> sqrt(x)
     except OverflowError:
         err = math.inf
     pw = 1.0 / float(order + 1)
@@ -159,7 +164,7 @@ def hermite_interp(tq, t, dt, y0, y1, f0, f1):
 
 
 def oderk_adapt(f, tb, y0, tspan, reltol=1e-5, abstol=1e-8, minstep=None, maxstep=None, initstep=0.0, points_all=True,
-                max_steps=0):
+                max_steps=0, libm_folded=False):
     """problem.rs:193-358.  Returns dict(tout, yout, accepted, rejected, status) — status 0 done, 1 minstep break,
     2 max_steps guard."""
     if not tspan:
@@ -171,7 +176,7 @@ def oderk_adapt(f, tb, y0, tspan, reltol=1e-5, abstol=1e-8, minstep=None, maxste
     tend = tspan[-1]
     minstep = abs(tend - t) / 1e18 if minstep is None else minstep
     maxstep = abs(tend - t) / 2.5 if maxstep is None else maxstep
-    h, tdir, f0 = hinit(f, y0, t, tend, order, reltol, abstol)
+    h, tdir, f0 = hinit(f, y0, t, tend, order, reltol, abstol, libm_folded)
     if initstep != 0.0:
         if abs(signum(initstep) - tdir) < EPS:
             dt = initstep
@@ -204,7 +209,7 @@ def oderk_adapt(f, tb, y0, tspan, reltol=1e-5, abstol=1e-8, minstep=None, maxste
         for d in range(len(y)):
             yerr[d] = (ytrial[d] - yerr[d]) * dt
             ytrial[d] = y[d] + (ytrial[d] * dt)
-        err, ndt, timeout = stepsize_hw92(dt, tdir, y, ytrial, yerr, order, timeout, abstol, reltol, maxstep)
+        err, ndt, timeout = stepsize_hw92(dt, tdir, y, ytrial, yerr, order, timeout, abstol, reltol, maxstep, libm_folded)
         if err < 1.0:
             acc += 1
             f1 = list(ks[S - 1]) if fsal else f(t + dt, ytrial)

@@ -434,3 +434,28 @@ def test_randomised_option_sweep_bit_exact(deq, oracle):
         assert np.array_equal(sol.accepted, ref["accepted"]) and np.array_equal(sol.rejected, ref["rejected"]), tag
         assert np.array_equal(sol.status, ref["status"]) and np.array_equal(sol.nfe, ref["nfe"]), tag
         assert np.array_equal(sol.final, ref["yfinal"], equal_nan=True) and np.array_equal(sol.t_reached, ref["t_reached"]), tag
+
+
+def test_llvm_folded_libm_flavour_bit_exact(deq, oracle):
+    """Libm.LlvmFolded (sqrt for the error norm, exp10 in hinit — what an optimised rustc build evaluates) is bit-identical
+    to the oracle run in the same flavour, and differs from the as-written flavour on some trajectories."""
+    from diffeq_b200 import synth
+    y0 = synth.lorenz_ics(0, 4096)
+    ref = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, y0, [0.0, 10.0], oracle.opts(1e-8, 1e-8, libm_folded=1))
+    o = deq.OdeOptionMap().insert(deq.Reltol(1e-8), deq.Abstol(1e-8), deq.Libm.LlvmFolded)
+    p = _problem(deq, deq.System.Lorenz, LOR, y0, [0.0, 10.0])
+    sol = p.solve(deq.Ode.Ode45, o)
+    assert np.array_equal(sol.final, ref["yfinal"]) and np.array_equal(sol.accepted, ref["accepted"])
+    assert np.array_equal(sol.rejected, ref["rejected"]) and np.array_equal(sol.t_reached, ref["t_reached"])
+    written = p.solve(deq.Ode.Ode45, deq.OdeOptionMap().insert(deq.Reltol(1e-8), deq.Abstol(1e-8)))
+    frac = float((written.final != sol.final).any(axis=1).mean())
+    print(f"trajectories whose final state differs between the two libm flavours: {frac:.3f}")
+    assert np.array_equal(written.accepted, sol.accepted)          # same step counts either way on this config
+    y0v, mu = synth.vdp_sweep(0, 300, 300)
+    ts = deq.linspace(0.0, 20.0, 400)
+    rd = oracle.ensemble_dense(oracle.ODE45FE, oracle.VANDERPOL, mu, y0v, ts, oracle.opts(1e-6, 1e-8, libm_folded=1))
+    sd = _problem(deq, deq.System.VanDerPol, mu, y0v, ts).solve(
+        deq.Ode.Ode45fe, deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8), deq.Output.Tspan, deq.Libm.LlvmFolded))
+    want = rd["out"].transpose(2, 1, 0)
+    m = ~np.isnan(want)
+    assert np.array_equal(sd.nvalid, rd["nvalid"]) and np.array_equal(sd.yout[m], want[m])

@@ -75,6 +75,8 @@ def test_oracle_adaptive_goldens(oracle, case):
     for k, v in case["options"].items():
         if k == "points_all":
             kw["points"] = 0 if v else 1
+        elif k == "libm_folded":
+            kw["libm_folded"] = int(v)
         else:
             kw[k] = float.fromhex(v) if isinstance(v, str) else v
     r = oracle.solve_adaptive(getattr(oracle, case["method"].upper()), getattr(oracle, case["system"].upper()),

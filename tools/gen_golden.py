@@ -184,6 +184,13 @@ def main():
     adapt("rk23_textbook_lorenz", "Ode23", "Lorenz", LOR, [0.1, 0.0, 0.0], ["list", 0.0, 2.0], [0.0, 2.0], tset="textbook")
     adapt("rk21_textbook_lorenz", "Ode21", "Lorenz", LOR, [0.1, 0.0, 0.0], ["list", 0.0, 1.0], [0.0, 1.0], tset="textbook", reltol=1e-3,
           abstol=1e-3)
+    # the libm calls as an LLVM-optimised build folds them (pow(x,0.5) -> sqrt, pow(10,x) -> exp10)
+    adapt("dopri5_lorenz_t10_1e-8_libm_folded", "Ode45", "Lorenz", LOR, [0.1, 0.0, 0.0], ["list", 0.0, 10.0], [0.0, 10.0], reltol=1e-8,
+          abstol=1e-8, libm_folded=True)
+    adapt("dopri5_lorenz_t100_default_libm_folded", "Ode45", "Lorenz", LOR, [0.1, 0.0, 0.0], ["list", 0.0, 100.0], [0.0, 100.0],
+          libm_folded=True)
+    adapt("rk45_vdp_mu1.0_dense1000_libm_folded", "Ode45fe", "VanDerPol", [1.0], [2.0, 0.0], ["linspace", 0.0, 20.0, 1000],
+          linspace(0.0, 20.0, 1000), reltol=1e-6, abstol=1e-8, libm_folded=True)
     for m in ("Ode21", "Ode23", "Ode78"):  # the reference's broken tableaus: step-size collapse, guarded
         adapt(f"{m}_reference_collapse", m, "Lorenz", LOR, [1.0, 2.0, 20.0], ["list", 0.0, 0.01], [0.0, 0.01], reltol=1e-3, abstol=1e-3,
               max_steps=3000)
