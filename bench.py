@@ -270,11 +270,17 @@ def main():
     dev_ms_max, e2e_s_max, wall_max, fast_ms_max, e2e_fast_s_max = t.tolist()
     steps_all, e2e_steps_all, fast_steps_all, e2e_fast_steps_all = c.tolist()
 
-    def roofline(kernel_ms_list, steps_local, kernel_name, mode_note):
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^20 trajectories (ncu --set full, profiles/r1_final_*_kernel_
+    # ncu_full_summary.csv); it scales with the trajectory count, not with the step count
+    NCU_DRAM_BYTES = {"parity": 62.727168e6 + 14.766592e6, "fast": 64.369920e6 + 14.953216e6}
+
+    def roofline(kernel_ms_list, steps_local, kernel_name, mode_note, traffic_key):
         kms = sum(kernel_ms_list) / len(kernel_ms_list)
         achieved = (steps_local / args.steps) * FLOP_PER_STEP / (kms * 1e-3) / 1e12
         return {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None, "kernel": kernel_name,
+                "frac": achieved / fp64_peak if fp64_peak else None,
+                "traffic": NCU_DRAM_BYTES[traffic_key] * (ntraj / float(1 << 20)), "traffic_unit": "bytes per launch (DRAM, ncu)",
+                "kernel": kernel_name,
                 "kernel_ms": kms, "flop_per_step": FLOP_PER_STEP, "arithmetic": mode_note,
                 "peak_source": "DFMA-stream microbenchmark measured in this run (deq_measure_fp64_peak); MEASURED_PEAKS.json "
                                "has no FP64 figure; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2 TFLOP/s",
@@ -295,11 +301,11 @@ def main():
                     "ms_per_step": 1e3 * e2e_s_max / args.steps},
             "gpu_launches": 2 * args.steps,
             "accepted_only_steps_per_s": (tot_par["accepted"] * world) / (dev_ms_max / args.steps * 1e-3),
-            "roofline": roofline(kernel_ms, steps_done, "deqk::adapt_kernel<Dopri5<false>, Lorenz, false, MODE_FINAL, FAST=false>", par_note),
+            "roofline": roofline(kernel_ms, steps_done, "deqk::adapt_kernel<Dopri5<false>, Lorenz, false, MODE_FINAL, FAST=false>", par_note, "parity"),
             "fast_mode": {"value": fast_steps_all / (fast_ms_max * 1e-3), "unit": UNIT, "ms_per_step": fast_ms_max / args.steps,
                           "e2e": {"value": e2e_fast_steps_all / e2e_fast_s_max, "unit": UNIT, "ms_per_step": 1e3 * e2e_fast_s_max / args.steps},
                           "roofline": roofline(fast_kernel_ms, fast_steps, "deqk::adapt_kernel<Dopri5<false>, Lorenz, false, MODE_FINAL, FAST=true>",
-                                               "FMA counted as 2 flop; algorithmic flop per step attempt from SURVEY.md 8(d)")},
+                                               "FMA counted as 2 flop; algorithmic flop per step attempt from SURVEY.md 8(d)", "fast")},
             "mode_check": mode_check,
             "final_gather_ms": gather_ms,
             "clocks": clocks, "wall_s_timed_region": wall_max,
