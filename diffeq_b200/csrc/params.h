@@ -11,7 +11,10 @@ enum : int { MODE_FINAL = 0, MODE_DENSE = 1 };
 enum : int { REC_TSPAN = 0, REC_COUNT = 1, REC_WRITE = 2 };
 enum : uint8_t { ST_DONE = 0, ST_MINSTEP_BREAK = 1, ST_MAX_STEPS = 2 };
 
-constexpr int BLOCK = 128;
+#ifndef DEQ_BLOCK
+#define DEQ_BLOCK 128
+#endif
+constexpr int BLOCK = DEQ_BLOCK;
 constexpr int MAX_NP = 8;
 
 struct SharedParams { double v[MAX_NP]; };

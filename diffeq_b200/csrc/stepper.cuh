@@ -99,17 +99,23 @@ __device__ __forceinline__ double max_abs_nonan(double a, double b) {
 __device__ __forceinline__ double sel_max(double c, double x) { return x > c ? x : c; }
 __device__ __forceinline__ double sel_min(double c, double x) { return x < c ? x : c; }
 
-constexpr int BURST_ATTEMPTS = 8;
+#ifndef DEQ_BURST
+#define DEQ_BURST 8
+#endif
+constexpr int BURST_ATTEMPTS = DEQ_BURST;
 
-// 1/x to full double precision without the IEEE corner-case handling (x is a positive, normal error scale):
-// MUFU.RCP64H seed + Newton steps.  FAST mode only.
+// 1/x to ~2^-40 relative accuracy without the IEEE corner-case handling (x is a positive, normal error scale):
+// MUFU.RCP64H seed + one Newton step.  FAST mode only.
 __device__ __forceinline__ double rcp_fast(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     double e = __fma_rn(-x, r, 1.0);   // seed is good to ~2^-20
     r = __fma_rn(r, e, r);             // ~2^-40
+#ifdef DEQ_RCP_TWO_STEPS                // 2^-40 is far below what the step-size controller can resolve; the second step is off
     e = __fma_rn(-x, r, 1.0);
-    return __fma_rn(r, e, r);          // ~2^-80 -> rounded double
+    r = __fma_rn(r, e, r);             // ~2^-80 -> rounded double
+#endif
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -247,6 +253,9 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     uint32_t acc = 0, rej = 0, attempts = 0;
     unsigned long long it = 1, wpos = 0, wbase = 0;
     unsigned long long tot_acc = 0, tot_rej = 0, tot_nfe = 0;
+#ifdef DEQ_FINALIZE_OUTSIDE
+    uint8_t finished = 0xff;
+#endif
 #pragma unroll
     for (int d = 0; d < N; ++d) { cy[d] = 0.0; ck[d] = 0.0; }
 #pragma unroll
@@ -434,7 +443,15 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     timeout = 5;
                 }
             }
+#ifdef DEQ_FINALIZE_OUTSIDE
+            if (fin != 0xff) { finished = fin; break; }
+        }
+        if (finished != 0xff) {
+            const uint8_t fin = finished;
+            finished = 0xff;
+#else
             if (fin != 0xff) {
+#endif
                 const uint32_t nfe = 2u + attempts * (uint32_t)(S - 1) + (FSAL ? 0u : acc);
 #pragma unroll
                 for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = cy[d];
@@ -450,8 +467,12 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                 }
                 tot_acc += acc; tot_rej += rej; tot_nfe += nfe;
                 active = false;
+#ifdef DEQ_FINALIZE_OUTSIDE
+        }
+#else
             }
         }
+#endif
     }
     // ensemble totals: warp reduce, one atomic per warp
 #pragma unroll
