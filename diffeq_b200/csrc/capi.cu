@@ -27,8 +27,10 @@ deq_status fail(deq_status s, const std::string& msg) { g_err = msg; return s; }
 #define CK(call)                                                                                       \
     do {                                                                                               \
         cudaError_t e_ = (call);                                                                       \
-        if (e_ != cudaSuccess)                                                                         \
+        if (e_ != cudaSuccess) {                                                                       \
+            cudaGetLastError(); /* clear the per-thread last-error so the next call starts clean */    \
             return fail(DEQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+        }                                                                                              \
     } while (0)
 
 const deql::TbEntry g_tb[deql::TB_COUNT] = {
@@ -302,8 +304,10 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
 #define CKR(call)                                                                                      \
     do {                                                                                               \
         cudaError_t e_ = (call);                                                                       \
-        if (e_ != cudaSuccess)                                                                         \
+        if (e_ != cudaSuccess) {                                                                       \
+            cudaGetLastError();                                                                        \
             return bail(fail(DEQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)));       \
+        }                                                                                              \
     } while (0)
 
     CKR(cudaEventCreate(&r->ev0));

@@ -459,3 +459,19 @@ def test_llvm_folded_libm_flavour_bit_exact(deq, oracle):
     want = rd["out"].transpose(2, 1, 0)
     m = ~np.isnan(want)
     assert np.array_equal(sd.nvalid, rd["nvalid"]) and np.array_equal(sd.yout[m], want[m])
+
+
+def test_out_of_memory_fails_cleanly_and_library_stays_usable(deq, oracle):
+    """A dense-output request far beyond the 180 GB of HBM returns a CUDA error through the ABI (no crash, no fallback) and
+    the next solve still works and is still bit-exact."""
+    from diffeq_b200 import synth
+    y0, mu = synth.vdp_sweep(0, 1 << 16, 1 << 16)
+    ts = deq.linspace(0.0, 20.0, 400000)            # 2^16 x 4e5 x 2 x 8 B = 419 GB
+    p = _problem(deq, deq.System.VanDerPol, mu, y0, ts)
+    with pytest.raises(deq.OdeError) as e:
+        p.solve(deq.Ode.Ode45fe, deq.OdeOptionMap().insert(deq.Output.Tspan))
+    assert e.value.kind == "Cuda"
+    y1 = synth.lorenz_ics(0, 300)
+    sol = _problem(deq, deq.System.Lorenz, LOR, y1, [0.0, 1.0]).solve(deq.Ode.Ode45)
+    ref = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, y1, [0.0, 1.0])
+    assert np.array_equal(sol.final, ref["yfinal"])
