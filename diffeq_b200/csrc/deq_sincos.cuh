@@ -109,9 +109,42 @@ DEQ_HD double do_sincos(double a, double da, int n, const ST& tab) {
     return (n & 2) ? -r : r;
 }
 
-// Range dispatch of s_sin.c `__sin` / `__cos`, arranged so that a warp diverges at most two ways in the expensive part:
-// every range first produces (a, da, n) — cheap, a handful of operations — and then ONE do_sin / do_cos evaluation
-// follows.  The arithmetic of each range is exactly glibc's.
+// do_sin and do_cos evaluated side by side and selected: every lane of a warp runs the same instruction stream whatever
+// quadrant its argument fell into (on the GPU the two-way branch cost a warp both paths anyway, plus the divergence
+// bookkeeping).  Each flavour's arithmetic is exactly glibc's do_sin / do_cos above; only the small-argument Taylor
+// branch of do_sin stays a branch.
+template <class ST>
+DEQ_HD double sincos_dual(double a, double da, int n, const ST& tab) {
+    const bool want_cos = (n & 1) != 0;
+    const double ax = fabs(a);
+    double r;
+    if (!want_cos && ax < 0.126) {
+        r = taylor_sin(a, da);
+    } else {
+        const double u = ax + sc::big;
+        const double xr = ax - (u - sc::big);
+        const int k = (int)(uint32_t)asu64(u) * 4;
+        const double sn = tab.at(k), ssn = tab.at(k + 1), cs = tab.at(k + 2), ccs = tab.at(k + 3);
+        // do_sin flavour
+        const double dxs = (a <= 0) ? -da : da;
+        const double xxs = xr * xr;
+        const double ss = xr + fma_(xr * xxs, fma_(xxs, sc::sn5, sc::sn3), dxs);
+        const double csn = fma_(xr, dxs, xxs * fma_(xxs, fma_(xxs, sc::cs6, sc::cs4), sc::cs2));
+        const double rs = copysign_(sn + fma_(ss, cs, fma_(-csn, sn, fma_(ss, ccs, ssn))), a);
+        // do_cos flavour
+        const double dxc = (a < 0) ? -da : da;
+        const double xc = xr + dxc;
+        const double xxc = xc * xc;
+        const double sc_ = fma_(xc * xxc, fma_(xxc, sc::sn5, sc::sn3), xc);
+        const double cc = xxc * fma_(xxc, fma_(xxc, sc::cs6, sc::cs4), sc::cs2);
+        const double rc = cs + fma_(-sc_, sn, fma_(-cc, cs, fma_(-sc_, ssn, ccs)));
+        r = want_cos ? rc : rs;
+    }
+    return r;
+}
+
+// Range dispatch of s_sin.c `__sin` / `__cos`: every range first produces (a, da, n) — cheap, a handful of operations —
+// and then ONE sincos_dual evaluation follows.  The arithmetic of each range is exactly glibc's.
 template <class ST>
 DEQ_HD double sin_glibc(double x, const ST& tab) {
     const uint32_t k = (uint32_t)(asu64(x) >> 32) & 0x7fffffffu;
@@ -123,7 +156,7 @@ DEQ_HD double sin_glibc(double x, const ST& tab) {
     if (k < 0x3feb6000u) { a = x; da = 0.0; n = 0; }
     else if (k < 0x400368fdu) { a = sc::hp0 - fabs(x); da = sc::hp1; n = 1; from_cos = true; }
     else n = reduce_sincos(x, a, da);
-    const double r = (n & 1) ? do_cos(a, da, tab) : do_sin(a, da, tab);
+    const double r = sincos_dual(a, da, n, tab);
     if (from_cos) return copysign_(r, x);
     return (n & 2) ? -r : r;
 }
@@ -142,7 +175,7 @@ DEQ_HD double cos_glibc(double x, const ST& tab) {
         da = (y - a) + sc::hp1;
         n = 0;
     } else n = reduce_sincos(x, a, da) + 1;
-    const double r = (n & 1) ? do_cos(a, da, tab) : do_sin(a, da, tab);
+    const double r = sincos_dual(a, da, n, tab);
     return (n & 2) ? -r : r;
 }
 
