@@ -91,6 +91,12 @@ class Libm(enum.IntEnum):
     LlvmFolded = 1
 
 
+class DenseLayout(enum.IntEnum):
+    """deq_dense_layout: SoA [n][ntspan][ntraj] (sorted sweeps) or TrajMajor [ntraj][ntspan][n] (smem-staged, any order)."""
+    SoA = 0
+    TrajMajor = 1
+
+
 class Precision(enum.IntEnum):
     F64 = 0
     F32 = 1
@@ -106,7 +112,7 @@ class _Options(C.Structure):
     _fields_ = [("reltol", C.c_double), ("abstol", C.c_double), ("has_minstep", C.c_int), ("minstep", C.c_double),
                 ("has_maxstep", C.c_int), ("maxstep", C.c_double), ("initstep", C.c_double), ("points", C.c_int),
                 ("output", C.c_int), ("max_steps", C.c_uint64), ("refill", C.c_int), ("async_", C.c_int),
-                ("mode", C.c_int), ("precision", C.c_int), ("libm", C.c_int)]
+                ("mode", C.c_int), ("precision", C.c_int), ("libm", C.c_int), ("dense_layout", C.c_int)]
 
 
 # The symbols include/diffeq_b200.h declares (checked by tests/test_abi.py).
@@ -265,6 +271,8 @@ class OdeOptionMap(dict):
                 self["Precision"] = o
             elif isinstance(o, Libm):
                 self["Libm"] = o
+            elif isinstance(o, DenseLayout):
+                self["DenseLayout"] = o
             else:
                 self[o.name] = o.v
         return self
@@ -283,6 +291,7 @@ class OdeOptionMap(dict):
         if "Mode" in self: o.mode = int(self["Mode"])
         if "Precision" in self: o.precision = int(self["Precision"])
         if "Libm" in self: o.libm = int(self["Libm"])
+        if "DenseLayout" in self: o.dense_layout = int(self["DenseLayout"])
         return o
 
 
@@ -377,14 +386,19 @@ class OdeProblem:
             sol.yout_flat = np.empty((rows, self.n))
             _check(L.deq_result_all_copy(res, C.c_size_t(0), C.c_size_t(self.ntraj), _ptr(sol.tout_flat), _ptr(sol.yout_flat)))
         if o.output == Output.Tspan and nt > 0:
-            dense = np.full((self.n, nt, self.ntraj), np.nan)
+            tm = o.dense_layout == DenseLayout.TrajMajor and adaptive
+            dense = np.full((self.ntraj, nt, self.n) if tm else (self.n, nt, self.ntraj), np.nan)
             nv = np.empty(self.ntraj, np.uint32)
             _check(L.deq_result_dense(res, C.c_size_t(0), C.c_size_t(self.ntraj), _ptr(dense), _ptr(nv, C.c_uint32)))
             idx = np.arange(nt)[:, None]
             invalid = (idx >= nv[None, :]) & (idx != nt - 1)
-            dense[:, invalid] = np.nan
+            if tm:
+                dense[invalid.T] = np.nan
+                sol.yout = dense
+            else:
+                dense[:, invalid] = np.nan
+                sol.yout = np.ascontiguousarray(dense.transpose(2, 1, 0))
             sol.tout = self.tspan.copy()
-            sol.yout = np.ascontiguousarray(dense.transpose(2, 1, 0))
             sol.nvalid = nv
         return sol
 

@@ -91,7 +91,7 @@ struct deq_ensemble {
 struct deq_result {
     size_t ntraj = 0, nt = 0;
     int n = 0;
-    bool fixed = false, dense = false;
+    bool fixed = false, dense = false, traj_major = false;
     cudaStream_t stream = nullptr;
     double* d_yfinal = nullptr;
     uint32_t *d_acc = nullptr, *d_rej = nullptr, *d_nfe = nullptr, *d_nvalid = nullptr;
@@ -286,6 +286,9 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
     if (o.mode != DEQ_MODE_PARITY && o.mode != DEQ_MODE_FAST) return fail(DEQ_ERR_INVALID_ARG, "unknown arithmetic mode");
     if (o.precision != DEQ_PRECISION_F64 && o.precision != DEQ_PRECISION_F32) return fail(DEQ_ERR_INVALID_ARG, "unknown precision");
     if (o.libm != DEQ_LIBM_AS_WRITTEN && o.libm != DEQ_LIBM_LLVM_FOLDED) return fail(DEQ_ERR_INVALID_ARG, "unknown libm flavour");
+    if (o.dense_layout != DEQ_LAYOUT_SOA && o.dense_layout != DEQ_LAYOUT_TRAJ_MAJOR) return fail(DEQ_ERR_INVALID_ARG, "unknown dense layout");
+    if (o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR && (o.precision == DEQ_PRECISION_F32))
+        return fail(DEQ_ERR_UNSUPPORTED, "the trajectory-major dense layout is implemented for the f64 kernels");
     if (o.precision == DEQ_PRECISION_F32 && (e->rhs.kind != 0 || o.output == DEQ_OUT_ALL))
         return fail(DEQ_ERR_UNSUPPORTED, "the f32 mode covers the built-in systems with FINAL / TSPAN output");
     ensure_pool();
@@ -368,7 +371,8 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         P.t_reached = r->d_treached; P.dense = r->d_dense; P.nvalid = r->d_nvalid;
         P.work_counter = r->d_scalars; P.totals = r->d_scalars + 1;
         const int mode = (want_dense || want_all) ? deqk::MODE_DENSE : deqk::MODE_FINAL;
-        P.rec_mode = want_all ? deqk::REC_COUNT : deqk::REC_TSPAN;
+        P.rec_mode = want_all ? deqk::REC_COUNT : (o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR ? deqk::REC_TSPAN_TM : deqk::REC_TSPAN);
+        r->traj_major = want_dense && o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR;
         P.rec_counts = r->d_rec_counts;
         auto launch_adapt = [&](std::string* err) -> int {  // 0 ok, 1 cuda error (g_err set), 2 nvrtc error
             if (e->rhs.kind == 0) {
@@ -476,6 +480,13 @@ deq_status deq_result_dense(deq_result* r, size_t b, size_t e, double* out, uint
     if (b > e || e > r->ntraj) return fail(DEQ_ERR_INVALID_ARG, "trajectory range out of bounds");
     const size_t w = e - b;
     if (w == 0) return DEQ_OK;
+    if (r->traj_major) {  // [ntraj][nt][n]: the slice is contiguous
+        const size_t per = (size_t)r->n * r->nt;
+        CK(cudaMemcpyAsync(out, r->d_dense + b * per, w * per * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+        if (nvalid) CK(cudaMemcpyAsync(nvalid, r->d_nvalid + b, w * 4, cudaMemcpyDeviceToHost, r->stream));
+        CK(cudaStreamSynchronize(r->stream));
+        return DEQ_OK;
+    }
     // rows of [n*nt][ntraj] restricted to columns [b,e)
     CK(cudaMemcpy2DAsync(out, w * sizeof(double), r->d_dense + b, r->ntraj * sizeof(double), w * sizeof(double),
                          (size_t)r->n * r->nt, cudaMemcpyDeviceToHost, r->stream));
@@ -518,6 +529,12 @@ deq_status deq_result_trajectory(deq_result* r, size_t traj, double* yout) {
     if (!r || !yout) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
     if (!r->dense || !r->d_dense) return fail(DEQ_ERR_INVALID_ARG, "solve was not run with output = DEQ_OUT_TSPAN");
     if (traj >= r->ntraj) return fail(DEQ_ERR_INVALID_ARG, "trajectory index out of bounds");
+    if (r->traj_major) {
+        const size_t per = (size_t)r->n * r->nt;
+        CK(cudaMemcpyAsync(yout, r->d_dense + traj * per, per * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+        CK(cudaStreamSynchronize(r->stream));
+        return DEQ_OK;
+    }
     std::vector<double> tmp((size_t)r->n * r->nt);
     CK(cudaMemcpy2DAsync(tmp.data(), sizeof(double), r->d_dense + traj, r->ntraj * sizeof(double), sizeof(double),
                          (size_t)r->n * r->nt, cudaMemcpyDeviceToHost, r->stream));

@@ -44,11 +44,11 @@ using TB = deqt::Feh78<true>;
 #define DEQ_CAT(a, b) DEQ_CAT2(a, b)
 
 template <class K>
-static int persistent_grid(K kernel, unsigned long long ntraj) {
+static int persistent_grid(K kernel, unsigned long long ntraj, size_t dyn_smem = 0) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, deqk::BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, deqk::BLOCK, dyn_smem);
     if (per_sm < 1) per_sm = 1;
     unsigned long long want = (ntraj + deqk::BLOCK - 1) / deqk::BLOCK;
     unsigned long long cap = (unsigned long long)sms * per_sm;
@@ -67,8 +67,10 @@ template <class F, bool PT, int MODE>
 static cudaError_t launch_adapt_t(const deqk::AdaptParams& P, int grid_blocks, cudaStream_t st) {
     if constexpr (TB::ADAPTIVE) {
         auto kernel = deqk::adapt_kernel<TB, F, PT, MODE, kFast>;
-        const int grid = grid_blocks > 0 ? grid_blocks : persistent_grid(kernel, P.ntraj);
-        kernel<<<grid, deqk::BLOCK, 0, st>>>(P);
+        const size_t smem = (MODE == deqk::MODE_DENSE && P.rec_mode == deqk::REC_TSPAN_TM) ? deqk::STAGE_BYTES : 0;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int grid = grid_blocks > 0 ? grid_blocks : persistent_grid(kernel, P.ntraj, smem);
+        kernel<<<grid, deqk::BLOCK, smem, st>>>(P);
         return cudaGetLastError();
     } else {
         (void)P; (void)grid_blocks; (void)st;

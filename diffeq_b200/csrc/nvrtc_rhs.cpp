@@ -164,9 +164,9 @@ void retain(Program* p) { if (p) p->refs.fetch_add(1); }
 void release(Program* p) { if (p && p->refs.fetch_sub(1) == 1) delete p; }
 
 template <class P>
-static bool launch(const Kernel& k, unsigned grid, const P& params, cudaStream_t st, std::string* err) {
+static bool launch(const Kernel& k, unsigned grid, const P& params, cudaStream_t st, std::string* err, size_t smem = 0) {
     void* args[] = {(void*)&params};
-    cudaError_t ce = cudaLaunchKernel((const void*)k.fn, dim3(grid), dim3(deqk::BLOCK), args, 0, st);
+    cudaError_t ce = cudaLaunchKernel((const void*)k.fn, dim3(grid), dim3(deqk::BLOCK), args, smem, st);
     if (ce != cudaSuccess) { if (err) *err = std::string("cudaLaunchKernel: ") + cudaGetErrorString(ce); return false; }
     return true;
 }
@@ -184,8 +184,13 @@ bool launch_adapt(Program* p, int tb, int pt, int mode, bool fast, const deqk::A
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    unsigned long long want = (P.ntraj + deqk::BLOCK - 1) / deqk::BLOCK, cap = (unsigned long long)sms * k.blocks_per_sm;
-    return launch(k, (unsigned)(want < cap ? (want ? want : 1) : cap), P, st, err);
+    const size_t smem = ((mode & 1) == deqk::MODE_DENSE && P.rec_mode == deqk::REC_TSPAN_TM) ? 32u * deqk::BLOCK * sizeof(double) : 0;
+    int per_sm = k.blocks_per_sm;
+    if (smem) {  // the staged layout lowers the resident-CTA count
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k.fn, deqk::BLOCK, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 2; }
+    }
+    unsigned long long want = (P.ntraj + deqk::BLOCK - 1) / deqk::BLOCK, cap = (unsigned long long)sms * per_sm;
+    return launch(k, (unsigned)(want < cap ? (want ? want : 1) : cap), P, st, err, smem);
 }
 
 bool launch_fixed(Program* p, int tb, int pt, int all, const deqk::FixedParams& P, cudaStream_t st, std::string* err) {

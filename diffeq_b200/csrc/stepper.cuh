@@ -217,6 +217,83 @@ __global__ void __launch_bounds__(BLOCK) hinit_kernel(const HinitParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Shared-memory staging of dense output (trajectory-major layout, REC_TSPAN_TM).
+//
+// In the SoA layout [n][ntspan][ntraj] a warp's stores coalesce only while its lanes sit at the same output row — true for
+// a parameter-sorted sweep (8.4 sectors per request measured on config 3), false for an arbitrary ensemble, where every
+// lane writes its own row and a store instruction degenerates into 32 single-sector transactions (measured 6.4x slower
+// on the permuted sweep).  Here every lane appends its rows to a private 32-double ring in shared memory
+// (ring[col][lane ^ col]: conflict-free for the owner's appends and for the cooperative reads) and the lanes that are
+// currently converged drain full 128-byte lines together: one coalesced store per 16 doubles instead of 16 scattered
+// ones.  Output layout: out[traj][row][component], i.e. one contiguous `Vec<Y>`-like stream per trajectory.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef DEQ_STAGE_COLS
+#define DEQ_STAGE_COLS 32
+#endif
+constexpr int STAGE_COLS = DEQ_STAGE_COLS;       // doubles per lane in the ring (a power of two)
+constexpr int STAGE_LINE = DEQ_STAGE_COLS / 2;   // doubles drained at a time (16 doubles = one 128-byte line)
+constexpr unsigned STAGE_BYTES = STAGE_COLS * BLOCK * sizeof(double);   // dynamic shared memory, requested only by
+                                                                        // launches that use the staged layout
+extern __shared__ double s_stage_dyn[];
+
+struct StageLane {
+    unsigned head = 0, cnt = 0;      // ring position of the oldest element, number of buffered doubles
+    unsigned long long gpos = 0;     // global index (in doubles) the oldest element goes to
+};
+
+__device__ __forceinline__ double& stage_ref(double* stage, unsigned col, unsigned lane) {
+    return stage[col * BLOCK + (threadIdx.x & ~31u) + (lane ^ (col & 31u))];
+}
+
+// Drain one STAGE_LINE of every participating lane whose ring holds at least that much (all == false), or everything that
+// is left (all == true, used when a trajectory finishes).  The lanes that are converged here split the work items evenly:
+// item i = element (i % LINE) of the (i / LINE)-th pending lane, so 32 lanes write two full lines per iteration with three
+// shuffles and no vote inside the loop.
+__device__ __forceinline__ void stage_drain(double* stage, double* out, StageLane& s, bool all) {
+    const unsigned am = __activemask();
+    const unsigned lane = threadIdx.x & 31u;
+    __syncwarp(am);  // the owners' appends are visible to the helpers
+    const unsigned rank = __popc(am & ((1u << lane) - 1u)), m = __popc(am);
+    if (!all) {
+        const unsigned pending = __ballot_sync(am, s.cnt >= (unsigned)STAGE_LINE);
+        if (pending == 0u) return;
+        const unsigned W = (unsigned)STAGE_LINE * __popc(pending);
+        for (unsigned base = 0; base < W; base += m) {  // uniform trip count over the participating lanes
+            const unsigned i = base + rank;
+            const bool has = i < W;
+            const unsigned src = has ? __fns(pending, 0, (int)(i / STAGE_LINE) + 1) : lane;
+            const unsigned h = __shfl_sync(am, s.head, src);
+            const unsigned long long g = __shfl_sync(am, s.gpos, src);
+            const unsigned e = i % STAGE_LINE;
+            if (has) out[g + e] = stage_ref(stage, (h + e) & (STAGE_COLS - 1), src);
+        }
+        if ((pending >> lane) & 1u) { s.head = (s.head + STAGE_LINE) & (STAGE_COLS - 1); s.cnt -= STAGE_LINE; s.gpos += STAGE_LINE; }
+    } else {
+        unsigned pending = __ballot_sync(am, s.cnt > 0u);
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1u;
+            const unsigned h = __shfl_sync(am, s.head, src);
+            const unsigned c = __shfl_sync(am, s.cnt, src);
+            const unsigned long long g = __shfl_sync(am, s.gpos, src);
+            for (unsigned e = rank; e < c; e += m) out[g + e] = stage_ref(stage, (h + e) & (STAGE_COLS - 1), (unsigned)src);
+            if ((int)lane == src) { s.head = (s.head + c) & (STAGE_COLS - 1); s.cnt = 0; s.gpos += c; }
+        }
+    }
+    __syncwarp(am);  // helpers are done reading before the owners append again
+}
+
+__device__ __forceinline__ void stage_append(double* stage, double* out, StageLane& s, double v) {
+    const unsigned lane = threadIdx.x & 31u;
+    if (s.cnt == (unsigned)STAGE_COLS) {  // ring full inside one step (many tspan points per step): the owner drains a line alone
+        for (unsigned e = 0; e < (unsigned)STAGE_LINE; ++e) out[s.gpos + e] = stage_ref(stage, (s.head + e) & (STAGE_COLS - 1), lane);
+        s.head = (s.head + STAGE_LINE) & (STAGE_COLS - 1); s.cnt -= STAGE_LINE; s.gpos += STAGE_LINE;
+    }
+    stage_ref(stage, (s.head + s.cnt) & (STAGE_COLS - 1), lane) = v;
+    ++s.cnt;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // oderk_adapt (problem.rs:193-358), Points::All semantics.
 // ---------------------------------------------------------------------------------------------------------------
 template <class TB, class F, bool PT, int MODE, bool FAST>
@@ -253,6 +330,8 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     uint32_t acc = 0, rej = 0, attempts = 0;
     unsigned long long it = 1, wpos = 0, wbase = 0;
     unsigned long long tot_acc = 0, tot_rej = 0, tot_nfe = 0;
+    double* const stage = s_stage_dyn;
+    StageLane sl;
 #ifdef DEQ_FINALIZE_OUTSIDE
     uint8_t finished = 0xff;
 #endif
@@ -289,6 +368,10 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                         if (P.rec_mode == REC_TSPAN) {
 #pragma unroll
                             for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt) * P.ntraj + traj] = cy[d];
+                        } else if (P.rec_mode == REC_TSPAN_TM) {  // staged trajectory-major stream: row 0 = y0
+                            sl.head = 0; sl.cnt = 0; sl.gpos = traj * P.nt * (unsigned long long)N;
+#pragma unroll
+                            for (int d = 0; d < N; ++d) stage_append(stage, P.dense, sl, cy[d]);
                         } else {  // ragged Points::All stream: row 0 = (t0, y0)
                             wpos = P.rec_mode == REC_WRITE ? P.rec_offsets[traj] : 0ull;
                             wbase = wpos;
@@ -311,6 +394,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
         // finishes inside a burst idles for at most BURST-1 attempts out of the ~10^3 its trajectory took. ----
 #pragma unroll 1
         for (int burst = 0; burst < BURST_ATTEMPTS && active; ++burst) {
+            if (MODE == MODE_DENSE && P.rec_mode == REC_TSPAN_TM) stage_drain(stage, P.dense, sl, false);
             // one step attempt (loop body of problem.rs:260-352)
             uint8_t fin = 0xff;  // 0xff: keep going
             if (attempts >= max_steps) {
@@ -408,15 +492,16 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                                                  ((ytrial[d] - cy[d]) * (1. - 2. * theta) + k[0][d] * (theta - 1.) * dt +
                                                   f1[d] * theta * dt) * theta * (theta - 1.);
                                 if (P.rec_mode == REC_TSPAN) P.dense[((unsigned long long)d * P.nt + it) * P.ntraj + traj] = v;
+                                else if (P.rec_mode == REC_TSPAN_TM) stage_append(stage, P.dense, sl, v);
                                 else if (P.rec_mode == REC_WRITE) P.rec_y[wpos * N + d] = v;
                             }
-                            if (P.rec_mode != REC_TSPAN) {
+                            if (P.rec_mode == REC_COUNT || P.rec_mode == REC_WRITE) {
                                 if (P.rec_mode == REC_WRITE) P.rec_t[wpos] = tq;
                                 ++wpos;
                             }
                             ++it;
                         }
-                        if (P.rec_mode != REC_TSPAN) {  // "also store every step taken" (problem.rs:320-322)
+                        if (P.rec_mode == REC_COUNT || P.rec_mode == REC_WRITE) {  // "also store every step taken" (problem.rs:320-322)
                             if (P.rec_mode == REC_WRITE) {
                                 P.rec_t[wpos] = tn;
 #pragma unroll
@@ -460,6 +545,10 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     if (P.rec_mode == REC_TSPAN) {
 #pragma unroll
                         for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt + (P.nt - 1)) * P.ntraj + traj] = cy[d];
+                    } else if (P.rec_mode == REC_TSPAN_TM) {
+                        stage_drain(stage, P.dense, sl, true);   // ends with a __syncwarp: the helpers' stores precede the row below
+#pragma unroll
+                        for (int d = 0; d < N; ++d) P.dense[(traj * P.nt + (P.nt - 1)) * (unsigned long long)N + d] = cy[d];
                     } else if (P.rec_mode == REC_COUNT) {
                         P.rec_counts[traj] = (uint32_t)(wpos - wbase);
                     }

@@ -82,6 +82,12 @@ typedef enum deq_precision { DEQ_PRECISION_F64 = 0, DEQ_PRECISION_F32 = 1 } deq_
  * determined without a Rust toolchain, so both are provided, each bit-exact against the oracle in the same flavour. */
 typedef enum deq_libm { DEQ_LIBM_AS_WRITTEN = 0, DEQ_LIBM_LLVM_FOLDED = 1 } deq_libm;
 
+/* Memory layout of DEQ_OUT_TSPAN (adaptive methods).  SOA [n][ntspan][ntraj] coalesces when neighbouring trajectories
+ * advance together (parameter-sorted sweeps).  TRAJ_MAJOR [ntraj][ntspan][n] is one contiguous stream per trajectory —
+ * the reference's Vec<Y> shape — written through per-lane shared-memory staging with cooperative 128-byte stores; it is
+ * the fast choice for ensembles in arbitrary order (6x on a permuted Van der Pol sweep). */
+typedef enum deq_dense_layout { DEQ_LAYOUT_SOA = 0, DEQ_LAYOUT_TRAJ_MAJOR = 1 } deq_dense_layout;
+
 /* Per-trajectory completion code (the reference returns Ok(partial) silently in the first two cases). */
 typedef enum deq_traj_status {
     DEQ_TRAJ_DONE = 0,
@@ -109,6 +115,7 @@ typedef struct deq_options {
     int mode;            /* deq_mode, default DEQ_MODE_PARITY (adaptive methods only; fixed-step is always parity) */
     int precision;       /* deq_precision, default DEQ_PRECISION_F64 */
     int libm;            /* deq_libm, default DEQ_LIBM_AS_WRITTEN (PARITY mode only) */
+    int dense_layout;    /* deq_dense_layout, default DEQ_LAYOUT_SOA */
 } deq_options;
 
 typedef struct deq_rhs deq_rhs;
@@ -163,7 +170,8 @@ deq_status deq_result_final(deq_result* res, double* y /* host [ntraj][n] */);
 deq_status deq_result_counts(deq_result* res, uint32_t* accepted, uint32_t* rejected, uint32_t* nfe,
                              uint8_t* status, double* t_reached /* each host [ntraj], any may be NULL */);
 deq_status deq_result_totals(deq_result* res, uint64_t* accepted, uint64_t* rejected, uint64_t* nfe);
-/* DEQ_OUT_TSPAN: rows of trajectories [traj_begin, traj_end) into host out[n][ntspan][traj_end-traj_begin];
+/* DEQ_OUT_TSPAN: rows of trajectories [traj_begin, traj_end) into host out[n][ntspan][traj_end-traj_begin] (SOA) or
+ * out[traj_end-traj_begin][ntspan][n] (TRAJ_MAJOR);
  * nvalid (may be NULL) receives, per trajectory, how many leading tspan rows the reference would have emitted. */
 deq_status deq_result_dense(deq_result* res, size_t traj_begin, size_t traj_end, double* out, uint32_t* nvalid);
 /* DEQ_OUT_ALL: offsets[ntraj+1] — trajectory i owns rows [offsets[i], offsets[i+1]) of the ragged (tout, yout). */

@@ -33,6 +33,7 @@ pub struct deq_options {
     pub mode: c_int,
     pub precision: c_int,
     pub libm: c_int,
+    pub dense_layout: c_int,
 }
 
 #[repr(C)] pub struct deq_rhs { _p: [u8; 0] }

@@ -475,3 +475,32 @@ def test_out_of_memory_fails_cleanly_and_library_stays_usable(deq, oracle):
     sol = _problem(deq, deq.System.Lorenz, LOR, y1, [0.0, 1.0]).solve(deq.Ode.Ode45)
     ref = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, y1, [0.0, 1.0])
     assert np.array_equal(sol.final, ref["yfinal"])
+
+
+@pytest.mark.parametrize("order", ["sorted", "permuted"])
+def test_trajectory_major_staged_dense_output(deq, oracle, order):
+    """DenseLayout.TrajMajor (per-lane shared-memory staging, cooperative 128-byte stores) returns exactly the rows of the
+    SoA path / the oracle, for a sorted and for a randomly permuted parameter sweep, ragged ensemble size, and a tspan so
+    dense that one step emits more rows than the staging ring holds."""
+    from diffeq_b200 import synth
+    n = 1000 + 37
+    y0, mu = synth.vdp_sweep(0, n, n)
+    if order == "permuted":
+        mu = mu[np.random.default_rng(3).permutation(n)].copy()
+    for npts in (1000, 23, 9001):
+        ts = deq.linspace(0.0, 20.0, npts)
+        ref = oracle.ensemble_dense(oracle.ODE45FE, oracle.VANDERPOL, mu, y0, ts, oracle.opts(1e-6, 1e-8))
+        o = deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8), deq.Output.Tspan, deq.DenseLayout.TrajMajor)
+        sol = _problem(deq, deq.System.VanDerPol, mu, y0, ts).solve(deq.Ode.Ode45fe, o)
+        want = ref["out"].transpose(2, 1, 0)
+        m = ~np.isnan(want)
+        assert np.array_equal(sol.nvalid, ref["nvalid"]), npts
+        assert np.array_equal(np.isnan(sol.yout), np.isnan(want)), npts
+        assert np.array_equal(sol.yout[m], want[m]), npts
+    # Lorenz (n = 3: rows straddle the 16-double lines) in FAST mode agrees with its own SoA output bit for bit
+    yl = synth.lorenz_ics(0, 333)
+    tl = deq.linspace(0.0, 2.0, 301)
+    a = _problem(deq, deq.System.Lorenz, LOR, yl, tl).solve(deq.Ode.Ode45, deq.OdeOptionMap().insert(deq.Output.Tspan, deq.Mode.Fast))
+    b = _problem(deq, deq.System.Lorenz, LOR, yl, tl).solve(
+        deq.Ode.Ode45, deq.OdeOptionMap().insert(deq.Output.Tspan, deq.Mode.Fast, deq.DenseLayout.TrajMajor))
+    assert np.array_equal(a.yout, b.yout, equal_nan=True)
