@@ -504,3 +504,23 @@ def test_trajectory_major_staged_dense_output(deq, oracle, order):
     b = _problem(deq, deq.System.Lorenz, LOR, yl, tl).solve(
         deq.Ode.Ode45, deq.OdeOptionMap().insert(deq.Output.Tspan, deq.Mode.Fast, deq.DenseLayout.TrajMajor))
     assert np.array_equal(a.yout, b.yout, equal_nan=True)
+
+
+def test_nvrtc_max_dimension_high_order(deq):
+    """n = 16 (the largest state the register-resident steppers accept) with the 13-stage Fehlberg 7(8): 8 decoupled
+    oscillators with frequencies 1..8 through NVRTC, against the exact solution; also the fixed-step RK4 path."""
+    src = ("__device__ void rhs(double t, const double* y, double* dy, const double* p) {\n"
+           "  for (int i = 0; i < 8; ++i) { double w = p[0] * (i + 1); dy[2 * i] = w * y[2 * i + 1]; dy[2 * i + 1] = -w * y[2 * i]; }\n}\n")
+    rhs = deq.Rhs.from_source(src, 16, 1)
+    y0 = np.tile(np.array([1.0, 0.0] * 8), (70, 1))
+    T = 1.5
+    want = np.array([f(k * T) for k in range(1, 9) for f in (np.cos, lambda x: -np.sin(x))])
+    o = deq.OdeOptionMap().insert(deq.Reltol(1e-11), deq.Abstol(1e-11))
+    sol = deq.OdeProblem.builder().fun(rhs).params([1.0]).init(y0).tspan([0.0, T]).build().solve(
+        deq.Ode.Ode78, o, tableau_set=deq.TableauSet.Textbook)
+    assert np.all(sol.status == 0)
+    np.testing.assert_allclose(sol.final, np.tile(want, (70, 1)), rtol=0, atol=2e-9)
+    fx = deq.OdeProblem.builder().fun(rhs).params([1.0]).init(y0[:3]).tspan(deq.linspace(0.0, T, 3001)).build().solve(deq.Ode.Ode4)
+    np.testing.assert_allclose(fx.final, np.tile(want, (3, 1)), rtol=0, atol=1e-9)
+    with pytest.raises(deq.OdeError):
+        deq.Rhs.from_source(src, 17, 1)       # beyond the supported state dimension
