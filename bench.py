@@ -208,6 +208,8 @@ def main():
     dev_ms, steps_done, kernel_ms, wall, tot_par = device_arm(opts_par, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
     fast_ms, fast_steps, fast_kernel_ms, _, tot_fast = device_arm(opts_fast)
+    opts_fold = D.OdeOptionMap().insert(D.Reltol(RTOL), D.Abstol(ATOL), D.Mode.Parity, D.Libm.LlvmFolded)
+    fold_ms, fold_steps, fold_kernel_ms, _, tot_fold = device_arm(opts_fold)
     # full-size parity property: both arithmetic modes must take exactly the same accepted / rejected steps, and the
     # final states must agree within the north-star tolerance (10 x rtol)
     f_fast = prob.solve(D.Ode.Ode45, opts_fast).final
@@ -262,13 +264,13 @@ def main():
         assert sum(p.shape[0] for p in parts) == ntraj * world and torch.equal(parts[rank], loc)
 
     # ---------------- reduce over ranks ----------------
-    t = torch.tensor([dev_ms, e2e_s, wall, fast_ms, e2e_fast_s], dtype=torch.float64, device="cuda")
-    c = torch.tensor([steps_done, e2e_steps, fast_steps, e2e_fast_steps], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s, wall, fast_ms, e2e_fast_s, fold_ms], dtype=torch.float64, device="cuda")
+    c = torch.tensor([steps_done, e2e_steps, fast_steps, e2e_fast_steps, fold_steps], dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_s_max, wall_max, fast_ms_max, e2e_fast_s_max = t.tolist()
-    steps_all, e2e_steps_all, fast_steps_all, e2e_fast_steps_all = c.tolist()
+    dev_ms_max, e2e_s_max, wall_max, fast_ms_max, e2e_fast_s_max, fold_ms_max = t.tolist()
+    steps_all, e2e_steps_all, fast_steps_all, e2e_fast_steps_all, fold_steps_all = c.tolist()
 
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^20 trajectories (ncu --set full, profiles/r1_final_*_kernel_
     # ncu_full_summary.csv); it scales with the trajectory count, not with the step count
@@ -306,6 +308,13 @@ def main():
                           "e2e": {"value": e2e_fast_steps_all / e2e_fast_s_max, "unit": UNIT, "ms_per_step": 1e3 * e2e_fast_s_max / args.steps},
                           "roofline": roofline(fast_kernel_ms, fast_steps, "deqk::adapt_kernel<Dopri5<false>, Lorenz, false, MODE_FINAL, FAST=true>",
                                                "FMA counted as 2 flop; algorithmic flop per step attempt from SURVEY.md 8(d)", "fast")},
+            "parity_llvm_folded_libm": {
+                "value": fold_steps_all / (fold_ms_max * 1e-3), "unit": UNIT, "ms_per_step": fold_ms_max / args.steps,
+                "step_totals_identical_to_headline": bool(tot_fold == tot_par),
+                "roofline": roofline(fold_kernel_ms, fold_steps, "deqk::adapt_kernel<Dopri5<false>, Lorenz, false, MODE_FINAL, FAST=false> (libm_folded)",
+                                     par_note, "parity"),
+                "note": "bit-exact PARITY arithmetic with the libm calls an LLVM-optimised build of the crate makes (sqrt for the error norm, "
+                        "exp10 in hinit; DESIGN.md 4.1) — one pow per step instead of two"},
             "mode_check": mode_check,
             "final_gather_ms": gather_ms,
             "clocks": clocks, "wall_s_timed_region": wall_max,
