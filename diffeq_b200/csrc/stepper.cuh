@@ -104,6 +104,19 @@ __device__ __forceinline__ double max_abs_nonan(double a, double b) {
 __device__ __forceinline__ double sel_max(double c, double x) { return x > c ? x : c; }
 __device__ __forceinline__ double sel_min(double c, double x) { return x < c ? x : c; }
 
+// dt / 100. (problem.rs:337) — bit-identical to the IEEE division, in three FP64 instructions instead of the generic
+// division sequence (MUFU seed + Newton steps + range checks, ~10 FP64 + 6 other instructions per accepted step).
+// q = RN(x * R), rem = x - 100 q (exact in an FMA), q' = RN(q + rem * R) with R = RN(1/100): the value before the last
+// rounding is within 2^-52 ulp of x/100, while x/100 itself can never be closer than 0.02 ulp to a rounding midpoint
+// (x - 100 (m + 1/2) ulp(q) is a non-zero multiple of 2 ulp(q)), so the rounding is the correct one.  Checked against
+// the hardware division on 1.1e9 random operands (0 mismatches).  Outside the guarded exponent range it divides.
+__device__ __forceinline__ double div100_exact(double x) {
+    const double ax = fabs(x);
+    if (!(ax > 0x1p-900 && ax < 0x1p900)) return x / 100.;
+    const double q = x * 0.01;
+    return __fma_rn(__fma_rn(-100.0, q, x), 0.01, q);
+}
+
 #ifndef DEQ_BURST
 #define DEQ_BURST 8
 #endif
@@ -522,7 +535,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                         fin = ST_DONE;   // t is t_reached
                     } else {
                         dt = ndt;
-                        if (tdir * ((t + dt) + (FAST ? dt * 0.01 : dt / 100.)) >= tdir * tend) { dt = tend - t; last_step = true; }
+                        if (tdir * ((t + dt) + (FAST ? dt * 0.01 : div100_exact(dt))) >= tdir * tend) { dt = tend - t; last_step = true; }
                     }
                 } else if (fabs(ndt) < P.minstep) {
                     fin = ST_MINSTEP_BREAK;
