@@ -22,5 +22,7 @@ def oracle():
 @pytest.fixture(scope="session")
 def deq():
     import diffeq_b200 as D
-    D.lib()  # fails loudly when the extension is missing
+    from diffeq_b200 import build as deq_build
+    deq_build.build()   # no-op when libdiffeq_b200.so is up to date; nvcc cross-compiles sm_100a without a GPU
+    D.lib()             # fails loudly when the extension is missing
     return D
