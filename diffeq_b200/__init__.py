@@ -119,7 +119,7 @@ class _Options(C.Structure):
 ABI_SYMBOLS = [
     "deq_last_error_message", "deq_version", "deq_rhs_builtin", "deq_rhs_from_source", "deq_rhs_dim",
     "deq_rhs_nparams", "deq_rhs_destroy", "deq_tspan_linspace", "deq_ensemble_create", "deq_ensemble_create_device",
-    "deq_ensemble_destroy", "deq_ensemble_ntraj", "deq_set_stream", "deq_set_device", "deq_get_device", "deq_options_default", "deq_solve",
+    "deq_ensemble_destroy", "deq_ensemble_ntraj", "deq_set_stream", "deq_set_device", "deq_get_device", "deq_solve_host", "deq_options_default", "deq_solve",
     "deq_result_final", "deq_result_counts", "deq_result_totals", "deq_result_dense", "deq_result_all_offsets",
     "deq_result_all_copy", "deq_result_device_ptrs",
     "deq_result_trajectory", "deq_result_kernel_ms", "deq_result_destroy", "deq_tableau_get", "deq_host_alloc",
@@ -506,3 +506,25 @@ def solve_host(rhs, y0, params, tspan, ode, opts=None, out_final=None, out_accep
     if return_totals:
         return out_final, out_accepted, out_rejected, totals
     return out_final, out_accepted, out_rejected
+
+
+def solve_host_multi(rhs, y0, params, tspan, ode, opts=None, devices=None, tableau_set=TableauSet.Reference):
+    """`deq_solve_host`: one call on host buffers, sharded over `devices` (list of CUDA ordinals; None = current device) with
+    one host thread per GPU inside the library.  Returns dict(final, accepted, rejected, nfe, status, t_reached)."""
+    L = lib()
+    y0 = _f64(y0)
+    if y0.ndim == 1:
+        y0 = y0[None, :]
+    ntraj, n = y0.shape
+    params = _f64(params) if params is not None else None
+    tspan = _f64(tspan)
+    o = (opts if opts is not None else OdeOptionMap()).to_c()
+    per = int(params is not None and params.ndim == 2)
+    dev = (C.c_int * len(devices))(*devices) if devices else None
+    out = dict(final=np.empty((ntraj, n)), accepted=np.zeros(ntraj, np.uint32), rejected=np.zeros(ntraj, np.uint32),
+               nfe=np.zeros(ntraj, np.uint32), status=np.zeros(ntraj, np.uint8), t_reached=np.zeros(ntraj))
+    _check(L.deq_solve_host(rhs._h, C.c_size_t(ntraj), _ptr(y0), _ptr(params), per, _ptr(tspan), C.c_size_t(len(tspan)), int(ode),
+                            int(tableau_set), C.byref(o), dev, len(devices) if devices else 0, _ptr(out["final"]),
+                            _ptr(out["accepted"], C.c_uint32), _ptr(out["rejected"], C.c_uint32), _ptr(out["nfe"], C.c_uint32),
+                            _ptr(out["status"], C.c_uint8), _ptr(out["t_reached"])))
+    return out

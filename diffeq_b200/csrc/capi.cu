@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/diffeq_b200.h"
 #include "launch.h"
@@ -562,6 +563,60 @@ void deq_result_destroy(deq_result* r) {
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
     delete r;
+}
+
+// One-shot multi-GPU solve on host buffers: contiguous shards of the trajectory range, one host thread and one stream per
+// device, no inter-GPU traffic; every shard writes its slice of the caller's output arrays.
+deq_status deq_solve_host(const deq_rhs* rhs, size_t ntraj, const double* y0, const double* params, int params_per_traj,
+                          const double* tspan, size_t ntspan, int method, int tableau_set, const deq_options* opts,
+                          const int* devices, int ndevices, double* yfinal, uint32_t* accepted, uint32_t* rejected,
+                          uint32_t* nfe, uint8_t* status, double* t_reached) {
+    if (!rhs) return fail(DEQ_ERR_UNINITIALIZED, "Required problem must be initialized");
+    if (!y0 && ntraj) return fail(DEQ_ERR_UNINITIALIZED, "Initial starting point must be initialized");
+    if (!tspan) return fail(DEQ_ERR_UNINITIALIZED, "Time span must be initialized");
+    if (!yfinal) return fail(DEQ_ERR_INVALID_ARG, "yfinal is NULL");
+    deq_options o = opts ? *opts : deq_options_default();
+    if (o.output != DEQ_OUT_FINAL) return fail(DEQ_ERR_INVALID_ARG, "deq_solve_host returns final states and counters only");
+    o.async = 0;
+    int cur = 0;
+    CK(cudaGetDevice(&cur));
+    std::vector<int> devs;
+    if (devices && ndevices > 0) devs.assign(devices, devices + ndevices); else devs.push_back(cur);
+    const size_t nd = devs.size(), n = (size_t)rhs->n, np = (size_t)rhs->np;
+    deql::TableauInfo info;
+    { const int tb = tb_of(method, tableau_set); if (tb == -1) return fail(DEQ_ERR_UNSUPPORTED, "stiff (Rosenbrock) methods are not part of the RK hot path"); if (tb < 0) return fail(DEQ_ERR_INVALID_ARG, "unknown method"); g_tb[tb].info(&info); }
+    std::vector<deq_status> rc(nd, DEQ_OK);
+    std::vector<std::string> msg(nd);
+    auto work = [&](size_t k) {
+        const size_t base = ntraj / nd, extra = ntraj % nd;
+        const size_t b = k * base + (k < extra ? k : extra), e = b + base + (k < extra ? 1 : 0);
+        auto bad = [&](deq_status s) { rc[k] = s; msg[k] = g_err; };
+        if (cudaSetDevice(devs[k]) != cudaSuccess) { rc[k] = DEQ_ERR_CUDA; msg[k] = "cudaSetDevice failed"; cudaGetLastError(); return; }
+        deq_ensemble* ens = nullptr;
+        deq_result* res = nullptr;
+        deq_status s = deq_ensemble_create(rhs, e - b, y0 + b * n, (params && params_per_traj) ? params + b * np : params, params_per_traj,
+                                           tspan, ntspan, &ens);
+        if (s) { bad(s); return; }
+        s = deq_solve(ens, method, tableau_set, &o, &res);
+        if (!s && e > b && ntspan) s = deq_result_final(res, yfinal + b * n);
+        if (!s && info.adaptive && e > b && ntspan)
+            s = deq_result_counts(res, accepted ? accepted + b : nullptr, rejected ? rejected + b : nullptr, nfe ? nfe + b : nullptr,
+                                  status ? status + b : nullptr, t_reached ? t_reached + b : nullptr);
+        if (s) bad(s);
+        if (res) deq_result_destroy(res);
+        deq_ensemble_destroy(ens);
+    };
+    if (nd == 1 && devs[0] == cur) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t k = 0; k < nd; ++k) th.emplace_back(work, k);
+        for (auto& t : th) t.join();
+        cudaSetDevice(cur);
+    }
+    for (size_t k = 0; k < nd; ++k)
+        if (rc[k]) return fail(rc[k], "device " + std::to_string(devs[k]) + ": " + msg[k]);
+    return DEQ_OK;
 }
 
 deq_status deq_tableau_get(int method, int set, int* stages, double* a, double* b, double* c, int* adaptive,

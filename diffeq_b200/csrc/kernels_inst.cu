@@ -56,10 +56,10 @@ static int persistent_grid(K kernel, unsigned long long ntraj, size_t dyn_smem =
 }
 
 #ifdef DEQ_FAST_TU
-constexpr bool kFast = true;    // this object is compiled with -fmad=true: FMA contraction everywhere
+[[maybe_unused]] constexpr bool kFast = true;    // this object is compiled with -fmad=true: FMA contraction everywhere
 #define DEQ_LAUNCH_ADAPT DEQ_CAT(launch_adapt_fast_, DEQ_TB)
 #else
-constexpr bool kFast = false;   // parity object, -fmad=false
+[[maybe_unused]] constexpr bool kFast = false;   // parity object, -fmad=false
 #define DEQ_LAUNCH_ADAPT DEQ_CAT(launch_adapt_, DEQ_TB)
 #endif
 

@@ -164,6 +164,15 @@ deq_options deq_options_default(void);
 deq_status deq_solve(deq_ensemble* ens, int method /* deq_method */, int tableau_set /* deq_tableau_set */,
                      const deq_options* opts, deq_result** out);
 
+/* One call for an ensemble on HOST buffers, optionally sharded over several GPUs of the box: trajectories are
+ * split into contiguous blocks, one host thread + stream per device, no inter-GPU traffic; results land in the caller's
+ * arrays (yfinal [ntraj][n]; the counter arrays [ntraj] may each be NULL; ignored for fixed-step methods).  devices == NULL
+ * or ndevices <= 0 uses the current device.  The result of trajectory i does not depend on the device count. */
+deq_status deq_solve_host(const deq_rhs* rhs, size_t ntraj, const double* y0, const double* params, int params_per_traj,
+                          const double* tspan, size_t ntspan, int method, int tableau_set, const deq_options* opts,
+                          const int* devices, int ndevices, double* yfinal, uint32_t* accepted, uint32_t* rejected,
+                          uint32_t* nfe, uint8_t* status, double* t_reached);
+
 /* ---- result: replaces OdeSolution{tout,yout} (src/ode/solution.rs:22-29) + the Diagnostics the reference
  * counts but drops (problem.rs:957-970).  All getters synchronise with the solve first. ---- */
 deq_status deq_result_final(deq_result* res, double* y /* host [ntraj][n] */);

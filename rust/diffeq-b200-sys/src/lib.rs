@@ -63,6 +63,10 @@ extern "C" {
     pub fn deq_options_default() -> deq_options;
     pub fn deq_solve(ens: *mut deq_ensemble, method: c_int, tableau_set: c_int, opts: *const deq_options,
                      out: *mut *mut deq_result) -> deq_status;
+    pub fn deq_solve_host(rhs: *const deq_rhs, ntraj: usize, y0: *const c_double, params: *const c_double, params_per_traj: c_int,
+                          tspan: *const c_double, ntspan: usize, method: c_int, tableau_set: c_int, opts: *const deq_options,
+                          devices: *const c_int, ndevices: c_int, yfinal: *mut c_double, accepted: *mut u32, rejected: *mut u32,
+                          nfe: *mut u32, status: *mut u8, t_reached: *mut c_double) -> deq_status;
     pub fn deq_result_final(res: *mut deq_result, y: *mut c_double) -> deq_status;
     pub fn deq_result_counts(res: *mut deq_result, accepted: *mut u32, rejected: *mut u32, nfe: *mut u32,
                              status: *mut u8, t_reached: *mut c_double) -> deq_status;

@@ -524,3 +524,23 @@ def test_nvrtc_max_dimension_high_order(deq):
     np.testing.assert_allclose(fx.final, np.tile(want, (3, 1)), rtol=0, atol=1e-9)
     with pytest.raises(deq.OdeError):
         deq.Rhs.from_source(src, 17, 1)       # beyond the supported state dimension
+
+
+def test_in_library_multi_gpu_solve_host(deq, oracle):
+    """deq_solve_host shards an ensemble over the GPUs of the box with one host thread per device; trajectory i's result
+    does not depend on the device count (runs with however many GPUs are visible; 1 is a valid count)."""
+    import torch
+    from diffeq_b200 import synth
+    ndev = torch.cuda.device_count()
+    y0 = synth.lorenz_ics(0, 5003)
+    o = deq.OdeOptionMap().insert(deq.Reltol(1e-8), deq.Abstol(1e-8))
+    ref = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, y0, [0.0, 2.0], oracle.opts(1e-8, 1e-8))
+    rhs = deq.Rhs.builtin(deq.System.Lorenz)
+    for devices in ([0], list(range(ndev)), [0] * 3):   # the last one: three shards on one GPU (partition invariance)
+        out = deq.solve_host_multi(rhs, y0, LOR, [0.0, 2.0], deq.Ode.Ode45, o, devices=devices)
+        assert np.array_equal(out["final"], ref["yfinal"]), devices
+        assert np.array_equal(out["accepted"], ref["accepted"]) and np.array_equal(out["t_reached"], ref["t_reached"]), devices
+    fx = deq.solve_host_multi(rhs, y0[:100], LOR, deq.linspace(0.0, 1.0, 101), deq.Ode.Ode4, devices=list(range(ndev)))
+    assert np.array_equal(fx["final"], oracle.ensemble_fixed(oracle.ODE4, oracle.LORENZ, LOR, y0[:100], oracle.linspace(0.0, 1.0, 101)))
+    with pytest.raises(deq.OdeError):
+        deq.solve_host_multi(rhs, y0, LOR, [0.0, 2.0], deq.Ode.Ode45, o, devices=[ndev + 7])
