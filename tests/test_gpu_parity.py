@@ -544,3 +544,63 @@ def test_in_library_multi_gpu_solve_host(deq, oracle):
     assert np.array_equal(fx["final"], oracle.ensemble_fixed(oracle.ODE4, oracle.LORENZ, LOR, y0[:100], oracle.linspace(0.0, 1.0, 101)))
     with pytest.raises(deq.OdeError):
         deq.solve_host_multi(rhs, y0, LOR, [0.0, 2.0], deq.Ode.Ode45, o, devices=[ndev + 7])
+
+
+def test_golden_fixtures_through_the_cuda_path(deq):
+    """Every committed golden case (tests/golden/solver_cases.json: known answers of the independent Python restatement,
+    reference tableaus parsed from runge_kutta.rs) reproduced by the CUDA path directly — no oracle in between."""
+    import hashlib, json, os
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solver_cases.json")))
+    fh = lambda v: [fh(x) for x in v] if isinstance(v, list) else float.fromhex(v)  # noqa: E731
+    ran = 0
+    for c in cases:
+        ts = [float(x) for x in c["tspan"][1:]] if c["tspan"][0] == "list" else deq.linspace(c["tspan"][1], c["tspan"][2], c["tspan"][3])
+        prob = _problem(deq, getattr(deq.System, c["system"]), fh(c["params"]), fh(c["y0"]), ts)
+        if c["kind"] == "fixed":
+            sol = prob.solve(getattr(deq.Ode, c["method"]), deq.OdeOptionMap().insert(deq.Output.Tspan))
+            assert sol.final[0].tolist() == fh(c["final"]), c["name"]
+            assert hashlib.sha256(np.ascontiguousarray(sol.yout[0], dtype="<f8").tobytes()).hexdigest() == c["sha256_yout"], c["name"]
+        else:
+            opt = c["options"]
+            if opt.get("points_all") is False:
+                continue   # Points::Specified: reference-broken, rejected by the product (covered by the oracle goldens)
+            o = deq.OdeOptionMap().insert(deq.Output.All)
+            for k, cls in (("reltol", deq.Reltol), ("abstol", deq.Abstol), ("minstep", deq.Minstep), ("maxstep", deq.Maxstep), ("initstep", deq.Initstep)):
+                if k in opt:
+                    o.insert(cls(float.fromhex(opt[k])))
+            if "max_steps" in opt:
+                o.insert(deq.MaxSteps(opt["max_steps"]))
+            if opt.get("libm_folded"):
+                o.insert(deq.Libm.LlvmFolded)
+            sol = prob.solve(getattr(deq.Ode, c["method"]), o, tableau_set=0 if c["tableau_set"] == "reference" else 1)
+            tout, yout = sol.trajectory(0)
+            assert (int(sol.accepted[0]), int(sol.rejected[0]), int(sol.status[0]), len(tout)) == (c["accepted"], c["rejected"], c["status"], c["nout"]), c["name"]
+            assert sol.final[0].tolist() == fh(c["final"]), c["name"]
+            assert hashlib.sha256(np.ascontiguousarray(tout, dtype="<f8").tobytes()).hexdigest() == c["sha256_tout"], c["name"]
+            assert hashlib.sha256(np.ascontiguousarray(yout, dtype="<f8").tobytes()).hexdigest() == c["sha256_yout"], c["name"]
+        ran += 1
+    assert ran >= 30
+
+
+def test_full_size_config2_properties(deq, oracle):
+    """BASELINE config 2 at its full size (2^20 trajectories, T = 10), checked through size-independent properties: the
+    result of trajectory i is independent of the partition (one solve vs four shards) and of the scheduling (lane refill vs
+    static warps), the device-side totals equal the sums of the per-trajectory counters, every trajectory finishes, and a
+    random sample of 1500 trajectories equals the oracle bit for bit."""
+    from diffeq_b200 import synth
+    n = 1 << 20
+    y0 = synth.lorenz_ics(0, n)
+    o = deq.OdeOptionMap().insert(deq.Reltol(1e-8), deq.Abstol(1e-8))
+    full = _problem(deq, deq.System.Lorenz, LOR, y0, [0.0, 10.0]).solve(deq.Ode.Ode45, o)
+    assert np.all(full.status == 0) and np.all(full.t_reached == 10.0)
+    assert full.totals["accepted"] == int(full.accepted.sum(dtype=np.int64)) and full.totals["rejected"] == int(full.rejected.sum(dtype=np.int64))
+    assert full.totals["nfe"] == int(full.nfe.sum(dtype=np.int64)) == 2 * n + 6 * (full.totals["accepted"] + full.totals["rejected"])
+    for b, e in ((0, 300001), (300001, 524288), (524288, 1000000), (1000000, n)):
+        part = _problem(deq, deq.System.Lorenz, LOR, y0[b:e], [0.0, 10.0]).solve(deq.Ode.Ode45, o)
+        assert np.array_equal(part.final, full.final[b:e]) and np.array_equal(part.accepted, full.accepted[b:e])
+    static = _problem(deq, deq.System.Lorenz, LOR, y0, [0.0, 10.0]).solve(deq.Ode.Ode45, deq.OdeOptionMap().insert(deq.Reltol(1e-8), deq.Abstol(1e-8), deq.Refill(0)))
+    assert np.array_equal(static.final, full.final) and np.array_equal(static.rejected, full.rejected)
+    idx = np.sort(np.random.default_rng(11).choice(n, 1500, replace=False))
+    ref = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, y0[idx], [0.0, 10.0], oracle.opts(1e-8, 1e-8))
+    assert np.array_equal(full.final[idx], ref["yfinal"]) and np.array_equal(full.accepted[idx], ref["accepted"])
+    assert np.array_equal(full.rejected[idx], ref["rejected"])
