@@ -604,3 +604,34 @@ def test_full_size_config2_properties(deq, oracle):
     ref = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, y0[idx], [0.0, 10.0], oracle.opts(1e-8, 1e-8))
     assert np.array_equal(full.final[idx], ref["yfinal"]) and np.array_equal(full.accepted[idx], ref["accepted"])
     assert np.array_equal(full.rejected[idx], ref["rejected"])
+
+
+def test_full_size_config3_dense_slices(deq, oracle):
+    """BASELINE config 3 at 2^20 trajectories x 1000 rows (16.8 GB on the device, both layouts): three slices of the dense
+    output are copied back and must equal the oracle's rows bit for bit; nvalid and the step counters likewise."""
+    import ctypes as C
+    from diffeq_b200 import synth
+    n = 1 << 20
+    y0, mu = synth.vdp_sweep(0, n, n)
+    ts = deq.linspace(0.0, 20.0, 1000)
+    L = deq.lib()
+    prob = _problem(deq, deq.System.VanDerPol, mu, y0, ts)
+    for layout in (deq.DenseLayout.SoA, deq.DenseLayout.TrajMajor):
+        o = deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8), deq.Output.Tspan, layout).to_c()
+        res = C.c_void_p()
+        assert L.deq_solve(prob._h, int(deq.Ode.Ode45fe), 0, C.byref(o), C.byref(res)) == 0
+        try:
+            for b in (0, 524288 - 17, n - 64):
+                e = b + 64
+                ref = oracle.ensemble_dense(oracle.ODE45FE, oracle.VANDERPOL, mu[b:e], y0[b:e], ts, oracle.opts(1e-6, 1e-8))
+                shape = (64, 1000, 2) if layout == deq.DenseLayout.TrajMajor else (2, 1000, 64)
+                got = np.empty(shape); nv = np.empty(64, np.uint32)
+                assert L.deq_result_dense(res, C.c_size_t(b), C.c_size_t(e), got.ctypes.data_as(C.POINTER(C.c_double)),
+                                          nv.ctypes.data_as(C.POINTER(C.c_uint32))) == 0
+                if layout == deq.DenseLayout.SoA:
+                    got = got.transpose(2, 1, 0)
+                want = ref["out"].transpose(2, 1, 0)
+                m = ~np.isnan(want)
+                assert np.array_equal(nv, ref["nvalid"]) and np.array_equal(got[m], want[m]), (layout, b)
+        finally:
+            L.deq_result_destroy(res)
