@@ -371,8 +371,9 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         P.yfinal = r->d_yfinal; P.accepted = r->d_acc; P.rejected = r->d_rej; P.nfe = r->d_nfe; P.status = r->d_status;
         P.t_reached = r->d_treached; P.dense = r->d_dense; P.nvalid = r->d_nvalid;
         P.work_counter = r->d_scalars; P.totals = r->d_scalars + 1;
-        const int mode = (want_dense || want_all) ? deqk::MODE_DENSE : deqk::MODE_FINAL;
-        P.rec_mode = want_all ? deqk::REC_COUNT : (o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR ? deqk::REC_TSPAN_TM : deqk::REC_TSPAN);
+        const int mode = want_all ? deqk::MODE_REC
+                         : want_dense ? (o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR ? deqk::MODE_DENSE_TM : deqk::MODE_DENSE) : deqk::MODE_FINAL;
+        P.rec_mode = deqk::REC_COUNT;
         r->traj_major = want_dense && o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR;
         P.rec_counts = r->d_rec_counts;
         auto launch_adapt = [&](std::string* err) -> int {  // 0 ok, 1 cuda error (g_err set), 2 nvrtc error

@@ -67,7 +67,7 @@ template <class F, bool PT, int MODE>
 static cudaError_t launch_adapt_t(const deqk::AdaptParams& P, int grid_blocks, cudaStream_t st) {
     if constexpr (TB::ADAPTIVE) {
         auto kernel = deqk::adapt_kernel<TB, F, PT, MODE, kFast>;
-        const size_t smem = (MODE == deqk::MODE_DENSE && P.rec_mode == deqk::REC_TSPAN_TM) ? deqk::STAGE_BYTES : 0;
+        const size_t smem = MODE == deqk::MODE_DENSE_TM ? deqk::STAGE_BYTES : 0;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int grid = grid_blocks > 0 ? grid_blocks : persistent_grid(kernel, P.ntraj, smem);
         kernel<<<grid, deqk::BLOCK, smem, st>>>(P);
@@ -80,10 +80,17 @@ static cudaError_t launch_adapt_t(const deqk::AdaptParams& P, int grid_blocks, c
 
 template <class F>
 static cudaError_t launch_adapt_f(int pt, int mode, const deqk::AdaptParams& P, int grid_blocks, cudaStream_t st) {
-    if (pt) return mode == deqk::MODE_DENSE ? launch_adapt_t<F, true, deqk::MODE_DENSE>(P, grid_blocks, st)
-                                            : launch_adapt_t<F, true, deqk::MODE_FINAL>(P, grid_blocks, st);
-    return mode == deqk::MODE_DENSE ? launch_adapt_t<F, false, deqk::MODE_DENSE>(P, grid_blocks, st)
-                                    : launch_adapt_t<F, false, deqk::MODE_FINAL>(P, grid_blocks, st);
+    switch (mode * 2 + (pt ? 1 : 0)) {
+        case deqk::MODE_FINAL * 2: return launch_adapt_t<F, false, deqk::MODE_FINAL>(P, grid_blocks, st);
+        case deqk::MODE_FINAL * 2 + 1: return launch_adapt_t<F, true, deqk::MODE_FINAL>(P, grid_blocks, st);
+        case deqk::MODE_DENSE * 2: return launch_adapt_t<F, false, deqk::MODE_DENSE>(P, grid_blocks, st);
+        case deqk::MODE_DENSE * 2 + 1: return launch_adapt_t<F, true, deqk::MODE_DENSE>(P, grid_blocks, st);
+        case deqk::MODE_DENSE_TM * 2: return launch_adapt_t<F, false, deqk::MODE_DENSE_TM>(P, grid_blocks, st);
+        case deqk::MODE_DENSE_TM * 2 + 1: return launch_adapt_t<F, true, deqk::MODE_DENSE_TM>(P, grid_blocks, st);
+        case deqk::MODE_REC * 2: return launch_adapt_t<F, false, deqk::MODE_REC>(P, grid_blocks, st);
+        case deqk::MODE_REC * 2 + 1: return launch_adapt_t<F, true, deqk::MODE_REC>(P, grid_blocks, st);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t DEQ_LAUNCH_ADAPT(int sys, int pt, int mode, const deqk::AdaptParams& P, int grid_blocks, cudaStream_t st) {

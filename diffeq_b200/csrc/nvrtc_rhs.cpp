@@ -140,11 +140,11 @@ static bool get_kernel(Program* p, int kind, int tb, int pt, int mode, Kernel* o
     std::ostringstream ne;
     const char* b = pt ? "true" : "false";
     if (kind == 0) ne << "&deqk::hinit_kernel<DeqUserRhs, " << b << ">";
-    else if (kind == 1) ne << "&deqk::adapt_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode & 1) << ", "
-                           << ((mode & 2) ? "true" : "false") << ">";
+    else if (kind == 1) ne << "&deqk::adapt_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode & 3) << ", "
+                           << ((mode & 4) ? "true" : "false") << ">";
     else ne << "&deqk::fixed_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode ? "true" : "false") << ">";
     Kernel k;
-    if (!compile(p, ne.str(), kind == 1 && (mode & 2), &k, err)) return false;
+    if (!compile(p, ne.str(), kind == 1 && (mode & 4), &k, err)) return false;
     p->cache[key] = k;
     *out = k;
     return true;
@@ -180,11 +180,11 @@ bool launch_hinit(Program* p, int pt, const deqk::HinitParams& P, cudaStream_t s
 bool launch_adapt(Program* p, int tb, int pt, int mode, bool fast, const deqk::AdaptParams& P, cudaStream_t st,
                   std::string* err) {
     Kernel k;
-    if (!get_kernel(p, 1, tb, pt ? 1 : 0, (mode & 1) | (fast ? 2 : 0), &k, err)) return false;
+    if (!get_kernel(p, 1, tb, pt ? 1 : 0, (mode & 3) | (fast ? 4 : 0), &k, err)) return false;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = ((mode & 1) == deqk::MODE_DENSE && P.rec_mode == deqk::REC_TSPAN_TM) ? 32u * deqk::BLOCK * sizeof(double) : 0;
+    const size_t smem = mode == deqk::MODE_DENSE_TM ? 32u * deqk::BLOCK * sizeof(double) : 0;
     int per_sm = k.blocks_per_sm;
     if (smem) {  // the staged layout lowers the resident-CTA count
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k.fn, deqk::BLOCK, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 2; }

@@ -6,9 +6,9 @@
 
 namespace deqk {
 
-enum : int { MODE_FINAL = 0, MODE_DENSE = 1 };
-// what a MODE_DENSE kernel records: tspan rows (SoA), or the reference's full ragged Points::All stream in two passes
-enum : int { REC_TSPAN = 0, REC_COUNT = 1, REC_WRITE = 2, REC_TSPAN_TM = 3 };
+enum : int { MODE_FINAL = 0, MODE_DENSE = 1, MODE_DENSE_TM = 2, MODE_REC = 3 };   // kernel template parameter
+// the two passes of a MODE_REC kernel (the reference's full ragged Points::All stream): count rows, then write them
+enum : int { REC_COUNT = 1, REC_WRITE = 2 };
 enum : uint8_t { ST_DONE = 0, ST_MINSTEP_BREAK = 1, ST_MAX_STEPS = 2 };
 
 #ifndef DEQ_BLOCK
@@ -37,9 +37,9 @@ struct AdaptParams {
     // outputs
     double* yfinal;        // [N][ntraj]
     uint32_t* accepted; uint32_t* rejected; uint32_t* nfe; uint8_t* status; double* t_reached;
-    double* dense;         // MODE_DENSE: [N][nt][ntraj] (REC_TSPAN) or [ntraj][nt][N] (REC_TSPAN_TM)
+    double* dense;         // MODE_DENSE: [N][nt][ntraj]; MODE_DENSE_TM: [ntraj][nt][N]
     uint32_t* nvalid;      // MODE_DENSE: number of leading tspan rows written (reference quirk)
-    int rec_mode;          // MODE_DENSE: REC_TSPAN / REC_COUNT / REC_WRITE
+    int rec_mode;          // MODE_REC: REC_COUNT / REC_WRITE
     uint32_t* rec_counts;  // REC_COUNT: rows of (tout, yout) the reference would produce, per trajectory
     const unsigned long long* rec_offsets;  // REC_WRITE: first row of each trajectory in rec_t / rec_y
     double* rec_t;         // REC_WRITE: tout, ragged, trajectory-major

@@ -318,6 +318,11 @@ template <class TB, class F, bool PT, int MODE, bool FAST>
 __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const AdaptParams P) {
     constexpr int N = F::N, S = TB::S;
     constexpr bool FSAL = deqt::fsal_of(TB::data());
+    // what this instantiation records besides the final state (compile time, so the hot loop carries no mode tests):
+    constexpr bool SOA = MODE == MODE_DENSE;      // tspan rows, [N][nt][ntraj]
+    constexpr bool TM = MODE == MODE_DENSE_TM;    // tspan rows, [ntraj][nt][N], staged through shared memory
+    constexpr bool REC = MODE == MODE_REC;        // ragged Points::All stream, counting pass or writing pass (P.rec_mode)
+    constexpr bool ROWS = MODE != MODE_FINAL;     // the tspan cursor `it` is tracked
     DEQ_TAB(TB);
     constexpr double PW = 1. / (double)(TB::ORDER_MIN + 1);
 
@@ -382,11 +387,11 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     timeout = 0;
                     last_step = fabs((t + dt) - tend) <= DBL_EPSILON;
                     acc = 0; rej = 0; attempts = 0; it = 1;
-                    if (MODE == MODE_DENSE) {
-                        if (P.rec_mode == REC_TSPAN) {
+                    if (ROWS) {
+                        if (SOA) {
 #pragma unroll
                             for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt) * P.ntraj + traj] = cy[d];
-                        } else if (P.rec_mode == REC_TSPAN_TM) {  // staged trajectory-major stream: row 0 = y0
+                        } else if (TM) {  // staged trajectory-major stream: row 0 = y0
                             sl.head = 0; sl.cnt = 0; sl.gpos = traj * P.nt * (unsigned long long)N;
 #pragma unroll
                             for (int d = 0; d < N; ++d) stage_append(stage, P.dense, sl, cy[d]);
@@ -412,7 +417,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
         // finishes inside a burst idles for at most BURST-1 attempts out of the ~10^3 its trajectory took. ----
 #pragma unroll 1
         for (int burst = 0; burst < BURST_ATTEMPTS && active; ++burst) {
-            if (MODE == MODE_DENSE && P.rec_mode == REC_TSPAN_TM) stage_drain(stage, P.dense, sl, false);
+            if (TM) stage_drain(stage, P.dense, sl, false);
             // one step attempt (loop body of problem.rs:260-352)
             uint8_t fin = 0xff;  // 0xff: keep going
             if (attempts >= max_steps) {
@@ -497,7 +502,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     } else {
                         F::eval(t + dt, ytrial, f1, prm);
                     }
-                    if (MODE == MODE_DENSE) {
+                    if (ROWS) {
                         // Points::All :303-319 — Hermite values at tspan points strictly inside (t, t+dt)
                         const double tn = t + dt;
                         while (it < P.nt) {
@@ -509,17 +514,17 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                                 const double v = (cy[d] * (1. - theta) + ytrial[d] * theta) +
                                                  ((ytrial[d] - cy[d]) * (1. - 2. * theta) + k[0][d] * (theta - 1.) * dt +
                                                   f1[d] * theta * dt) * theta * (theta - 1.);
-                                if (P.rec_mode == REC_TSPAN) P.dense[((unsigned long long)d * P.nt + it) * P.ntraj + traj] = v;
-                                else if (P.rec_mode == REC_TSPAN_TM) stage_append(stage, P.dense, sl, v);
-                                else if (P.rec_mode == REC_WRITE) P.rec_y[wpos * N + d] = v;
+                                if (SOA) P.dense[((unsigned long long)d * P.nt + it) * P.ntraj + traj] = v;
+                                else if (TM) stage_append(stage, P.dense, sl, v);
+                                else if (REC && P.rec_mode == REC_WRITE) P.rec_y[wpos * N + d] = v;
                             }
-                            if (P.rec_mode == REC_COUNT || P.rec_mode == REC_WRITE) {
+                            if (REC) {
                                 if (P.rec_mode == REC_WRITE) P.rec_t[wpos] = tq;
                                 ++wpos;
                             }
                             ++it;
                         }
-                        if (P.rec_mode == REC_COUNT || P.rec_mode == REC_WRITE) {  // "also store every step taken" (problem.rs:320-322)
+                        if (REC) {  // "also store every step taken" (problem.rs:320-322)
                             if (P.rec_mode == REC_WRITE) {
                                 P.rec_t[wpos] = tn;
 #pragma unroll
@@ -559,15 +564,15 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
 #pragma unroll
                 for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = cy[d];
                 P.accepted[traj] = acc; P.rejected[traj] = rej; P.nfe[traj] = nfe; P.status[traj] = fin; P.t_reached[traj] = t;
-                if (MODE == MODE_DENSE) {
-                    if (P.rec_mode == REC_TSPAN) {
+                if (ROWS) {
+                    if (SOA) {
 #pragma unroll
                         for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt + (P.nt - 1)) * P.ntraj + traj] = cy[d];
-                    } else if (P.rec_mode == REC_TSPAN_TM) {
+                    } else if (TM) {
                         stage_drain(stage, P.dense, sl, true);   // ends with a __syncwarp: the helpers' stores precede the row below
 #pragma unroll
                         for (int d = 0; d < N; ++d) P.dense[(traj * P.nt + (P.nt - 1)) * (unsigned long long)N + d] = cy[d];
-                    } else if (P.rec_mode == REC_COUNT) {
+                    } else if (REC && P.rec_mode == REC_COUNT) {
                         P.rec_counts[traj] = (uint32_t)(wpos - wbase);
                     }
                     P.nvalid[traj] = (uint32_t)it;
