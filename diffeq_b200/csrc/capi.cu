@@ -104,7 +104,7 @@ struct deq_result {
     bool all = false;
     uint32_t* d_rec_counts = nullptr;
     unsigned long long* d_rec_offsets = nullptr;
-    double *d_rec_t = nullptr, *d_rec_y = nullptr;
+    double* d_rec_rows = nullptr;  // rows [t, y...] interleaved, trajectory-major
     std::vector<unsigned long long> rec_offsets;  // [ntraj + 1], host
     unsigned long long* d_scalars = nullptr;  // [0] work counter, [1..3] totals
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -401,10 +401,9 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
             for (size_t i = 0; i < ntraj; ++i) r->rec_offsets[i + 1] = r->rec_offsets[i] + counts[i];
             const unsigned long long total = r->rec_offsets[ntraj];
             CKR(cudaMemcpyAsync(r->d_rec_offsets, r->rec_offsets.data(), (ntraj + 1) * 8, cudaMemcpyHostToDevice, st));
-            CKR(dalloc(&r->d_rec_t, total, st));
-            CKR(dalloc(&r->d_rec_y, total * n, st));
+            CKR(dalloc(&r->d_rec_rows, total * (n + 1), st));
             CKR(cudaMemsetAsync(r->d_scalars, 0, 4 * sizeof(unsigned long long), st));
-            P.rec_mode = deqk::REC_WRITE; P.rec_offsets = r->d_rec_offsets; P.rec_t = r->d_rec_t; P.rec_y = r->d_rec_y;
+            P.rec_mode = deqk::REC_WRITE; P.rec_offsets = r->d_rec_offsets; P.rec_rows = r->d_rec_rows;
             CKR(cudaEventRecord(r->ev0, st));
             rc = launch_adapt(&err);
             if (rc == 1) return bail(DEQ_ERR_CUDA);
@@ -512,11 +511,16 @@ deq_status deq_result_all_copy(deq_result* r, size_t b, size_t e, double* tout, 
     if (!r->all) return fail(DEQ_ERR_INVALID_ARG, "solve was not run with output = DEQ_OUT_ALL");
     if (b > e || e > r->ntraj) return fail(DEQ_ERR_INVALID_ARG, "trajectory range out of bounds");
     const unsigned long long r0 = r->rec_offsets[b], r1 = r->rec_offsets[e];
-    if (r1 > r0) {
-        CK(cudaMemcpyAsync(tout, r->d_rec_t + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, r->stream));
-        CK(cudaMemcpyAsync(yout, r->d_rec_y + r0 * r->n, (r1 - r0) * r->n * 8, cudaMemcpyDeviceToHost, r->stream));
+    if (r1 > r0) {  // device rows are [t, y...] interleaved (one staged stream per trajectory): split them for the caller
+        const size_t w = (size_t)r->n + 1, rows = (size_t)(r1 - r0);
+        std::vector<double> tmp(rows * w);
+        CK(cudaMemcpyAsync(tmp.data(), r->d_rec_rows + r0 * w, rows * w * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+        CK(cudaStreamSynchronize(r->stream));
+        for (size_t i = 0; i < rows; ++i) {
+            tout[i] = tmp[i * w];
+            for (int d = 0; d < r->n; ++d) yout[i * r->n + d] = tmp[i * w + 1 + d];
+        }
     }
-    CK(cudaStreamSynchronize(r->stream));
     return DEQ_OK;
 }
 
@@ -560,7 +564,7 @@ void deq_result_destroy(deq_result* r) {
     cudaStream_t st = r->stream;
     dfree(r->d_yfinal, st); dfree(r->d_acc, st); dfree(r->d_rej, st); dfree(r->d_nfe, st); dfree(r->d_nvalid, st);
     dfree(r->d_status, st); dfree(r->d_treached, st); dfree(r->d_dense, st); dfree(r->d_f0, st); dfree(r->d_h0, st);
-    dfree(r->d_scalars, st); dfree(r->d_rec_counts, st); dfree(r->d_rec_offsets, st); dfree(r->d_rec_t, st); dfree(r->d_rec_y, st);
+    dfree(r->d_scalars, st); dfree(r->d_rec_counts, st); dfree(r->d_rec_offsets, st); dfree(r->d_rec_rows, st);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
     delete r;

@@ -67,7 +67,7 @@ template <class F, bool PT, int MODE>
 static cudaError_t launch_adapt_t(const deqk::AdaptParams& P, int grid_blocks, cudaStream_t st) {
     if constexpr (TB::ADAPTIVE) {
         auto kernel = deqk::adapt_kernel<TB, F, PT, MODE, kFast>;
-        const size_t smem = MODE == deqk::MODE_DENSE_TM ? deqk::STAGE_BYTES : 0;
+        const size_t smem = (MODE == deqk::MODE_DENSE_TM || (MODE == deqk::MODE_REC && P.rec_mode == deqk::REC_WRITE)) ? deqk::STAGE_BYTES : 0;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int grid = grid_blocks > 0 ? grid_blocks : persistent_grid(kernel, P.ntraj, smem);
         kernel<<<grid, deqk::BLOCK, smem, st>>>(P);

@@ -184,7 +184,7 @@ bool launch_adapt(Program* p, int tb, int pt, int mode, bool fast, const deqk::A
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = mode == deqk::MODE_DENSE_TM ? 32u * deqk::BLOCK * sizeof(double) : 0;
+    const size_t smem = (mode == deqk::MODE_DENSE_TM || (mode == deqk::MODE_REC && P.rec_mode == deqk::REC_WRITE)) ? 32u * deqk::BLOCK * sizeof(double) : 0;
     int per_sm = k.blocks_per_sm;
     if (smem) {  // the staged layout lowers the resident-CTA count
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k.fn, deqk::BLOCK, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 2; }

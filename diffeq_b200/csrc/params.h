@@ -41,9 +41,8 @@ struct AdaptParams {
     uint32_t* nvalid;      // MODE_DENSE: number of leading tspan rows written (reference quirk)
     int rec_mode;          // MODE_REC: REC_COUNT / REC_WRITE
     uint32_t* rec_counts;  // REC_COUNT: rows of (tout, yout) the reference would produce, per trajectory
-    const unsigned long long* rec_offsets;  // REC_WRITE: first row of each trajectory in rec_t / rec_y
-    double* rec_t;         // REC_WRITE: tout, ragged, trajectory-major
-    double* rec_y;         // REC_WRITE: yout rows [N] (AoS like the reference's Vec<Y>)
+    const unsigned long long* rec_offsets;  // REC_WRITE: first row of each trajectory in rec_rows
+    double* rec_rows;      // REC_WRITE: rows [t, y_0 .. y_{N-1}] of all trajectories, ragged, trajectory-major (staged writes)
     unsigned long long* work_counter;  // zeroed before launch
     unsigned long long* totals;        // [3] += accepted, rejected, nfe over the ensemble
 };

@@ -395,13 +395,13 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                             sl.head = 0; sl.cnt = 0; sl.gpos = traj * P.nt * (unsigned long long)N;
 #pragma unroll
                             for (int d = 0; d < N; ++d) stage_append(stage, P.dense, sl, cy[d]);
-                        } else {  // ragged Points::All stream: row 0 = (t0, y0)
-                            wpos = P.rec_mode == REC_WRITE ? P.rec_offsets[traj] : 0ull;
-                            wbase = wpos;
+                        } else {  // ragged Points::All stream, rows [t, y...] interleaved and staged: row 0 = (t0, y0)
+                            wpos = 0ull; wbase = 0ull;
                             if (P.rec_mode == REC_WRITE) {
-                                P.rec_t[wpos] = t;
+                                sl.head = 0; sl.cnt = 0; sl.gpos = P.rec_offsets[traj] * (unsigned long long)(N + 1);
+                                stage_append(stage, P.rec_rows, sl, t);
 #pragma unroll
-                                for (int d = 0; d < N; ++d) P.rec_y[wpos * N + d] = cy[d];
+                                for (int d = 0; d < N; ++d) stage_append(stage, P.rec_rows, sl, cy[d]);
                             }
                             ++wpos;
                         }
@@ -418,6 +418,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
 #pragma unroll 1
         for (int burst = 0; burst < BURST_ATTEMPTS && active; ++burst) {
             if (TM) stage_drain(stage, P.dense, sl, false);
+            if (REC && P.rec_mode == REC_WRITE) stage_drain(stage, P.rec_rows, sl, false);
             // one step attempt (loop body of problem.rs:260-352)
             uint8_t fin = 0xff;  // 0xff: keep going
             if (attempts >= max_steps) {
@@ -509,6 +510,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                             const double tq = __ldg(P.tspan + it);
                             if (!(tdir * t < tdir * tq && tdir * tq < tdir * tn)) break;
                             const double theta = (tq - t) / dt;
+                            if (REC && P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, tq);
 #pragma unroll
                             for (int d = 0; d < N; ++d) {
                                 const double v = (cy[d] * (1. - theta) + ytrial[d] * theta) +
@@ -516,19 +518,16 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                                                   f1[d] * theta * dt) * theta * (theta - 1.);
                                 if (SOA) P.dense[((unsigned long long)d * P.nt + it) * P.ntraj + traj] = v;
                                 else if (TM) stage_append(stage, P.dense, sl, v);
-                                else if (REC && P.rec_mode == REC_WRITE) P.rec_y[wpos * N + d] = v;
+                                else if (REC && P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, v);
                             }
-                            if (REC) {
-                                if (P.rec_mode == REC_WRITE) P.rec_t[wpos] = tq;
-                                ++wpos;
-                            }
+                            if (REC) ++wpos;
                             ++it;
                         }
                         if (REC) {  // "also store every step taken" (problem.rs:320-322)
                             if (P.rec_mode == REC_WRITE) {
-                                P.rec_t[wpos] = tn;
+                                stage_append(stage, P.rec_rows, sl, tn);
 #pragma unroll
-                                for (int d = 0; d < N; ++d) P.rec_y[wpos * N + d] = ytrial[d];
+                                for (int d = 0; d < N; ++d) stage_append(stage, P.rec_rows, sl, ytrial[d]);
                             }
                             ++wpos;
                         }
@@ -574,6 +573,8 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                         for (int d = 0; d < N; ++d) P.dense[(traj * P.nt + (P.nt - 1)) * (unsigned long long)N + d] = cy[d];
                     } else if (REC && P.rec_mode == REC_COUNT) {
                         P.rec_counts[traj] = (uint32_t)(wpos - wbase);
+                    } else if (REC) {
+                        stage_drain(stage, P.rec_rows, sl, true);
                     }
                     P.nvalid[traj] = (uint32_t)it;
                 }
