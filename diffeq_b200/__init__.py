@@ -117,7 +117,7 @@ class _Options(C.Structure):
 
 # The symbols include/diffeq_b200.h declares (checked by tests/test_abi.py).
 ABI_SYMBOLS = [
-    "deq_last_error_message", "deq_version", "deq_rhs_builtin", "deq_rhs_from_source", "deq_rhs_dim",
+    "deq_last_error_message", "deq_version", "deq_abi_options_size", "deq_rhs_builtin", "deq_rhs_from_source", "deq_rhs_dim",
     "deq_rhs_nparams", "deq_rhs_destroy", "deq_tspan_linspace", "deq_ensemble_create", "deq_ensemble_create_device",
     "deq_ensemble_destroy", "deq_ensemble_ntraj", "deq_set_stream", "deq_set_device", "deq_get_device", "deq_solve_host", "deq_options_default", "deq_solve",
     "deq_result_final", "deq_result_counts", "deq_result_totals", "deq_result_dense", "deq_result_all_offsets",
@@ -139,8 +139,11 @@ def lib():
         L.deq_version.restype = C.c_char_p
         L.deq_options_default.restype = _Options
         L.deq_ensemble_ntraj.restype = C.c_size_t
+        L.deq_abi_options_size.restype = C.c_size_t
         for name in ABI_SYMBOLS:
             getattr(L, name)
+        if L.deq_abi_options_size() != C.sizeof(_Options):
+            raise ImportError("diffeq_b200: deq_options layout of the Python binding does not match the library")
         _lib = L
     return _lib
 

@@ -179,6 +179,7 @@ extern "C" {
 
 const char* deq_last_error_message(void) { return g_err.c_str(); }
 const char* deq_version(void) { return "diffeq_b200 0.1 (sm_100a)"; }
+size_t deq_abi_options_size(void) { return sizeof(deq_options); }
 
 deq_status deq_rhs_builtin(int system, deq_rhs** out) {
     if (!out) return fail(DEQ_ERR_INVALID_ARG, "out is NULL");

@@ -124,6 +124,8 @@ typedef struct deq_result deq_result;
 
 const char* deq_last_error_message(void);
 const char* deq_version(void);
+/* sizeof(deq_options) as compiled into the library: lets a foreign binding verify its struct layout. */
+size_t deq_abi_options_size(void);
 
 /* ---- right-hand side: replaces the closure `F: Fn(f64,&Y)->Y` (problem.rs:32-36) ---- */
 deq_status deq_rhs_builtin(int system /* deq_system */, deq_rhs** out);

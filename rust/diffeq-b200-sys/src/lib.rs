@@ -43,6 +43,7 @@ pub struct deq_options {
 extern "C" {
     pub fn deq_last_error_message() -> *const c_char;
     pub fn deq_version() -> *const c_char;
+    pub fn deq_abi_options_size() -> usize;
     pub fn deq_rhs_builtin(system: c_int, out: *mut *mut deq_rhs) -> deq_status;
     pub fn deq_rhs_from_source(cuda_src: *const c_char, n: c_int, nparams: c_int, out: *mut *mut deq_rhs) -> deq_status;
     pub fn deq_rhs_dim(rhs: *const deq_rhs) -> c_int;

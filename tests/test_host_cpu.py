@@ -153,3 +153,18 @@ def test_c_abi_is_c99_clean_and_links_from_c(deq):
                            "-L" + libdir, "-ldiffeq_b200", "-Wl,-rpath," + libdir, "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "ABI_VERSION" in out.stdout and ("ABI_OK" in out.stdout or "ABI_NO_GPU" in out.stdout), out.stdout
+
+
+def test_missing_extension_fails_loudly():
+    """No CPU fallback: with the shared library absent the package refuses to work (ImportError), it does not fall back."""
+    code = "import diffeq_b200 as D\ntry:\n    D.lib()\nexcept ImportError as e:\n    print('IMPORT_ERROR', 'no CPU fallback' in str(e))\n"
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT,
+                         env=dict(os.environ, DEQ_LIB="/nonexistent/libdiffeq_b200.so"))
+    assert "IMPORT_ERROR True" in out.stdout, out.stdout + out.stderr
+
+
+def test_binding_struct_layout_matches_library(deq):
+    import ctypes as C
+    assert deq.lib().deq_abi_options_size() == C.sizeof(deq._Options)
+    o = deq.lib().deq_options_default()
+    assert (o.max_steps, o.refill, o.mode, o.precision, o.libm, o.dense_layout, o.output) == (10_000_000, 1, 0, 0, 0, 0, 0)
