@@ -635,3 +635,32 @@ def test_full_size_config3_dense_slices(deq, oracle):
                 assert np.array_equal(nv, ref["nvalid"]) and np.array_equal(got[m], want[m]), (layout, b)
         finally:
             L.deq_result_destroy(res)
+
+
+def test_concurrent_handles_from_several_host_threads(deq, oracle):
+    """Distinct handles may be used concurrently from different threads (include/diffeq_b200.h threading contract): four
+    host threads solve four different ensembles at the same time; every result equals the oracle's."""
+    import threading
+    from diffeq_b200 import synth
+    jobs = [("Ode45", "Lorenz", synth.lorenz_ics(0, 3000), np.array(LOR), [0.0, 3.0], 1e-8),
+            ("Ode45fe", "VanDerPol", *synth.vdp_sweep(0, 2000, 2000), [0.0, 10.0], 1e-6),
+            ("Ode45", "Lorenz", synth.lorenz_ics(5000, 7000), np.array(LOR), [0.0, 2.0], 1e-6),
+            ("Ode78", "Pendulum", synth.pendulum_ics(0, 1500), synth.PENDULUM_PARAMS, [0.0, 5.0], 1e-10)]
+    out, errs = [None] * len(jobs), []
+
+    def run(i):
+        try:
+            m, s, y0, p, ts, tol = jobs[i]
+            for _ in range(3):
+                out[i] = _problem(deq, getattr(deq.System, s), p, y0, ts).solve(
+                    getattr(deq.Ode, m), deq.OdeOptionMap().insert(deq.Reltol(tol), deq.Abstol(tol)), tableau_set=1)
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for i, (m, s, y0, p, ts, tol) in enumerate(jobs):
+        ref = oracle.ensemble_adaptive(getattr(oracle, m.upper()), getattr(oracle, s.upper()), p, y0, ts, oracle.opts(tol, tol), 1)
+        assert np.array_equal(out[i].final, ref["yfinal"]) and np.array_equal(out[i].accepted, ref["accepted"]), i
