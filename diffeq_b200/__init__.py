@@ -343,6 +343,26 @@ class OdeProblem:
     def builder():
         return OdeBuilder()
 
+    @classmethod
+    def from_device(cls, rhs, d_y0_soa_ptr, ntraj, tspan, params=None, d_params_soa_ptr=None):
+        """Ensemble whose inputs are already resident on the current GPU in the library layout (`deq_ensemble_create_device`):
+        d_y0_soa_ptr -> f64 [n][ntraj]; per-trajectory parameters as a device pointer to [nparams][ntraj], or shared host
+        values in `params`.  The caller keeps the device buffers alive for the lifetime of the problem."""
+        self = cls.__new__(cls)
+        self._rhs, self._single = rhs, False
+        self.ntraj, self.n = int(ntraj), rhs.dim
+        self.tspan = _f64(tspan)
+        h = C.c_void_p()
+        if d_params_soa_ptr is not None:
+            pp, per = C.cast(C.c_void_p(int(d_params_soa_ptr)), C.POINTER(C.c_double)), 1
+        else:
+            self._params_host = _f64(params) if params is not None else None
+            pp, per = _ptr(self._params_host), 0
+        _check(lib().deq_ensemble_create_device(rhs._h, C.c_size_t(self.ntraj), C.cast(C.c_void_p(int(d_y0_soa_ptr)), C.POINTER(C.c_double)),
+                                                pp, per, _ptr(self.tspan), C.c_size_t(len(self.tspan)), C.byref(h)))
+        self._h = h
+        return self
+
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:
             _lib.deq_ensemble_destroy(self._h)

@@ -41,6 +41,19 @@ __device__ const double g_log_tab[256] = {DEQ_LOG_TAB_INIT};
 // per step attempt).  Not `const` on purpose, so the front end does not fold the values back into immediates.
 template <class TB>
 __constant__ deqt::Data<TB::S> c_tab = TB::data();
+
+// FAST mode: combined error weights b - b* (one FMA chain for the error estimate instead of two for p and q).
+template <int S_>
+struct ErrWeights { double e[S_]; };
+template <class TB>
+constexpr ErrWeights<TB::S> make_err_weights() {
+    ErrWeights<TB::S> w{};
+    constexpr auto d = TB::data();
+    for (int s = 0; s < TB::S; ++s) w.e[s] = d.b[s][0] - d.b[s][1];
+    return w;
+}
+template <class TB>
+__constant__ ErrWeights<TB::S> c_errw = make_err_weights<TB>();
 #ifndef DEQ_TAB_CONST
 #define DEQ_TAB_CONST 1
 #endif
@@ -473,7 +486,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
 #pragma unroll
                         for (int s = 0; s < S; ++s) {
                             if (tbc.b[s][0] != 0.0) p = __fma_rn(k[s][d], tb.b[s][0], p);
-                            if (tbc.b[s][0] - tbc.b[s][1] != 0.0) e = __fma_rn(k[s][d], tbc.b[s][0] - tbc.b[s][1], e);
+                            if (tbc.b[s][0] - tbc.b[s][1] != 0.0) e = __fma_rn(k[s][d], c_errw<TB>.e[s], e);
                         }
                         yerr[d] = e * dt;
                         ytrial[d] = __fma_rn(p, dt, cy[d]);

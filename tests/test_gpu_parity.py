@@ -664,3 +664,41 @@ def test_concurrent_handles_from_several_host_threads(deq, oracle):
     for i, (m, s, y0, p, ts, tol) in enumerate(jobs):
         ref = oracle.ensemble_adaptive(getattr(oracle, m.upper()), getattr(oracle, s.upper()), p, y0, ts, oracle.opts(tol, tol), 1)
         assert np.array_equal(out[i].final, ref["yfinal"]) and np.array_equal(out[i].accepted, ref["accepted"]), i
+
+
+def test_device_resident_inputs_and_outputs(deq, oracle):
+    """deq_ensemble_create_device / deq_result_device_ptrs: inputs and results stay on the GPU in the library's SoA layout
+    (here owned by torch tensors); values equal the oracle's."""
+    import ctypes as C
+    import torch
+    from diffeq_b200 import synth
+    n = 3001
+    y0v, mu = synth.vdp_sweep(0, n, n)
+    d_y0 = torch.from_numpy(np.ascontiguousarray(y0v.T)).cuda()          # [2][n]
+    d_mu = torch.from_numpy(np.ascontiguousarray(mu.T)).cuda()           # [1][n]
+    torch.cuda.synchronize()
+    rhs = deq.Rhs.builtin(deq.System.VanDerPol)
+    prob = deq.OdeProblem.from_device(rhs, d_y0.data_ptr(), n, [0.0, 20.0], d_params_soa_ptr=d_mu.data_ptr())
+    ref = oracle.ensemble_adaptive(oracle.ODE45FE, oracle.VANDERPOL, mu, y0v, [0.0, 20.0], oracle.opts(1e-6, 1e-8))
+    sol = prob.solve(deq.Ode.Ode45fe, deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8)))
+    assert np.array_equal(sol.final, ref["yfinal"]) and np.array_equal(sol.accepted, ref["accepted"])
+    # raw device view of the result
+    L = deq.lib()
+    o = deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8)).to_c()
+    res = C.c_void_p(); yf = C.POINTER(C.c_double)(); dn = C.POINTER(C.c_double)()
+    assert L.deq_solve(prob._h, int(deq.Ode.Ode45fe), 0, C.byref(o), C.byref(res)) == 0
+    try:
+        assert L.deq_result_device_ptrs(res, C.byref(yf), C.byref(dn)) == 0 and not dn
+        addr = C.cast(yf, C.c_void_p).value
+        rt = C.CDLL("libcudart.so.12")                      # any CUDA runtime can read the library's device buffer
+        host = np.empty((2, n))
+        assert rt.cudaMemcpy(host.ctypes.data_as(C.c_void_p), C.c_void_p(addr), C.c_size_t(2 * n * 8), 2) == 0
+        assert np.array_equal(host.T, ref["yfinal"])
+    finally:
+        L.deq_result_destroy(res)
+    # shared parameters variant
+    y0l = synth.lorenz_ics(0, 500)
+    d_l = torch.from_numpy(np.ascontiguousarray(y0l.T)).cuda()
+    pl = deq.OdeProblem.from_device(deq.Rhs.builtin(deq.System.Lorenz), d_l.data_ptr(), 500, [0.0, 1.0], params=LOR)
+    rl = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, y0l, [0.0, 1.0])
+    assert np.array_equal(pl.solve(deq.Ode.Ode45).final, rl["yfinal"])
