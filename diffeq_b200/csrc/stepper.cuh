@@ -455,20 +455,24 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                         yerr[d] = (p - q) * dt;
                         ytrial[d] = cy[d] + (p * dt);
                     }
-                    // stepsize_hw92 :801-845
-                    bool isnan_trial = false;
+                    // stepsize_hw92 :801-845.  The reference first scans the trial state for NaN (-> err = 10, dt *= 0.2,
+                    // timeout = 5).  A NaN trial component makes the scaled error sum NaN as well, so the scan only has to
+                    // run when the sum is NaN — one test on the hot path instead of N.
+                    double ssum = 0.0;
 #pragma unroll
-                    for (int d = 0; d < N; ++d) isnan_trial = isnan_trial || (ytrial[d] != ytrial[d]);
+                    for (int d = 0; d < N; ++d) {
+                        const double e = yerr[d] / (max_abs_nonan(cy[d], ytrial[d]) * reltol + abstol);
+                        const double a = fabs(e);
+                        ssum = ssum + a * a;
+                    }
+                    bool isnan_trial = false;
+                    if (ssum != ssum) {
+#pragma unroll
+                        for (int d = 0; d < N; ++d) isnan_trial = isnan_trial || (ytrial[d] != ytrial[d]);
+                    }
                     if (isnan_trial) {
                         accept = false; ndt = 0.2 * dt; timeout = 5;   // err = 10
                     } else {
-                        double ssum = 0.0;
-#pragma unroll
-                        for (int d = 0; d < N; ++d) {
-                            const double e = yerr[d] / (max_abs_nonan(cy[d], ytrial[d]) * reltol + abstol);
-                            const double a = fabs(e);
-                            ssum = ssum + a * a;
-                        }
                         const double err = P.libm_folded ? sqrt(ssum) : deqm::pow_glibc(ssum, 0.5, T);
                         const double g = deqm::pow_glibc(1.0 / err, PW, T) * 0.8;
                         double nd = sel_min(P.maxstep, (sel_max(0.2, g) * tdir) * dt);
