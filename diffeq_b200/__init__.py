@@ -531,9 +531,10 @@ def solve_host(rhs, y0, params, tspan, ode, opts=None, out_final=None, out_accep
     return out_final, out_accepted, out_rejected
 
 
-def solve_host_multi(rhs, y0, params, tspan, ode, opts=None, devices=None, tableau_set=TableauSet.Reference):
-    """`deq_solve_host`: one call on host buffers, sharded over `devices` (list of CUDA ordinals; None = current device) with
-    one host thread per GPU inside the library.  Returns dict(final, accepted, rejected, nfe, status, t_reached)."""
+def solve_host_multi(rhs, y0, params, tspan, ode, opts=None, devices=None, tableau_set=TableauSet.Reference, out=None):
+    """`deq_solve_host`: one C-ABI call on host buffers, sharded over `devices` (list of CUDA ordinals; None = current device)
+    with one host thread per GPU inside the library.  Returns dict(final, accepted, rejected, nfe, status, t_reached); pass
+    `out` (a dict of preallocated, ideally pinned, arrays with those keys) to avoid allocating the results per call."""
     L = lib()
     y0 = _f64(y0)
     if y0.ndim == 1:
@@ -544,10 +545,11 @@ def solve_host_multi(rhs, y0, params, tspan, ode, opts=None, devices=None, table
     o = (opts if opts is not None else OdeOptionMap()).to_c()
     per = int(params is not None and params.ndim == 2)
     dev = (C.c_int * len(devices))(*devices) if devices else None
-    out = dict(final=np.empty((ntraj, n)), accepted=np.zeros(ntraj, np.uint32), rejected=np.zeros(ntraj, np.uint32),
-               nfe=np.zeros(ntraj, np.uint32), status=np.zeros(ntraj, np.uint8), t_reached=np.zeros(ntraj))
+    if out is None:
+        out = dict(final=np.empty((ntraj, n)), accepted=np.zeros(ntraj, np.uint32), rejected=np.zeros(ntraj, np.uint32),
+                   nfe=np.zeros(ntraj, np.uint32), status=np.zeros(ntraj, np.uint8), t_reached=np.zeros(ntraj))
     _check(L.deq_solve_host(rhs._h, C.c_size_t(ntraj), _ptr(y0), _ptr(params), per, _ptr(tspan), C.c_size_t(len(tspan)), int(ode),
                             int(tableau_set), C.byref(o), dev, len(devices) if devices else 0, _ptr(out["final"]),
-                            _ptr(out["accepted"], C.c_uint32), _ptr(out["rejected"], C.c_uint32), _ptr(out["nfe"], C.c_uint32),
-                            _ptr(out["status"], C.c_uint8), _ptr(out["t_reached"])))
+                            _ptr(out.get("accepted"), C.c_uint32), _ptr(out.get("rejected"), C.c_uint32), _ptr(out.get("nfe"), C.c_uint32),
+                            _ptr(out.get("status"), C.c_uint8), _ptr(out.get("t_reached"))))
     return out
