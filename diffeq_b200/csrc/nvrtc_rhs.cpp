@@ -69,6 +69,11 @@ const char* tb_type(int tb) {
 
 struct Kernel { cudaLibrary_t lib = nullptr; cudaKernel_t fn = nullptr; int blocks_per_sm = 0; };
 
+// Process-wide cache of compiled kernels keyed by (user source, n, nparams, kernel instantiation): creating the same
+// right-hand side again — e.g. one deq_rhs per worker thread — does not recompile.  Entries live until process exit.
+std::mutex g_cache_mu;
+std::map<std::string, Kernel> g_cache;
+
 }  // namespace
 
 namespace deqn {
@@ -79,7 +84,7 @@ struct Program {
     int n = 0, np = 0;
     std::mutex mu;
     std::map<std::tuple<int, int, int, int>, Kernel> cache;  // (kind, tb, pt, mode)
-    ~Program() { for (auto& kv : cache) if (kv.second.lib) cudaLibraryUnload(kv.second.lib); }
+    // compiled libraries are owned by the process-wide cache, not by the Program
 };
 
 static bool compile(Program* p, const std::string& name_expr, bool fmad, Kernel* out, std::string* err) {
@@ -144,7 +149,18 @@ static bool get_kernel(Program* p, int kind, int tb, int pt, int mode, Kernel* o
                            << ((mode & 4) ? "true" : "false") << ">";
     else ne << "&deqk::fixed_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode ? "true" : "false") << ">";
     Kernel k;
-    if (!compile(p, ne.str(), kind == 1 && (mode & 4), &k, err)) return false;
+    const bool fmad = kind == 1 && (mode & 4);
+    const std::string gkey = std::to_string(p->n) + "|" + std::to_string(p->np) + "|" + ne.str() + (fmad ? "|fast|" : "|parity|") + p->user_src;
+    {
+        std::lock_guard<std::mutex> gg(g_cache_mu);
+        auto git = g_cache.find(gkey);
+        if (git != g_cache.end()) { p->cache[key] = git->second; *out = git->second; return true; }
+    }
+    if (!compile(p, ne.str(), fmad, &k, err)) return false;
+    {
+        std::lock_guard<std::mutex> gg(g_cache_mu);
+        g_cache[gkey] = k;
+    }
     p->cache[key] = k;
     *out = k;
     return true;

@@ -253,6 +253,29 @@ def test_nvrtc_user_rhs_matches_oracle(deq, oracle):
     assert np.array_equal(sd.nvalid, rd["nvalid"]) and np.array_equal(sd.yout[m], want[m])
 
 
+def test_nvrtc_same_source_reuses_compiled_kernel(deq):
+    """A second deq_rhs from the same source (the first one already destroyed) hits the process-wide kernel cache:
+    same results, and the second solve is not slowed by a recompile."""
+    import time
+    from diffeq_b200 import synth
+    y0 = synth.lorenz_ics(3, 256)
+    o = deq.OdeOptionMap().insert(deq.Reltol(1e-7), deq.Abstol(1e-9))
+
+    def run():
+        rhs = deq.Rhs.from_source(USER_LORENZ + "// cache-test\n", 3, 3)
+        t0 = time.perf_counter()
+        s = deq.OdeProblem.builder().fun(rhs).params(LOR).init(y0).tspan([0.0, 2.0]).build().solve(deq.Ode.Ode23, o)
+        dt = time.perf_counter() - t0
+        fin = s.final.copy()
+        del s, rhs
+        return fin, dt
+
+    a, ta = run()
+    b, tb = run()
+    assert np.array_equal(a, b)
+    assert tb < 0.5 * ta, (ta, tb)      # first call pays the NVRTC compile (hundreds of ms), the second does not
+
+
 def test_nvrtc_compile_error_is_reported(deq):
     with pytest.raises(deq.OdeError) as e:
         deq.Rhs.from_source("__device__ void rhs(double t, const double* y, double* dy, const double* p) { dy[0] = undefined_symbol; }", 1, 0)
