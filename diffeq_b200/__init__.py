@@ -122,7 +122,7 @@ ABI_SYMBOLS = [
     "deq_ensemble_destroy", "deq_ensemble_ntraj", "deq_set_stream", "deq_set_device", "deq_get_device", "deq_solve_host", "deq_options_default", "deq_solve",
     "deq_result_final", "deq_result_counts", "deq_result_totals", "deq_result_dense", "deq_result_all_offsets",
     "deq_result_all_copy", "deq_result_device_ptrs",
-    "deq_result_trajectory", "deq_result_kernel_ms", "deq_result_destroy", "deq_tableau_get", "deq_host_alloc",
+    "deq_result_trajectory", "deq_result_kernel_ms", "deq_result_destroy", "deq_tableau_get", "deq_rosenbrock_get", "deq_host_alloc",
     "deq_host_free", "deq_test_pow", "deq_test_log10", "deq_measure_fp64_peak",
 ]
 
@@ -186,6 +186,26 @@ def tableau(method, tableau_set=TableauSet.Reference):
     s = S.value
     return dict(S=s, a=a[:s * s].reshape(s, s).copy(), b=b[:2 * s].reshape(s, 2).copy(), c=c[:s].copy(),
                 adaptive=bool(ad.value), order_min=om.value, fsal=bool(fs.value))
+
+
+STIFF = (Ode.Ode23s, Ode.Ode4skr, Ode.Ode4ss)
+
+
+def _traits(method, tableau_set=TableauSet.Reference):
+    """(adaptive, has_counters, stiff) of a method.  The stiff members of `Ode` (problem.rs:139,143-144) have no Butcher
+    tableau; ode23s is adaptive, oderosenbrock walks the tspan grid but can stop a trajectory (InvalidMatrix)."""
+    method = Ode(int(method))
+    if method in STIFF:
+        return method == Ode.Ode23s, True, True
+    ad = tableau(method, tableau_set)["adaptive"]
+    return ad, ad, False
+
+
+def rosenbrock_coeffs(method):
+    """`RosenbrockCoeffs::kr4()` / `s4()` (rosenbrock.rs:14-118) as the kernels hold them."""
+    g = C.c_double(); a = np.zeros(16); b = np.zeros(4); c = np.zeros(16)
+    _check(lib().deq_rosenbrock_get(int(method), C.byref(g), _ptr(a), _ptr(b), _ptr(c)))
+    return dict(gamma=g.value, a=a.reshape(4, 4), b=b, c=c.reshape(4, 4))
 
 
 def measure_fp64_peak():
@@ -376,11 +396,12 @@ class OdeProblem:
         L = lib()
         _check(L.deq_solve(self._h, int(ode), int(tableau_set), C.byref(o), C.byref(res)))
         try:
-            return self._collect(res, o, fetch, tableau(ode, tableau_set)["adaptive"])
+            return self._collect(res, o, fetch, _traits(ode, tableau_set))
         finally:
             L.deq_result_destroy(res)
 
-    def _collect(self, res, o, fetch, adaptive):
+    def _collect(self, res, o, fetch, traits):
+        adaptive, has_counts, stiff = traits
         L = lib()
         sol = OdeSolution()
         ms = C.c_float()
@@ -395,7 +416,7 @@ class OdeProblem:
         sol.final = np.empty((self.ntraj, self.n))
         if self.ntraj and not (nt == 0):
             _check(L.deq_result_final(res, _ptr(sol.final)))
-        if adaptive and nt > 0:
+        if has_counts and nt > 0:
             sol.accepted = np.empty(self.ntraj, np.uint32); sol.rejected = np.empty(self.ntraj, np.uint32)
             sol.nfe = np.empty(self.ntraj, np.uint32); sol.status = np.empty(self.ntraj, np.uint8)
             sol.t_reached = np.empty(self.ntraj)
@@ -409,19 +430,22 @@ class OdeProblem:
             sol.yout_flat = np.empty((rows, self.n))
             _check(L.deq_result_all_copy(res, C.c_size_t(0), C.c_size_t(self.ntraj), _ptr(sol.tout_flat), _ptr(sol.yout_flat)))
         if o.output == Output.Tspan and nt > 0:
-            tm = o.dense_layout == DenseLayout.TrajMajor and adaptive
+            tm = o.dense_layout == DenseLayout.TrajMajor and adaptive and not stiff
             dense = np.full((self.ntraj, nt, self.n) if tm else (self.n, nt, self.ntraj), np.nan)
             nv = np.empty(self.ntraj, np.uint32)
             _check(L.deq_result_dense(res, C.c_size_t(0), C.c_size_t(self.ntraj), _ptr(dense), _ptr(nv, C.c_uint32)))
             idx = np.arange(nt)[:, None]
-            invalid = (idx >= nv[None, :]) & (idx != nt - 1)
+            invalid = idx >= nv[None, :]
+            if not stiff:   # oderk_adapt always pushes the end point as the last row (problem.rs:320-322)
+                invalid &= idx != nt - 1
             if tm:
                 dense[invalid.T] = np.nan
                 sol.yout = dense
             else:
                 dense[:, invalid] = np.nan
                 sol.yout = np.ascontiguousarray(dense.transpose(2, 1, 0))
-            sol.tout = self.tspan.copy()
+            # oderosenbrock returns `tout: diff(tspan)` (problem.rs:572,639 — sic, one element short of yout)
+            sol.tout = np.diff(self.tspan) if (stiff and not adaptive) else self.tspan.copy()
             sol.nvalid = nv
         return sol
 
@@ -435,6 +459,9 @@ class OdeProblem:
     def ode45_dp(self, opts=None, **kw): return self.solve(Ode.Ode45, opts, **kw)
     def ode45_fe(self, opts=None, **kw): return self.solve(Ode.Ode45fe, opts, **kw)
     def ode78(self, opts=None, **kw): return self.solve(Ode.Ode78, opts, **kw)
+    def ode23s(self, opts=None, **kw): return self.solve(Ode.Ode23s, opts, **kw)     # problem.rs:409
+    def ode4s_kr(self, opts=None, **kw): return self.solve(Ode.Ode4skr, opts, **kw)  # problem.rs:643
+    def ode4s_s(self, opts=None, **kw): return self.solve(Ode.Ode4ss, opts, **kw)    # problem.rs:648
 
 
 class OdeBuilder:
@@ -499,7 +526,7 @@ def solve_host(rhs, y0, params, tspan, ode, opts=None, out_final=None, out_accep
     tspan = _f64(tspan)
     o = (opts if opts is not None else OdeOptionMap()).to_c()
     per = int(params is not None and params.ndim == 2)
-    adaptive = tableau(ode, tableau_set)["adaptive"]
+    adaptive = _traits(ode, tableau_set)[1]
     ens = C.c_void_p(); res = C.c_void_p()
     _check(L.deq_ensemble_create(rhs._h, C.c_size_t(ntraj), _ptr(y0), _ptr(params), per, _ptr(tspan),
                                  C.c_size_t(len(tspan)), C.byref(ens)))

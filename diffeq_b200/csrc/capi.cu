@@ -62,6 +62,11 @@ int tb_of(int method, int set) {
 
 double signum(double x) { return std::isnan(x) ? x : std::copysign(1.0, x); }  // f64::signum
 
+// Stiff members of the `Ode` enum (mod.rs:14-26; problem.rs:139,143-144): 1 ode23s, 2 oderosenbrock kr4, 3 oderosenbrock s4.
+int stiff_kind(int method) {
+    switch (method) { case DEQ_ODE23S: return 1; case DEQ_ODE4SKR: return 2; case DEQ_ODE4SS: return 3; default: return 0; }
+}
+
 }  // namespace
 
 namespace deql {
@@ -93,6 +98,7 @@ struct deq_result {
     size_t ntraj = 0, nt = 0;
     int n = 0;
     bool fixed = false, dense = false, traj_major = false;
+    bool rosen = false;  // oderosenbrock: a fixed-grid solve that still carries per-trajectory counters and status
     cudaStream_t stream = nullptr;
     double* d_yfinal = nullptr;
     uint32_t *d_acc = nullptr, *d_rej = nullptr, *d_nfe = nullptr, *d_nvalid = nullptr;
@@ -277,13 +283,28 @@ deq_options deq_options_default(void) {
     return o;
 }
 
+// (method, set) -> tableau id + description.  The stiff methods have no Butcher tableau: ode23s is described as an adaptive
+// 3-stage FSAL scheme whose hinit order is 3 (problem.rs:435), oderosenbrock as a 4-stage fixed-grid scheme.
+static deq_status resolve_method(int method, int tableau_set, int* tb, int* sk, deql::TableauInfo* info) {
+    *tb = tb_of(method, tableau_set);
+    *sk = stiff_kind(method);
+    if (*tb < 0 && !*sk) return fail(DEQ_ERR_INVALID_ARG, "unknown method");
+    if (*sk) {
+        std::memset(info, 0, sizeof(*info));
+        info->S = *sk == 1 ? 3 : 4; info->adaptive = *sk == 1; info->order_min = 3; info->fsal = *sk == 1;
+    } else {
+        g_tb[*tb].info(info);
+    }
+    return DEQ_OK;
+}
+
 deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_options* opts_in, deq_result** out) {
     if (!e || !out) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
     if (tableau_set != DEQ_TABLEAU_REFERENCE && tableau_set != DEQ_TABLEAU_TEXTBOOK)
         return fail(DEQ_ERR_INVALID_ARG, "unknown tableau set");
-    const int tb = tb_of(method, tableau_set);
-    if (tb == -1) return fail(DEQ_ERR_UNSUPPORTED, "stiff (Rosenbrock) methods are not part of the RK hot path");
-    if (tb < 0) return fail(DEQ_ERR_INVALID_ARG, "unknown method");
+    int tb = -2, sk = 0;
+    deql::TableauInfo info;
+    if (deq_status ms = resolve_method(method, tableau_set, &tb, &sk, &info)) return ms;
     const deq_options o = opts_in ? *opts_in : deq_options_default();
     if (o.mode != DEQ_MODE_PARITY && o.mode != DEQ_MODE_FAST) return fail(DEQ_ERR_INVALID_ARG, "unknown arithmetic mode");
     if (o.precision != DEQ_PRECISION_F64 && o.precision != DEQ_PRECISION_F32) return fail(DEQ_ERR_INVALID_ARG, "unknown precision");
@@ -293,12 +314,21 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         return fail(DEQ_ERR_UNSUPPORTED, "the trajectory-major dense layout is implemented for the f64 kernels");
     if (o.precision == DEQ_PRECISION_F32 && (e->rhs.kind != 0 || o.output == DEQ_OUT_ALL))
         return fail(DEQ_ERR_UNSUPPORTED, "the f32 mode covers the built-in systems with FINAL / TSPAN output");
-    ensure_pool();
-    deql::TableauInfo info;
-    g_tb[tb].info(&info);
-    cudaStream_t st = g_stream;
     const int n = e->rhs.n;
     const size_t ntraj = e->ntraj, nt = e->nt;
+    if (sk) {
+        if (n > 3) return fail(DEQ_ERR_UNSUPPORTED, "the stiff solvers carry systems of dimension <= 3 (closed-form try_inverse; see stiff.cuh)");
+        if (o.precision != DEQ_PRECISION_F64) return fail(DEQ_ERR_UNSUPPORTED, "the stiff solvers are f64 only");
+        if (o.output == DEQ_OUT_TSPAN && o.dense_layout != DEQ_LAYOUT_SOA) return fail(DEQ_ERR_UNSUPPORTED, "the stiff solvers write tspan rows in the SoA layout");
+        if (o.points != DEQ_POINTS_ALL && o.points != DEQ_POINTS_SPECIFIED) return fail(DEQ_ERR_INVALID_ARG, "unknown points kind");
+        // ode23s rescans the whole tspan on every accepted step (problem.rs:519); the kernel walks a cursor instead, which
+        // emits the same rows only if the grid is monotone
+        bool up = true, down = true;
+        for (size_t i = 0; i + 1 < nt; ++i) { up = up && e->tspan[i] <= e->tspan[i + 1]; down = down && e->tspan[i] >= e->tspan[i + 1]; }
+        if (sk == 1 && o.output != DEQ_OUT_FINAL && !(up || down)) return fail(DEQ_ERR_INVALID_ARG, "ode23s row output needs a monotone tspan");
+    }
+    ensure_pool();
+    cudaStream_t st = g_stream;
     const bool want_dense = o.output == DEQ_OUT_TSPAN;
     const bool want_all = o.output == DEQ_OUT_ALL;
     if (o.output != DEQ_OUT_FINAL && !want_dense && !want_all) return fail(DEQ_ERR_INVALID_ARG, "unknown output kind");
@@ -323,7 +353,8 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
     if (!info.adaptive && want_all)
         return bail(fail(DEQ_ERR_INVALID_ARG, "fixed-step methods output exactly the tspan rows: use DEQ_OUT_TSPAN"));
     if (!info.adaptive) {
-        // ---- oderk_fixed ----
+        // ---- oderk_fixed / oderosenbrock ----
+        if (nt == 0 && sk) { *out = r; r->ntraj = 0; return DEQ_OK; }  // problem.rs:567-570: nothing to solve
         if (nt == 0) return bail(fail(DEQ_ERR_INVALID_ARG, "fixed-step methods need a non-empty tspan (the reference panics, problem.rs:377)"));
         CKR(dalloc(&r->d_yfinal, ntraj * n, st));
         if (want_dense) CKR(dalloc(&r->d_dense, ntraj * n * nt, st));
@@ -331,18 +362,26 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         P.y0 = e->d_y0; P.params = e->d_params; P.shared = e->shared; P.tspan = e->d_tspan; P.nt = nt; P.ntraj = ntraj;
         P.yfinal = r->d_yfinal; P.yall = r->d_dense;
         r->fixed_nfe_per_traj = (uint64_t)info.S * (nt - 1);
+        if (sk) {  // a Rosenbrock step can stop a trajectory (InvalidMatrix): per-trajectory bookkeeping like the adaptive path
+            r->rosen = true;
+            CKR(dalloc(&r->d_acc, ntraj, st)); CKR(dalloc(&r->d_rej, ntraj, st)); CKR(dalloc(&r->d_nfe, ntraj, st));
+            CKR(dalloc(&r->d_status, ntraj, st)); CKR(dalloc(&r->d_treached, ntraj, st)); CKR(dalloc(&r->d_nvalid, ntraj, st));
+            P.accepted = r->d_acc; P.rejected = r->d_rej; P.nfe = r->d_nfe; P.status = r->d_status; P.t_reached = r->d_treached;
+            P.nvalid = r->d_nvalid; P.totals = r->d_scalars + 1;
+        }
         CKR(cudaEventRecord(r->ev0, st));
         if (ntraj) {
-            if (e->rhs.kind == 0) CKR(g_tb[tb].fixed(e->rhs.sys, e->per_traj, want_dense ? 1 : 0, P, st));
-            else {
-                std::string err;
-                if (!deqn::launch_fixed(e->rhs.prog, tb, e->per_traj, want_dense ? 1 : 0, P, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
-            }
+            std::string err;
+            if (sk) {
+                if (e->rhs.kind == 0) CKR(deql::launch_rosenbrock(sk - 2, e->rhs.sys, e->per_traj, want_dense ? 1 : 0, P, st));
+                else if (!deqn::launch_rosenbrock(e->rhs.prog, sk - 2, e->per_traj, want_dense ? 1 : 0, P, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
+            } else if (e->rhs.kind == 0) CKR(g_tb[tb].fixed(e->rhs.sys, e->per_traj, want_dense ? 1 : 0, P, st));
+            else if (!deqn::launch_fixed(e->rhs.prog, tb, e->per_traj, want_dense ? 1 : 0, P, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
         }
         CKR(cudaEventRecord(r->ev1, st));
     } else {
         // ---- oderk_adapt ----
-        if (o.points != DEQ_POINTS_ALL)
+        if (!sk && o.points != DEQ_POINTS_ALL)
             return bail(fail(DEQ_ERR_UNSUPPORTED, "Points::Specified re-reads y from the output vector in the reference (problem.rs:262) and yields wrong trajectories; use DEQ_POINTS_ALL with output = DEQ_OUT_TSPAN"));
         if (nt == 0) { *out = r; r->ntraj = 0; return DEQ_OK; }  // problem.rs:211-214: nothing to solve
         if (want_dense && nt < 2) return bail(fail(DEQ_ERR_INVALID_ARG, "DEQ_OUT_TSPAN needs at least 2 tspan points"));
@@ -350,7 +389,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         const double t0 = e->tspan[0], tend = e->tspan[nt - 1];
         const double tdir = signum(tend - t0);
         if (tdir == 0.) return bail(fail(DEQ_ERR_ZERO_TIMESPAN, "Zero time span is not allowed"));
-        if (o.initstep != 0. && !(std::fabs(signum(o.initstep) - tdir) < DBL_EPSILON))
+        if (!sk && o.initstep != 0. && !(std::fabs(signum(o.initstep) - tdir) < DBL_EPSILON))   // ode23s takes |initstep| (problem.rs:443)
             return bail(fail(DEQ_ERR_INVALID_INITSTEP, "Initial step has wrong sign"));
         CKR(dalloc(&r->d_yfinal, ntraj * n, st));
         CKR(dalloc(&r->d_acc, ntraj, st)); CKR(dalloc(&r->d_rej, ntraj, st)); CKR(dalloc(&r->d_nfe, ntraj, st));
@@ -372,12 +411,19 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         P.yfinal = r->d_yfinal; P.accepted = r->d_acc; P.rejected = r->d_rej; P.nfe = r->d_nfe; P.status = r->d_status;
         P.t_reached = r->d_treached; P.dense = r->d_dense; P.nvalid = r->d_nvalid;
         P.work_counter = r->d_scalars; P.totals = r->d_scalars + 1;
+        P.true_inverse = sk && tableau_set == DEQ_TABLEAU_TEXTBOOK; P.points_specified = o.points == DEQ_POINTS_SPECIFIED;
         const int mode = want_all ? deqk::MODE_REC
                          : want_dense ? (o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR ? deqk::MODE_DENSE_TM : deqk::MODE_DENSE) : deqk::MODE_FINAL;
         P.rec_mode = deqk::REC_COUNT;
         r->traj_major = want_dense && o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR;
         P.rec_counts = r->d_rec_counts;
         auto launch_adapt = [&](std::string* err) -> int {  // 0 ok, 1 cuda error (g_err set), 2 nvrtc error
+            if (sk) {  // ode23s: one arithmetic flavour (DEQ_MODE_FAST runs the same kernel)
+                if (e->rhs.kind != 0) return deqn::launch_ode23s(e->rhs.prog, e->per_traj, mode, P, st, err) ? 0 : 2;
+                cudaError_t ce = deql::launch_ode23s(e->rhs.sys, e->per_traj, mode, P, st);
+                if (ce != cudaSuccess) { fail(DEQ_ERR_CUDA, std::string("ode23s kernel launch: ") + cudaGetErrorString(ce)); return 1; }
+                return 0;
+            }
             if (e->rhs.kind == 0) {
                 deql::AdaptLaunchFn fn = o.precision == DEQ_PRECISION_F32 ? g_tb[tb].adapt_f32 : o.mode == DEQ_MODE_FAST ? g_tb[tb].adapt_fast : g_tb[tb].adapt;
                 cudaError_t ce = fn(e->rhs.sys, e->per_traj, mode, P, 0, st);
@@ -410,17 +456,13 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
             if (rc == 1) return bail(DEQ_ERR_CUDA);
             if (rc == 2) return bail(fail(DEQ_ERR_NVRTC, err));
         } else if (ntraj) {
-            if (e->rhs.kind == 0) {
-                CKR(deql::launch_hinit(e->rhs.sys, e->per_traj, H, st));
-                CKR(cudaEventRecord(r->ev0, st));
-                deql::AdaptLaunchFn fn = o.precision == DEQ_PRECISION_F32 ? g_tb[tb].adapt_f32 : o.mode == DEQ_MODE_FAST ? g_tb[tb].adapt_fast : g_tb[tb].adapt;
-                CKR(fn(e->rhs.sys, e->per_traj, mode, P, 0, st));
-            } else {
-                std::string err;
-                if (!deqn::launch_hinit(e->rhs.prog, e->per_traj, H, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
-                CKR(cudaEventRecord(r->ev0, st));
-                if (!deqn::launch_adapt(e->rhs.prog, tb, e->per_traj, mode, o.mode == DEQ_MODE_FAST, P, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
-            }
+            std::string err;
+            if (e->rhs.kind == 0) CKR(deql::launch_hinit(e->rhs.sys, e->per_traj, H, st));
+            else if (!deqn::launch_hinit(e->rhs.prog, e->per_traj, H, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
+            CKR(cudaEventRecord(r->ev0, st));
+            const int rc = launch_adapt(&err);
+            if (rc == 1) return bail(DEQ_ERR_CUDA);
+            if (rc == 2) return bail(fail(DEQ_ERR_NVRTC, err));
         } else {
             CKR(cudaEventRecord(r->ev0, st));
         }
@@ -448,7 +490,7 @@ deq_status deq_result_final(deq_result* r, double* y) {
 deq_status deq_result_counts(deq_result* r, uint32_t* accepted, uint32_t* rejected, uint32_t* nfe, uint8_t* status,
                              double* t_reached) {
     if (!r) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
-    if (r->fixed) return fail(DEQ_ERR_INVALID_ARG, "fixed-step solves carry no per-trajectory counters");
+    if (r->fixed && !r->rosen) return fail(DEQ_ERR_INVALID_ARG, "fixed-step solves carry no per-trajectory counters");
     if (r->ntraj == 0) return DEQ_OK;
     const size_t n = r->ntraj;
     if (accepted) CK(cudaMemcpyAsync(accepted, r->d_acc, n * 4, cudaMemcpyDeviceToHost, r->stream));
@@ -467,7 +509,7 @@ deq_status deq_result_totals(deq_result* r, uint64_t* accepted, uint64_t* reject
         CK(cudaMemcpyAsync(h, r->d_scalars, sizeof(h), cudaMemcpyDeviceToHost, r->stream));
         CK(cudaStreamSynchronize(r->stream));
     }
-    if (r->fixed) {  // every trajectory takes nt-1 steps of S evaluations
+    if (r->fixed && !r->rosen) {  // every trajectory takes nt-1 steps of S evaluations
         h[1] = (unsigned long long)r->ntraj * (r->nt ? r->nt - 1 : 0); h[2] = 0; h[3] = r->fixed_nfe_per_traj * r->ntraj;
     }
     if (accepted) *accepted = h[1];
@@ -493,7 +535,7 @@ deq_status deq_result_dense(deq_result* r, size_t b, size_t e, double* out, uint
     CK(cudaMemcpy2DAsync(out, w * sizeof(double), r->d_dense + b, r->ntraj * sizeof(double), w * sizeof(double),
                          (size_t)r->n * r->nt, cudaMemcpyDeviceToHost, r->stream));
     if (nvalid) {
-        if (r->fixed) { CK(cudaStreamSynchronize(r->stream)); for (size_t i = 0; i < w; ++i) nvalid[i] = (uint32_t)r->nt; }
+        if (r->fixed && !r->rosen) { CK(cudaStreamSynchronize(r->stream)); for (size_t i = 0; i < w; ++i) nvalid[i] = (uint32_t)r->nt; }
         else CK(cudaMemcpyAsync(nvalid, r->d_nvalid + b, w * 4, cudaMemcpyDeviceToHost, r->stream));
     }
     CK(cudaStreamSynchronize(r->stream));
@@ -590,7 +632,8 @@ deq_status deq_solve_host(const deq_rhs* rhs, size_t ntraj, const double* y0, co
     if (devices && ndevices > 0) devs.assign(devices, devices + ndevices); else devs.push_back(cur);
     const size_t nd = devs.size(), n = (size_t)rhs->n, np = (size_t)rhs->np;
     deql::TableauInfo info;
-    { const int tb = tb_of(method, tableau_set); if (tb == -1) return fail(DEQ_ERR_UNSUPPORTED, "stiff (Rosenbrock) methods are not part of the RK hot path"); if (tb < 0) return fail(DEQ_ERR_INVALID_ARG, "unknown method"); g_tb[tb].info(&info); }
+    int sk = 0;
+    { int tb = -2; if (deq_status ms = resolve_method(method, tableau_set, &tb, &sk, &info)) return ms; }
     std::vector<deq_status> rc(nd, DEQ_OK);
     std::vector<std::string> msg(nd);
     auto work = [&](size_t k) {
@@ -605,7 +648,7 @@ deq_status deq_solve_host(const deq_rhs* rhs, size_t ntraj, const double* y0, co
         if (s) { bad(s); return; }
         s = deq_solve(ens, method, tableau_set, &o, &res);
         if (!s && e > b && ntspan) s = deq_result_final(res, yfinal + b * n);
-        if (!s && info.adaptive && e > b && ntspan)
+        if (!s && (info.adaptive || sk) && e > b && ntspan)
             s = deq_result_counts(res, accepted ? accepted + b : nullptr, rejected ? rejected + b : nullptr, nfe ? nfe + b : nullptr,
                                   status ? status + b : nullptr, t_reached ? t_reached + b : nullptr);
         if (s) bad(s);
@@ -628,7 +671,7 @@ deq_status deq_solve_host(const deq_rhs* rhs, size_t ntraj, const double* y0, co
 deq_status deq_tableau_get(int method, int set, int* stages, double* a, double* b, double* c, int* adaptive,
                            int* order_min, int* fsal) {
     const int tb = tb_of(method, set);
-    if (tb == -1) return fail(DEQ_ERR_UNSUPPORTED, "stiff (Rosenbrock) methods are not part of the RK hot path");
+    if (tb == -1) return fail(DEQ_ERR_UNSUPPORTED, "the stiff methods have no Butcher tableau (see deq_rosenbrock_get)");
     if (tb < 0) return fail(DEQ_ERR_INVALID_ARG, "unknown method");
     deql::TableauInfo info;
     g_tb[tb].info(&info);
@@ -639,6 +682,18 @@ deq_status deq_tableau_get(int method, int set, int* stages, double* a, double* 
     if (a) std::memcpy(a, info.a, sizeof(double) * info.S * info.S);
     if (b) std::memcpy(b, info.b, sizeof(double) * info.S * 2);
     if (c) std::memcpy(c, info.c, sizeof(double) * info.S);
+    return DEQ_OK;
+}
+
+deq_status deq_rosenbrock_get(int method, double* gamma, double* a, double* b, double* c) {
+    const int sk = stiff_kind(method);
+    if (sk < 2) return fail(DEQ_ERR_INVALID_ARG, "deq_rosenbrock_get takes DEQ_ODE4SKR or DEQ_ODE4SS");
+    double g = 0., aa[16], bb[4], cc[16];
+    deql::rosenbrock_info(sk - 2, &g, aa, bb, cc);
+    if (gamma) *gamma = g;
+    if (a) std::memcpy(a, aa, sizeof(aa));
+    if (b) std::memcpy(b, bb, sizeof(bb));
+    if (c) std::memcpy(c, cc, sizeof(cc));
     return DEQ_OK;
 }
 

@@ -37,6 +37,11 @@ DEQ_DECL_TB(0) DEQ_DECL_TB(1) DEQ_DECL_TB(2) DEQ_DECL_TB(3) DEQ_DECL_TB(4) DEQ_D
 DEQ_DECL_TB(7) DEQ_DECL_TB(8) DEQ_DECL_TB(9) DEQ_DECL_TB(10) DEQ_DECL_TB(11) DEQ_DECL_TB(12)
 #undef DEQ_DECL_TB
 
+// stiff solvers (kernels_stiff.cu): ode23s, and oderosenbrock with `which` = 0 kr4 (Ode4skr) / 1 s4 (Ode4ss)
+cudaError_t launch_ode23s(int sys, int per_traj_params, int mode, const deqk::AdaptParams& P, cudaStream_t st);
+cudaError_t launch_rosenbrock(int which, int sys, int per_traj_params, int all, const deqk::FixedParams& P, cudaStream_t st);
+void rosenbrock_info(int which, double* gamma, double* a /*[16]*/, double* b /*[4]*/, double* c /*[16]*/);
+
 // hinit pre-pass and small helpers live in kernels_common.cu
 cudaError_t launch_hinit(int sys, int per_traj_params, const deqk::HinitParams& P, cudaStream_t st);
 cudaError_t launch_transpose_to_soa(const double* d_aos, double* d_soa, unsigned long long ntraj, int n, cudaStream_t st);

@@ -87,7 +87,7 @@ struct Program {
     // compiled libraries are owned by the process-wide cache, not by the Program
 };
 
-static bool compile(Program* p, const std::string& name_expr, bool fmad, Kernel* out, std::string* err) {
+static bool compile(Program* p, const std::string& name_expr, bool fmad, Kernel* out, std::string* err, bool stiff = false) {
     Nvrtc* rt = nvrtc(err);
     if (!rt) return false;
     std::ostringstream src;
@@ -95,7 +95,7 @@ static bool compile(Program* p, const std::string& name_expr, bool fmad, Kernel*
         << "__device__ void rhs(double t, const double* y, double* dy, const double* p);\n"
         << "#include \"rhs.cuh\"\n"
         << "#line 1 \"user_rhs.cu\"\n" << p->user_src << "\n#line 1 \"deq_user_glue.cu\"\n"
-        << "#include \"stepper.cuh\"\n"
+        << (stiff ? "#include \"stiff.cuh\"\n" : "#include \"stepper.cuh\"\n")
         << "struct DeqUserRhs {\n  static constexpr int N = DEQ_USER_N, NP = DEQ_USER_NP;\n"
         << "  static constexpr bool USES_SINCOS = true;  // user code may call deq_sin / deq_cos (3.5 KB of shared memory)\n"
         << "  __device__ __forceinline__ static void eval(double t, const double* y, double* dy, const double* p) { rhs(t, y, dy, p); }\n};\n";
@@ -147,7 +147,9 @@ static bool get_kernel(Program* p, int kind, int tb, int pt, int mode, Kernel* o
     if (kind == 0) ne << "&deqk::hinit_kernel<DeqUserRhs, " << b << ">";
     else if (kind == 1) ne << "&deqk::adapt_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode & 3) << ", "
                            << ((mode & 4) ? "true" : "false") << ">";
-    else ne << "&deqk::fixed_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode ? "true" : "false") << ">";
+    else if (kind == 2) ne << "&deqk::fixed_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode ? "true" : "false") << ">";
+    else if (kind == 3) ne << "&deqk::ode23s_kernel<DeqUserRhs, " << b << ", " << (mode & 3) << ">";
+    else ne << "&deqk::rosenbrock_kernel<" << (tb == 0 ? "deqk::Kr4" : "deqk::S4") << ", DeqUserRhs, " << b << ", " << (mode ? "true" : "false") << ">";
     Kernel k;
     const bool fmad = kind == 1 && (mode & 4);
     const std::string gkey = std::to_string(p->n) + "|" + std::to_string(p->np) + "|" + ne.str() + (fmad ? "|fast|" : "|parity|") + p->user_src;
@@ -156,7 +158,7 @@ static bool get_kernel(Program* p, int kind, int tb, int pt, int mode, Kernel* o
         auto git = g_cache.find(gkey);
         if (git != g_cache.end()) { p->cache[key] = git->second; *out = git->second; return true; }
     }
-    if (!compile(p, ne.str(), fmad, &k, err)) return false;
+    if (!compile(p, ne.str(), fmad, &k, err, kind >= 3)) return false;
     {
         std::lock_guard<std::mutex> gg(g_cache_mu);
         g_cache[gkey] = k;
@@ -212,6 +214,26 @@ bool launch_adapt(Program* p, int tb, int pt, int mode, bool fast, const deqk::A
 bool launch_fixed(Program* p, int tb, int pt, int all, const deqk::FixedParams& P, cudaStream_t st, std::string* err) {
     Kernel k;
     if (!get_kernel(p, 2, tb, pt ? 1 : 0, all ? 1 : 0, &k, err)) return false;
+    return launch(k, (unsigned)((P.ntraj + deqk::BLOCK - 1) / deqk::BLOCK), P, st, err);
+}
+
+static unsigned persistent_blocks(const Kernel& k, unsigned long long ntraj) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned long long want = (ntraj + deqk::BLOCK - 1) / deqk::BLOCK, cap = (unsigned long long)sms * k.blocks_per_sm;
+    return (unsigned)(want < cap ? (want ? want : 1) : cap);
+}
+
+bool launch_ode23s(Program* p, int pt, int mode, const deqk::AdaptParams& P, cudaStream_t st, std::string* err) {
+    Kernel k;
+    if (!get_kernel(p, 3, 0, pt ? 1 : 0, mode & 3, &k, err)) return false;
+    return launch(k, persistent_blocks(k, P.ntraj), P, st, err);
+}
+
+bool launch_rosenbrock(Program* p, int which, int pt, int all, const deqk::FixedParams& P, cudaStream_t st, std::string* err) {
+    Kernel k;
+    if (!get_kernel(p, 4, which, pt ? 1 : 0, all ? 1 : 0, &k, err)) return false;
     return launch(k, (unsigned)((P.ntraj + deqk::BLOCK - 1) / deqk::BLOCK), P, st, err);
 }
 

@@ -9,7 +9,8 @@ namespace deqk {
 enum : int { MODE_FINAL = 0, MODE_DENSE = 1, MODE_DENSE_TM = 2, MODE_REC = 3 };   // kernel template parameter
 // the two passes of a MODE_REC kernel (the reference's full ragged Points::All stream): count rows, then write them
 enum : int { REC_COUNT = 1, REC_WRITE = 2 };
-enum : uint8_t { ST_DONE = 0, ST_MINSTEP_BREAK = 1, ST_MAX_STEPS = 2 };
+enum : uint8_t { ST_DONE = 0, ST_MINSTEP_BREAK = 1, ST_MAX_STEPS = 2,
+                 ST_INVALID_MATRIX = 3 };   // stiff path: try_inverse() failed (the reference's OdeError::InvalidMatrix)
 
 #ifndef DEQ_BLOCK
 #define DEQ_BLOCK 128
@@ -45,6 +46,9 @@ struct AdaptParams {
     double* rec_rows;      // REC_WRITE: rows [t, y_0 .. y_{N-1}] of all trajectories, ragged, trajectory-major (staged writes)
     unsigned long long* work_counter;  // zeroed before launch
     unsigned long long* totals;        // [3] += accepted, rejected, nfe over the ensemble
+    // ode23s only (stiff.cuh)
+    int true_inverse;      // TEXTBOOK set: invert W = I - h d J itself, not its packed LU factors (problem.rs:469,481)
+    int points_specified;  // Points::Specified: MODE_REC rows are the tspan points only (problem.rs:536)
 };
 
 struct HinitParams {
@@ -61,6 +65,9 @@ struct FixedParams {
     const double* tspan; unsigned long long nt; unsigned long long ntraj;
     double* yfinal;   // [N][ntraj]
     double* yall;     // [N][nt][ntraj] or nullptr
+    // oderosenbrock only (stiff.cuh): per-trajectory bookkeeping, a step can stop a trajectory (InvalidMatrix)
+    uint32_t* accepted; uint32_t* rejected; uint32_t* nfe; uint8_t* status; double* t_reached; uint32_t* nvalid;
+    unsigned long long* totals;
 };
 
 }  // namespace deqk

@@ -1,0 +1,421 @@
+// stiff.cuh — the stiff solvers of the `Ode` enum, one trajectory per thread:
+//   ode23s_kernel      modified Rosenbrock triple, adaptive      /root/reference/src/ode/problem.rs:409-557
+//   rosenbrock_kernel  4-stage Rosenbrock on the tspan grid      /root/reference/src/ode/problem.rs:560-640
+//                      (coefficient sets rosenbrock.rs:16-68 kr4, :71-117 s4)
+//   fdjacobian         forward-difference Jacobian               /root/reference/src/ode/problem.rs:903-926
+//
+// Same parity contract as stepper.cuh: IEEE f64, -fmad=false, the reference's operation order.  The n x n linear
+// algebra of the reference goes through nalgebra 0.20 (DMatrix operators, lu(), try_inverse()); it is restated here for
+// n <= 3 with every matrix in registers (all indices are compile-time after unrolling):
+//   * M * v             column-ordered accumulation  y = M[:,0] v0;  y = M[:,j] v_j + y
+//   * lu()              partial pivoting on the first largest |.|, multipliers a_ji * (1 / pivot), exactly-zero pivot
+//                       columns skipped; only the packed factors survive (`lu_internal()`), the permutation is dropped
+//   * try_inverse()     adjugate formulas for n = 1, 2, 3; a zero determinant is the reference's OdeError::InvalidMatrix
+//                       (per-trajectory status ST_INVALID_MATRIX here)
+// The reference inverts the PACKED LU matrix of W = I - h d J rather than W (problem.rs:469,481); that is what the
+// REFERENCE set reproduces.  P.true_inverse (TEXTBOOK set) inverts W itself — Shampine & Reichelt's method.
+#pragma once
+#include "stepper.cuh"
+
+namespace deqk {
+
+template <int N>
+__device__ __forceinline__ void na_gemv(const double (&m)[N][N], const double (&v)[N], double (&y)[N]) {
+#pragma unroll
+    for (int r = 0; r < N; ++r) y[r] = m[r][0] * v[0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) {
+#pragma unroll
+        for (int r = 0; r < N; ++r) y[r] = m[r][j] * v[j] + y[r];
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void na_lu_packed(double (&m)[N][N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        int piv = i;
+        double best = fabs(m[i][i]);
+#pragma unroll
+        for (int r = i + 1; r < N; ++r) { const double v = fabs(m[r][i]); if (v > best) { best = v; piv = r; } }
+        // swap rows i and piv (all columns: the ones left of i by swap_rows, the rest inside gauss_step_swap)
+#pragma unroll
+        for (int r = i + 1; r < N; ++r) {
+            if (piv == r) {
+#pragma unroll
+                for (int c = 0; c < N; ++c) { const double tmp = m[i][c]; m[i][c] = m[r][c]; m[r][c] = tmp; }
+            }
+        }
+        const double diag = m[i][i];
+        if (diag != 0.0) {
+            const double inv = 1.0 / diag;
+#pragma unroll
+            for (int r = i + 1; r < N; ++r) m[r][i] = m[r][i] * inv;
+#pragma unroll
+            for (int k = i + 1; k < N; ++k) {
+                const double a = -m[i][k];
+#pragma unroll
+                for (int r = i + 1; r < N; ++r) m[r][k] = a * m[r][i] + m[r][k];
+            }
+        }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ bool na_try_inverse(const double (&m)[N][N], double (&o)[N][N]) {
+    static_assert(N >= 1 && N <= 3, "the stiff path carries n <= 3 (closed-form try_inverse)");
+    if constexpr (N == 1) {
+        const double det = m[0][0];
+        if (det == 0.0) return false;
+        o[0][0] = 1.0 / det;
+    } else if constexpr (N == 2) {
+        const double m11 = m[0][0], m12 = m[0][1], m21 = m[1][0], m22 = m[1][1];
+        const double det = m11 * m22 - m21 * m12;
+        if (det == 0.0) return false;
+        o[0][0] = m22 / det; o[0][1] = -m12 / det; o[1][0] = -m21 / det; o[1][1] = m11 / det;
+    } else {
+        const double m11 = m[0][0], m12 = m[0][1], m13 = m[0][2], m21 = m[1][0], m22 = m[1][1], m23 = m[1][2],
+                     m31 = m[2][0], m32 = m[2][1], m33 = m[2][2];
+        const double minor_m12_m23 = m22 * m33 - m32 * m23;
+        const double minor_m11_m23 = m21 * m33 - m31 * m23;
+        const double minor_m11_m22 = m21 * m32 - m31 * m22;
+        const double det = m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22;
+        if (det == 0.0) return false;
+        o[0][0] = minor_m12_m23 / det; o[0][1] = (m13 * m32 - m33 * m12) / det; o[0][2] = (m12 * m23 - m22 * m13) / det;
+        o[1][0] = -minor_m11_m23 / det; o[1][1] = (m11 * m33 - m31 * m13) / det; o[1][2] = (m13 * m21 - m23 * m11) / det;
+        o[2][0] = minor_m11_m22 / det; o[2][1] = (m12 * m31 - m32 * m11) / det; o[2][2] = (m11 * m22 - m21 * m12) / det;
+    }
+    return true;
+}
+
+// fdjacobian (problem.rs:903-926).  `ftx` = f(t, x): the reference evaluates it again at the top of fdjacobian; every
+// caller here already holds that very value (same t, same x, a deterministic f), so it is passed in.
+template <class F>
+__device__ __forceinline__ void fdjacobian(double t, const double (&x)[F::N], const double (&ftx)[F::N], const double* prm,
+                                           double (&J)[F::N][F::N]) {
+    constexpr int N = F::N;
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        double xj = x[c];
+        if (xj == 0.0) xj += 1.0;
+        const double dxj = xj * 0.01;
+        double tmp[N], yj[N];
+#pragma unroll
+        for (int d = 0; d < N; ++d) tmp[d] = x[d];
+        tmp[c] += dxj;
+        F::eval(t, tmp, yj, prm);
+#pragma unroll
+        for (int r = 0; r < N; ++r) J[r][c] = (yj[r] - ftx[r]) / dxj;
+    }
+}
+
+template <int N, class TT>
+__device__ __forceinline__ double pnorm2(const double (&v)[N], int libm_folded, const TT& T) {   // types.rs:109-115, P(2)
+    double s = 0.0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) { const double a = fabs(v[d]); s = s + a * a; }
+    return libm_folded ? sqrt(s) : deqm::pow_glibc(s, 0.5, T);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ode23s (problem.rs:409-557).  Persistent lanes re-filled from a global counter like adapt_kernel.  MODE_FINAL: loop
+// state at exit; MODE_DENSE: the rows the reference pushes for the tspan times, SoA [N][nt][ntraj]; MODE_REC: the full
+// (tout, yout) stream, rows [t, y...], counting pass then writing pass.  The reference rescans the whole tspan on every
+// accepted step (:519); for a monotone tspan a cursor yields the same rows (capi.cu rejects a non-monotone one).
+// ---------------------------------------------------------------------------------------------------------------
+template <class F, bool PT, int MODE>
+__global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
+    constexpr int N = F::N;
+    constexpr bool SOA = MODE == MODE_DENSE, REC = MODE == MODE_REC, ROWS = MODE != MODE_FINAL;
+    static_assert(MODE != MODE_DENSE_TM, "the stiff path writes SoA rows");
+    constexpr double SQ2 = 1.4142135623730951;      // 2f64.sqrt()
+    constexpr double D = 1. / (2. + SQ2);
+    constexpr double E32 = 6. + SQ2;
+
+    __shared__ uint64_t s_exp[256];
+    __shared__ double s_powlog[384];
+    for (int i = threadIdx.x; i < 256; i += BLOCK) s_exp[i] = g_exp_tab[i];
+    for (int i = threadIdx.x; i < 384; i += BLOCK) s_powlog[i] = g_powlog_tab[i];
+    if (F::USES_SINCOS) deqm::sincos_stage();
+    __syncthreads();
+    const deqm::SmemTables T{(unsigned)__cvta_generic_to_shared(s_exp), (unsigned)__cvta_generic_to_shared(s_powlog), 0u};
+
+    const unsigned lane = threadIdx.x & 31u;
+    const double tdir = P.tdir, tfinal = P.tend, reltol = P.reltol, abstol = P.abstol;
+    const uint32_t max_steps = P.max_steps == 0ull || P.max_steps > 0xffffffffull ? 0xffffffffu : (uint32_t)P.max_steps;
+
+    bool active = false, pool_empty = false;
+    unsigned long long traj = 0, it = 1, wpos = 0;
+    double t = 0.0, h = 0.0, tlast = 0.0;
+    double y[N], f0[N], jac[N][N], prm[F::NP ? F::NP : 1];
+    uint32_t acc = 0, rej = 0, attempts = 0, nv = 1;
+    unsigned long long tot_acc = 0, tot_rej = 0, tot_nfe = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        y[d] = 0.0; f0[d] = 0.0;
+#pragma unroll
+        for (int c = 0; c < N; ++c) jac[d][c] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < (F::NP ? F::NP : 1); ++j) prm[j] = 0.0;
+
+    auto emit = [&](double tq, const double (&v)[N]) {   // one REC row
+        if (P.rec_mode == REC_WRITE) {
+            double* row = P.rec_rows + (P.rec_offsets[traj] + wpos) * (unsigned long long)(N + 1);
+            row[0] = tq;
+#pragma unroll
+            for (int d = 0; d < N; ++d) row[1 + d] = v[d];
+        }
+        ++wpos;
+    };
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle != 0u && !pool_empty && (P.refill || idle == 0xffffffffu)) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + (unsigned long long)__popc(idle) >= P.ntraj) pool_empty = true;
+            if (!active) {
+                const unsigned long long my = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
+                if (my < P.ntraj) {
+                    traj = my;
+                    active = true;
+                    load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
+#pragma unroll
+                    for (int d = 0; d < N; ++d) {
+                        y[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
+                        f0[d] = P.f0[(unsigned long long)d * P.ntraj + traj];   // init.f0 (:435-441)
+                    }
+                    t = P.t0;
+                    const double hh = P.use_initstep ? P.initstep : P.h0[traj];
+                    h = tdir * fmin(fabs(hh), P.maxstep);                      // :443
+                    acc = 0; rej = 0; attempts = 0; it = 1; wpos = 0; nv = 1; tlast = t;
+                    if (SOA) {
+#pragma unroll
+                        for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt) * P.ntraj + traj] = y[d];
+                    }
+                    if (REC) emit(t, y);
+                    fdjacobian<F>(t, y, f0, prm, jac);                         // :454
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) break;
+
+#pragma unroll 1
+        for (int burst = 0; burst < BURST_ATTEMPTS && active; ++burst) {
+            uint8_t fin = 0xff;
+            bool invalid = false;
+            const double rem = fabs(t - tfinal);
+            if (!(rem > 0.)) {
+                fin = ST_DONE;
+            } else if (!(P.minstep < fabs(h))) {
+                fin = ST_MINSTEP_BREAK;           // the while condition :462 ends the loop before tfinal, silently
+            } else if (attempts >= max_steps) {
+                fin = ST_MAX_STEPS;
+            } else {
+                ++attempts;
+                if (rem < fabs(h)) h = tfinal - t;
+                const double hd = h * D;
+                double w[N][N];
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+#pragma unroll
+                    for (int c = 0; c < N; ++c) w[r][c] = (r == c ? 1.0 : 0.0) - jac[r][c] * hd;
+                }
+                if (N != 1 && !P.true_inverse) na_lu_packed<N>(w);
+                double fdt[N];
+                F::eval(t + h / 100., y, fdt, prm);
+                const double sc = hd / (h / 100.);
+#pragma unroll
+                for (int i = 0; i < N; ++i) fdt[i] = (fdt[i] - f0[i]) * sc;
+                double winv[N][N];
+                if (!na_try_inverse<N>(w, winv)) {
+                    fin = ST_INVALID_MATRIX; invalid = true;
+                } else {
+                    double rhs[N], k1[N], k2[N], k3[N], f1[N], f2[N], ynew[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) rhs[i] = f0[i] + fdt[i];
+                    na_gemv<N>(winv, rhs, k1);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) rhs[i] = y[i] + (k1[i] * 0.5) * h;
+                    F::eval(t + 0.5 * h, rhs, f1, prm);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) rhs[i] = f1[i] - k1[i];
+                    na_gemv<N>(winv, rhs, k2);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) { k2[i] = k2[i] + k1[i]; ynew[i] = y[i] + k2[i] * h; }
+                    const double tn = t + h;
+                    F::eval(tn, ynew, f2, prm);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) rhs[i] = ((f2[i] - (k2[i] - f1[i]) * E32) - (k1[i] - f0[i]) * 2.) + fdt[i];
+                    na_gemv<N>(winv, rhs, k3);
+                    double kerr[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) kerr[i] = (k1[i] - k2[i] * 2.) + k3[i];
+                    const double err = pnorm2<N>(kerr, P.libm_folded, T) * (fabs(h) / 6.);
+                    const double delta = fmax(fmax(pnorm2<N>(y, P.libm_folded, T), pnorm2<N>(ynew, P.libm_folded, T)) * reltol, abstol);
+                    if (err <= delta) {
+                        acc += 1;
+                        if (ROWS) {
+                            while (it < P.nt) {                                  // :519-534
+                                const double tq = __ldg(P.tspan + it);
+                                if (tq <= t) { ++it; continue; }                 // can never satisfy `toi > t` again
+                                if (!(tq <= tn)) break;
+                                const double s = (tq - t) / h;
+                                const double c1 = (s * (1. - s)) / (1. - 2. * D);
+                                const double c2 = (s * (s - 2. * D)) / (1. - 2. * D);
+                                double ytmp[N];
+#pragma unroll
+                                for (int i = 0; i < N; ++i) ytmp[i] = y[i] + (k1[i] * c1 + k2[i] * c2) * h;
+                                if (SOA) {
+#pragma unroll
+                                    for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt + it) * P.ntraj + traj] = ytmp[d];
+                                    nv = (uint32_t)it + 1u;
+                                }
+                                if (REC) emit(tq, ytmp);
+                                tlast = tq;
+                                ++it;
+                            }
+                            if (REC && !P.points_specified && fabs(tlast - tn) > DBL_EPSILON) { emit(tn, ynew); tlast = tn; }   // :536-542
+                        }
+                        t = tn;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) { y[i] = ynew[i]; f0[i] = f2[i]; }
+                        fdjacobian<F>(t, y, f0, prm, jac);                       // :549
+                    } else {
+                        rej += 1;
+                    }
+                    const double r = delta / err;
+                    h = fmin(P.maxstep, (deqm::pow_glibc(r, 1. / 3., T) * fabs(h)) * 0.8) * tdir;   // :552-553
+                }
+            }
+            if (fin != 0xff) {
+                // evaluations the reference performs: hinit 2 (1 with an explicit initstep), N+1 per Jacobian, 3 per attempt
+                const uint32_t nfe = (P.use_initstep ? 1u : 2u) + (uint32_t)(N + 1) * (1u + acc) + 3u * (attempts - (invalid ? 1u : 0u)) + (invalid ? 1u : 0u);
+#pragma unroll
+                for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = y[d];
+                P.accepted[traj] = acc; P.rejected[traj] = rej; P.nfe[traj] = nfe; P.status[traj] = fin; P.t_reached[traj] = t;
+                if (ROWS) P.nvalid[traj] = SOA ? nv : (uint32_t)it;
+                if (REC && P.rec_mode == REC_COUNT) P.rec_counts[traj] = (uint32_t)wpos;
+                tot_acc += acc; tot_rej += rej; tot_nfe += nfe;
+                active = false;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tot_acc += __shfl_down_sync(0xffffffffu, tot_acc, o);
+        tot_rej += __shfl_down_sync(0xffffffffu, tot_rej, o);
+        tot_nfe += __shfl_down_sync(0xffffffffu, tot_nfe, o);
+    }
+    if (lane == 0) {
+        atomicAdd(P.totals + 0, tot_acc); atomicAdd(P.totals + 1, tot_rej); atomicAdd(P.totals + 2, tot_nfe);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// oderosenbrock (problem.rs:560-640): one step per tspan interval, hs = tspan[i+1] - tspan[i].  Reference quirks kept:
+// `.take(i - 1)` (:614) leaves the newest stage out of the a/c sums, the c-term is added AFTER the multiplication with
+// the inverse (:620-625), and `b` doubles as the time nodes (:593,623).  With these the scheme is not the textbook
+// Kaps-Rentrop/Shampine method and diverges on ordinary problems; it is reproduced, not repaired.
+// ---------------------------------------------------------------------------------------------------------------
+struct RosenbrockCoeffs { double gamma, a[4][4], b[4], c[4][4]; };
+struct Kr4 {   // rosenbrock.rs:16-68 (Matrix4::new takes its arguments row-major: a[i][j] = a[(i, j)])
+    static constexpr RosenbrockCoeffs data() {
+        return RosenbrockCoeffs{0.231,
+            {{0., 0., 0., 0.}, {2., 0., 0., 0.}, {4.452470820736, 4.16352878860, 0., 0.}, {4.452470820736, 4.16352878860, 0., 0.}},
+            {3.95750374663, 4.62489238836, 0.617477263873, 1.2826129456},
+            {{0., 0., 0., 0.}, {-5.07167533877, 0., 0., 0.}, {6.02015272865, 0.1597500684673, 0., 0.}, {-1.856343618677, -8.50538085819, -2.08407513602, 0.0}}};
+    }
+};
+struct S4 {    // rosenbrock.rs:71-117
+    static constexpr RosenbrockCoeffs data() {
+        return RosenbrockCoeffs{0.5,
+            {{0., 0., 0., 0.}, {2., 0., 0., 0.}, {48. / 25., 6. / 250., 0., 0.}, {48. / 25., 6. / 250., 0., 0.}},
+            {19. / 9., 1. / 2., 25. / 108., 125. / 108.},
+            {{0., 0., 0., 0.}, {-8., 0., 0., 0.}, {372. / 25., 12. / 5., 0., 0.}, {-112. / 125., -54. / 125., -2. / 5., 0.}}};
+    }
+};
+
+template <class RC, class F, bool PT, bool ALL>
+__global__ void __launch_bounds__(BLOCK) rosenbrock_kernel(const FixedParams P) {
+    constexpr int N = F::N;
+    constexpr RosenbrockCoeffs co = RC::data();
+    if (F::USES_SINCOS) { deqm::sincos_stage(); __syncthreads(); }
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long traj = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;
+    unsigned long long steps = 0, nfe = 0;
+    if (traj < P.ntraj) {
+        double prm[F::NP ? F::NP : 1];
+        load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
+        double x[N];
+#pragma unroll
+        for (int d = 0; d < N; ++d) x[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
+        if (ALL) {
+#pragma unroll
+            for (int d = 0; d < N; ++d) P.yall[((unsigned long long)d * P.nt) * P.ntraj + traj] = x[d];
+        }
+        uint8_t st = ST_DONE;
+        double ts = P.nt ? __ldg(P.tspan) : 0.0;
+        for (unsigned long long i = 0; i + 1 < P.nt; ++i) {
+            const double tnext = __ldg(P.tspan + i + 1);
+            const double hs = tnext - ts;
+            double ftx[N], dfdx[N][N], jac[N][N], jinv[N][N];
+            F::eval(ts, x, ftx, prm);
+            fdjacobian<F>(ts, x, ftx, prm, dfdx);
+            nfe += N + 1;
+            const double dg = 1. / (co.gamma * hs);
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+#pragma unroll
+                for (int c = 0; c < N; ++c) jac[r][c] = (r == c ? dg : 0.0) - dfdx[r][c];
+            }
+            if (!na_try_inverse<N>(jac, jinv)) { st = ST_INVALID_MATRIX; break; }
+            double g[4][N], fx[N], nx[N];
+            F::eval(ts + co.b[0] * hs, x, fx, prm);
+            na_gemv<N>(jinv, fx, g[0]);
+#pragma unroll
+            for (int d = 0; d < N; ++d) nx[d] = x[d] + g[0][d] * co.b[0];
+#pragma unroll
+            for (int s = 1; s < 4; ++s) {
+                double dx[N], df[N], xa[N];
+#pragma unroll
+                for (int d = 0; d < N; ++d) { dx[d] = 0.0; df[d] = 0.0; }
+#pragma unroll
+                for (int j = 0; j < s - 1; ++j) {
+#pragma unroll
+                    for (int d = 0; d < N; ++d) { dx[d] = dx[d] + g[j][d] * co.a[s][j]; df[d] = df[d] + g[j][d] * co.c[s][j]; }
+                }
+#pragma unroll
+                for (int d = 0; d < N; ++d) xa[d] = x[d] + dx[d];
+                F::eval(ts + co.b[s] * hs, xa, fx, prm);
+                na_gemv<N>(jinv, fx, g[s]);
+                const double ih = 1. / hs;
+#pragma unroll
+                for (int d = 0; d < N; ++d) { g[s][d] = g[s][d] + df[d] * ih; nx[d] = nx[d] + g[s][d] * co.b[s]; }
+            }
+            nfe += 4;
+#pragma unroll
+            for (int d = 0; d < N; ++d) x[d] = nx[d];
+            if (ALL) {
+#pragma unroll
+                for (int d = 0; d < N; ++d) P.yall[((unsigned long long)d * P.nt + (i + 1)) * P.ntraj + traj] = x[d];
+            }
+            ++steps;
+            ts = tnext;
+        }
+#pragma unroll
+        for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = x[d];
+        P.accepted[traj] = (uint32_t)steps; P.rejected[traj] = 0u; P.nfe[traj] = (uint32_t)nfe; P.status[traj] = st;
+        P.t_reached[traj] = ts; P.nvalid[traj] = (uint32_t)(P.nt ? steps + 1 : 0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        steps += __shfl_down_sync(0xffffffffu, steps, o);
+        nfe += __shfl_down_sync(0xffffffffu, nfe, o);
+    }
+    if (lane == 0) { atomicAdd(P.totals + 0, steps); atomicAdd(P.totals + 2, nfe); }
+}
+
+}  // namespace deqk

@@ -7,7 +7,7 @@ reference's messages.
 """
 import json
 
-from . import Ode, OdeOptionMap, OdeProblem, Output, Rhs, System, tableau
+from . import Ode, OdeOptionMap, OdeProblem, Output, Rhs, System, _traits
 from .synth import LORENZ_PARAMS
 
 
@@ -28,7 +28,7 @@ def solve_lorenz_attractor(config_json):
         raise ValueError(f"Can't solve for {len(init)} dimensional type")   # lib.rs:46-51
     problem = (OdeProblem.builder().tspan_linspace(start, end, num).fun(Rhs.builtin(System.Lorenz))
                .params(LORENZ_PARAMS).init(init).build())            # lib.rs:53-58
-    adaptive = tableau(ode)["adaptive"]                              # raises Unsupported for the stiff methods
+    adaptive = _traits(ode)[0]                                       # ode23s included; oderosenbrock is grid-stepped
     opts = OdeOptionMap().insert(Output.All if adaptive else Output.Tspan)   # Default::default() options, Points::All
     sol = problem.solve(ode, opts)
     if adaptive:

@@ -32,10 +32,11 @@ typedef enum deq_status {
     DEQ_ERR_NAN = 3,               /* OdeError::NAN (never produced by the RK path) */
     DEQ_ERR_ZERO_TIMESPAN = 4,     /* OdeError::ZeroTimeSpan (unreachable for f64: signum(0) == 1) */
     DEQ_ERR_INVALID_INITSTEP = 5,  /* OdeError::InvalidInitstep (problem.rs:232-237) */
-    DEQ_ERR_INVALID_MATRIX = 6,    /* OdeError::InvalidMatrix (Rosenbrock only) */
+    DEQ_ERR_INVALID_MATRIX = 6,    /* OdeError::InvalidMatrix (problem.rs:481,588).  In an ensemble the failing trajectory
+                                      stops with DEQ_TRAJ_INVALID_MATRIX and deq_solve itself succeeds */
     DEQ_ERR_CUDA = 7,
     DEQ_ERR_NVRTC = 8,
-    DEQ_ERR_UNSUPPORTED = 9,       /* Ode23s / Ode4skr / Ode4ss: stiff path, not built yet */
+    DEQ_ERR_UNSUPPORTED = 9,       /* a combination this build does not carry (e.g. stiff methods with n > 3) */
     DEQ_ERR_INVALID_ARG = 10
 } deq_status;
 
@@ -46,13 +47,16 @@ typedef enum deq_method {
 } deq_method;
 
 /* Which coefficients the adaptive tableaus use: REFERENCE = bug-for-bug runge_kutta.rs:231-817,
- * TEXTBOOK = corrected rk21 / rk23 / dopri5 c[3] / feh78. */
+ * TEXTBOOK = corrected rk21 / rk23 / dopri5 c[3] / feh78.  For DEQ_ODE23S: REFERENCE inverts the packed LU factors of
+ * W = I - h d J like problem.rs:469,481 does; TEXTBOOK inverts W itself (Shampine & Reichelt's ode23s). */
 typedef enum deq_tableau_set { DEQ_TABLEAU_REFERENCE = 0, DEQ_TABLEAU_TEXTBOOK = 1 } deq_tableau_set;
 
 typedef enum deq_system { DEQ_SYS_LORENZ = 0, DEQ_SYS_VANDERPOL = 1, DEQ_SYS_PENDULUM = 2 } deq_system;
 
-/* `Points` (src/ode/options.rs:120-137).  Only Points::All is reference-valid (Specified re-reads y from the
- * output vector, problem.rs:262) and is rejected with DEQ_ERR_UNSUPPORTED; use deq_output for tspan-only rows. */
+/* `Points` (src/ode/options.rs:120-137).  For the explicit adaptive methods only Points::All is reference-valid
+ * (Specified re-reads y from the output vector, problem.rs:262) and Specified is rejected with DEQ_ERR_UNSUPPORTED; use
+ * deq_output for tspan-only rows.  DEQ_ODE23S honours both (problem.rs:536): with DEQ_OUT_ALL, Specified yields the rows at
+ * the tspan times only, All adds every step end point. */
 typedef enum deq_points { DEQ_POINTS_ALL = 0, DEQ_POINTS_SPECIFIED = 1 } deq_points;
 
 /* What deq_solve materialises. */
@@ -92,7 +96,8 @@ typedef enum deq_dense_layout { DEQ_LAYOUT_SOA = 0, DEQ_LAYOUT_TRAJ_MAJOR = 1 } 
 typedef enum deq_traj_status {
     DEQ_TRAJ_DONE = 0,
     DEQ_TRAJ_MINSTEP_BREAK = 1,  /* |dt| < minstep: problem.rs:342-344 */
-    DEQ_TRAJ_MAX_STEPS = 2       /* extension: options.max_steps reached */
+    DEQ_TRAJ_MAX_STEPS = 2,      /* extension: options.max_steps reached */
+    DEQ_TRAJ_INVALID_MATRIX = 3  /* stiff methods: try_inverse() hit a zero determinant (OdeError::InvalidMatrix) */
 } deq_traj_status;
 
 /* AdaptiveOptions (src/ode/options.rs:49-70); defaults from options.rs:283-299 and problem.rs:219-225.
@@ -201,6 +206,9 @@ void deq_result_destroy(deq_result* res);
 /* Tableau introspection (runge_kutta.rs:87-100): a[S*S] row-major, b[S*2] (stepping, error), c[S]. */
 deq_status deq_tableau_get(int method, int tableau_set, int* stages, double* a, double* b, double* c,
                            int* adaptive, int* order_min, int* fsal);
+/* Rosenbrock coefficient sets (rosenbrock.rs:14-118) of DEQ_ODE4SKR (kr4) / DEQ_ODE4SS (s4): gamma, a[16], b[4], c[16],
+ * matrices row-major. */
+deq_status deq_rosenbrock_get(int method, double* gamma, double* a, double* b, double* c);
 /* Pinned host memory for fast H2D / D2H of caller buffers. */
 deq_status deq_host_alloc(size_t bytes, void** out);
 void deq_host_free(void* p);

@@ -78,7 +78,7 @@ public:
         int adaptive = 0;
         deq_tableau_get((int)ode, set, nullptr, nullptr, nullptr, nullptr, &adaptive, nullptr, nullptr);
         deq_status b = DEQ_OK;
-        if (adaptive) { s.accepted.resize(ntraj_); s.rejected.resize(ntraj_); b = deq_result_counts(r, s.accepted.data(), s.rejected.data(), nullptr, nullptr, nullptr); }
+        if (adaptive || ode == Ode::Ode23s || ode == Ode::Ode4skr || ode == Ode::Ode4ss) { s.accepted.resize(ntraj_); s.rejected.resize(ntraj_); b = deq_result_counts(r, s.accepted.data(), s.rejected.data(), nullptr, nullptr, nullptr); }
         deq_result_destroy(r);
         check(a); check(b);
         for (size_t i = 0; i < ntraj_; ++i) s.yout.emplace_back(flat.begin() + i * n_, flat.begin() + (i + 1) * n_);
@@ -89,6 +89,9 @@ public:
     OdeSolution ode45_fe(const OdeOptionMap& o = OdeOptionMap()) { return solve(Ode::Ode45fe, o); }
     OdeSolution ode78(const OdeOptionMap& o = OdeOptionMap()) { return solve(Ode::Ode78, o); }
     OdeSolution ode4() { return solve(Ode::Ode4); }
+    OdeSolution ode23s(const OdeOptionMap& o = OdeOptionMap()) { return solve(Ode::Ode23s, o); }   // problem.rs:409
+    OdeSolution ode4s_kr() { return solve(Ode::Ode4skr); }                                        // problem.rs:643
+    OdeSolution ode4s_s() { return solve(Ode::Ode4ss); }                                          // problem.rs:648
 private:
     friend class OdeBuilder;
     OdeProblem(deq_ensemble* h, size_t n, size_t ntraj, std::vector<double> t) : h_(h), n_(n), ntraj_(ntraj), tspan_(std::move(t)) {}

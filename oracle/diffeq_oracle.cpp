@@ -426,6 +426,261 @@ int solve_adapt(const Tableau& tb, const double* y0, const double* tspan, size_t
     return OK;
 }
 
+
+// ==========================================================================================
+// Stiff path: ode23s problem.rs:409-557, oderosenbrock problem.rs:560-640, fdjacobian :903-926,
+// coefficient sets rosenbrock.rs:14-118.
+//
+// Third-party arithmetic on this path: nalgebra = "0.20" (Cargo.toml; not vendored, no Cargo.lock), used through
+// DMatrix/DVector operators, `lu()`, `lu_internal()` and `try_inverse()` at problem.rs:466-504,584-625.  Restated from
+// nalgebra's published algorithms (UNPINNED: no reference test exercises them and the crate cannot be built here):
+//   * `&A * s`, `&A - &B`, `&a + &b`            elementwise, one rounding per element;
+//   * `&M * &v` (gemm -> gemv -> axcpy)         y = M[:,0]*v0, then y = M[:,j]*v_j + y for j = 1.. (column order);
+//   * `M.lu()` (linalg/lu.rs)                   partial pivoting on the first largest |.| of the column (icamax),
+//                                               multipliers l = a_ji * (1/pivot), update a_jk = (-p_k)*l_j + a_jk,
+//                                               a column whose pivot is exactly zero is skipped;
+//     `lu_internal()`                           the packed L\U matrix, permutation dropped;
+//   * `M.try_inverse()` (linalg/inverse.rs)     closed-form adjugate formulas for n = 1, 2, 3 — n >= 4 (4x4 cofactor
+//                                               routine / LU inverse) is not restated: the stiff path is n <= 3 here.
+// ==========================================================================================
+enum { ST_INVALID_MATRIX = 3 };
+
+template <int N>
+inline void na_lu_packed(double m[N][N]) {
+    for (int i = 0; i < N; ++i) {
+        int piv = i; double best = std::fabs(m[i][i]);
+        for (int r = i + 1; r < N; ++r) { const double v = std::fabs(m[r][i]); if (v > best) { best = v; piv = r; } }
+        const double diag = m[piv][i];
+        if (diag == 0.0) continue;
+        if (piv != i) for (int c = 0; c < N; ++c) { const double tmp = m[i][c]; m[i][c] = m[piv][c]; m[piv][c] = tmp; }
+        const double inv = 1.0 / diag;
+        for (int r = i + 1; r < N; ++r) m[r][i] = m[r][i] * inv;
+        for (int k = i + 1; k < N; ++k) {
+            const double a = -m[i][k];
+            for (int r = i + 1; r < N; ++r) m[r][k] = a * m[r][i] + m[r][k];
+        }
+    }
+}
+
+template <int N>
+inline bool na_try_inverse(const double m[N][N], double o[N][N]) {
+    static_assert(N >= 1 && N <= 3, "try_inverse restated for n <= 3");
+    if constexpr (N == 1) {
+        const double det = m[0][0];
+        if (det == 0.0) return false;
+        o[0][0] = 1.0 / det;
+    } else if constexpr (N == 2) {
+        const double m11 = m[0][0], m12 = m[0][1], m21 = m[1][0], m22 = m[1][1];
+        const double det = m11 * m22 - m21 * m12;
+        if (det == 0.0) return false;
+        o[0][0] = m22 / det; o[0][1] = -m12 / det; o[1][0] = -m21 / det; o[1][1] = m11 / det;
+    } else {
+        const double m11 = m[0][0], m12 = m[0][1], m13 = m[0][2], m21 = m[1][0], m22 = m[1][1], m23 = m[1][2],
+                     m31 = m[2][0], m32 = m[2][1], m33 = m[2][2];
+        const double minor_m12_m23 = m22 * m33 - m32 * m23;
+        const double minor_m11_m23 = m21 * m33 - m31 * m23;
+        const double minor_m11_m22 = m21 * m32 - m31 * m22;
+        const double det = m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22;
+        if (det == 0.0) return false;
+        o[0][0] = minor_m12_m23 / det; o[0][1] = (m13 * m32 - m33 * m12) / det; o[0][2] = (m12 * m23 - m22 * m13) / det;
+        o[1][0] = -minor_m11_m23 / det; o[1][1] = (m11 * m33 - m31 * m13) / det; o[1][2] = (m13 * m21 - m23 * m11) / det;
+        o[2][0] = minor_m11_m22 / det; o[2][1] = (m12 * m31 - m32 * m11) / det; o[2][2] = (m11 * m22 - m21 * m12) / det;
+    }
+    return true;
+}
+
+template <int N>
+inline void na_gemv(const double m[N][N], const double* v, double* y) {
+    for (int r = 0; r < N; ++r) y[r] = m[r][0] * v[0];
+    for (int j = 1; j < N; ++j)
+        for (int r = 0; r < N; ++r) y[r] = m[r][j] * v[j] + y[r];
+}
+
+// fdjacobian, problem.rs:903-926
+template <int N, class F>
+inline void fdjacobian(double t, const double* x, const double* p, double J[N][N], uint32_t& nfe) {
+    double ftx[N];
+    F::eval(t, x, ftx, p);
+    for (int c = 0; c < N; ++c) {
+        double xj = x[c];
+        if (xj == 0.0) xj += 1.0;
+        const double dxj = xj * 0.01;
+        double tmp[N], yj[N];
+        for (int d = 0; d < N; ++d) tmp[d] = x[d];
+        tmp[c] += dxj;
+        F::eval(t, tmp, yj, p);
+        for (int r = 0; r < N; ++r) J[r][c] = (yj[r] - ftx[r]) / dxj;
+    }
+    nfe += N + 1;
+}
+
+template <int N>
+inline double pnorm2(const double* v, int libm_folded) {   // types.rs:109-115 with PNorm::default() = P(2)
+    double s = 0.0;
+    for (int d = 0; d < N; ++d) { const double a = std::fabs(v[d]); s = s + a * a; }
+    return libm_folded ? std::sqrt(s) : std::pow(s, 1.0 * (1. / 2.0));
+}
+
+// ode23s, problem.rs:409-557.  `true_inverse` (TEXTBOOK set) inverts W itself instead of its packed LU factors
+// (the reference's `w.lu().lu_internal().clone()` followed by `try_inverse`, :469,481).
+template <int N, class F>
+int solve_ode23s(const double* y0, const double* tspan, size_t nt, const double* p, const Opts& o, bool true_inverse,
+                 Sink& sink, Counters& cnt, double* yfinal) {
+    if (nt == 0) return OK;
+    double t = tspan[0];
+    const double tfinal = tspan[nt - 1];
+    const double reltol = o.reltol, abstol = o.abstol;
+    const double minstep = o.has_minstep ? o.minstep : std::fabs(tfinal - t) / 1e18;
+    const double maxstep = o.has_maxstep ? o.maxstep : std::fabs(tfinal - t) / 2.5;
+    const double two_sqrt = std::sqrt(2.0);
+    const double d = 1. / (2. + two_sqrt);
+    const double e32 = 6. + two_sqrt;
+    double hh, tdir, f0[N];
+    if (o.initstep == 0.) {
+        hinit<N, F>(y0, t, tfinal, 3, reltol, abstol, p, hh, tdir, f0, o.libm_folded);
+        cnt.nfe += 2;
+    } else {
+        hh = o.initstep; tdir = signum(tfinal - t);
+        F::eval(t, y0, f0, p);
+        cnt.nfe += 1;
+    }
+    double h = tdir * fmin_rs(std::fabs(hh), maxstep);
+    sink.push(t, y0, 0);
+    double tlast = t;   // tout[tout.len() - 1]
+    double jac[N][N];
+    fdjacobian<N, F>(t, y0, p, jac, cnt.nfe);
+    double y[N];
+    for (int i = 0; i < N; ++i) y[i] = y0[i];
+    uint64_t attempts = 0;
+    cnt.status = ST_DONE;
+    bool guard = false;
+    while (std::fabs(t - tfinal) > 0. && minstep < std::fabs(h)) {
+        if (o.max_steps && attempts >= o.max_steps) { guard = true; break; }
+        ++attempts;
+        if (std::fabs(t - tfinal) < std::fabs(h)) h = tfinal - t;
+        const double hd = 1.0 * (h * d);
+        double w[N][N];
+        for (int r = 0; r < N; ++r)
+            for (int c = 0; c < N; ++c) w[r][c] = (r == c ? 1.0 : 0.0) - jac[r][c] * hd;
+        if (N * N != 1 && !true_inverse) na_lu_packed<N>(w);
+        double fdt[N];
+        F::eval(t + h / 100., y, fdt, p);
+        for (int i = 0; i < N; ++i) { const double fdti = fdt[i] - f0[i]; fdt[i] = fdti * ((h * d) / (h / 100.)); }
+        double winv[N][N];
+        if (!na_try_inverse<N>(w, winv)) { cnt.nfe += 1; cnt.status = ST_INVALID_MATRIX; cnt.t_reached = t; if (yfinal) for (int i = 0; i < N; ++i) yfinal[i] = y[i]; return OK; }
+        double rhs[N], k1[N], k2[N], k3[N], f1[N], f2[N], f1y[N], ynew[N];
+        for (int i = 0; i < N; ++i) rhs[i] = f0[i] + fdt[i];
+        na_gemv<N>(winv, rhs, k1);
+        for (int i = 0; i < N; ++i) f1y[i] = y[i] + k1[i] * 0.5 * h;
+        F::eval(t + 0.5 * h, f1y, f1, p);
+        for (int i = 0; i < N; ++i) rhs[i] = f1[i] - k1[i];
+        na_gemv<N>(winv, rhs, k2);
+        for (int i = 0; i < N; ++i) k2[i] = k2[i] + k1[i];
+        for (int i = 0; i < N; ++i) ynew[i] = y[i] + k2[i] * h;
+        F::eval(t + h, ynew, f2, p);
+        cnt.nfe += 3;
+        for (int i = 0; i < N; ++i) rhs[i] = ((f2[i] - (k2[i] - f1[i]) * (1.0 * e32)) - (k1[i] - f0[i]) * (1.0 * 2.)) + fdt[i];
+        na_gemv<N>(winv, rhs, k3);
+        double kerr[N];
+        for (int i = 0; i < N; ++i) kerr[i] = (k1[i] - k2[i] * (1.0 * 2.)) + k3[i];
+        const double err = pnorm2<N>(kerr, o.libm_folded) * (std::fabs(h) / 6.);
+        const double delta = fmax_rs(fmax_rs(pnorm2<N>(y, o.libm_folded), pnorm2<N>(ynew, o.libm_folded)) * reltol, 1.0 * abstol);
+        if (err <= delta) {
+            cnt.accepted += 1;
+            for (size_t q = 0; q < nt; ++q) {
+                const double toi = tspan[q];
+                if (toi > t && toi <= t + h) {
+                    const double s = (toi - t) / h;
+                    const double c1 = 1.0 * (s * (1. - s) / (1. - 2. * d));
+                    const double c2 = 1.0 * (s * (s - 2. * d) / (1. - 2. * d));
+                    double ytmp[N];
+                    for (int i = 0; i < N; ++i) { const double kt = k1[i] * c1 + k2[i] * c2; ytmp[i] = y[i] + kt * h; }
+                    sink.push(toi, ytmp, (long long)q);
+                    tlast = toi;
+                }
+            }
+            if (o.points == 0 && std::fabs(tlast - (t + h)) > DBL_EPSILON) { sink.push(t + h, ynew, -1); tlast = t + h; }
+            t += h;
+            for (int i = 0; i < N; ++i) { y[i] = ynew[i]; f0[i] = f2[i]; }
+            fdjacobian<N, F>(t, y, p, jac, cnt.nfe);
+        } else {
+            cnt.rejected += 1;
+        }
+        const double r = delta / err;
+        h = fmin_rs(maxstep, std::pow(r, 1. / 3.) * std::fabs(h) * 0.8) * tdir;
+    }
+    if (guard) cnt.status = ST_MAX_STEPS;
+    else if (std::fabs(t - tfinal) > 0.) cnt.status = ST_MINSTEP_BREAK;   // the loop ended on `minstep < |h|` (silently, like the reference)
+    cnt.t_reached = t;
+    if (yfinal) for (int i = 0; i < N; ++i) yfinal[i] = y[i];
+    return OK;
+}
+
+struct RosenbrockCoeffs { double gamma, a[4][4], b[4], c[4][4]; };
+// rosenbrock.rs:16-68 and :71-117 (Matrix4::new takes its arguments row-major: a[i][j] = a[(i, j)])
+inline RosenbrockCoeffs rosenbrock_coeffs(int which) {
+    if (which == 0)
+        return RosenbrockCoeffs{0.231,
+            {{0., 0., 0., 0.}, {2., 0., 0., 0.}, {4.452470820736, 4.16352878860, 0., 0.}, {4.452470820736, 4.16352878860, 0., 0.}},
+            {3.95750374663, 4.62489238836, 0.617477263873, 1.2826129456},
+            {{0., 0., 0., 0.}, {-5.07167533877, 0., 0., 0.}, {6.02015272865, 0.1597500684673, 0., 0.}, {-1.856343618677, -8.50538085819, -2.08407513602, 0.0}}};
+    return RosenbrockCoeffs{0.5,
+        {{0., 0., 0., 0.}, {2., 0., 0., 0.}, {48. / 25., 6. / 250., 0., 0.}, {48. / 25., 6. / 250., 0., 0.}},
+        {19. / 9., 1. / 2., 25. / 108., 125. / 108.},
+        {{0., 0., 0., 0.}, {-8., 0., 0., 0.}, {372. / 25., 12. / 5., 0., 0.}, {-112. / 125., -54. / 125., -2. / 5., 0.}}};
+}
+
+// oderosenbrock, problem.rs:560-640.  yout [nt][N] (rows after an InvalidMatrix stop are left untouched); the
+// reference returns tout = diff(tspan) (sic, :572,639) — callers of the oracle rebuild that from tspan.
+template <int N, class F>
+int solve_rosenbrock(const RosenbrockCoeffs& co, const double* y0, const double* tspan, size_t nt, const double* p,
+                     double* yout, double* yfinal, uint8_t* status, uint32_t* nfe_out, size_t* rows) {
+    uint32_t nfe = 0;
+    double x[N];
+    for (int i = 0; i < N; ++i) x[i] = y0[i];
+    if (yout) for (int i = 0; i < N; ++i) yout[i] = x[i];
+    size_t nrows = nt ? 1 : 0;
+    uint8_t st = ST_DONE;
+    for (size_t solstep = 0; solstep + 1 < nt; ++solstep) {
+        const double hs = tspan[solstep + 1] - tspan[solstep];
+        const double ts = tspan[solstep];
+        double xs[N];
+        for (int i = 0; i < N; ++i) xs[i] = x[i];
+        double dfdx[N][N], jac[N][N], jinv[N][N];
+        fdjacobian<N, F>(ts, xs, p, dfdx, nfe);
+        const double dg = 1.0 * (1. / (co.gamma * hs));
+        for (int r = 0; r < N; ++r)
+            for (int c = 0; c < N; ++c) jac[r][c] = (r == c ? dg : 0.0) - dfdx[r][c];
+        if (!na_try_inverse<N>(jac, jinv)) { st = ST_INVALID_MATRIX; break; }
+        double g[4][N], fx[N];
+        F::eval(ts + co.b[0] * hs, xs, fx, p); ++nfe;
+        na_gemv<N>(jinv, fx, g[0]);
+        double nx[N];
+        for (int i = 0; i < N; ++i) nx[i] = x[i];
+        for (int i = 0; i < N; ++i) nx[i] += g[0][i] * co.b[0];
+        for (int i = 1; i < 4; ++i) {
+            double dx[N], df[N];
+            for (int d = 0; d < N; ++d) { dx[d] = 0.0; df[d] = 0.0; }
+            for (int j = 0; j < i - 1; ++j)                 // `.take(i - 1)` (:614): the newest stage is left out
+                for (int d = 0; d < N; ++d) { dx[d] += g[j][d] * co.a[i][j]; df[d] += g[j][d] * co.c[i][j]; }
+            double xa[N];
+            for (int d = 0; d < N; ++d) xa[d] = xs[d] + dx[d];
+            F::eval(ts + co.b[i] * hs, xa, fx, p); ++nfe;
+            na_gemv<N>(jinv, fx, g[i]);
+            for (int d = 0; d < N; ++d) g[i][d] = g[i][d] + df[d] * (1. / hs);
+            for (int d = 0; d < N; ++d) nx[d] += g[i][d] * co.b[i];
+        }
+        for (int i = 0; i < N; ++i) x[i] = nx[i];
+        if (yout) for (int i = 0; i < N; ++i) yout[(solstep + 1) * N + i] = x[i];
+        ++nrows;
+    }
+    if (yfinal) for (int i = 0; i < N; ++i) yfinal[i] = x[i];
+    if (status) *status = st;
+    if (nfe_out) *nfe_out = nfe;
+    if (rows) *rows = nrows;
+    return OK;
+}
+
 template <class Fn>
 int dispatch_rhs(int rhs, Fn&& fn) {
     switch (rhs) {
@@ -596,6 +851,105 @@ int oracle_ensemble_fixed(int method, int rhs, size_t ntraj, const double* y0, c
         }
         return (int)OK;
     });
+}
+
+
+// ---- stiff path exports ----
+// Single trajectory ode23s.  Same calling convention as oracle_solve_adaptive; tableau set 1 (TEXTBOOK) = true W^-1.
+int oracle_solve_ode23s(int set, int rhs, const double* params, const double* y0, const double* tspan, size_t nt,
+                        const oracle_opts* o, double* tout, double* yout, size_t cap, size_t* nout, double* yfinal,
+                        uint32_t* counts, uint8_t* status, double* t_reached) {
+    Opts op{o->reltol, o->abstol, o->has_minstep, o->minstep, o->has_maxstep, o->maxstep, o->initstep, o->points, o->max_steps, o->libm_folded};
+    return dispatch_rhs(rhs, [&](auto f) {
+        using F = decltype(f);
+        if constexpr (F::N > 3) return (int)ERR_UNSUPPORTED; else {
+        Sink sink; sink.tout = tout; sink.yout = yout; sink.cap = cap; sink.N = F::N;
+        Counters c;
+        int rc = solve_ode23s<F::N, F>(y0, tspan, nt, params, op, set == 1, sink, c, yfinal);
+        if (nout) *nout = sink.n;
+        if (counts) { counts[0] = c.accepted; counts[1] = c.rejected; counts[2] = c.nfe; }
+        if (status) *status = c.status;
+        if (t_reached) *t_reached = c.t_reached;
+        return rc; }
+    });
+}
+
+// Ensemble ode23s: final loop state + counters, optionally the rows at the tspan times (dense SoA [n][nt][ntraj],
+// row q = value the reference pushed for tspan[q]; nvalid = 1 + index of the last tspan row pushed).
+int oracle_ensemble_ode23s(int set, int rhs, size_t ntraj, const double* y0, const double* params, int params_per_traj,
+                           const double* tspan, size_t nt, const oracle_opts* o, int nthreads, double* yfinal,
+                           uint32_t* accepted, uint32_t* rejected, uint32_t* nfe, uint8_t* status, double* t_reached,
+                           double* dense, uint32_t* nvalid, uint32_t* nrows) {
+    Opts op{o->reltol, o->abstol, o->has_minstep, o->minstep, o->has_maxstep, o->maxstep, o->initstep, o->points, o->max_steps, o->libm_folded};
+    const int np = oracle_rhs_nparams(rhs);
+    return dispatch_rhs(rhs, [&](auto f) {
+        using F = decltype(f);
+        constexpr int N = F::N;
+        if constexpr (N > 3) return (int)ERR_UNSUPPORTED; else {
+#ifdef _OPENMP
+        if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 64)
+        for (long long i = 0; i < (long long)ntraj; ++i) {
+            const double* p = params_per_traj ? params + (size_t)i * np : params;
+            Sink sink; sink.N = N;
+            if (dense) { sink.dense = dense; sink.nt = nt; sink.ntraj = ntraj; sink.traj = (size_t)i; }
+            Counters c; double yf[N];
+            solve_ode23s<N, F>(y0 + (size_t)i * N, tspan, nt, p, op, set == 1, sink, c, yf);
+            if (yfinal) for (int d = 0; d < N; ++d) yfinal[(size_t)i * N + d] = yf[d];
+            if (accepted) accepted[i] = c.accepted;
+            if (rejected) rejected[i] = c.rejected;
+            if (nfe) nfe[i] = c.nfe;
+            if (status) status[i] = c.status;
+            if (t_reached) t_reached[i] = c.t_reached;
+            if (nvalid) nvalid[i] = (uint32_t)sink.ndense;
+            if (nrows) nrows[i] = (uint32_t)sink.n;
+        }
+        return (int)OK; }
+    });
+}
+
+// Single trajectory Rosenbrock (which: 0 = kr4 / Ode4skr, 1 = s4 / Ode4ss).  yout [nt][n].
+int oracle_solve_rosenbrock(int which, int rhs, const double* params, const double* y0, const double* tspan, size_t nt,
+                            double* yout, double* yfinal, uint8_t* status, uint32_t* nfe, size_t* rows) {
+    if (which != 0 && which != 1) return ERR_INVALID_ARG;
+    const RosenbrockCoeffs co = rosenbrock_coeffs(which);
+    return dispatch_rhs(rhs, [&](auto f) {
+        using F = decltype(f);
+        if constexpr (F::N > 3) return (int)ERR_UNSUPPORTED; else
+        return solve_rosenbrock<F::N, F>(co, y0, tspan, nt, params, yout, yfinal, status, nfe, rows);
+    });
+}
+
+int oracle_ensemble_rosenbrock(int which, int rhs, size_t ntraj, const double* y0, const double* params,
+                               int params_per_traj, const double* tspan, size_t nt, int nthreads, double* yfinal,
+                               uint8_t* status, double* yall /* [ntraj][nt][n] or NULL */) {
+    if (which != 0 && which != 1) return ERR_INVALID_ARG;
+    const RosenbrockCoeffs co = rosenbrock_coeffs(which);
+    const int np = oracle_rhs_nparams(rhs);
+    return dispatch_rhs(rhs, [&](auto f) {
+        using F = decltype(f);
+        constexpr int N = F::N;
+        if constexpr (N > 3) return (int)ERR_UNSUPPORTED; else {
+#ifdef _OPENMP
+        if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 64)
+        for (long long i = 0; i < (long long)ntraj; ++i) {
+            const double* p = params_per_traj ? params + (size_t)i * np : params;
+            solve_rosenbrock<N, F>(co, y0 + (size_t)i * N, tspan, nt, p, yall ? yall + (size_t)i * nt * N : nullptr,
+                                   yfinal ? yfinal + (size_t)i * N : nullptr, status ? status + i : nullptr, nullptr, nullptr);
+        }
+        return (int)OK; }
+    });
+}
+
+int oracle_rosenbrock_coeffs(int which, double* gamma, double* a, double* b, double* c) {
+    if (which != 0 && which != 1) return ERR_INVALID_ARG;
+    const RosenbrockCoeffs co = rosenbrock_coeffs(which);
+    *gamma = co.gamma;
+    for (int i = 0; i < 4; ++i) { b[i] = co.b[i]; for (int j = 0; j < 4; ++j) { a[4 * i + j] = co.a[i][j]; c[4 * i + j] = co.c[i][j]; } }
+    return OK;
 }
 
 int oracle_num_threads(void) {

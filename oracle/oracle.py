@@ -21,7 +21,8 @@ FEULER, HEUN, MIDPOINT, ODE23, ODE23S, ODE4, ODE45, ODE45FE, ODE4SKR, ODE4SS, OD
 LORENZ, VANDERPOL, PENDULUM = 0, 1, 2
 REFERENCE, TEXTBOOK = 0, 1
 POINTS_ALL, POINTS_SPECIFIED = 0, 1
-ST_DONE, ST_MINSTEP_BREAK, ST_MAX_STEPS = 0, 1, 2
+ST_DONE, ST_MINSTEP_BREAK, ST_MAX_STEPS, ST_INVALID_MATRIX = 0, 1, 2, 3
+KR4, S4 = 0, 1   # RosenbrockCoeffs::kr4 / s4 (rosenbrock.rs:16,71) = Ode::Ode4skr / Ode::Ode4ss
 
 
 class Opts(C.Structure):
@@ -183,6 +184,81 @@ def ensemble_fixed(method, rhs, params, y0, tspan, nthreads=0):
     if rc:
         raise RuntimeError(f"oracle_ensemble_fixed rc={rc}")
     return yf
+
+
+# ---- stiff path: ode23s problem.rs:409-557, oderosenbrock problem.rs:560-640 ----
+def solve_ode23s(rhs, params, y0, tspan, o=None, tset=REFERENCE, want_all=True):
+    """Single trajectory ode23s.  tset=TEXTBOOK inverts W itself instead of its packed LU factors."""
+    o = o or opts()
+    params, y0, tspan = _f64(params), _f64(y0), _f64(tspan)
+    n = rhs_dim(rhs)
+    L = lib()
+    nout = C.c_size_t(); cnt = (C.c_uint32 * 3)(); st = C.c_uint8(); tr = C.c_double()
+    yfin = np.empty(n)
+    args = [tset, rhs, _p(params), _p(y0), _p(tspan), C.c_size_t(len(tspan)), C.byref(o)]
+    rc = L.oracle_solve_ode23s(*args, None, None, C.c_size_t(0), C.byref(nout), _p(yfin), cnt, C.byref(st), C.byref(tr))
+    if rc:
+        return dict(rc=rc)
+    res = dict(rc=0, nout=nout.value, yfinal=yfin, accepted=cnt[0], rejected=cnt[1], nfe=cnt[2], status=st.value,
+               t_reached=tr.value)
+    if want_all:
+        tout = np.empty(nout.value); yout = np.empty((nout.value, n))
+        L.oracle_solve_ode23s(*args, _p(tout), _p(yout), C.c_size_t(nout.value), C.byref(nout), _p(yfin), cnt,
+                              C.byref(st), C.byref(tr))
+        res.update(tout=tout, yout=yout)
+    return res
+
+
+def ensemble_ode23s(rhs, params, y0, tspan, o=None, tset=REFERENCE, nthreads=0, dense=False):
+    o = o or opts()
+    y0, tspan = _f64(y0), _f64(tspan)
+    ntraj, n = y0.shape
+    params, per = _ens_params(params, ntraj, rhs_nparams(rhs))
+    yf = np.empty((ntraj, n)); acc = np.empty(ntraj, np.uint32); rej = np.empty(ntraj, np.uint32)
+    nfe = np.empty(ntraj, np.uint32); st = np.empty(ntraj, np.uint8); tr = np.empty(ntraj)
+    nv = np.empty(ntraj, np.uint32); nrows = np.empty(ntraj, np.uint32)
+    out = np.full((n, len(tspan), ntraj), np.nan) if dense else None
+    rc = lib().oracle_ensemble_ode23s(tset, rhs, C.c_size_t(ntraj), _p(y0), _p(params), per, _p(tspan),
+                                      C.c_size_t(len(tspan)), C.byref(o), nthreads, _p(yf), _p(acc, C.c_uint32),
+                                      _p(rej, C.c_uint32), _p(nfe, C.c_uint32), _p(st, C.c_uint8), _p(tr), _p(out),
+                                      _p(nv, C.c_uint32), _p(nrows, C.c_uint32))
+    if rc:
+        raise RuntimeError(f"oracle_ensemble_ode23s rc={rc}")
+    return dict(yfinal=yf, accepted=acc, rejected=rej, nfe=nfe, status=st, t_reached=tr, out=out, nvalid=nv, nrows=nrows)
+
+
+def solve_rosenbrock(which, rhs, params, y0, tspan):
+    """Single trajectory oderosenbrock.  Returns yout[rows][n] and tout = diff(tspan) as the reference does (sic)."""
+    params, y0, tspan = _f64(params), _f64(y0), _f64(tspan)
+    n = rhs_dim(rhs)
+    yout = np.full((len(tspan), n), np.nan); yfin = np.empty(n)
+    st = C.c_uint8(); nfe = C.c_uint32(); rows = C.c_size_t()
+    rc = lib().oracle_solve_rosenbrock(which, rhs, _p(params), _p(y0), _p(tspan), C.c_size_t(len(tspan)), _p(yout),
+                                       _p(yfin), C.byref(st), C.byref(nfe), C.byref(rows))
+    if rc:
+        raise RuntimeError(f"oracle_solve_rosenbrock rc={rc}")
+    return dict(tout=np.diff(tspan), yout=yout[:rows.value], yfinal=yfin, status=st.value, nfe=nfe.value)
+
+
+def ensemble_rosenbrock(which, rhs, params, y0, tspan, nthreads=0, want_all=False):
+    y0, tspan = _f64(y0), _f64(tspan)
+    ntraj, n = y0.shape
+    params, per = _ens_params(params, ntraj, rhs_nparams(rhs))
+    yf = np.empty((ntraj, n)); st = np.empty(ntraj, np.uint8)
+    yall = np.full((ntraj, len(tspan), n), np.nan) if want_all else None
+    rc = lib().oracle_ensemble_rosenbrock(which, rhs, C.c_size_t(ntraj), _p(y0), _p(params), per, _p(tspan),
+                                          C.c_size_t(len(tspan)), nthreads, _p(yf), _p(st, C.c_uint8), _p(yall))
+    if rc:
+        raise RuntimeError(f"oracle_ensemble_rosenbrock rc={rc}")
+    return dict(yfinal=yf, status=st, yall=yall)
+
+
+def rosenbrock_coeffs(which):
+    g = C.c_double(); a = np.zeros(16); b = np.zeros(4); c = np.zeros(16)
+    rc = lib().oracle_rosenbrock_coeffs(which, C.byref(g), _p(a), _p(b), _p(c))
+    if rc:
+        raise ValueError(f"oracle_rosenbrock_coeffs rc={rc}")
+    return dict(gamma=g.value, a=a.reshape(4, 4), b=b, c=c.reshape(4, 4))
 
 
 def num_threads():

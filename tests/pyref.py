@@ -242,3 +242,239 @@ def oderk_adapt(f, tb, y0, tspan, reltol=1e-5, abstol=1e-8, minstep=None, maxste
             dt = ndt
             timeout = 5
     return dict(tout=tout, yout=ys, accepted=acc, rejected=rej, status=status)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Stiff path: ode23s (problem.rs:409-557), oderosenbrock (problem.rs:560-650), fdjacobian (:903-926),
+# coefficient sets rosenbrock.rs:14-118.  The dense linear algebra is nalgebra 0.20 (Cargo.toml: nalgebra = "0.20"; not
+# vendored, no Cargo.lock), restated here from its published algorithms:
+#   * `&A * s`, `&A - &B`, `&a + &b`: elementwise;
+#   * `&M * &v` (gemm -> gemv -> axcpy): y = M[:,0]*v0, then y = M[:,j]*v_j + y for j = 1.. (column order);
+#   * `M.lu()` (linalg/lu.rs): partial pivoting on the first largest |.| (icamax), multipliers = a_ji * (1/pivot),
+#     trailing update a_jk = (-p_k)*l_j + a_jk, columns with a zero pivot skipped; `lu_internal()` is the packed L\U
+#     matrix WITHOUT the permutation;
+#   * `M.try_inverse()` (linalg/inverse.rs): closed-form adjugate formulas for n = 1, 2, 3 (n >= 4 is not restated here).
+# ---------------------------------------------------------------------------------------------------------------------
+SQRT2 = math.sqrt(2.0)
+
+
+def na_lu_packed(m):
+    n = len(m)
+    m = [list(r) for r in m]
+    for i in range(n):
+        piv, best = i, abs(m[i][i])
+        for r in range(i + 1, n):
+            if abs(m[r][i]) > best:
+                best, piv = abs(m[r][i]), r
+        diag = m[piv][i]
+        if diag == 0.0:
+            continue
+        if piv != i:
+            m[i], m[piv] = m[piv], m[i]          # columns < i, column i and columns > i are all swapped
+        inv = 1.0 / diag
+        for r in range(i + 1, n):
+            m[r][i] = m[r][i] * inv
+        for k in range(i + 1, n):
+            a = -m[i][k]
+            for r in range(i + 1, n):
+                m[r][k] = a * m[r][i] + m[r][k]
+    return m
+
+
+def na_try_inverse(m):
+    n = len(m)
+    if n == 1:
+        d = m[0][0]
+        return None if d == 0.0 else [[1.0 / d]]
+    if n == 2:
+        m11, m12, m21, m22 = m[0][0], m[0][1], m[1][0], m[1][1]
+        det = m11 * m22 - m21 * m12
+        if det == 0.0:
+            return None
+        return [[m22 / det, -m12 / det], [-m21 / det, m11 / det]]
+    if n == 3:
+        (m11, m12, m13), (m21, m22, m23), (m31, m32, m33) = m
+        minor_m12_m23 = m22 * m33 - m32 * m23
+        minor_m11_m23 = m21 * m33 - m31 * m23
+        minor_m11_m22 = m21 * m32 - m31 * m22
+        det = m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22
+        if det == 0.0:
+            return None
+        return [[minor_m12_m23 / det, (m13 * m32 - m33 * m12) / det, (m12 * m23 - m22 * m13) / det],
+                [-minor_m11_m23 / det, (m11 * m33 - m31 * m13) / det, (m13 * m21 - m23 * m11) / det],
+                [minor_m11_m22 / det, (m12 * m31 - m32 * m11) / det, (m11 * m22 - m21 * m12) / det]]
+    raise NotImplementedError("try_inverse for n >= 4")
+
+
+def na_gemv(m, v):
+    n = len(v)
+    y = [m[r][0] * v[0] for r in range(n)]
+    for j in range(1, n):
+        for r in range(n):
+            y[r] = m[r][j] * v[j] + y[r]
+    return y
+
+
+def fdjacobian(f, t, x):
+    """problem.rs:903-926"""
+    ftx = f(t, x)
+    n = len(ftx)
+    J = [[0.0] * n for _ in range(n)]
+    for c in range(n):
+        xj = x[c]
+        if xj == 0.0:
+            xj += 1.0
+        dxj = xj * 0.01
+        tmp = list(x)
+        tmp[c] += dxj
+        yj = f(t, tmp)
+        for r in range(n):
+            J[r][c] = (yj[r] - ftx[r]) / dxj
+    return J
+
+
+def pnorm2(v, libm_folded=False):
+    s = 0.0
+    for x in v:
+        s = s + abs(x) * abs(x)
+    try:
+        return math.sqrt(s) if libm_folded else math.pow(s, 1.0 * (1.0 / 2.0))
+    except OverflowError:
+        return math.inf
+
+
+def ode23s(f, y0, tspan, reltol=1e-5, abstol=1e-8, minstep=None, maxstep=None, initstep=0.0, points_all=True,
+           max_steps=0, libm_folded=False, true_inverse=False):
+    """problem.rs:409-557.  status 0 done, 1 loop left because |h| <= minstep before tfinal, 2 max_steps guard,
+    3 InvalidMatrix.  true_inverse=True is the TEXTBOOK variant (W^-1 instead of the inverse of the packed LU)."""
+    if not tspan:
+        return dict(tout=[], yout=[], accepted=0, rejected=0, status=0, t=0.0, y=[])
+    t = tspan[0]
+    tfinal = tspan[-1]
+    minstep = abs(tfinal - t) / 1e18 if minstep is None else minstep
+    maxstep = abs(tfinal - t) / 2.5 if maxstep is None else maxstep
+    d = 1.0 / (2.0 + SQRT2)
+    e32 = 6.0 + SQRT2
+    if initstep == 0.0:
+        h0, tdir, f0 = hinit(f, y0, t, tfinal, 3, reltol, abstol, libm_folded)
+    else:
+        h0, tdir, f0 = initstep, signum(tfinal - t), f(t, y0)
+    h = tdir * fmin(abs(h0), maxstep)
+    tout = [t]
+    yout = [list(y0)]
+    jac = fdjacobian(f, t, y0)
+    n = len(y0)
+    y = list(y0)
+    f0 = list(f0)
+    acc = rej = attempts = 0
+    status = 0
+    while abs(t - tfinal) > 0.0 and minstep < abs(h):
+        if max_steps and attempts >= max_steps:
+            status = 2
+            break
+        attempts += 1
+        if abs(t - tfinal) < abs(h):
+            h = tfinal - t
+        hd = h * d
+        w = [[(1.0 if r == c else 0.0) - jac[r][c] * (1.0 * hd) for c in range(n)] for r in range(n)]
+        if n * n != 1 and not true_inverse:
+            w = na_lu_packed(w)
+        fdt = f(t + h / 100.0, y)
+        for i in range(n):
+            fdt[i] = (fdt[i] - f0[i]) * (hd / (h / 100.0))
+        winv = na_try_inverse(w)
+        if winv is None:
+            status = 3
+            break
+        k1 = na_gemv(winv, [f0[i] + fdt[i] for i in range(n)])
+        f1y = [y[i] + k1[i] * 0.5 * h for i in range(n)]
+        f1 = f(t + 0.5 * h, f1y)
+        k2 = na_gemv(winv, [f1[i] - k1[i] for i in range(n)])
+        k2 = [k2[i] + k1[i] for i in range(n)]
+        ynew = [y[i] + k2[i] * h for i in range(n)]
+        f2 = f(t + h, ynew)
+        k3 = na_gemv(winv, [((f2[i] - (k2[i] - f1[i]) * (1.0 * e32)) - (k1[i] - f0[i]) * (1.0 * 2.0)) + fdt[i] for i in range(n)])
+        kerr = [(k1[i] - k2[i] * (1.0 * 2.0)) + k3[i] for i in range(n)]
+        err = pnorm2(kerr, libm_folded) * (abs(h) / 6.0)
+        delta = fmax(fmax(pnorm2(y, libm_folded), pnorm2(ynew, libm_folded)) * reltol, 1.0 * abstol)
+        if err <= delta:
+            acc += 1
+            for toi in tspan:
+                if toi > t and toi <= t + h:
+                    s = (toi - t) / h
+                    tout.append(toi)
+                    c1 = 1.0 * (s * (1.0 - s) / (1.0 - 2.0 * d))
+                    c2 = 1.0 * (s * (s - 2.0 * d) / (1.0 - 2.0 * d))
+                    yout.append([y[i] + (k1[i] * c1 + k2[i] * c2) * h for i in range(n)])
+            if points_all and abs(tout[-1] - (t + h)) > EPS:
+                tout.append(t + h)
+                yout.append(list(ynew))
+            t += h
+            y = ynew
+            f0 = f2
+            jac = fdjacobian(f, t, y)
+        else:
+            rej += 1
+        r = delta / err if err != 0.0 else (math.inf if delta > 0.0 else math.nan)
+        try:
+            g = math.pow(r, 1.0 / 3.0)
+        except (OverflowError, ValueError):
+            g = math.nan if r != r else math.inf
+        h = fmin(maxstep, g * abs(h) * 0.8) * tdir
+    else:
+        status = 0 if not (abs(t - tfinal) > 0.0) else 1
+    return dict(tout=tout, yout=yout, accepted=acc, rejected=rej, status=status, t=t, y=y)
+
+
+ROSENBROCK = {
+    # rosenbrock.rs:16-68 (Matrix4::new is row-major: a[i][j] below is a[(i, j)])
+    "kr4": dict(gamma=0.231,
+                a=[[0., 0., 0., 0.], [2., 0., 0., 0.], [4.452_470_820_736, 4.163_528_788_60, 0., 0.],
+                   [4.452_470_820_736, 4.163_528_788_60, 0., 0.]],
+                b=[3.957_503_746_63, 4.624_892_388_36, 0.617_477_263_873, 1.282_612_945_6],
+                c=[[0., 0., 0., 0.], [-5.071_675_338_77, 0., 0., 0.], [6.020_152_728_65, 0.159_750_068_467_3, 0., 0.],
+                   [-1.856_343_618_677, -8.505_380_858_19, -2.084_075_136_02, 0.0]]),
+    # rosenbrock.rs:71-117
+    "s4": dict(gamma=0.5,
+               a=[[0., 0., 0., 0.], [2., 0., 0., 0.], [48. / 25., 6. / 250., 0., 0.], [48. / 25., 6. / 250., 0., 0.]],
+               b=[19. / 9., 1. / 2., 25. / 108., 125. / 108.],
+               c=[[0., 0., 0., 0.], [-8., 0., 0., 0.], [372. / 25., 12. / 5., 0., 0.],
+                  [-112. / 125., -54. / 125., -2. / 5., 0.]]),
+}
+
+
+def oderosenbrock(f, co, y0, tspan):
+    """problem.rs:560-640.  Returns dict(tout = diff(tspan) (sic), yout, status 0 | 3 InvalidMatrix)."""
+    if not tspan:
+        return dict(tout=[], yout=[], status=0)
+    hvec = [tspan[i + 1] - tspan[i] for i in range(len(tspan) - 1)]
+    n = len(y0)
+    x = [list(y0)]
+    for solstep, hs in enumerate(hvec):
+        ts = tspan[solstep]
+        xs = list(x[solstep])
+        dfdx = fdjacobian(f, ts, xs)
+        dg = 1.0 * (1.0 / (co["gamma"] * hs))
+        jac = [[(dg if r == c else 0.0) - dfdx[r][c] for c in range(n)] for r in range(n)]
+        jinv = na_try_inverse(jac)
+        if jinv is None:
+            return dict(tout=hvec, yout=x, status=3)
+        g = [na_gemv(jinv, f(ts + co["b"][0] * hs, xs))]
+        nx = list(x[-1])
+        for i in range(n):
+            nx[i] += g[0][i] * co["b"][0]
+        for i in range(1, 4):
+            dx = [0.0] * n
+            df = [0.0] * n
+            for j in range(min(len(g), i - 1)):
+                for dd in range(n):
+                    dx[dd] += g[j][dd] * co["a"][i][j]
+                    df[dd] += g[j][dd] * co["c"][i][j]
+            fx = f(ts + co["b"][i] * hs, [xs[dd] + dx[dd] for dd in range(n)])
+            gv = na_gemv(jinv, fx)
+            gv = [gv[dd] + df[dd] * (1.0 / hs) for dd in range(n)]
+            for dd in range(n):
+                nx[dd] += gv[dd] * co["b"][i]
+            g.append(gv)
+        x.append(nx)
+    return dict(tout=hvec, yout=x, status=0)

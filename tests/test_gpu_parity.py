@@ -195,7 +195,7 @@ def test_error_behaviour(deq):
         p.solve(deq.Ode.Ode45, deq.OdeOptionMap().insert(deq.Initstep(-0.1)))   # problem.rs:232-237
     assert e.value.kind == "InvalidInitstep"
     with pytest.raises(deq.OdeError) as e:
-        p.solve(deq.Ode.Ode23s)
+        p.solve(deq.Ode.Ode23s, deq.OdeOptionMap().insert(deq.Precision.F32))   # the stiff solvers are f64 only
     assert e.value.kind == "Unsupported"
     with pytest.raises(deq.OdeError) as e:
         deq.OdeProblem.builder().fun(deq.Rhs.builtin(0)).params(LOR).init([0.1, 0, 0]).build()  # problem.rs:99-101

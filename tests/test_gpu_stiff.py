@@ -1,0 +1,291 @@
+"""GPU parity of the stiff solvers: ode23s (problem.rs:409-557) and oderosenbrock kr4 / s4
+(problem.rs:560-650) through the C ABI against the CPU oracle and the committed goldens — every assert BIT-EXACT.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+STIFF = json.load(open(os.path.join(HERE, "golden", "stiff_cases.json")))
+LOR = [10.0, 28.0, 8.0 / 3.0]
+
+
+def fh(v):
+    return [fh(x) for x in v] if isinstance(v, list) else float.fromhex(v)
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a, dtype="<f8").tobytes()).hexdigest()
+
+
+def _problem(D, system, params, y0, tspan):
+    return D.OdeProblem.builder().fun(D.Rhs.builtin(system)).params(params).init(y0).tspan(tspan).build()
+
+
+def _tspan(deq, desc):
+    return [float(x) for x in desc[1:]] if desc[0] == "list" else deq.linspace(desc[1], desc[2], desc[3])
+
+
+def _options(deq, opt, *extra):
+    o = deq.OdeOptionMap().insert(*extra)
+    for k, cls in (("reltol", deq.Reltol), ("abstol", deq.Abstol), ("minstep", deq.Minstep), ("maxstep", deq.Maxstep), ("initstep", deq.Initstep)):
+        if k in opt:
+            o.insert(cls(float.fromhex(opt[k])))
+    if "max_steps" in opt:
+        o.insert(deq.MaxSteps(opt["max_steps"]))
+    if opt.get("libm_folded"):
+        o.insert(deq.Libm.LlvmFolded)
+    if opt.get("points_all") is False:
+        o.insert(deq.Points.Specified)
+    return o
+
+
+def test_device_pow_special_operands(deq, oracle):
+    """The step-size update pow(delta/err, 1/3) and the norms pow(s, 0.5) meet 0, inf and NaN on the stiff path."""
+    x = np.array([0.0, np.inf, np.nan, 1.0, 5e-324, 1e-320, 1.7e308, 0.0, np.inf, np.nan, 2.0, 1e-300])
+    y = np.array([1 / 3] * 7 + [0.5] * 5)
+    got = deq.device_pow(x, y)
+    L = oracle.lib()
+    ref = np.array([L.oracle_pow(float(a), float(b)) for a, b in zip(x, y)])
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+    rng = np.random.default_rng(5)
+    x = np.exp(rng.uniform(-60, 60, 200000))
+    got = deq.device_pow(x, np.full_like(x, 1 / 3))
+    ref = np.array([L.oracle_pow(float(a), 1 / 3) for a in x[:40000]])
+    assert np.array_equal(got[:40000].view(np.uint64), ref.view(np.uint64))
+
+
+def test_rosenbrock_coefficients(deq):
+    for which, m in (("kr4", deq.Ode.Ode4skr), ("s4", deq.Ode.Ode4ss)):
+        g = STIFF["rosenbrock_coeffs"][which]
+        co = deq.rosenbrock_coeffs(m)
+        assert co["gamma"] == float.fromhex(g["gamma"])
+        assert co["a"].tolist() == fh(g["a"]) and co["b"].tolist() == fh(g["b"]) and co["c"].tolist() == fh(g["c"])
+
+
+def test_stiff_goldens_through_the_cuda_path(deq):
+    """Every committed stiff golden (known answers of the independent Python restatement) reproduced by the CUDA path
+    directly: the complete (tout, yout) streams by SHA-256, the counters, the exit status."""
+    ran = 0
+    for c in STIFF["cases"]:
+        ts = _tspan(deq, c["tspan"])
+        prob = _problem(deq, getattr(deq.System, c["system"]), fh(c["params"]), fh(c["y0"]), ts)
+        if c["kind"] == "ode23s":
+            sol = prob.solve(deq.Ode.Ode23s, _options(deq, c["options"], deq.Output.All), tableau_set=0 if c["tableau_set"] == "reference" else 1)
+            tout, yout = sol.trajectory(0)
+            assert (int(sol.accepted[0]), int(sol.rejected[0]), int(sol.status[0]), len(tout)) == (c["accepted"], c["rejected"], c["status"], c["nout"]), c["name"]
+            assert sol.final[0].tolist() == fh(c["final"]) and sol.t_reached[0] == float.fromhex(c["t_reached"]), c["name"]
+            assert digest(tout) == c["sha256_tout"] and digest(yout) == c["sha256_yout"], c["name"]
+        else:
+            sol = prob.solve(deq.Ode.Ode4skr if c["which"] == "kr4" else deq.Ode.Ode4ss, deq.OdeOptionMap().insert(deq.Output.Tspan))
+            nv = int(sol.nvalid[0])
+            assert (int(sol.status[0]), nv) == (c["status"], c["nout"]), c["name"]
+            assert digest(sol.yout[0][:nv]) == c["sha256_yout"] and digest(sol.tout) == c["sha256_tout"], c["name"]
+            assert sol.final[0].tolist() == fh(c["final"]), c["name"]
+        ran += 1
+    assert ran == len(STIFF["cases"]) >= 30
+
+
+@pytest.mark.parametrize("tset", [0, 1])
+@pytest.mark.parametrize("folded", [0, 1])
+def test_ode23s_vdp_sweep_final(deq, oracle, tset, folded):
+    """Van der Pol stiffness sweep mu = 0.1 .. 1000 (the natural ode23s workload), final state + every counter."""
+    n = 1003
+    mu = np.geomspace(0.1, 1000.0, n)[:, None]
+    y0 = np.tile([2.0, 0.0], (n, 1))
+    ts = [0.0, 20.0]
+    ref = oracle.ensemble_ode23s(oracle.VANDERPOL, mu, y0, ts, oracle.opts(1e-5, 1e-8, libm_folded=folded), tset=tset)
+    o = deq.OdeOptionMap().insert(deq.Reltol(1e-5), deq.Abstol(1e-8))
+    if folded:
+        o.insert(deq.Libm.LlvmFolded)
+    sol = _problem(deq, deq.System.VanDerPol, mu, y0, ts).solve(deq.Ode.Ode23s, o, tableau_set=tset)
+    for k in ("accepted", "rejected", "nfe", "status", "t_reached"):
+        assert np.array_equal(getattr(sol, k), ref[k]), k
+    assert np.array_equal(sol.final, ref["yfinal"])
+    assert sol.totals == dict(accepted=int(ref["accepted"].sum()), rejected=int(ref["rejected"].sum()), nfe=int(ref["nfe"].sum()))
+    assert (sol.status == 0).all()
+
+
+@pytest.mark.parametrize("system", ["Lorenz", "Pendulum"])
+def test_ode23s_three_and_two_dimensional_systems(deq, oracle, system):
+    from diffeq_b200 import synth
+    n = 300
+    if system == "Lorenz":
+        y0, params, ts = synth.lorenz_ics(0, n), np.array(LOR), [0.0, 1.5]
+    else:
+        y0, params, ts = synth.pendulum_ics(0, n), synth.PENDULUM_PARAMS, [0.0, 4.0]
+    for tset in (0, 1):
+        ref = oracle.ensemble_ode23s(getattr(oracle, system.upper()), params, y0, ts, oracle.opts(1e-6, 1e-9), tset=tset)
+        sol = _problem(deq, getattr(deq.System, system), params, y0, ts).solve(
+            deq.Ode.Ode23s, deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-9)), tableau_set=tset)
+        assert np.array_equal(sol.final, ref["yfinal"]) and np.array_equal(sol.accepted, ref["accepted"])
+        assert np.array_equal(sol.rejected, ref["rejected"]) and np.array_equal(sol.nfe, ref["nfe"])
+
+
+def test_ode23s_dense_rows_and_ragged_stream(deq, oracle):
+    """Output.Tspan = the rows the reference pushes for the tspan times; Output.All = its complete (tout, yout), with
+    Points::All and Points::Specified (problem.rs:519-542)."""
+    n = 130
+    mu = np.geomspace(0.5, 200.0, n)[:, None]
+    y0 = np.tile([2.0, 0.0], (n, 1))
+    ts = deq.linspace(0.0, 30.0, 77)
+    oo = oracle.opts(1e-5, 1e-8)
+    ref = oracle.ensemble_ode23s(oracle.VANDERPOL, mu, y0, ts, oo, dense=True)
+    prob = _problem(deq, deq.System.VanDerPol, mu, y0, ts)
+    base = (deq.Reltol(1e-5), deq.Abstol(1e-8))
+    sol = prob.solve(deq.Ode.Ode23s, deq.OdeOptionMap().insert(*base, deq.Output.Tspan))
+    assert np.array_equal(sol.nvalid, ref["nvalid"]) and (sol.nvalid == len(ts)).all()
+    assert np.array_equal(sol.yout, ref["out"].transpose(2, 1, 0))
+    assert np.array_equal(sol.final, ref["yfinal"])
+    for pts, opt in ((0, deq.Points.All), (1, deq.Points.Specified)):
+        sa = prob.solve(deq.Ode.Ode23s, deq.OdeOptionMap().insert(*base, deq.Output.All, opt))
+        oo.points = pts
+        for i in (0, 1, 57, n - 1):
+            one = oracle.solve_ode23s(oracle.VANDERPOL, mu[i], y0[i], ts, oo)
+            tout, yout = sa.trajectory(i)
+            assert np.array_equal(tout, one["tout"]) and np.array_equal(yout, one["yout"]), (pts, i)
+        if pts == 1:
+            assert all(np.array_equal(sa.trajectory(i)[0], ts) for i in range(n))
+    oo.points = 0
+
+
+def test_ode23s_scheduling_and_partition_invariance(deq):
+    n = 2000
+    mu = np.geomspace(0.1, 300.0, n)[:, None]
+    y0 = np.tile([2.0, 0.0], (n, 1))
+    a = _problem(deq, deq.System.VanDerPol, mu, y0, [0.0, 10.0]).solve(deq.Ode.Ode23s, deq.OdeOptionMap().insert(deq.Refill(1)))
+    b = _problem(deq, deq.System.VanDerPol, mu, y0, [0.0, 10.0]).solve(deq.Ode.Ode23s, deq.OdeOptionMap().insert(deq.Refill(0)))
+    c = _problem(deq, deq.System.VanDerPol, mu[700:1500], y0[700:1500], [0.0, 10.0]).solve(deq.Ode.Ode23s)
+    assert np.array_equal(a.final, b.final) and np.array_equal(a.accepted, b.accepted)
+    assert np.array_equal(a.final[700:1500], c.final) and np.array_equal(a.rejected[700:1500], c.rejected)
+    # DEQ_MODE_FAST has no separate stiff arithmetic: same kernel, same bits
+    f = _problem(deq, deq.System.VanDerPol, mu, y0, [0.0, 10.0]).solve(deq.Ode.Ode23s, deq.OdeOptionMap().insert(deq.Mode.Fast))
+    assert np.array_equal(a.final, f.final)
+
+
+@pytest.mark.parametrize("which", ["kr4", "s4"])
+@pytest.mark.parametrize("system", ["Lorenz", "VanDerPol", "Pendulum"])
+def test_rosenbrock_ensembles(deq, oracle, which, system):
+    """oderosenbrock reproduced bug-for-bug (it diverges on ordinary problems — inf/NaN rows must match too)."""
+    from diffeq_b200 import synth
+    n = 257
+    if system == "Lorenz":
+        y0, params = synth.lorenz_ics(0, n), np.array(LOR)
+    elif system == "VanDerPol":
+        y0, params = synth.vdp_sweep(0, n, n)
+    else:
+        y0, params = synth.pendulum_ics(0, n), synth.PENDULUM_PARAMS
+    ts = deq.linspace(0.0, 0.3, 61)
+    w = oracle.KR4 if which == "kr4" else oracle.S4
+    m = deq.Ode.Ode4skr if which == "kr4" else deq.Ode.Ode4ss
+    ref = oracle.ensemble_rosenbrock(w, getattr(oracle, system.upper()), params, y0, ts, want_all=True)
+    prob = _problem(deq, getattr(deq.System, system), params, y0, ts)
+    sol = prob.solve(m)
+    assert np.array_equal(sol.final, ref["yfinal"], equal_nan=True) and np.array_equal(sol.status, ref["status"])
+    assert (sol.accepted == len(ts) - 1).all() and (sol.t_reached == ts[-1]).all()
+    dense = prob.solve(m, deq.OdeOptionMap().insert(deq.Output.Tspan))
+    assert np.array_equal(dense.yout, ref["yall"], equal_nan=True)
+    assert len(dense.tout) == len(ts) - 1 and np.array_equal(dense.tout, np.diff(ts))   # problem.rs:572,639 (sic)
+    assert dense.totals["accepted"] == n * (len(ts) - 1)
+
+
+def test_invalid_matrix_is_a_per_trajectory_status(deq, oracle):
+    """OdeError::InvalidMatrix (problem.rs:481,588) stops the failing trajectory only."""
+    y0 = np.array([[0.0, 0.0, 0.0], [1.0, 2.0, 20.0], [0.0, 0.0, 0.0]])
+    prm = np.array([[10.0, 0.0, -4.0], [10.0, 28.0, 8 / 3], [10.0, 0.0, -4.0]])
+    h = float.fromhex("0x1.b504f333f9de6p-1")
+    o = deq.OdeOptionMap().insert(deq.Initstep(h), deq.Maxstep(5.0))
+    sol = _problem(deq, deq.System.Lorenz, prm, y0, [0.0, 10.0]).solve(deq.Ode.Ode23s, o)
+    ref = oracle.ensemble_ode23s(oracle.LORENZ, prm, y0, [0.0, 10.0], oracle.opts(initstep=h, maxstep=5.0))
+    assert sol.status.tolist() == [3, 0, 3] == ref["status"].tolist()
+    assert np.array_equal(sol.final, ref["yfinal"]) and np.array_equal(sol.nfe, ref["nfe"])
+    ts = [0.0, 0.25, 0.75, 9.0]
+    sr = _problem(deq, deq.System.Lorenz, prm, y0, ts).solve(deq.Ode.Ode4ss, deq.OdeOptionMap().insert(deq.Output.Tspan))
+    rr = oracle.ensemble_rosenbrock(oracle.S4, oracle.LORENZ, prm, y0, ts, want_all=True)
+    assert sr.status.tolist() == [3, 0, 3] == rr["status"].tolist() and sr.nvalid.tolist() == [2, 4, 2]
+    assert np.array_equal(sr.final, rr["yfinal"], equal_nan=True)
+    assert np.array_equal(sr.yout[1], rr["yall"][1], equal_nan=True) and np.array_equal(sr.yout[0][:2], rr["yall"][0][:2])
+
+
+USER_VDP = r'''
+__device__ void rhs(double t, const double* v, double* d, const double* p) {
+    d[0] = v[1];
+    d[1] = p[0] * (1.0 - v[0] * v[0]) * v[1] - v[0];
+}
+'''
+USER_ROBER_LIKE = r'''
+// one-dimensional stiff decay towards cos(t): y' = -p0 (y - cos t)
+__device__ void rhs(double t, const double* y, double* d, const double* p) { d[0] = -p[0] * (y[0] - deq_cos(t)); }
+'''
+
+
+def test_stiff_nvrtc_user_rhs(deq, oracle):
+    """User CUDA source runs through the same stiff templates: bit-exact vs the built-in system and the oracle."""
+    n = 200
+    mu = np.geomspace(0.2, 500.0, n)[:, None]
+    y0 = np.tile([2.0, 0.0], (n, 1))
+    rhs = deq.Rhs.from_source(USER_VDP, 2, 1)
+    ts = deq.linspace(0.0, 15.0, 31)
+    ref = oracle.ensemble_ode23s(oracle.VANDERPOL, mu, y0, ts, oracle.opts(), dense=True)
+    sol = deq.OdeProblem.builder().fun(rhs).params(mu).init(y0).tspan(ts).build().solve(deq.Ode.Ode23s, deq.OdeOptionMap().insert(deq.Output.Tspan))
+    assert np.array_equal(sol.final, ref["yfinal"]) and np.array_equal(sol.accepted, ref["accepted"])
+    assert np.array_equal(sol.yout, ref["out"].transpose(2, 1, 0))
+    tr = np.linspace(0.0, 0.2, 21)
+    rr = oracle.ensemble_rosenbrock(oracle.KR4, oracle.VANDERPOL, mu, y0, tr)
+    sr = deq.OdeProblem.builder().fun(rhs).params(mu).init(y0).tspan(tr).build().solve(deq.Ode.Ode4skr)
+    assert np.array_equal(sr.final, rr["yfinal"], equal_nan=True)
+    # n = 1 (the reference skips the LU for a 1x1 Jacobian, problem.rs:467): TEXTBOOK and REFERENCE coincide and converge
+    r1 = deq.Rhs.from_source(USER_ROBER_LIKE, 1, 1)
+    p1 = deq.OdeProblem.builder().fun(r1).params([1000.0]).init([[0.0]]).tspan([0.0, 3.0]).build()
+    o = deq.OdeOptionMap().insert(deq.Reltol(1e-7), deq.Abstol(1e-10))
+    a, b = p1.solve(deq.Ode.Ode23s, o, tableau_set=0), p1.solve(deq.Ode.Ode23s, o, tableau_set=1)
+    assert np.array_equal(a.final, b.final) and int(a.status[0]) == 0
+    lam, t = 1000.0, 3.0   # exact: y = (lam^2 cos t + lam sin t) / (1 + lam^2) + C e^{-lam t}
+    exact = (lam * lam * np.cos(t) + lam * np.sin(t)) / (1 + lam * lam)
+    assert abs(a.final[0, 0] - exact) < 1e-5
+
+
+def test_stiff_argument_checks(deq):
+    src = "__device__ void rhs(double t, const double* y, double* dy, const double* p) { for (int i = 0; i < 4; ++i) dy[i] = -y[i]; }"
+    p4 = deq.OdeProblem.builder().fun(deq.Rhs.from_source(src, 4, 0)).init([[1.0, 1.0, 1.0, 1.0]]).tspan([0.0, 1.0]).build()
+    for m in (deq.Ode.Ode23s, deq.Ode.Ode4skr, deq.Ode.Ode4ss):
+        with pytest.raises(deq.OdeError) as e:
+            p4.solve(m)
+        assert e.value.kind == "Unsupported"
+    p = _problem(deq, deq.System.VanDerPol, [1.0], [2.0, 0.0], [0.0, 2.0, 1.0, 3.0])
+    with pytest.raises(deq.OdeError):
+        p.solve(deq.Ode.Ode23s, deq.OdeOptionMap().insert(deq.Output.Tspan))     # non-monotone tspan with row output
+    assert p.solve(deq.Ode.Ode23s).status[0] == 0                                   # final-state output does not care
+    # empty tspan: nothing to solve (problem.rs:413-416, 567-570)
+    e0 = _problem(deq, deq.System.VanDerPol, [1.0], [2.0, 0.0], [])
+    assert e0.solve(deq.Ode.Ode23s).totals["accepted"] == 0 and e0.solve(deq.Ode.Ode4ss).totals["accepted"] == 0
+    with pytest.raises(deq.OdeError):
+        p.solve(deq.Ode.Ode23s, deq.OdeOptionMap().insert(deq.Output.Tspan, deq.DenseLayout.TrajMajor))
+
+
+def test_stiff_one_shot_host_call(deq, oracle):
+    """deq_solve_host (the e2e entry point) carries the stiff methods, counters included."""
+    n = 500
+    mu = np.geomspace(0.1, 100.0, n)[:, None]
+    y0 = np.tile([2.0, 0.0], (n, 1))
+    ref = oracle.ensemble_ode23s(oracle.VANDERPOL, mu, y0, [0.0, 5.0], oracle.opts())
+    out = deq.solve_host_multi(deq.Rhs.builtin(deq.System.VanDerPol), y0, mu, [0.0, 5.0], deq.Ode.Ode23s, deq.OdeOptionMap(), devices=[0, 0])
+    assert np.array_equal(out["final"], ref["yfinal"]) and np.array_equal(out["accepted"], ref["accepted"])
+    assert np.array_equal(out["status"], ref["status"]) and np.array_equal(out["t_reached"], ref["t_reached"])
+
+
+def test_ode23s_textbook_accuracy_on_device(deq):
+    """TEXTBOOK ode23s on the GPU against scipy Radau on a stiff Van der Pol sample."""
+    from scipy.integrate import solve_ivp
+    mus = [1.0, 30.0, 300.0]
+    y0 = np.tile([2.0, 0.0], (3, 1))
+    o = deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-9))
+    sol = _problem(deq, deq.System.VanDerPol, np.array(mus)[:, None], y0, [0.0, 40.0]).solve(deq.Ode.Ode23s, o, tableau_set=1)
+    for i, mu in enumerate(mus):
+        ref = solve_ivp(lambda t, v: [v[1], mu * (1 - v[0] ** 2) * v[1] - v[0]], (0.0, 40.0), [2.0, 0.0], method="Radau", rtol=1e-10, atol=1e-12)
+        assert abs(sol.final[i, 0] - ref.y[0, -1]) < 5e-3 * max(1.0, abs(ref.y[0, -1])), (mu, sol.final[i], ref.y[:, -1])

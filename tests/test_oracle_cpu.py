@@ -122,3 +122,91 @@ def test_oracle_ensemble_matches_single(oracle):
     lut = {t: y for t, y in zip(s["tout"], s["yout"])}
     for k in range(1, int(d["nvalid"][3])):
         assert np.array_equal(d["out"][:, k, 3], lut[ts[k]])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Stiff path: ode23s / oderosenbrock.  Goldens come from tests/pyref.py (tools/gen_golden.py stiff), the
+# Rosenbrock coefficient sets are parsed from the reference's rosenbrock.rs.
+# ---------------------------------------------------------------------------------------------------------------------
+STIFF = json.load(open(os.path.join(GOLD, "stiff_cases.json")))
+
+
+def _stiff_opts(oracle, case):
+    kw = {}
+    for k, v in case["options"].items():
+        if k == "points_all":
+            kw["points"] = 0 if v else 1
+        elif k == "libm_folded":
+            kw["libm_folded"] = int(v)
+        else:
+            kw[k] = float.fromhex(v) if isinstance(v, str) else v
+    return oracle.opts(**kw)
+
+
+@pytest.mark.parametrize("which", ["kr4", "s4"])
+def test_oracle_rosenbrock_coeffs_match_reference_source(oracle, which):
+    g = STIFF["rosenbrock_coeffs"][which]
+    co = oracle.rosenbrock_coeffs(oracle.KR4 if which == "kr4" else oracle.S4)
+    assert co["gamma"] == float.fromhex(g["gamma"])
+    assert co["a"].tolist() == fh(g["a"]) and co["b"].tolist() == fh(g["b"]) and co["c"].tolist() == fh(g["c"])
+    # the transcription slips of the reference's kr4 versus Kaps-Rentrop (a31 = 4.5247..., c32 = 0.15975068...) are kept
+    if which == "kr4":
+        assert co["a"][2][0] == 4.452470820736 and co["c"][2][1] == 0.1597500684673
+
+
+@pytest.mark.parametrize("case", [c for c in STIFF["cases"] if c["kind"] == "ode23s"], ids=lambda c: c["name"])
+def test_oracle_ode23s_goldens(oracle, case):
+    ts = tspan_of(case["tspan"])
+    r = oracle.solve_ode23s(getattr(oracle, case["system"].upper()), fh(case["params"]), fh(case["y0"]), ts,
+                            _stiff_opts(oracle, case), tset=0 if case["tableau_set"] == "reference" else 1)
+    assert r["rc"] == 0
+    assert (r["accepted"], r["rejected"], r["status"], r["nout"]) == (case["accepted"], case["rejected"], case["status"], case["nout"])
+    assert r["yfinal"].tolist() == fh(case["final"]) and r["t_reached"] == float.fromhex(case["t_reached"])
+    for i, (t, y) in case["rows"].items():
+        assert r["tout"][int(i)] == float.fromhex(t) and r["yout"][int(i)].tolist() == fh(y)
+    assert digest(r["tout"]) == case["sha256_tout"] and digest(r["yout"]) == case["sha256_yout"]
+
+
+@pytest.mark.parametrize("case", [c for c in STIFF["cases"] if c["kind"] == "rosenbrock"], ids=lambda c: c["name"])
+def test_oracle_rosenbrock_goldens(oracle, case):
+    ts = tspan_of(case["tspan"])
+    r = oracle.solve_rosenbrock(oracle.KR4 if case["which"] == "kr4" else oracle.S4, getattr(oracle, case["system"].upper()),
+                                fh(case["params"]), fh(case["y0"]), ts)
+    assert (r["status"], len(r["yout"])) == (case["status"], case["nout"])
+    for i, y in case["rows"].items():
+        assert r["yout"][int(i)].tolist() == fh(y)
+    assert digest(r["tout"]) == case["sha256_tout"] and digest(r["yout"]) == case["sha256_yout"]
+    assert len(r["tout"]) == max(len(ts) - 1, 0)          # `tout: diff(tspan)` (problem.rs:572,639), one short of yout
+
+
+def test_oracle_stiff_ensemble_matches_single(oracle):
+    """The OpenMP ensemble drivers run the same per-trajectory code as the single-trajectory entry points."""
+    mus = np.array([[0.5], [5.0], [50.0], [500.0]])
+    y0 = np.tile([2.0, 0.0], (4, 1))
+    ts = np.linspace(0.0, 30.0, 16)
+    o = oracle.opts(1e-5, 1e-8)
+    ens = oracle.ensemble_ode23s(oracle.VANDERPOL, mus, y0, ts, o, dense=True)
+    for i in range(4):
+        one = oracle.solve_ode23s(oracle.VANDERPOL, mus[i], y0[i], ts, o)
+        assert np.array_equal(ens["yfinal"][i], one["yfinal"]) and ens["accepted"][i] == one["accepted"]
+        assert ens["nrows"][i] == one["nout"] and ens["nfe"][i] == one["nfe"]
+        rows = {t: y for t, y in zip(one["tout"], one["yout"])}
+        for q in range(int(ens["nvalid"][i])):
+            assert np.array_equal(ens["out"][:, q, i], rows[ts[q]])
+    er = oracle.ensemble_rosenbrock(oracle.S4, oracle.VANDERPOL, mus, y0, np.linspace(0, 0.2, 21), want_all=True)
+    for i in range(4):
+        one = oracle.solve_rosenbrock(oracle.S4, oracle.VANDERPOL, mus[i], y0[i], np.linspace(0, 0.2, 21))
+        assert np.array_equal(er["yall"][i], one["yout"]) and np.array_equal(er["yfinal"][i], one["yfinal"])
+
+
+def test_ode23s_textbook_variant_converges():
+    """TEXTBOOK ode23s (true W^-1) is a working stiff solver: Van der Pol mu = 100 against scipy's Radau."""
+    import sys
+    sys.path.insert(0, HERE)
+    import pyref
+    from scipy.integrate import solve_ivp
+    mu = 100.0
+    r = pyref.ode23s(pyref.vanderpol([mu]), [2.0, 0.0], [0.0, 150.0], reltol=1e-6, abstol=1e-9, true_inverse=True)
+    ref = solve_ivp(lambda t, v: [v[1], mu * (1 - v[0] ** 2) * v[1] - v[0]], (0.0, 150.0), [2.0, 0.0], method="Radau",
+                    rtol=1e-10, atol=1e-12)
+    assert r["status"] == 0 and abs(r["y"][0] - ref.y[0, -1]) < 2e-3 * abs(ref.y[0, -1])

@@ -198,5 +198,85 @@ def main():
     print(f"wrote {len(cases)} solver cases and {len(ref)} x 2 tableaus to {OUT}")
 
 
+def parse_rosenbrock():
+    """RosenbrockCoeffs::kr4 / s4 parsed from src/ode/rosenbrock.rs (Matrix4::new / Vector4::new are row-major)."""
+    src = open(os.path.join(os.path.dirname(REF), "rosenbrock.rs")).read()
+    out = {}
+    for m in re.finditer(r"pub fn (\w+)\(\) -> Self \{", src):
+        name = m.group(1)
+        end = src.index("Self {", m.end())
+        body = src[m.end():end]
+        tail = src[end:src.index("}", end)]
+        gamma = float(re.search(r"gamma:\s*([0-9.]+)", tail).group(1))
+        a, b, c = _args(body, "let a ="), _args(body, "let b ="), _args(body, "let c =")
+        assert len(a) == 16 and len(b) == 4 and len(c) == 16
+        out[name] = dict(gamma=gamma, a=[a[4 * i:4 * i + 4] for i in range(4)], b=b, c=[c[4 * i:4 * i + 4] for i in range(4)])
+    return out
+
+
+def main_stiff():
+    """stiff_cases.json: ode23s / oderosenbrock known-answer vectors from tests/pyref.py."""
+    ros = parse_rosenbrock()
+    assert ros["kr4"] == pyref.ROSENBROCK["kr4"] and ros["s4"] == pyref.ROSENBROCK["s4"], "pyref coefficients differ from rosenbrock.rs"
+    LOR = [10.0, 28.0, 8.0 / 3.0]
+    PEN = [0.5, 1.2, 2.0 / 3.0]
+    cases = []
+
+    def ode23s(name, system, params, y0, tspan_desc, tspan, tset="reference", **kw):
+        r = pyref.ode23s(SYS[system](params), y0, tspan, true_inverse=(tset == "textbook"), **kw)
+        n = len(r["tout"])
+        keep = sorted(set([0, 1, 2, n // 2, n - 2, n - 1]) & set(range(n)))
+        cases.append(dict(name=name, kind="ode23s", system=system, tableau_set=tset, params=hx(params), y0=hx(y0), tspan=tspan_desc,
+                          options={k: (hx(v) if isinstance(v, float) else v) for k, v in kw.items()},
+                          accepted=r["accepted"], rejected=r["rejected"], status=r["status"], nout=n, final=hx(r["y"]),
+                          t_reached=hx(r["t"]), rows={str(i): [hx(r["tout"][i]), hx(r["yout"][i])] for i in keep},
+                          sha256_tout=digest(r["tout"]), sha256_yout=digest(r["yout"])))
+
+    def rosen(name, which, system, params, y0, tspan_desc, tspan):
+        r = pyref.oderosenbrock(SYS[system](params), ros[which], y0, tspan)
+        n = len(r["yout"])
+        keep = sorted(set([0, 1, 2, n // 2, n - 1]) & set(range(n)))
+        cases.append(dict(name=name, kind="rosenbrock", which=which, system=system, params=hx(params), y0=hx(y0), tspan=tspan_desc,
+                          status=r["status"], nout=n, final=hx(r["yout"][-1]), rows={str(i): hx(r["yout"][i]) for i in keep},
+                          sha256_tout=digest(r["tout"]), sha256_yout=digest(r["yout"])))
+
+    for tset in ("reference", "textbook"):
+        for mu in (1.0, 10.0, 1000.0):
+            ode23s(f"ode23s_{tset}_vdp_mu{mu}", "VanDerPol", [mu], [2.0, 0.0], ["list", 0.0, 20.0], [0.0, 20.0], tset=tset)
+        ode23s(f"ode23s_{tset}_vdp_mu100_dense", "VanDerPol", [100.0], [2.0, 0.0], ["linspace", 0.0, 200.0, 400],
+               linspace(0.0, 200.0, 400), tset=tset, reltol=1e-6, abstol=1e-8)
+        ode23s(f"ode23s_{tset}_lorenz", "Lorenz", LOR, [0.1, 0.0, 0.0], ["list", 0.0, 1.0, 2.5, 5.0], [0.0, 1.0, 2.5, 5.0], tset=tset)
+        ode23s(f"ode23s_{tset}_pendulum", "Pendulum", PEN, [1.0, 0.5], ["list", 0.0, 3.0, 10.0], [0.0, 3.0, 10.0], tset=tset,
+               reltol=1e-7, abstol=1e-9)
+    ode23s("ode23s_specified_points", "VanDerPol", [5.0], [2.0, 0.0], ["linspace", 0.0, 10.0, 101], linspace(0.0, 10.0, 101),
+           points_all=False)
+    ode23s("ode23s_backward", "Lorenz", LOR, [1.0, 2.0, 20.0], ["list", 0.0, -0.5, -1.0], [0.0, -0.5, -1.0], max_steps=3000)
+    ode23s("ode23s_initstep_maxstep", "VanDerPol", [3.0], [2.0, 0.0], ["list", 0.0, 5.0], [0.0, 5.0], initstep=0.01, maxstep=0.05)
+    ode23s("ode23s_negative_initstep_is_abs", "VanDerPol", [3.0], [2.0, 0.0], ["list", 0.0, 1.0], [0.0, 1.0], initstep=-0.01)
+    ode23s("ode23s_minstep_exit", "VanDerPol", [50.0], [2.0, 0.0], ["list", 0.0, 100.0], [0.0, 100.0], minstep=0.05)
+    ode23s("ode23s_zero_state_jacobian", "Lorenz", LOR, [0.0, 0.0, 0.0], ["list", 0.0, 1.0], [0.0, 1.0], max_steps=500)
+    ode23s("ode23s_libm_folded", "VanDerPol", [10.0], [2.0, 0.0], ["list", 0.0, 20.0], [0.0, 20.0], libm_folded=True)
+    # OdeError::InvalidMatrix (problem.rs:481,588): Lorenz at the origin with rho = 0, beta = -4 has d f_z / d z = 4 exactly, so
+    # W_zz = 1 - 4 (h d) vanishes for h d = 0.25 (h = 0x1.b504f333f9de6p-1) and (1/(gamma h) - 4) for gamma h = 0.25
+    ode23s("ode23s_invalid_matrix", "Lorenz", [10.0, 0.0, -4.0], [0.0, 0.0, 0.0], ["list", 0.0, 10.0], [0.0, 10.0],
+           initstep=float.fromhex("0x1.b504f333f9de6p-1"), maxstep=5.0)
+    ode23s("ode23s_minstep_midrun", "VanDerPol", [1000.0], [2.0, 0.0], ["list", 0.0, 2000.0], [0.0, 2000.0], minstep=3e-4)
+    ode23s("ode23s_zero_span", "Lorenz", LOR, [1.0, 2.0, 20.0], ["list", 1.0, 1.0], [1.0, 1.0])
+    for which in ("kr4", "s4"):
+        rosen(f"{which}_vdp", which, "VanDerPol", [5.0], [2.0, 0.0], ["linspace", 0.0, 0.39, 40], linspace(0.0, 0.39, 40))
+        rosen(f"{which}_lorenz", which, "Lorenz", LOR, [0.1, 0.0, 0.0], ["linspace", 0.0, 0.05, 51], linspace(0.0, 0.05, 51))
+        rosen(f"{which}_pendulum", which, "Pendulum", PEN, [1.0, 0.5], ["list", 0.0, 0.1, 0.15, 0.4], [0.0, 0.1, 0.15, 0.4])
+        rosen(f"{which}_invalid_matrix_step2", which, "Lorenz", [10.0, 0.0, -4.0], [0.0, 0.0, 0.0],
+              ["list", 0.0, 0.25, 0.25 + 0.25 / ros[which]["gamma"], 9.0], [0.0, 0.25, 0.25 + 0.25 / ros[which]["gamma"], 9.0])
+        rosen(f"{which}_single_point", which, "Lorenz", LOR, [0.1, 0.0, 0.0], ["list", 0.0], [0.0])
+    json.dump({"rosenbrock_coeffs": {k: dict(gamma=hx(v["gamma"]), a=hx(v["a"]), b=hx(v["b"]), c=hx(v["c"])) for k, v in ros.items()},
+               "cases": cases}, open(os.path.join(OUT, "stiff_cases.json"), "w"), indent=0)
+    print(f"wrote {len(cases)} stiff cases to {OUT}")
+
+
 if __name__ == "__main__":
-    main()
+    if "stiff" in sys.argv[1:]:
+        main_stiff()       # leaves tableaus.json / solver_cases.json untouched
+    else:
+        main()
+        main_stiff()
