@@ -264,6 +264,21 @@ def main():
         gather_ms = g0.elapsed_time(g1)
         assert sum(p.shape[0] for p in parts) == ntraj * world and torch.equal(parts[rank], loc)
 
+    # ---------------- stiff path, informational: ode23s on a Van der Pol stiffness sweep ----------------
+    stiff = None
+    if rank == 0:
+        ns = 1 << 18
+        mu = np.geomspace(0.1, 1000.0, ns)[:, None]
+        sp = D.OdeProblem.builder().fun(D.Rhs.builtin(D.System.VanDerPol)).params(mu).init(np.tile([2.0, 0.0], (ns, 1))).tspan([0.0, 20.0]).build()
+        so = D.OdeOptionMap().insert(D.Reltol(1e-5), D.Abstol(1e-8), D.MaxSteps(20000))
+        stiff = {"workload": "2^18 Van der Pol, mu = geomspace(0.1, 1000), y0 = [2, 0], tspan [0, 20], ode23s rtol 1e-5 atol 1e-8, max_steps 20000"}
+        for name, tset in (("reference", 0), ("textbook", 1)):
+            sp.solve(D.Ode.Ode23s, so, tableau_set=tset, fetch=False)
+            r = sp.solve(D.Ode.Ode23s, so, tableau_set=tset, fetch=False)
+            att = r.totals["accepted"] + r.totals["rejected"]
+            stiff[name] = {"steps_per_s": att / (r.kernel_ms * 1e-3), "kernel_ms": r.kernel_ms, "step_attempts": att}
+        del sp
+
     # ---------------- reduce over ranks ----------------
     t = torch.tensor([dev_ms, e2e_s, wall, fast_ms, e2e_fast_s, fold_ms], dtype=torch.float64, device="cuda")
     c = torch.tensor([steps_done, e2e_steps, fast_steps, e2e_fast_steps, fold_steps], dtype=torch.float64, device="cuda")
@@ -317,6 +332,7 @@ def main():
                 "note": "bit-exact PARITY arithmetic with the libm calls an LLVM-optimised build of the crate makes (sqrt for the error norm, "
                         "exp10 in hinit; DESIGN.md 4.1) — one pow per step instead of two"},
             "mode_check": mode_check,
+            "stiff_ode23s": stiff,
             "final_gather_ms": gather_ms,
             "clocks": clocks, "wall_s_timed_region": wall_max,
         }

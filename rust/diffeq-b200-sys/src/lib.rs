@@ -84,6 +84,7 @@ extern "C" {
     pub fn deq_result_destroy(res: *mut deq_result);
     pub fn deq_tableau_get(method: c_int, tableau_set: c_int, stages: *mut c_int, a: *mut c_double, b: *mut c_double,
                            c: *mut c_double, adaptive: *mut c_int, order_min: *mut c_int, fsal: *mut c_int) -> deq_status;
+    pub fn deq_rosenbrock_get(method: c_int, gamma: *mut c_double, a: *mut c_double, b: *mut c_double, c: *mut c_double) -> deq_status;
     pub fn deq_host_alloc(bytes: usize, out: *mut *mut c_void) -> deq_status;
     pub fn deq_host_free(p: *mut c_void);
     pub fn deq_test_pow(x: *const c_double, y: *const c_double, out: *mut c_double, n: usize) -> deq_status;

@@ -140,5 +140,9 @@ impl OdeProblem {
     pub fn ode45_fe(&self, opts: OdeOptionMap) -> Result<OdeSolution, OdeError> { self.solve(Ode::Ode45fe, opts) }
     pub fn ode78(&self, opts: OdeOptionMap) -> Result<OdeSolution, OdeError> { self.solve(Ode::Ode78, opts) }
     pub fn ode4(&self) -> Result<OdeSolution, OdeError> { self.solve(Ode::Ode4, OdeOptionMap::default()) }
+    /// problem.rs:409 — per-trajectory status 3 maps to the reference's Err(OdeError::InvalidMatrix) for a single problem
+    pub fn ode23s(&self, opts: OdeOptionMap) -> Result<OdeSolution, OdeError> { self.solve(Ode::Ode23s, opts) }
+    pub fn ode4s_kr(&self) -> Result<OdeSolution, OdeError> { self.solve(Ode::Ode4skr, OdeOptionMap::default()) }   // problem.rs:643
+    pub fn ode4s_s(&self) -> Result<OdeSolution, OdeError> { self.solve(Ode::Ode4ss, OdeOptionMap::default()) }     // problem.rs:648
 }
 impl Drop for OdeProblem { fn drop(&mut self) { unsafe { sys::deq_ensemble_destroy(self.h) } } }

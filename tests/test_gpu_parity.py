@@ -264,7 +264,7 @@ def test_nvrtc_same_source_reuses_compiled_kernel(deq):
     def run():
         rhs = deq.Rhs.from_source(USER_LORENZ + "// cache-test\n", 3, 3)
         t0 = time.perf_counter()
-        s = deq.OdeProblem.builder().fun(rhs).params(LOR).init(y0).tspan([0.0, 2.0]).build().solve(deq.Ode.Ode23, o)
+        s = deq.OdeProblem.builder().fun(rhs).params(LOR).init(y0).tspan([0.0, 2.0]).build().solve(deq.Ode.Ode45fe, o)
         dt = time.perf_counter() - t0
         fin = s.final.copy()
         del s, rhs
