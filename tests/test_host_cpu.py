@@ -54,6 +54,22 @@ def test_product_tableaus_match_reference_source(deq):
             assert np.array_equal(t["b"] if g["adaptive"] else t["b"][:, 0], gb if g["adaptive"] else gb[:, 0])
 
 
+def test_product_rosenbrock_coefficients_match_reference_source(deq):
+    """The kernels' kr4 / s4 sets (stiff.cuh) against the values parsed from rosenbrock.rs (tools/gen_golden.py stiff)."""
+    gold = json.load(open(os.path.join(HERE, "golden", "stiff_cases.json")))["rosenbrock_coeffs"]
+    fh = lambda v: [fh(x) for x in v] if isinstance(v, list) else float.fromhex(v)  # noqa: E731
+    for which, m in (("kr4", deq.Ode.Ode4skr), ("s4", deq.Ode.Ode4ss)):
+        co, g = deq.rosenbrock_coeffs(m), gold[which]
+        assert co["gamma"] == fh(g["gamma"]) and co["a"].tolist() == fh(g["a"]) and co["b"].tolist() == fh(g["b"]) and co["c"].tolist() == fh(g["c"])
+    with pytest.raises(deq.OdeError):
+        deq.rosenbrock_coeffs(deq.Ode.Ode45)
+    with pytest.raises(deq.OdeError) as e:
+        deq.tableau(deq.Ode.Ode23s)          # the stiff methods have no Butcher tableau
+    assert e.value.kind == "Unsupported"
+    assert deq._traits(deq.Ode.Ode23s) == (True, True, True) and deq._traits(deq.Ode.Ode4ss) == (False, True, True)
+    assert deq._traits(deq.Ode.Ode45) == (True, True, False) and deq._traits(deq.Ode.Ode4) == (False, False, False)
+
+
 def test_ode_enum_and_from_str(deq):
     """mod.rs:14-46: variant order and the FromStr table (no name for Ode45fe; "ode4s" -> Ode4ss)."""
     assert [e.name for e in deq.Ode][:11] == ["Feuler", "Heun", "Midpoint", "Ode23", "Ode23s", "Ode4", "Ode45", "Ode45fe",
