@@ -381,8 +381,14 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         CKR(cudaEventRecord(r->ev1, st));
     } else {
         // ---- oderk_adapt ----
-        if (!sk && o.points != DEQ_POINTS_ALL)
-            return bail(fail(DEQ_ERR_UNSUPPORTED, "Points::Specified re-reads y from the output vector in the reference (problem.rs:262) and yields wrong trajectories; use DEQ_POINTS_ALL with output = DEQ_OUT_TSPAN"));
+        // Points::Specified on the explicit path (problem.rs:284-300) is reproduced with the reference's defect (y re-read from
+        // the output vector, :262): parity arithmetic, final state or the full stream (whose rows are exactly the tspan points)
+        const bool spec = !sk && o.points == DEQ_POINTS_SPECIFIED;
+        if (!sk && o.points != DEQ_POINTS_ALL && !spec) return bail(fail(DEQ_ERR_INVALID_ARG, "unknown points kind"));
+        if (spec && (o.mode != DEQ_MODE_PARITY || o.precision != DEQ_PRECISION_F64))
+            return bail(fail(DEQ_ERR_UNSUPPORTED, "Points::Specified is carried by the f64 parity kernels only"));
+        if (spec && want_dense)
+            return bail(fail(DEQ_ERR_UNSUPPORTED, "Points::Specified: use output = DEQ_OUT_ALL (every row of that stream is a tspan point) or DEQ_OUT_FINAL"));
         if (nt == 0) { *out = r; r->ntraj = 0; return DEQ_OK; }  // problem.rs:211-214: nothing to solve
         if (want_dense && nt < 2) return bail(fail(DEQ_ERR_INVALID_ARG, "DEQ_OUT_TSPAN needs at least 2 tspan points"));
         r->all = want_all;
@@ -396,7 +402,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         CKR(dalloc(&r->d_status, ntraj, st)); CKR(dalloc(&r->d_treached, ntraj, st));
         CKR(dalloc(&r->d_f0, ntraj * n, st)); CKR(dalloc(&r->d_h0, ntraj, st));
         if (want_dense) { CKR(dalloc(&r->d_dense, ntraj * n * nt, st)); CKR(dalloc(&r->d_nvalid, ntraj, st)); }
-        if (want_all) { CKR(dalloc(&r->d_nvalid, ntraj, st)); CKR(dalloc(&r->d_rec_counts, ntraj, st)); CKR(dalloc(&r->d_rec_offsets, ntraj + 1, st)); }
+        if (want_all || spec) { CKR(dalloc(&r->d_nvalid, ntraj, st)); CKR(dalloc(&r->d_rec_counts, ntraj, st)); CKR(dalloc(&r->d_rec_offsets, ntraj + 1, st)); }
         deqk::HinitParams H{};
         H.y0 = e->d_y0; H.params = e->d_params; H.shared = e->shared; H.ntraj = ntraj; H.t0 = t0; H.tend = tend;
         H.reltol = o.reltol; H.abstol = o.abstol; H.order = info.order_min; H.f0 = r->d_f0; H.h0 = r->d_h0;
@@ -412,8 +418,9 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         P.t_reached = r->d_treached; P.dense = r->d_dense; P.nvalid = r->d_nvalid;
         P.work_counter = r->d_scalars; P.totals = r->d_scalars + 1;
         P.true_inverse = sk && tableau_set == DEQ_TABLEAU_TEXTBOOK; P.points_specified = o.points == DEQ_POINTS_SPECIFIED;
-        const int mode = want_all ? deqk::MODE_REC
-                         : want_dense ? (o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR ? deqk::MODE_DENSE_TM : deqk::MODE_DENSE) : deqk::MODE_FINAL;
+        const int mode = spec ? (int)deqk::MODE_REC_SPEC   // a final-state request runs its counting pass only
+                         : want_all ? (int)deqk::MODE_REC
+                         : want_dense ? (o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR ? (int)deqk::MODE_DENSE_TM : (int)deqk::MODE_DENSE) : (int)deqk::MODE_FINAL;
         P.rec_mode = deqk::REC_COUNT;
         r->traj_major = want_dense && o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR;
         P.rec_counts = r->d_rec_counts;

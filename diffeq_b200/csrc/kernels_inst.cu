@@ -63,10 +63,10 @@ static int persistent_grid(K kernel, unsigned long long ntraj, size_t dyn_smem =
 #define DEQ_LAUNCH_ADAPT DEQ_CAT(launch_adapt_, DEQ_TB)
 #endif
 
-template <class F, bool PT, int MODE>
+template <class F, bool PT, int MODE, bool SPEC = false>
 static cudaError_t launch_adapt_t(const deqk::AdaptParams& P, int grid_blocks, cudaStream_t st) {
-    if constexpr (TB::ADAPTIVE) {
-        auto kernel = deqk::adapt_kernel<TB, F, PT, MODE, kFast>;
+    if constexpr (TB::ADAPTIVE && !(SPEC && kFast)) {
+        auto kernel = deqk::adapt_kernel<TB, F, PT, MODE, kFast, SPEC>;
         const size_t smem = (MODE == deqk::MODE_DENSE_TM || (MODE == deqk::MODE_REC && P.rec_mode == deqk::REC_WRITE)) ? deqk::STAGE_BYTES : 0;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int grid = grid_blocks > 0 ? grid_blocks : persistent_grid(kernel, P.ntraj, smem);
@@ -89,6 +89,8 @@ static cudaError_t launch_adapt_f(int pt, int mode, const deqk::AdaptParams& P, 
         case deqk::MODE_DENSE_TM * 2 + 1: return launch_adapt_t<F, true, deqk::MODE_DENSE_TM>(P, grid_blocks, st);
         case deqk::MODE_REC * 2: return launch_adapt_t<F, false, deqk::MODE_REC>(P, grid_blocks, st);
         case deqk::MODE_REC * 2 + 1: return launch_adapt_t<F, true, deqk::MODE_REC>(P, grid_blocks, st);
+        case deqk::MODE_REC_SPEC * 2: return launch_adapt_t<F, false, deqk::MODE_REC, true>(P, grid_blocks, st);       // Points::Specified
+        case deqk::MODE_REC_SPEC * 2 + 1: return launch_adapt_t<F, true, deqk::MODE_REC, true>(P, grid_blocks, st);
         default: return cudaErrorInvalidValue;
     }
 }

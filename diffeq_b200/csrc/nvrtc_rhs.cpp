@@ -146,7 +146,7 @@ static bool get_kernel(Program* p, int kind, int tb, int pt, int mode, Kernel* o
     const char* b = pt ? "true" : "false";
     if (kind == 0) ne << "&deqk::hinit_kernel<DeqUserRhs, " << b << ">";
     else if (kind == 1) ne << "&deqk::adapt_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode & 3) << ", "
-                           << ((mode & 4) ? "true" : "false") << ">";
+                           << ((mode & 4) ? "true" : "false") << ", " << ((mode & 8) ? "true" : "false") << ">";
     else if (kind == 2) ne << "&deqk::fixed_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode ? "true" : "false") << ">";
     else if (kind == 3) ne << "&deqk::ode23s_kernel<DeqUserRhs, " << b << ", " << (mode & 3) << ">";
     else ne << "&deqk::rosenbrock_kernel<" << (tb == 0 ? "deqk::Kr4" : "deqk::S4") << ", DeqUserRhs, " << b << ", " << (mode ? "true" : "false") << ">";
@@ -198,7 +198,9 @@ bool launch_hinit(Program* p, int pt, const deqk::HinitParams& P, cudaStream_t s
 bool launch_adapt(Program* p, int tb, int pt, int mode, bool fast, const deqk::AdaptParams& P, cudaStream_t st,
                   std::string* err) {
     Kernel k;
-    if (!get_kernel(p, 1, tb, pt ? 1 : 0, (mode & 3) | (fast ? 4 : 0), &k, err)) return false;
+    const bool spec = mode == deqk::MODE_REC_SPEC;   // Points::Specified flavour of MODE_REC
+    if (spec) mode = deqk::MODE_REC;
+    if (!get_kernel(p, 1, tb, pt ? 1 : 0, (mode & 3) | (fast ? 4 : 0) | (spec ? 8 : 0), &k, err)) return false;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -327,8 +327,13 @@ __device__ __forceinline__ void stage_append(double* stage, double* out, StageLa
 // ---------------------------------------------------------------------------------------------------------------
 // oderk_adapt (problem.rs:193-358), Points::All semantics.
 // ---------------------------------------------------------------------------------------------------------------
-template <class TB, class F, bool PT, int MODE, bool FAST>
+// SPEC = Points::Specified (problem.rs:284-300), reproduced with its defect: the step starts from `y` re-read from the OUTPUT
+// vector (:262) — the last row pushed, which only moves when a tspan point is emitted — while the stages start from the true
+// state (:261).  Instantiated for MODE_REC only (every row of the stream is a tspan point; the counting pass alone serves
+// a final-state request), PARITY arithmetic only.
+template <class TB, class F, bool PT, int MODE, bool FAST, bool SPEC = false>
 __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const AdaptParams P) {
+    static_assert(!SPEC || (MODE == MODE_REC && !FAST), "Points::Specified: MODE_REC, parity arithmetic");
     constexpr int N = F::N, S = TB::S;
     constexpr bool FSAL = deqt::fsal_of(TB::data());
     // what this instantiation records besides the final state (compile time, so the hot loop carries no mode tests):
@@ -361,6 +366,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     unsigned long long traj = 0;
     double t = 0.0, dt = 0.0;
     double cy[N], ck[N], prm[F::NP ? F::NP : 1];
+    double yl[N];   // SPEC only: ys[ys.len() - 1], the last row of the output vector (dead code otherwise)
     unsigned timeout = 0;
     bool last_step = false;
     uint32_t acc = 0, rej = 0, attempts = 0;
@@ -373,6 +379,8 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
 #endif
 #pragma unroll
     for (int d = 0; d < N; ++d) { cy[d] = 0.0; ck[d] = 0.0; }
+#pragma unroll
+    for (int d = 0; d < N; ++d) yl[d] = 0.0;
 #pragma unroll
     for (int j = 0; j < (F::NP ? F::NP : 1); ++j) prm[j] = 0.0;
 
@@ -394,6 +402,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     for (int d = 0; d < N; ++d) {
                         cy[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
                         ck[d] = P.f0[(unsigned long long)d * P.ntraj + traj];
+                        if (SPEC) yl[d] = cy[d];
                     }
                     t = P.t0;
                     dt = P.use_initstep ? P.initstep : P.h0[traj];
@@ -446,14 +455,17 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                 double ndt;
                 bool accept;
                 if (!FAST) {
-                    // embedded_step :761-771  (y == cy under Points::All)
+                    // embedded_step :761-771  (y == cy under Points::All; the last output row under Points::Specified)
+                    double ys[N];
+#pragma unroll
+                    for (int d = 0; d < N; ++d) ys[d] = SPEC ? yl[d] : cy[d];
 #pragma unroll
                     for (int d = 0; d < N; ++d) {
                         double p = 0.0, q = 0.0;
 #pragma unroll
                         for (int s = 0; s < S; ++s) { p = p + k[s][d] * tb.b[s][0]; q = q + k[s][d] * tb.b[s][1]; }
                         yerr[d] = (p - q) * dt;
-                        ytrial[d] = cy[d] + (p * dt);
+                        ytrial[d] = ys[d] + (p * dt);
                     }
                     // stepsize_hw92 :801-845.  The reference first scans the trial state for NaN (-> err = 10, dt *= 0.2,
                     // timeout = 5).  A NaN trial component makes the scaled error sum NaN as well, so the scan only has to
@@ -461,7 +473,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     double ssum = 0.0;
 #pragma unroll
                     for (int d = 0; d < N; ++d) {
-                        const double e = yerr[d] / (max_abs_nonan(cy[d], ytrial[d]) * reltol + abstol);
+                        const double e = yerr[d] / (max_abs_nonan(ys[d], ytrial[d]) * reltol + abstol);
                         const double a = fabs(e);
                         ssum = ssum + a * a;
                     }
@@ -520,7 +532,30 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     } else {
                         F::eval(t + dt, ytrial, f1, prm);
                     }
-                    if (ROWS) {
+                    if (SPEC) {
+                        // Points::Specified :284-300 — every tspan point before t+dt, all remaining ones on the last step;
+                        // Hermite from the step's (lagging) y, each emitted row becomes the new last output row
+                        const double tn = t + dt;
+                        double y0s[N];
+#pragma unroll
+                        for (int d = 0; d < N; ++d) y0s[d] = yl[d];
+                        while (it < P.nt) {
+                            const double tq = __ldg(P.tspan + it);
+                            if (!(tdir * tq < tdir * tn || last_step)) break;
+                            const double theta = (tq - t) / dt;
+                            if (P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, tq);
+#pragma unroll
+                            for (int d = 0; d < N; ++d) {
+                                const double v = (y0s[d] * (1. - theta) + ytrial[d] * theta) +
+                                                 ((ytrial[d] - y0s[d]) * (1. - 2. * theta) + k[0][d] * (theta - 1.) * dt +
+                                                  f1[d] * theta * dt) * theta * (theta - 1.);
+                                if (P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, v);
+                                yl[d] = v;
+                            }
+                            ++wpos;
+                            ++it;
+                        }
+                    } else if (ROWS) {
                         // Points::All :303-319 — Hermite values at tspan points strictly inside (t, t+dt)
                         const double tn = t + dt;
                         while (it < P.nt) {
@@ -578,7 +613,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
 #endif
                 const uint32_t nfe = 2u + attempts * (uint32_t)(S - 1) + (FSAL ? 0u : acc);
 #pragma unroll
-                for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = cy[d];
+                for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = SPEC ? yl[d] : cy[d];
                 P.accepted[traj] = acc; P.rejected[traj] = rej; P.nfe[traj] = nfe; P.status[traj] = fin; P.t_reached[traj] = t;
                 if (ROWS) {
                     if (SOA) {

@@ -53,10 +53,12 @@ typedef enum deq_tableau_set { DEQ_TABLEAU_REFERENCE = 0, DEQ_TABLEAU_TEXTBOOK =
 
 typedef enum deq_system { DEQ_SYS_LORENZ = 0, DEQ_SYS_VANDERPOL = 1, DEQ_SYS_PENDULUM = 2 } deq_system;
 
-/* `Points` (src/ode/options.rs:120-137).  For the explicit adaptive methods only Points::All is reference-valid
- * (Specified re-reads y from the output vector, problem.rs:262) and Specified is rejected with DEQ_ERR_UNSUPPORTED; use
- * deq_output for tspan-only rows.  DEQ_ODE23S honours both (problem.rs:536): with DEQ_OUT_ALL, Specified yields the rows at
- * the tspan times only, All adds every step end point. */
+/* `Points` (src/ode/options.rs:120-137).  Points::All is the reference-valid choice.  Points::Specified on the explicit
+ * adaptive methods re-reads y from the output vector (problem.rs:262) and yields wrong trajectories whenever the tspan grid
+ * is coarser than the steps; it is reproduced bug-for-bug (f64 parity kernels, output = DEQ_OUT_FINAL or DEQ_OUT_ALL — the
+ * rows of that stream are exactly the tspan points; DEQ_OUT_TSPAN answers DEQ_ERR_UNSUPPORTED).  For correct tspan-only rows
+ * use DEQ_POINTS_ALL with output = DEQ_OUT_TSPAN.  DEQ_ODE23S honours both kinds (problem.rs:536): with DEQ_OUT_ALL,
+ * Specified yields the rows at the tspan times only, All adds every step end point. */
 typedef enum deq_points { DEQ_POINTS_ALL = 0, DEQ_POINTS_SPECIFIED = 1 } deq_points;
 
 /* What deq_solve materialises. */

@@ -585,9 +585,9 @@ def test_golden_fixtures_through_the_cuda_path(deq):
             assert hashlib.sha256(np.ascontiguousarray(sol.yout[0], dtype="<f8").tobytes()).hexdigest() == c["sha256_yout"], c["name"]
         else:
             opt = c["options"]
-            if opt.get("points_all") is False:
-                continue   # Points::Specified: reference-broken, rejected by the product (covered by the oracle goldens)
             o = deq.OdeOptionMap().insert(deq.Output.All)
+            if opt.get("points_all") is False:
+                o.insert(deq.Points.Specified)   # reproduced with the reference's defect (problem.rs:262)
             for k, cls in (("reltol", deq.Reltol), ("abstol", deq.Abstol), ("minstep", deq.Minstep), ("maxstep", deq.Maxstep), ("initstep", deq.Initstep)):
                 if k in opt:
                     o.insert(cls(float.fromhex(opt[k])))
@@ -602,7 +602,45 @@ def test_golden_fixtures_through_the_cuda_path(deq):
             assert hashlib.sha256(np.ascontiguousarray(tout, dtype="<f8").tobytes()).hexdigest() == c["sha256_tout"], c["name"]
             assert hashlib.sha256(np.ascontiguousarray(yout, dtype="<f8").tobytes()).hexdigest() == c["sha256_yout"], c["name"]
         ran += 1
-    assert ran >= 30
+    assert ran == len(cases) >= 34
+
+
+def test_points_specified_reproduces_the_reference_defect(deq, oracle):
+    """Points::Specified (problem.rs:284-300): y is re-read from the OUTPUT vector (:262), so the solver's notion of the state
+    lags behind whenever the tspan grid is coarser than the steps.  The product reproduces that stream bit for bit."""
+    from diffeq_b200 import synth
+    n = 300
+    y0, mu = synth.vdp_sweep(0, n, n)
+    ts = deq.linspace(0.0, 10.0, 41)
+    base = (deq.Reltol(1e-6), deq.Abstol(1e-8), deq.MaxSteps(20000), deq.Points.Specified)
+    prob = _problem(deq, deq.System.VanDerPol, mu, y0, ts)
+    sa = prob.solve(deq.Ode.Ode45fe, deq.OdeOptionMap().insert(*base, deq.Output.All))
+    sf = prob.solve(deq.Ode.Ode45fe, deq.OdeOptionMap().insert(*base))                       # final state only: counting pass
+    oo = oracle.opts(1e-6, 1e-8, points=oracle.POINTS_SPECIFIED, max_steps=20000)
+    ens = oracle.ensemble_adaptive(oracle.ODE45FE, oracle.VANDERPOL, mu, y0, ts, oo)
+    for s in (sa, sf):
+        assert np.array_equal(s.final, ens["yfinal"]) and np.array_equal(s.accepted, ens["accepted"])
+        assert np.array_equal(s.rejected, ens["rejected"]) and np.array_equal(s.status, ens["status"])
+        assert np.array_equal(s.nfe, ens["nfe"]) and np.array_equal(s.t_reached, ens["t_reached"])
+    for i in (0, 1, 150, n - 1):
+        one = oracle.solve_adaptive(oracle.ODE45FE, oracle.VANDERPOL, mu[i], y0[i], ts, oo)
+        tout, yout = sa.trajectory(i)
+        assert np.array_equal(tout, one["tout"]) and np.array_equal(yout, one["yout"]), i
+        assert np.array_equal(tout, ts[:len(tout)])                                           # rows are the tspan points
+    # user systems (NVRTC) and a 3-dimensional FSAL method
+    yl = synth.lorenz_ics(0, 64)
+    tl = deq.linspace(0.0, 1.0, 201)
+    ol = oracle.opts(1e-7, 1e-7, points=oracle.POINTS_SPECIFIED, max_steps=5000)
+    el = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, yl, tl, ol)
+    rhs = deq.Rhs.from_source(USER_LORENZ, 3, 3)
+    su = deq.OdeProblem.builder().fun(rhs).params(LOR).init(yl).tspan(tl).build().solve(
+        deq.Ode.Ode45, deq.OdeOptionMap().insert(deq.Reltol(1e-7), deq.Abstol(1e-7), deq.MaxSteps(5000), deq.Points.Specified, deq.Output.All))
+    assert np.array_equal(su.final, el["yfinal"]) and np.array_equal(su.accepted, el["accepted"])
+    with pytest.raises(deq.OdeError) as e:
+        prob.solve(deq.Ode.Ode45fe, deq.OdeOptionMap().insert(deq.Points.Specified, deq.Output.Tspan))
+    assert e.value.kind == "Unsupported"
+    with pytest.raises(deq.OdeError):
+        prob.solve(deq.Ode.Ode45fe, deq.OdeOptionMap().insert(deq.Points.Specified, deq.Mode.Fast))
 
 
 def test_full_size_config2_properties(deq, oracle):
