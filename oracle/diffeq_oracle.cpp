@@ -944,6 +944,19 @@ int oracle_ensemble_rosenbrock(int which, int rhs, size_t ntraj, const double* y
     });
 }
 
+// fdjacobian (problem.rs:903-926) on its own: J is [n][n] row-major (dfdx[(m, n)] = J[m * dim + n]).
+int oracle_fdjacobian(int rhs, const double* params, double t, const double* x, double* J) {
+    return dispatch_rhs(rhs, [&](auto f) {
+        using F = decltype(f);
+        constexpr int N = F::N;
+        double jac[N][N];
+        uint32_t nfe = 0;
+        fdjacobian<N, F>(t, x, params, jac, nfe);
+        for (int r = 0; r < N; ++r) for (int c = 0; c < N; ++c) J[r * N + c] = jac[r][c];
+        return (int)OK;
+    });
+}
+
 int oracle_rosenbrock_coeffs(int which, double* gamma, double* a, double* b, double* c) {
     if (which != 0 && which != 1) return ERR_INVALID_ARG;
     const RosenbrockCoeffs co = rosenbrock_coeffs(which);

@@ -253,6 +253,17 @@ def ensemble_rosenbrock(which, rhs, params, y0, tspan, nthreads=0, want_all=Fals
     return dict(yfinal=yf, status=st, yall=yall)
 
 
+def fdjacobian(rhs, params, t, x):
+    """`fdjacobian` (problem.rs:903-926): forward-difference Jacobian, [n][n]."""
+    params, x = _f64(params), _f64(x)
+    n = rhs_dim(rhs)
+    J = np.empty((n, n))
+    rc = lib().oracle_fdjacobian(rhs, _p(params), C.c_double(t), _p(x), _p(J))
+    if rc:
+        raise RuntimeError(f"oracle_fdjacobian rc={rc}")
+    return J
+
+
 def rosenbrock_coeffs(which):
     g = C.c_double(); a = np.zeros(16); b = np.zeros(4); c = np.zeros(16)
     rc = lib().oracle_rosenbrock_coeffs(which, C.byref(g), _p(a), _p(b), _p(c))

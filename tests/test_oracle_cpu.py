@@ -210,3 +210,23 @@ def test_ode23s_textbook_variant_converges():
     ref = solve_ivp(lambda t, v: [v[1], mu * (1 - v[0] ** 2) * v[1] - v[0]], (0.0, 150.0), [2.0, 0.0], method="Radau",
                     rtol=1e-10, atol=1e-12)
     assert r["status"] == 0 and abs(r["y"][0] - ref.y[0, -1]) < 2e-3 * abs(ref.y[0, -1])
+
+
+def test_reference_unit_tests_mirrored(oracle):
+    """The reference's own unit tests, restated against the oracle: runge_kutta.rs:823-836 (`is_consistent`, `is_fsal`),
+    problem.rs:1012-1034 (`diff_test`, `fdjacobian_test` on the Lorenz fixture Y0 = [0.1, 0, 0])."""
+    import sys
+    sys.path.insert(0, HERE)
+    import pyref
+    for m in ("FEULER", "MIDPOINT", "HEUN", "ODE21", "ODE4"):          # is_consistent_rk: a[(i, i-1)] == c[i]
+        t = oracle.tableau(getattr(oracle, m))
+        assert all(t["a"][i][i - 1] == t["c"][i] for i in range(1, t["S"])), m
+    assert not oracle.tableau(oracle.MIDPOINT)["fsal"] and oracle.tableau(oracle.ODE45)["fsal"]
+    r = oracle.solve_rosenbrock(oracle.S4, oracle.VANDERPOL, [1.0], [2.0, 0.0], [2.0, 6.0, 4.0, 16.0])
+    assert r["tout"].tolist() == [4.0, -2.0, 12.0]                      # diff(&[2, 6, 4, 16])
+    assert oracle.solve_rosenbrock(oracle.S4, oracle.VANDERPOL, [1.0], [2.0, 0.0], [])["tout"].tolist() == []
+    J = oracle.fdjacobian(oracle.LORENZ, [10.0, 28.0, 8.0 / 3.0], 0.0, [0.1, 0.0, 0.0])
+    assert J.shape == (3, 3)
+    assert J.tolist() == pyref.fdjacobian(pyref.lorenz([10.0, 28.0, 8.0 / 3.0]), 0.0, [0.1, 0.0, 0.0])
+    exact = np.array([[-10.0, 10.0, 0.0], [28.0, -1.0, -0.1], [0.0, 0.1, -8.0 / 3.0]])   # analytic Jacobian at Y0
+    assert np.allclose(J, exact, rtol=0, atol=2e-2)                      # "crude" indeed: dx = 1 % of x (or of 1 where x = 0)
