@@ -112,7 +112,8 @@ class _Options(C.Structure):
     _fields_ = [("reltol", C.c_double), ("abstol", C.c_double), ("has_minstep", C.c_int), ("minstep", C.c_double),
                 ("has_maxstep", C.c_int), ("maxstep", C.c_double), ("initstep", C.c_double), ("points", C.c_int),
                 ("output", C.c_int), ("max_steps", C.c_uint64), ("refill", C.c_int), ("async_", C.c_int),
-                ("mode", C.c_int), ("precision", C.c_int), ("libm", C.c_int), ("dense_layout", C.c_int)]
+                ("mode", C.c_int), ("precision", C.c_int), ("libm", C.c_int), ("dense_layout", C.c_int),
+                ("shard_chunk", C.c_uint64)]
 
 
 # The symbols include/diffeq_b200.h declares (checked by tests/test_abi.py).
@@ -276,6 +277,7 @@ class Initstep(_Opt): name = "Initstep"
 class MaxSteps(_Opt): name = "MaxSteps"      # extension (guard; the reference has none)
 class Refill(_Opt): name = "Refill"          # extension (scheduling only; results do not depend on it)
 class OutputOpt(_Opt): name = "Output"       # extension (what to materialise)
+class ShardChunk(_Opt): name = "ShardChunk"  # extension (multi-device deq_solve_host: block-cyclic chunk size, 0 = contiguous)
 
 
 class OdeOptionMap(dict):
@@ -315,6 +317,7 @@ class OdeOptionMap(dict):
         if "Precision" in self: o.precision = int(self["Precision"])
         if "Libm" in self: o.libm = int(self["Libm"])
         if "DenseLayout" in self: o.dense_layout = int(self["DenseLayout"])
+        if "ShardChunk" in self: o.shard_chunk = int(self["ShardChunk"])
         return o
 
 

@@ -8,6 +8,7 @@
 // Device memory is owned by the handles; all work goes to the calling thread's stream (deq_set_stream).
 #include <cuda_runtime.h>
 #include <cfloat>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -643,21 +644,61 @@ deq_status deq_solve_host(const deq_rhs* rhs, size_t ntraj, const double* y0, co
     { int tb = -2; if (deq_status ms = resolve_method(method, tableau_set, &tb, &sk, &info)) return ms; }
     std::vector<deq_status> rc(nd, DEQ_OK);
     std::vector<std::string> msg(nd);
+    const size_t chunk = (nd > 1 && o.shard_chunk > 0) ? (size_t)o.shard_chunk : 0;
     auto work = [&](size_t k) {
-        const size_t base = ntraj / nd, extra = ntraj % nd;
-        const size_t b = k * base + (k < extra ? k : extra), e = b + base + (k < extra ? 1 : 0);
         auto bad = [&](deq_status s) { rc[k] = s; msg[k] = g_err; };
         if (cudaSetDevice(devs[k]) != cudaSuccess) { rc[k] = DEQ_ERR_CUDA; msg[k] = "cudaSetDevice failed"; cudaGetLastError(); return; }
+        const bool per = params && params_per_traj;
+        // this shard's trajectories: one contiguous block, or (block-cyclic) chunks k, k + nd, k + 2 nd, ... packed together
+        size_t b = 0, cnt = 0;
+        std::vector<double> gy, gp, ry, rt;
+        std::vector<uint32_t> ra, rr, rn;
+        std::vector<uint8_t> rs;
+        if (!chunk) {
+            const size_t base = ntraj / nd, extra = ntraj % nd;
+            b = k * base + (k < extra ? k : extra);
+            cnt = base + (k < extra ? 1 : 0);
+        } else {
+            for (size_t c0 = k * chunk; c0 < ntraj; c0 += nd * chunk) cnt += std::min(chunk, ntraj - c0);
+            gy.resize(cnt * n); if (per) gp.resize(cnt * np);
+            size_t w = 0;
+            for (size_t c0 = k * chunk; c0 < ntraj; c0 += nd * chunk) {
+                const size_t len = std::min(chunk, ntraj - c0);
+                std::memcpy(gy.data() + w * n, y0 + c0 * n, len * n * sizeof(double));
+                if (per) std::memcpy(gp.data() + w * np, params + c0 * np, len * np * sizeof(double));
+                w += len;
+            }
+            ry.resize(cnt * n); ra.resize(cnt); rr.resize(cnt); rn.resize(cnt); rs.resize(cnt); rt.resize(cnt);
+        }
+        const double* sy = chunk ? gy.data() : y0 + b * n;
+        const double* sp = !per ? params : chunk ? gp.data() : params + b * np;
         deq_ensemble* ens = nullptr;
         deq_result* res = nullptr;
-        deq_status s = deq_ensemble_create(rhs, e - b, y0 + b * n, (params && params_per_traj) ? params + b * np : params, params_per_traj,
-                                           tspan, ntspan, &ens);
+        deq_status s = deq_ensemble_create(rhs, cnt, sy, sp, params_per_traj, tspan, ntspan, &ens);
         if (s) { bad(s); return; }
         s = deq_solve(ens, method, tableau_set, &o, &res);
-        if (!s && e > b && ntspan) s = deq_result_final(res, yfinal + b * n);
-        if (!s && (info.adaptive || sk) && e > b && ntspan)
-            s = deq_result_counts(res, accepted ? accepted + b : nullptr, rejected ? rejected + b : nullptr, nfe ? nfe + b : nullptr,
-                                  status ? status + b : nullptr, t_reached ? t_reached + b : nullptr);
+        const bool have = cnt && ntspan;
+        if (!s && have) s = deq_result_final(res, chunk ? ry.data() : yfinal + b * n);
+        if (!s && (info.adaptive || sk) && have) {
+            if (chunk) s = deq_result_counts(res, ra.data(), rr.data(), rn.data(), rs.data(), rt.data());
+            else s = deq_result_counts(res, accepted ? accepted + b : nullptr, rejected ? rejected + b : nullptr, nfe ? nfe + b : nullptr,
+                                       status ? status + b : nullptr, t_reached ? t_reached + b : nullptr);
+        }
+        if (!s && chunk && have) {   // scatter the packed results back to the caller's index order
+            size_t w = 0;
+            for (size_t c0 = k * chunk; c0 < ntraj; c0 += nd * chunk) {
+                const size_t len = std::min(chunk, ntraj - c0);
+                std::memcpy(yfinal + c0 * n, ry.data() + w * n, len * n * sizeof(double));
+                if (info.adaptive || sk) {
+                    if (accepted) std::memcpy(accepted + c0, ra.data() + w, len * 4);
+                    if (rejected) std::memcpy(rejected + c0, rr.data() + w, len * 4);
+                    if (nfe) std::memcpy(nfe + c0, rn.data() + w, len * 4);
+                    if (status) std::memcpy(status + c0, rs.data() + w, len);
+                    if (t_reached) std::memcpy(t_reached + c0, rt.data() + w, len * 8);
+                }
+                w += len;
+            }
+        }
         if (s) bad(s);
         if (res) deq_result_destroy(res);
         deq_ensemble_destroy(ens);

@@ -10,6 +10,18 @@ def shard_range(ntraj_total, rank, world):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def cyclic_indices(ntraj_total, rank, world, chunk):
+    """Block-cyclic alternative for parameter-sorted sweeps: chunk j of `chunk` consecutive trajectories
+    belongs to rank j % world.  Returns the global indices of rank's trajectories, ascending.  `deq_solve_host` does the
+    same inside the library when `deq_options.shard_chunk` > 0."""
+    import numpy as np
+    ntraj_total, chunk = int(ntraj_total), int(chunk)
+    starts = np.arange(rank * chunk, ntraj_total, world * chunk, dtype=np.int64)
+    if len(starts) == 0:
+        return np.empty(0, dtype=np.int64)
+    return np.concatenate([np.arange(s, min(s + chunk, ntraj_total), dtype=np.int64) for s in starts])
+
+
 def weak_range(ntraj_per_rank, rank):
     """Weak scaling: every rank integrates the same number of trajectories, indices are globally unique."""
     return rank * int(ntraj_per_rank), (rank + 1) * int(ntraj_per_rank)

@@ -123,6 +123,10 @@ typedef struct deq_options {
     int precision;       /* deq_precision, default DEQ_PRECISION_F64 */
     int libm;            /* deq_libm, default DEQ_LIBM_AS_WRITTEN (PARITY mode only) */
     int dense_layout;    /* deq_dense_layout, default DEQ_LAYOUT_SOA */
+    uint64_t shard_chunk; /* deq_solve_host over several devices: 0 (default) = contiguous equal blocks of the trajectory range;
+                            c > 0 = block-cyclic, chunk j of c trajectories goes to device j % ndevices — balances a
+                            parameter-sorted sweep whose step counts grow along the index range.  Results
+                            do not depend on it */
 } deq_options;
 
 typedef struct deq_rhs deq_rhs;

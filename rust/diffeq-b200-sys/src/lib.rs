@@ -34,6 +34,7 @@ pub struct deq_options {
     pub precision: c_int,
     pub libm: c_int,
     pub dense_layout: c_int,
+    pub shard_chunk: u64,
 }
 
 #[repr(C)] pub struct deq_rhs { _p: [u8; 0] }

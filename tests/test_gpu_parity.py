@@ -567,6 +567,16 @@ def test_in_library_multi_gpu_solve_host(deq, oracle):
     assert np.array_equal(fx["final"], oracle.ensemble_fixed(oracle.ODE4, oracle.LORENZ, LOR, y0[:100], oracle.linspace(0.0, 1.0, 101)))
     with pytest.raises(deq.OdeError):
         deq.solve_host_multi(rhs, y0, LOR, [0.0, 2.0], deq.Ode.Ode45, o, devices=[ndev + 7])
+    # block-cyclic sharding (deq_options.shard_chunk) for parameter-sorted sweeps: same results, trajectory by trajectory
+    from diffeq_b200 import synth as _s
+    yv, mu = _s.vdp_sweep(0, 1037, 1037)
+    rv = oracle.ensemble_adaptive(oracle.ODE45FE, oracle.VANDERPOL, mu, yv, [0.0, 10.0], oracle.opts(1e-6, 1e-8))
+    vd = deq.Rhs.builtin(deq.System.VanDerPol)
+    for chunk in (0, 1, 64, 5000):
+        oc = deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8), deq.ShardChunk(chunk))
+        out = deq.solve_host_multi(vd, yv, mu, [0.0, 10.0], deq.Ode.Ode45fe, oc, devices=[0] * 3 if ndev == 1 else list(range(ndev)))
+        assert np.array_equal(out["final"], rv["yfinal"]) and np.array_equal(out["accepted"], rv["accepted"]), chunk
+        assert np.array_equal(out["nfe"], rv["nfe"]) and np.array_equal(out["t_reached"], rv["t_reached"]), chunk
 
 
 def test_golden_fixtures_through_the_cuda_path(deq):

@@ -135,6 +135,17 @@ def test_shard_ranges():
     assert sharding.weak_range(100, 3) == (300, 400)
 
 
+def test_cyclic_shards_partition_the_index_range():
+    """Block-cyclic sharding (deq_options.shard_chunk): every trajectory belongs to exactly one rank."""
+    from diffeq_b200 import sharding
+    for ntraj, world, chunk in ((1000, 3, 64), (10, 4, 3), (5, 8, 2), (4096, 8, 512), (7, 2, 100)):
+        parts = [sharding.cyclic_indices(ntraj, r, world, chunk) for r in range(world)]
+        allidx = np.sort(np.concatenate(parts))
+        assert np.array_equal(allidx, np.arange(ntraj)), (ntraj, world, chunk)
+        assert all(np.all(np.diff(p) > 0) for p in parts if len(p) > 1)
+        assert parts[0][0] == 0 and (len(parts[1]) == 0 or parts[1][0] == chunk)
+
+
 def test_bench_reference_arm_prints_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=300)
