@@ -670,6 +670,7 @@ deq_status deq_solve_host(const deq_rhs* rhs, size_t ntraj, const double* y0, co
             }
             ry.resize(cnt * n); ra.resize(cnt); rr.resize(cnt); rn.resize(cnt); rs.resize(cnt); rt.resize(cnt);
         }
+        if (cnt == 0) return;   // more devices than chunks: nothing to do here
         const double* sy = chunk ? gy.data() : y0 + b * n;
         const double* sp = !per ? params : chunk ? gp.data() : params + b * np;
         deq_ensemble* ens = nullptr;

@@ -8,6 +8,7 @@ import diffeq_b200 as D
 from diffeq_b200 import synth
 
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 22
+T = float(sys.argv[2]) if len(sys.argv) > 2 else 20.0
 n = 1 << lg
 ndev = C.c_int()
 C.CDLL("libcudart.so.12").cudaGetDeviceCount(C.byref(ndev))
@@ -17,7 +18,7 @@ vd = D.Rhs.builtin(D.System.VanDerPol)
 
 def run(name, y0, mu, ts, ode, base, tset=D.TableauSet.Reference):
     out = None
-    for chunk in (0, 1 << 16, 1 << 12):
+    for chunk in (0, 1 << 16):
         o = D.OdeOptionMap().insert(*base, D.ShardChunk(chunk))
         best = None
         for rep in range(3):
@@ -35,8 +36,8 @@ def run(name, y0, mu, ts, ode, base, tset=D.TableauSet.Reference):
 
 
 y0, mu = synth.vdp_sweep(0, n, n)
-run("config-3 sweep (mu = 0.1..10 sorted), rk45 rtol 1e-6, T = 20, final states", y0, mu, [0.0, 20.0], D.Ode.Ode45fe,
+run(f"config-3 sweep (mu = 0.1..10 sorted), rk45 rtol 1e-6, T = {T}, final states", y0, mu, [0.0, T], D.Ode.Ode45fe,
     (D.Reltol(1e-6), D.Abstol(1e-8)))
 mus = np.geomspace(0.1, 1000.0, n)[:, None]
-run("stiffness sweep (mu = 0.1..1000 geometric), ode23s TEXTBOOK rtol 1e-5, T = 20, final states", np.tile([2.0, 0.0], (n, 1)), mus,
-    [0.0, 20.0], D.Ode.Ode23s, (D.Reltol(1e-5), D.Abstol(1e-8), D.MaxSteps(20000)), tset=D.TableauSet.Textbook)
+run(f"stiffness sweep (mu = 0.1..1000 geometric), ode23s TEXTBOOK rtol 1e-5, T = {T}, final states", np.tile([2.0, 0.0], (n, 1)), mus,
+    [0.0, T], D.Ode.Ode23s, (D.Reltol(1e-5), D.Abstol(1e-8), D.MaxSteps(200000)), tset=D.TableauSet.Textbook)

@@ -574,7 +574,7 @@ def test_in_library_multi_gpu_solve_host(deq, oracle):
     vd = deq.Rhs.builtin(deq.System.VanDerPol)
     for chunk in (0, 1, 64, 5000):
         oc = deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8), deq.ShardChunk(chunk))
-        out = deq.solve_host_multi(vd, yv, mu, [0.0, 10.0], deq.Ode.Ode45fe, oc, devices=[0] * 3 if ndev == 1 else list(range(ndev)))
+        out = deq.solve_host_multi(vd, yv, mu, [0.0, 10.0], deq.Ode.Ode45fe, oc, devices=[0] * 8 if ndev == 1 else list(range(ndev)))   # chunk 5000: seven empty shards
         assert np.array_equal(out["final"], rv["yfinal"]) and np.array_equal(out["accepted"], rv["accepted"]), chunk
         assert np.array_equal(out["nfe"], rv["nfe"]) and np.array_equal(out["t_reached"], rv["t_reached"]), chunk
 
