@@ -143,13 +143,37 @@ void ensure_pool() {
     done_dev = dev;
 }
 
+// Block-cyclic shards of deq_solve_host: the rows of this shard are runs (start, length) of the caller's arrays.  While the
+// list is set, upload_soa treats its host pointer as the base of the FULL array and copies run by run, so no host-side
+// packing is needed (and results go back the same way, download_runs).
+typedef std::vector<std::pair<size_t, size_t>> Runs;
+thread_local const Runs* g_runs = nullptr;
+
 deq_status upload_soa(const double* h_aos, size_t ntraj, int n, double** d_soa, cudaStream_t st) {
     double* d_aos = nullptr;
     CK(dalloc(&d_aos, ntraj * n, st));
     CK(dalloc(d_soa, ntraj * n, st));
+    if (g_runs) {
+        size_t w = 0;
+        for (const auto& run : *g_runs) {
+            CK(cudaMemcpyAsync(d_aos + w * n, h_aos + run.first * n, run.second * n * sizeof(double), cudaMemcpyHostToDevice, st));
+            w += run.second;
+        }
+    } else
     CK(cudaMemcpyAsync(d_aos, h_aos, ntraj * n * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(deql::launch_transpose_to_soa(d_aos, *d_soa, ntraj, n, st));
     dfree(d_aos, st);
+    return DEQ_OK;
+}
+
+// device array of `width`-byte rows, packed in shard order -> the runs of the caller's array `h_base`
+deq_status download_runs(const void* d_packed, size_t width, void* h_base, const Runs& runs, cudaStream_t st) {
+    if (!h_base) return DEQ_OK;
+    size_t w = 0;
+    for (const auto& run : runs) {
+        CK(cudaMemcpyAsync((char*)h_base + run.first * width, (const char*)d_packed + w * width, run.second * width, cudaMemcpyDeviceToHost, st));
+        w += run.second;
+    }
     return DEQ_OK;
 }
 
@@ -649,56 +673,45 @@ deq_status deq_solve_host(const deq_rhs* rhs, size_t ntraj, const double* y0, co
         auto bad = [&](deq_status s) { rc[k] = s; msg[k] = g_err; };
         if (cudaSetDevice(devs[k]) != cudaSuccess) { rc[k] = DEQ_ERR_CUDA; msg[k] = "cudaSetDevice failed"; cudaGetLastError(); return; }
         const bool per = params && params_per_traj;
-        // this shard's trajectories: one contiguous block, or (block-cyclic) chunks k, k + nd, k + 2 nd, ... packed together
+        // this shard's trajectories: one contiguous block, or (block-cyclic) the chunks k, k + nd, k + 2 nd, ... — copied run by
+        // run straight between the caller's arrays and the device, in both directions
         size_t b = 0, cnt = 0;
-        std::vector<double> gy, gp, ry, rt;
-        std::vector<uint32_t> ra, rr, rn;
-        std::vector<uint8_t> rs;
+        Runs runs;
         if (!chunk) {
             const size_t base = ntraj / nd, extra = ntraj % nd;
             b = k * base + (k < extra ? k : extra);
             cnt = base + (k < extra ? 1 : 0);
         } else {
-            for (size_t c0 = k * chunk; c0 < ntraj; c0 += nd * chunk) cnt += std::min(chunk, ntraj - c0);
-            gy.resize(cnt * n); if (per) gp.resize(cnt * np);
-            size_t w = 0;
-            for (size_t c0 = k * chunk; c0 < ntraj; c0 += nd * chunk) {
-                const size_t len = std::min(chunk, ntraj - c0);
-                std::memcpy(gy.data() + w * n, y0 + c0 * n, len * n * sizeof(double));
-                if (per) std::memcpy(gp.data() + w * np, params + c0 * np, len * np * sizeof(double));
-                w += len;
-            }
-            ry.resize(cnt * n); ra.resize(cnt); rr.resize(cnt); rn.resize(cnt); rs.resize(cnt); rt.resize(cnt);
+            for (size_t c0 = k * chunk; c0 < ntraj; c0 += nd * chunk) { runs.emplace_back(c0, std::min(chunk, ntraj - c0)); cnt += runs.back().second; }
         }
         if (cnt == 0) return;   // more devices than chunks: nothing to do here
-        const double* sy = chunk ? gy.data() : y0 + b * n;
-        const double* sp = !per ? params : chunk ? gp.data() : params + b * np;
         deq_ensemble* ens = nullptr;
         deq_result* res = nullptr;
-        deq_status s = deq_ensemble_create(rhs, cnt, sy, sp, params_per_traj, tspan, ntspan, &ens);
+        g_runs = chunk ? &runs : nullptr;
+        deq_status s = deq_ensemble_create(rhs, cnt, chunk ? y0 : y0 + b * n, (!per || chunk) ? params : params + b * np, params_per_traj, tspan, ntspan, &ens);
+        g_runs = nullptr;
         if (s) { bad(s); return; }
         s = deq_solve(ens, method, tableau_set, &o, &res);
-        const bool have = cnt && ntspan;
-        if (!s && have) s = deq_result_final(res, chunk ? ry.data() : yfinal + b * n);
-        if (!s && (info.adaptive || sk) && have) {
-            if (chunk) s = deq_result_counts(res, ra.data(), rr.data(), rn.data(), rs.data(), rt.data());
-            else s = deq_result_counts(res, accepted ? accepted + b : nullptr, rejected ? rejected + b : nullptr, nfe ? nfe + b : nullptr,
-                                       status ? status + b : nullptr, t_reached ? t_reached + b : nullptr);
-        }
-        if (!s && chunk && have) {   // scatter the packed results back to the caller's index order
-            size_t w = 0;
-            for (size_t c0 = k * chunk; c0 < ntraj; c0 += nd * chunk) {
-                const size_t len = std::min(chunk, ntraj - c0);
-                std::memcpy(yfinal + c0 * n, ry.data() + w * n, len * n * sizeof(double));
-                if (info.adaptive || sk) {
-                    if (accepted) std::memcpy(accepted + c0, ra.data() + w, len * 4);
-                    if (rejected) std::memcpy(rejected + c0, rr.data() + w, len * 4);
-                    if (nfe) std::memcpy(nfe + c0, rn.data() + w, len * 4);
-                    if (status) std::memcpy(status + c0, rs.data() + w, len);
-                    if (t_reached) std::memcpy(t_reached + c0, rt.data() + w, len * 8);
-                }
-                w += len;
-            }
+        const bool have = ntspan != 0, counts = info.adaptive || sk;
+        if (!s && have && !chunk) {
+            s = deq_result_final(res, yfinal + b * n);
+            if (!s && counts)
+                s = deq_result_counts(res, accepted ? accepted + b : nullptr, rejected ? rejected + b : nullptr, nfe ? nfe + b : nullptr,
+                                      status ? status + b : nullptr, t_reached ? t_reached + b : nullptr);
+        } else if (!s && have) {
+            cudaStream_t st = res->stream;
+            double* d_aos = nullptr;
+            auto ck = [&](cudaError_t e_) { if (e_ != cudaSuccess && !s) { cudaGetLastError(); s = fail(DEQ_ERR_CUDA, cudaGetErrorString(e_)); } };
+            ck(dalloc(&d_aos, cnt * n, st));
+            if (!s) ck(deql::launch_transpose_to_aos(res->d_yfinal, d_aos, cnt, (int)n, st));
+            if (!s) s = download_runs(d_aos, n * sizeof(double), yfinal, runs, st);
+            if (!s && counts) s = download_runs(res->d_acc, 4, accepted, runs, st);
+            if (!s && counts) s = download_runs(res->d_rej, 4, rejected, runs, st);
+            if (!s && counts) s = download_runs(res->d_nfe, 4, nfe, runs, st);
+            if (!s && counts) s = download_runs(res->d_status, 1, status, runs, st);
+            if (!s && counts) s = download_runs(res->d_treached, 8, t_reached, runs, st);
+            dfree(d_aos, st);
+            ck(cudaStreamSynchronize(st));
         }
         if (s) bad(s);
         if (res) deq_result_destroy(res);
