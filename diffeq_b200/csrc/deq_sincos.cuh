@@ -31,15 +31,43 @@ __device__ __forceinline__ void sincos_stage() {
 }
 #endif
 
+// Scalar constants of s_sin.c.  In device code they live in a __constant__ array (one LDCU.64 per use) instead of being
+// materialised as 64-bit immediates (two UMOV issue slots each - 17 per call before, measured on BASELINE config 4).
+#define DEQ_SCK_LIST(X) \
+    X(s1, -0x1.5555555555555p-3) X(s2, 0x1.1111111110ECEp-7) X(s3, -0x1.A01A019DB08B8p-13) X(s4, 0x1.71DE27B9A7ED9p-19) \
+    X(s5, -0x1.ADDFFC2FCDF59p-26) X(sn3, -1.66666666666664880952546298448555E-01) X(sn5, 8.33333214285722277379541354343671E-03) \
+    X(cs2, 4.99999999999999999999950396842453E-01) X(cs4, -4.16666666666664434524222570944589E-02) \
+    X(cs6, 1.38888874007937613028114285595617E-03) X(big, 0x1.8p45) X(hp0, 0x1.921FB54442D18p0) X(hp1, 0x1.1A62633145C07p-54) \
+    X(hpinv, 0x1.45F306DC9C883p-1) X(toint, 0x1.8p52) X(mp1, 0x1.921FB58p0) X(mp2, -0x1.DDE973Cp-27) X(pp3, -0x1.CB3B398p-55) \
+    X(pp4, -0x1.d747f23e32ed7p-83)
+namespace sck {
+enum : int {
+#define X(name, lit) name,
+    DEQ_SCK_LIST(X)
+#undef X
+    COUNT
+};
+}  // namespace sck
+#if defined(__CUDACC__)
+static __constant__ double c_sck[sck::COUNT] = {
+#define X(name, lit) lit,
+    DEQ_SCK_LIST(X)
+#undef X
+};
+#endif
 namespace sc {
-constexpr double s1 = -0x1.5555555555555p-3, s2 = 0x1.1111111110ECEp-7, s3 = -0x1.A01A019DB08B8p-13,
-                 s4 = 0x1.71DE27B9A7ED9p-19, s5 = -0x1.ADDFFC2FCDF59p-26;
-constexpr double sn3 = -1.66666666666664880952546298448555E-01, sn5 = 8.33333214285722277379541354343671E-03;
-constexpr double cs2 = 4.99999999999999999999950396842453E-01, cs4 = -4.16666666666664434524222570944589E-02,
-                 cs6 = 1.38888874007937613028114285595617E-03;
-constexpr double big = 0x1.8p45, hp0 = 0x1.921FB54442D18p0, hp1 = 0x1.1A62633145C07p-54;
-constexpr double hpinv = 0x1.45F306DC9C883p-1, toint = 0x1.8p52;
-constexpr double mp1 = 0x1.921FB58p0, mp2 = -0x1.DDE973Cp-27, pp3 = -0x1.CB3B398p-55, pp4 = -0x1.d747f23e32ed7p-83;
+DEQ_HD double sck_get(int i, double lit) {
+#if defined(__CUDA_ARCH__)
+    (void)lit;
+    return c_sck[i];
+#else
+    (void)i;
+    return lit;
+#endif
+}
+#define X(name, lit) DEQ_HD double name##_() { return sck_get(sck::name, lit); }
+DEQ_SCK_LIST(X)
+#undef X
 }  // namespace sc
 
 DEQ_HD double copysign_(double a, double b) {
@@ -49,10 +77,10 @@ DEQ_HD double copysign_(double a, double b) {
 // TAYLOR_SIN(xx, x, dx)
 DEQ_HD double taylor_sin(double x, double dx) {
     const double xx = x * x;
-    double p = fma_(xx, sc::s5, sc::s4);
-    p = fma_(xx, p, sc::s3);
-    p = fma_(xx, p, sc::s2);
-    p = fma_(xx, p, sc::s1);
+    double p = fma_(xx, sc::s5_(), sc::s4_());
+    p = fma_(xx, p, sc::s3_());
+    p = fma_(xx, p, sc::s2_());
+    p = fma_(xx, p, sc::s1_());
     const double t = fma_(xx, fma_(p, x, -(dx * 0.5)), dx);
     return t + x;
 }
@@ -63,11 +91,11 @@ DEQ_HD double do_sin(double x, double dx, const ST& tab) {
     if (fabs(x) < 0.126) return taylor_sin(x, dx);
     if (x <= 0) dx = -dx;
     const double ax = fabs(x);
-    const double u = ax + sc::big;
-    x = ax - (u - sc::big);
+    const double u = ax + sc::big_();
+    x = ax - (u - sc::big_());
     const double xx = x * x;
-    const double s = x + fma_(x * xx, fma_(xx, sc::sn5, sc::sn3), dx);
-    const double c = fma_(x, dx, xx * fma_(xx, fma_(xx, sc::cs6, sc::cs4), sc::cs2));
+    const double s = x + fma_(x * xx, fma_(xx, sc::sn5_(), sc::sn3_()), dx);
+    const double c = fma_(x, dx, xx * fma_(xx, fma_(xx, sc::cs6_(), sc::cs4_()), sc::cs2_()));
     const int k = (int)(uint32_t)asu64(u) * 4;
     const double sn = tab.at(k), ssn = tab.at(k + 1), cs = tab.at(k + 2), ccs = tab.at(k + 3);
     const double cor = fma_(s, cs, fma_(-c, sn, fma_(s, ccs, ssn)));
@@ -78,11 +106,11 @@ template <class ST>
 DEQ_HD double do_cos(double x, double dx, const ST& tab) {
     if (x < 0) dx = -dx;
     const double ax = fabs(x);
-    const double u = ax + sc::big;
-    x = (ax - (u - sc::big)) + dx;
+    const double u = ax + sc::big_();
+    x = (ax - (u - sc::big_())) + dx;
     const double xx = x * x;
-    const double s = fma_(x * xx, fma_(xx, sc::sn5, sc::sn3), x);
-    const double c = xx * fma_(xx, fma_(xx, sc::cs6, sc::cs4), sc::cs2);
+    const double s = fma_(x * xx, fma_(xx, sc::sn5_(), sc::sn3_()), x);
+    const double c = xx * fma_(xx, fma_(xx, sc::cs6_(), sc::cs4_()), sc::cs2_());
     const int k = (int)(uint32_t)asu64(u) * 4;
     const double sn = tab.at(k), ssn = tab.at(k + 1), cs = tab.at(k + 2), ccs = tab.at(k + 3);
     const double cor = fma_(-s, sn, fma_(-c, cs, fma_(-s, ssn, ccs)));
@@ -91,14 +119,14 @@ DEQ_HD double do_cos(double x, double dx, const ST& tab) {
 
 // reduce_sincos: x = n*pi/2 + (a + da)
 DEQ_HD int reduce_sincos(double x, double& a, double& da) {
-    const double t = fma_(x, sc::hpinv, sc::toint);
-    const double xn = t - sc::toint;
-    const double y = fma_(-xn, sc::mp2, fma_(-xn, sc::mp1, x));
+    const double t = fma_(x, sc::hpinv_(), sc::toint_());
+    const double xn = t - sc::toint_();
+    const double y = fma_(-xn, sc::mp2_(), fma_(-xn, sc::mp1_(), x));
     const int n = (int)(uint32_t)asu64(t) & 3;
-    const double t2 = fma_(-xn, sc::pp3, y);
-    double db = fma_(-xn, sc::pp3, y - t2);
-    const double b = fma_(-xn, sc::pp4, t2);
-    db = db + fma_(-xn, sc::pp4, t2 - b);
+    const double t2 = fma_(-xn, sc::pp3_(), y);
+    double db = fma_(-xn, sc::pp3_(), y - t2);
+    const double b = fma_(-xn, sc::pp4_(), t2);
+    db = db + fma_(-xn, sc::pp4_(), t2 - b);
     a = b; da = db;
     return n;
 }
@@ -121,30 +149,32 @@ DEQ_HD double sincos_dual(double a, double da, int n, const ST& tab) {
     if (!want_cos && ax < 0.126) {
         r = taylor_sin(a, da);
     } else {
-        const double u = ax + sc::big;
-        const double xr = ax - (u - sc::big);
+        const double u = ax + sc::big_();
+        const double xr = ax - (u - sc::big_());
         const int k = (int)(uint32_t)asu64(u) * 4;
         const double sn = tab.at(k), ssn = tab.at(k + 1), cs = tab.at(k + 2), ccs = tab.at(k + 3);
         // do_sin flavour
         const double dxs = (a <= 0) ? -da : da;
         const double xxs = xr * xr;
-        const double ss = xr + fma_(xr * xxs, fma_(xxs, sc::sn5, sc::sn3), dxs);
-        const double csn = fma_(xr, dxs, xxs * fma_(xxs, fma_(xxs, sc::cs6, sc::cs4), sc::cs2));
+        const double ss = xr + fma_(xr * xxs, fma_(xxs, sc::sn5_(), sc::sn3_()), dxs);
+        const double csn = fma_(xr, dxs, xxs * fma_(xxs, fma_(xxs, sc::cs6_(), sc::cs4_()), sc::cs2_()));
         const double rs = copysign_(sn + fma_(ss, cs, fma_(-csn, sn, fma_(ss, ccs, ssn))), a);
         // do_cos flavour
         const double dxc = (a < 0) ? -da : da;
         const double xc = xr + dxc;
         const double xxc = xc * xc;
-        const double sc_ = fma_(xc * xxc, fma_(xxc, sc::sn5, sc::sn3), xc);
-        const double cc = xxc * fma_(xxc, fma_(xxc, sc::cs6, sc::cs4), sc::cs2);
+        const double sc_ = fma_(xc * xxc, fma_(xxc, sc::sn5_(), sc::sn3_()), xc);
+        const double cc = xxc * fma_(xxc, fma_(xxc, sc::cs6_(), sc::cs4_()), sc::cs2_());
         const double rc = cs + fma_(-sc_, sn, fma_(-cc, cs, fma_(-sc_, ssn, ccs)));
         r = want_cos ? rc : rs;
     }
     return r;
 }
 
-// Range dispatch of s_sin.c `__sin` / `__cos`: every range first produces (a, da, n) — cheap, a handful of operations —
-// and then ONE sincos_dual evaluation follows.  The arithmetic of each range is exactly glibc's.
+// Range dispatch of s_sin.c `__sin` / `__cos`: every range first produces (a, da, n) and then ONE sincos_dual evaluation
+// follows.  The arithmetic of each range is exactly glibc's.  The three ordinary ranges are evaluated side by side and
+// selected (DEQ_SINCOS_BRANCHY restores the branches): a warp's lanes land in different ranges almost always (theta in
+// [-pi, pi], Omega t in [0, 6.7] on BASELINE config 4), so the branches cost a warp every path plus the divergence bookkeeping.
 template <class ST>
 DEQ_HD double sin_glibc(double x, const ST& tab) {
     const uint32_t k = (uint32_t)(asu64(x) >> 32) & 0x7fffffffu;
@@ -152,10 +182,19 @@ DEQ_HD double sin_glibc(double x, const ST& tab) {
     if (k >= 0x419921FBu) return sin(x);  // outside reduce_sincos' range (see header)
     double a, da;
     int n;
+#ifdef DEQ_SINCOS_BRANCHY
     bool from_cos = false;
     if (k < 0x3feb6000u) { a = x; da = 0.0; n = 0; }
-    else if (k < 0x400368fdu) { a = sc::hp0 - fabs(x); da = sc::hp1; n = 1; from_cos = true; }
+    else if (k < 0x400368fdu) { a = sc::hp0_() - fabs(x); da = sc::hp1_(); n = 1; from_cos = true; }
     else n = reduce_sincos(x, a, da);
+#else
+    const bool ra = k < 0x3feb6000u, rb = k < 0x400368fdu, from_cos = rb && !ra;
+    n = reduce_sincos(x, a, da);
+    const double ab = sc::hp0_() - fabs(x);
+    a = ra ? x : rb ? ab : a;
+    da = ra ? 0.0 : rb ? sc::hp1_() : da;
+    n = ra ? 0 : rb ? 1 : n;
+#endif
     const double r = sincos_dual(a, da, n, tab);
     if (from_cos) return copysign_(r, x);
     return (n & 2) ? -r : r;
@@ -168,13 +207,24 @@ DEQ_HD double cos_glibc(double x, const ST& tab) {
     if (k >= 0x419921FBu) return cos(x);
     double a, da;
     int n;
+#ifdef DEQ_SINCOS_BRANCHY
     if (k < 0x3feb6000u) { a = x; da = 0.0; n = 1; }
     else if (k < 0x400368fdu) {
-        const double y = sc::hp0 - fabs(x);
-        a = y + sc::hp1;
-        da = (y - a) + sc::hp1;
+        const double y = sc::hp0_() - fabs(x);
+        a = y + sc::hp1_();
+        da = (y - a) + sc::hp1_();
         n = 0;
     } else n = reduce_sincos(x, a, da) + 1;
+#else
+    const bool ra = k < 0x3feb6000u, rb = k < 0x400368fdu;
+    n = reduce_sincos(x, a, da) + 1;
+    const double y = sc::hp0_() - fabs(x);
+    const double ab = y + sc::hp1_();
+    const double dab = (y - ab) + sc::hp1_();
+    a = ra ? x : rb ? ab : a;
+    da = ra ? 0.0 : rb ? dab : da;
+    n = ra ? 1 : rb ? 0 : n;
+#endif
     const double r = sincos_dual(a, da, n, tab);
     return (n & 2) ? -r : r;
 }
