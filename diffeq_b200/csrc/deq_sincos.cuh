@@ -139,36 +139,36 @@ DEQ_HD double do_sincos(double a, double da, int n, const ST& tab) {
 
 // do_sin and do_cos evaluated side by side and selected: every lane of a warp runs the same instruction stream whatever
 // quadrant its argument fell into (on the GPU the two-way branch cost a warp both paths anyway, plus the divergence
-// bookkeeping).  Each flavour's arithmetic is exactly glibc's do_sin / do_cos above; only the small-argument Taylor
-// branch of do_sin stays a branch.
+// bookkeeping).  Each flavour's arithmetic is exactly glibc's do_sin / do_cos above, the small-argument Taylor branch of
+// do_sin included.
 template <class ST>
 DEQ_HD double sincos_dual(double a, double da, int n, const ST& tab) {
     const bool want_cos = (n & 1) != 0;
     const double ax = fabs(a);
-    double r;
-    if (!want_cos && ax < 0.126) {
-        r = taylor_sin(a, da);
-    } else {
-        const double u = ax + sc::big_();
-        const double xr = ax - (u - sc::big_());
-        const int k = (int)(uint32_t)asu64(u) * 4;
-        const double sn = tab.at(k), ssn = tab.at(k + 1), cs = tab.at(k + 2), ccs = tab.at(k + 3);
-        // do_sin flavour
-        const double dxs = (a <= 0) ? -da : da;
-        const double xxs = xr * xr;
-        const double ss = xr + fma_(xr * xxs, fma_(xxs, sc::sn5_(), sc::sn3_()), dxs);
-        const double csn = fma_(xr, dxs, xxs * fma_(xxs, fma_(xxs, sc::cs6_(), sc::cs4_()), sc::cs2_()));
-        const double rs = copysign_(sn + fma_(ss, cs, fma_(-csn, sn, fma_(ss, ccs, ssn))), a);
-        // do_cos flavour
-        const double dxc = (a < 0) ? -da : da;
-        const double xc = xr + dxc;
-        const double xxc = xc * xc;
-        const double sc_ = fma_(xc * xxc, fma_(xxc, sc::sn5_(), sc::sn3_()), xc);
-        const double cc = xxc * fma_(xxc, fma_(xxc, sc::cs6_(), sc::cs4_()), sc::cs2_());
-        const double rc = cs + fma_(-sc_, sn, fma_(-cc, cs, fma_(-sc_, ssn, ccs)));
-        r = want_cos ? rc : rs;
-    }
-    return r;
+    const double u = ax + sc::big_();
+    const double xr = ax - (u - sc::big_());
+    const int k = (int)(uint32_t)asu64(u) * 4;
+    const double sn = tab.at(k), ssn = tab.at(k + 1), cs = tab.at(k + 2), ccs = tab.at(k + 3);
+    // do_sin flavour
+    const double dxs = (a <= 0) ? -da : da;
+    const double xxs = xr * xr;
+    const double ss = xr + fma_(xr * xxs, fma_(xxs, sc::sn5_(), sc::sn3_()), dxs);
+    const double csn = fma_(xr, dxs, xxs * fma_(xxs, fma_(xxs, sc::cs6_(), sc::cs4_()), sc::cs2_()));
+    const double rs = copysign_(sn + fma_(ss, cs, fma_(-csn, sn, fma_(ss, ccs, ssn))), a);
+    // do_cos flavour
+    const double dxc = (a < 0) ? -da : da;
+    const double xc = xr + dxc;
+    const double xxc = xc * xc;
+    const double sc_ = fma_(xc * xxc, fma_(xxc, sc::sn5_(), sc::sn3_()), xc);
+    const double cc = xxc * fma_(xxc, fma_(xxc, sc::cs6_(), sc::cs4_()), sc::cs2_());
+    const double rc = cs + fma_(-sc_, sn, fma_(-cc, cs, fma_(-sc_, ssn, ccs)));
+#ifdef DEQ_SINCOS_BRANCHY
+    if (!want_cos && ax < 0.126) return taylor_sin(a, da);
+    return want_cos ? rc : rs;
+#else
+    const double rt = taylor_sin(a, da);   // do_sin's small-argument branch, evaluated alongside and selected
+    return want_cos ? rc : (ax < 0.126 ? rt : rs);
+#endif
 }
 
 // Range dispatch of s_sin.c `__sin` / `__cos`: every range first produces (a, da, n) and then ONE sincos_dual evaluation

@@ -45,6 +45,19 @@ DEQ_TRIG_HD double deq_cos(double x) {
 #endif
 }
 
+// sin(xs) and cos(xc) behind ONE call: half the call overhead of the pair above, and the two independent evaluations
+// interleave (the FP64 pipe has an 8-cycle dependent latency).  Same bits as deq_sin / deq_cos.
+struct DeqSinCos { double s, c; };
+DEQ_TRIG_HD DeqSinCos deq_sin_cos(double xs, double xc) {
+#if defined(__CUDA_ARCH__) && defined(DEQ_FAST_TU)
+    return DeqSinCos{sin(xs), cos(xc)};
+#elif defined(__CUDA_ARCH__)
+    return DeqSinCos{deqm::sin_glibc(xs, deqm::SinCosShared()), deqm::cos_glibc(xc, deqm::SinCosShared())};
+#else
+    return DeqSinCos{deqm::sin_glibc(xs, deqm::SinCosHost()), deqm::cos_glibc(xc, deqm::SinCosHost())};
+#endif
+}
+
 namespace deqr {
 
 // Lorenz-63, operation order of the reference's test fixture (problem.rs:989-1000); p = {sigma, rho, beta}.
@@ -89,8 +102,9 @@ struct Pendulum {
     static constexpr bool USES_SINCOS = true;
     DEQ_RHS_HD static void eval(double t, const double* v, double* d, const double* p) {
         const double th = v[0], w = v[1];
+        const DeqSinCos sc = deq_sin_cos(th, p[2] * t);
         d[0] = w;
-        d[1] = -p[0] * w - deq_sin(th) + p[1] * deq_cos(p[2] * t);
+        d[1] = -p[0] * w - sc.s + p[1] * sc.c;
     }
     DEQ_RHS_HD static void eval_r(float t, const float* v, float* d, const float* p) {
         const float th = v[0], w = v[1];
