@@ -289,3 +289,60 @@ def test_ode23s_textbook_accuracy_on_device(deq):
     for i, mu in enumerate(mus):
         ref = solve_ivp(lambda t, v: [v[1], mu * (1 - v[0] ** 2) * v[1] - v[0]], (0.0, 40.0), [2.0, 0.0], method="Radau", rtol=1e-10, atol=1e-12)
         assert abs(sol.final[i, 0] - ref.y[0, -1]) < 5e-3 * max(1.0, abs(ref.y[0, -1])), (mu, sol.final[i], ref.y[:, -1])
+
+
+def test_ode23s_randomised_option_sweep_bit_exact(deq, oracle):
+    """Seeded fuzz over systems, both W-inverse variants, libm flavours, tolerances, horizons, directions, step bounds, Points
+    kinds and tspan grids (with repeated points): final states, counters and sampled (tout, yout) streams bit-identical."""
+    from diffeq_b200 import synth
+    rng = np.random.default_rng(20261021)
+    for case in range(30):
+        system = ["Lorenz", "VanDerPol", "Pendulum"][case % 3]
+        n = int(rng.integers(1, 120))
+        if system == "Lorenz":
+            y0, params = synth.lorenz_ics(case * 1000, case * 1000 + n), np.array(LOR)
+        elif system == "VanDerPol":
+            y0, params = np.tile([2.0, 0.0], (n, 1)), 10.0 ** rng.uniform(-1, 2.5, (n, 1))
+        else:
+            y0, params = synth.pendulum_ics(case * 1000, case * 1000 + n), synth.PENDULUM_PARAMS
+        tset, folded = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        rtol, atol = 10.0 ** rng.uniform(-7, -3), 10.0 ** rng.uniform(-10, -5)
+        t0, span = float(rng.uniform(-1, 1)), float(10.0 ** rng.uniform(-1.5, 0.8))
+        npts = int(rng.integers(2, 40))
+        grid = np.sort(np.concatenate([[0.0, 1.0], rng.uniform(0, 1, npts - 2)]))
+        if npts > 4 and rng.random() < 0.3:
+            grid[2] = grid[1]                                   # a repeated tspan point
+        ts = t0 + span * grid
+        if rng.random() < 0.2:
+            ts = ts[::-1].copy()                                # backward: no tspan row is ever emitted (problem.rs:520)
+        pts = int(rng.random() < 0.4)
+        kw = dict(max_steps=4000, points=pts, libm_folded=folded)
+        o = deq.OdeOptionMap().insert(deq.Reltol(rtol), deq.Abstol(atol), deq.MaxSteps(4000), deq.Points.Specified if pts else deq.Points.All)
+        if folded:
+            o.insert(deq.Libm.LlvmFolded)
+        if rng.random() < 0.3:
+            kw["maxstep"] = span / float(rng.integers(3, 30)); o.insert(deq.Maxstep(kw["maxstep"]))
+        if rng.random() < 0.3:
+            kw["initstep"] = float(rng.choice([-1.0, 1.0]) * span * 10.0 ** rng.uniform(-5, -1)); o.insert(deq.Initstep(kw["initstep"]))
+        if rng.random() < 0.2:
+            kw["minstep"] = span * 10.0 ** rng.uniform(-6, -3); o.insert(deq.Minstep(kw["minstep"]))
+        oo = oracle.opts(rtol, atol, **kw)
+        ref = oracle.ensemble_ode23s(getattr(oracle, system.upper()), params, y0, ts, oo, tset=tset, dense=True)
+        prob = _problem(deq, getattr(deq.System, system), params, y0, ts)
+        tag = (case, system, n, tset, folded, rtol, atol, ts[0], ts[-1], kw)
+        sol = prob.solve(deq.Ode.Ode23s, o, tableau_set=tset)
+        for k in ("accepted", "rejected", "nfe", "status", "t_reached"):
+            assert np.array_equal(getattr(sol, k), ref[k]), (k, tag)
+        assert np.array_equal(sol.final, ref["yfinal"], equal_nan=True), tag
+        sa = prob.solve(deq.Ode.Ode23s, deq.OdeOptionMap(o).insert(deq.Output.All), tableau_set=tset)
+        assert np.array_equal(np.diff(sa.offsets).astype(np.uint32), ref["nrows"]), tag
+        for i in {0, n // 2, n - 1}:
+            one = oracle.solve_ode23s(getattr(oracle, system.upper()), params[i] if np.ndim(params) == 2 else params, y0[i], ts, oo, tset=tset)
+            tout, yout = sa.trajectory(i)
+            assert np.array_equal(tout, one["tout"]) and np.array_equal(yout, one["yout"], equal_nan=True), (i, tag)
+        sd = prob.solve(deq.Ode.Ode23s, deq.OdeOptionMap(o).insert(deq.Output.Tspan), tableau_set=tset)
+        assert np.array_equal(sd.nvalid, ref["nvalid"]), tag
+        want = ref["out"].transpose(2, 1, 0)
+        m = np.arange(len(ts))[None, :] < ref["nvalid"][:, None]
+        m &= ~np.isnan(want[:, :, 0])   # rows the reference never pushed (a tspan point equal to t0, a backward run) stay unset
+        assert np.array_equal(sd.yout[m], want[m]), tag
