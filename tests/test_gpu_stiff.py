@@ -346,3 +346,34 @@ def test_ode23s_randomised_option_sweep_bit_exact(deq, oracle):
         m = np.arange(len(ts))[None, :] < ref["nvalid"][:, None]
         m &= ~np.isnan(want[:, :, 0])   # rows the reference never pushed (a tspan point equal to t0, a backward run) stay unset
         assert np.array_equal(sd.yout[m], want[m]), tag
+
+
+def test_rosenbrock_randomised_grids_bit_exact(deq, oracle):
+    """oderosenbrock on irregular, repeated (hs = 0 -> 1/(gamma hs) = inf) and descending tspan grids: every row bit-identical,
+    inf / NaN included."""
+    from diffeq_b200 import synth
+    rng = np.random.default_rng(77)
+    for case in range(16):
+        system = ["Lorenz", "VanDerPol", "Pendulum"][case % 3]
+        which = case % 2
+        n = int(rng.integers(1, 90))
+        if system == "Lorenz":
+            y0, params = synth.lorenz_ics(case * 500, case * 500 + n), np.array(LOR)
+        elif system == "VanDerPol":
+            y0, params = np.tile([2.0, 0.0], (n, 1)), 10.0 ** rng.uniform(-1, 2, (n, 1))
+        else:
+            y0, params = synth.pendulum_ics(case * 500, case * 500 + n), synth.PENDULUM_PARAMS
+        npts = int(rng.integers(1, 30))
+        ts = np.cumsum(10.0 ** rng.uniform(-4, -1.5, npts)) + float(rng.uniform(-1, 1))
+        if npts > 3 and rng.random() < 0.4:
+            ts[2] = ts[1]
+        if rng.random() < 0.25:
+            ts = ts[::-1].copy()
+        ref = oracle.ensemble_rosenbrock(which, getattr(oracle, system.upper()), params, y0, ts, want_all=True)
+        sol = _problem(deq, getattr(deq.System, system), params, y0, ts).solve(
+            deq.Ode.Ode4skr if which == 0 else deq.Ode.Ode4ss, deq.OdeOptionMap().insert(deq.Output.Tspan))
+        tag = (case, system, which, n, npts)
+        assert np.array_equal(sol.status, ref["status"]), tag
+        assert np.array_equal(sol.final, ref["yfinal"], equal_nan=True), tag
+        m = np.arange(npts)[None, :] < sol.nvalid[:, None]
+        assert np.array_equal(sol.yout[m], ref["yall"][m], equal_nan=True), tag
