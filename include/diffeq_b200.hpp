@@ -42,6 +42,10 @@ struct OdeOptionMap {  // options.rs:8-25, defaults options.rs:283-299
     OdeOptionMap& maxstep(double v) { o.has_maxstep = 1; o.maxstep = v; return *this; }
     OdeOptionMap& initstep(double v) { o.initstep = v; return *this; }
     OdeOptionMap& mode(deq_mode m) { o.mode = m; return *this; }
+    OdeOptionMap& points(deq_points p) { o.points = p; return *this; }          // options.rs:120-137
+    OdeOptionMap& max_steps(uint64_t n) { o.max_steps = n; return *this; }      // extension (guard)
+    OdeOptionMap& libm(deq_libm l) { o.libm = l; return *this; }
+    OdeOptionMap& shard_chunk(uint64_t c) { o.shard_chunk = c; return *this; }
 };
 
 struct OdeSolution {  // solution.rs:22-29 (+ the diagnostics the reference drops)
@@ -84,6 +88,47 @@ public:
         for (size_t i = 0; i < ntraj_; ++i) s.yout.emplace_back(flat.begin() + i * n_, flat.begin() + (i + 1) * n_);
         if (!tspan_.empty()) s.tout.push_back(tspan_.back());
         return s;
+    }
+    // The reference-shaped result of every trajectory: the complete (tout, yout) that `OdeProblem::solve` returns for that
+    // problem (problem.rs:354-357 adaptive Points::All / Specified stream, :401-405 fixed grid, :556 ode23s, :639 oderosenbrock
+    // with its `tout = diff(tspan)`).  One OdeSolution per trajectory; accepted / rejected hold that trajectory's counters.
+    std::vector<OdeSolution> solve_trajectories(Ode ode, OdeOptionMap opts = OdeOptionMap(), deq_tableau_set set = DEQ_TABLEAU_REFERENCE) {
+        const bool stiff = ode == Ode::Ode23s || ode == Ode::Ode4skr || ode == Ode::Ode4ss;
+        int adaptive = ode == Ode::Ode23s;
+        if (!stiff) check(deq_tableau_get((int)ode, set, nullptr, nullptr, nullptr, nullptr, &adaptive, nullptr, nullptr));
+        opts.o.output = adaptive ? DEQ_OUT_ALL : DEQ_OUT_TSPAN;
+        deq_result* r = nullptr;
+        check(deq_solve(h_, (int)ode, set, &opts.o, &r));
+        std::vector<OdeSolution> out(ntraj_);
+        deq_status st = DEQ_OK;
+        const size_t nt = tspan_.size();
+        if (nt == 0) { deq_result_destroy(r); return out; }   // nothing to solve: OdeSolution::default()
+        if (adaptive) {
+            std::vector<uint64_t> off(ntraj_ + 1);
+            st = deq_result_all_offsets(r, off.data());
+            std::vector<double> t(off[ntraj_]), y(off[ntraj_] * n_);
+            std::vector<uint32_t> acc(ntraj_), rej(ntraj_);
+            if (!st) st = deq_result_all_copy(r, 0, ntraj_, t.data(), y.data());
+            if (!st) st = deq_result_counts(r, acc.data(), rej.data(), nullptr, nullptr, nullptr);
+            for (size_t i = 0; !st && i < ntraj_; ++i) {
+                out[i].tout.assign(t.begin() + off[i], t.begin() + off[i + 1]);
+                for (uint64_t k = off[i]; k < off[i + 1]; ++k) out[i].yout.emplace_back(y.begin() + k * n_, y.begin() + (k + 1) * n_);
+                out[i].accepted.assign(1, acc[i]); out[i].rejected.assign(1, rej[i]);
+            }
+        } else {
+            std::vector<double> rows(nt * n_);
+            std::vector<uint32_t> nv(ntraj_, (uint32_t)nt), nvtmp(1);
+            for (size_t i = 0; !st && i < ntraj_; ++i) {
+                st = deq_result_trajectory(r, i, rows.data());
+                if (!st && stiff) { std::vector<double> tmp((size_t)n_ * nt); st = deq_result_dense(r, i, i + 1, tmp.data(), nvtmp.data()); nv[i] = nvtmp[0]; }
+                for (size_t k = 0; !st && k < nv[i]; ++k) out[i].yout.emplace_back(rows.begin() + k * n_, rows.begin() + (k + 1) * n_);
+                if (stiff) for (size_t k = 0; k + 1 < nt; ++k) out[i].tout.push_back(tspan_[k + 1] - tspan_[k]);   // diff(tspan), sic
+                else out[i].tout = tspan_;
+            }
+        }
+        deq_result_destroy(r);
+        check(st);
+        return out;
     }
     OdeSolution ode45(const OdeOptionMap& o = OdeOptionMap()) { return solve(Ode::Ode45, o); }
     OdeSolution ode45_fe(const OdeOptionMap& o = OdeOptionMap()) { return solve(Ode::Ode45fe, o); }

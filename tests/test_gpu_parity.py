@@ -326,6 +326,17 @@ def test_cpp_host_mirror_on_gpu(deq, oracle):
     ref = oracle.solve_adaptive(oracle.ODE45, oracle.LORENZ, LOR, [0.1, 0.0, 0.0], [0.0, 1.0], oracle.opts(1e-8, 1e-8))
     assert tok[0] == "HPP_OK" and int(tok[1]) == 1000 and int(tok[2]) == ref["accepted"] and float(tok[3]) == ref["yfinal"][0]
     assert "HPP_ERR 1" in out.stdout   # Uninitialized, like OdeBuilder::build (problem.rs:92-104)
+    # solve_trajectories: the reference-shaped (tout, yout) of each problem
+    tr = [l for l in out.stdout.splitlines() if l.startswith("HPP_TRAJ")][0].replace("|", " ").split()[1:]
+    ts3 = [0.0, 0.5, 1.0]
+    a = oracle.solve_adaptive(oracle.ODE45, oracle.LORENZ, LOR, [0.1, 0.0, 0.0], ts3, oracle.opts(1e-8, 1e-8))
+    f = oracle.solve_fixed(oracle.ODE4, oracle.LORENZ, LOR, [1.0, 2.0, 20.0], ts3)
+    s3 = oracle.solve_ode23s(oracle.LORENZ, LOR, [0.1, 0.0, 0.0], ts3, oracle.opts())
+    k = oracle.solve_rosenbrock(oracle.S4, oracle.LORENZ, LOR, [0.1, 0.0, 0.0], ts3)
+    assert (int(tr[0]), int(tr[1]), int(tr[2]), float(tr[3])) == (a["nout"], a["nout"], a["accepted"], a["yout"][-1][0])
+    assert (int(tr[4]), float(tr[5])) == (3, f["yout"][-1][2])
+    assert (int(tr[6]), int(tr[7]), float(tr[8])) == (s3["nout"], s3["accepted"], s3["yout"][-1][0])
+    assert (int(tr[9]), int(tr[10])) == (len(k["tout"]), len(k["yout"])) == (2, 3)
 
 
 def test_ragged_points_all_output_matches_reference_shape(deq, oracle):
