@@ -450,9 +450,10 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         r->traj_major = want_dense && o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR;
         P.rec_counts = r->d_rec_counts;
         auto launch_adapt = [&](std::string* err) -> int {  // 0 ok, 1 cuda error (g_err set), 2 nvrtc error
-            if (sk) {  // ode23s: one arithmetic flavour (DEQ_MODE_FAST runs the same kernel)
-                if (e->rhs.kind != 0) return deqn::launch_ode23s(e->rhs.prog, e->per_traj, mode, P, st, err) ? 0 : 2;
-                cudaError_t ce = deql::launch_ode23s(e->rhs.sys, e->per_traj, mode, P, st);
+            if (sk) {  // ode23s
+                const bool fast = o.mode == DEQ_MODE_FAST;
+                if (e->rhs.kind != 0) return deqn::launch_ode23s(e->rhs.prog, e->per_traj, mode, fast, P, st, err) ? 0 : 2;
+                cudaError_t ce = fast ? deql::launch_ode23s_fast(e->rhs.sys, e->per_traj, mode, P, st) : deql::launch_ode23s(e->rhs.sys, e->per_traj, mode, P, st);
                 if (ce != cudaSuccess) { fail(DEQ_ERR_CUDA, std::string("ode23s kernel launch: ") + cudaGetErrorString(ce)); return 1; }
                 return 0;
             }

@@ -16,9 +16,17 @@ static int persistent_grid(K kernel, unsigned long long ntraj) {
     return (int)(want < cap ? (want ? want : 1) : cap);
 }
 
+#ifdef DEQ_FAST_TU
+constexpr bool kFast = true;     // this object is compiled with -fmad=true
+#define DEQ_LAUNCH_ODE23S launch_ode23s_fast
+#else
+constexpr bool kFast = false;
+#define DEQ_LAUNCH_ODE23S launch_ode23s
+#endif
+
 template <class F, bool PT, int MODE>
 static cudaError_t launch_ode23s_t(const deqk::AdaptParams& P, cudaStream_t st) {
-    auto kernel = deqk::ode23s_kernel<F, PT, MODE>;
+    auto kernel = deqk::ode23s_kernel<F, PT, MODE, kFast>;
     kernel<<<persistent_grid(kernel, P.ntraj), deqk::BLOCK, 0, st>>>(P);
     return cudaGetLastError();
 }
@@ -36,7 +44,7 @@ static cudaError_t launch_ode23s_f(int pt, int mode, const deqk::AdaptParams& P,
     }
 }
 
-cudaError_t launch_ode23s(int sys, int pt, int mode, const deqk::AdaptParams& P, cudaStream_t st) {
+cudaError_t DEQ_LAUNCH_ODE23S(int sys, int pt, int mode, const deqk::AdaptParams& P, cudaStream_t st) {
     switch (sys) {
         case 0: return launch_ode23s_f<deqr::Lorenz>(pt, mode, P, st);
         case 1: return launch_ode23s_f<deqr::VanDerPol>(pt, mode, P, st);
@@ -45,6 +53,7 @@ cudaError_t launch_ode23s(int sys, int pt, int mode, const deqk::AdaptParams& P,
     }
 }
 
+#ifndef DEQ_FAST_TU
 template <class RC, class F>
 static cudaError_t launch_rosenbrock_f(int pt, int all, const deqk::FixedParams& P, cudaStream_t st) {
     const unsigned grid = (unsigned)((P.ntraj + deqk::BLOCK - 1) / deqk::BLOCK);
@@ -75,5 +84,6 @@ void rosenbrock_info(int which, double* gamma, double* a, double* b, double* c) 
     };
     if (which == 0) fill(deqk::Kr4{}); else fill(deqk::S4{});
 }
+#endif  // !DEQ_FAST_TU
 
 }  // namespace deql

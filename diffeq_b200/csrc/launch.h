@@ -39,6 +39,7 @@ DEQ_DECL_TB(7) DEQ_DECL_TB(8) DEQ_DECL_TB(9) DEQ_DECL_TB(10) DEQ_DECL_TB(11) DEQ
 
 // stiff solvers (kernels_stiff.cu): ode23s, and oderosenbrock with `which` = 0 kr4 (Ode4skr) / 1 s4 (Ode4ss)
 cudaError_t launch_ode23s(int sys, int per_traj_params, int mode, const deqk::AdaptParams& P, cudaStream_t st);
+cudaError_t launch_ode23s_fast(int sys, int per_traj_params, int mode, const deqk::AdaptParams& P, cudaStream_t st);   // -fmad=true object
 cudaError_t launch_rosenbrock(int which, int sys, int per_traj_params, int all, const deqk::FixedParams& P, cudaStream_t st);
 void rosenbrock_info(int which, double* gamma, double* a /*[16]*/, double* b /*[4]*/, double* c /*[16]*/);
 

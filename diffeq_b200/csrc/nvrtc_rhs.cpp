@@ -148,10 +148,10 @@ static bool get_kernel(Program* p, int kind, int tb, int pt, int mode, Kernel* o
     else if (kind == 1) ne << "&deqk::adapt_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode & 3) << ", "
                            << ((mode & 4) ? "true" : "false") << ", " << ((mode & 8) ? "true" : "false") << ">";
     else if (kind == 2) ne << "&deqk::fixed_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode ? "true" : "false") << ">";
-    else if (kind == 3) ne << "&deqk::ode23s_kernel<DeqUserRhs, " << b << ", " << (mode & 3) << ">";
+    else if (kind == 3) ne << "&deqk::ode23s_kernel<DeqUserRhs, " << b << ", " << (mode & 3) << ", " << ((mode & 4) ? "true" : "false") << ">";
     else ne << "&deqk::rosenbrock_kernel<" << (tb == 0 ? "deqk::Kr4" : "deqk::S4") << ", DeqUserRhs, " << b << ", " << (mode ? "true" : "false") << ">";
     Kernel k;
-    const bool fmad = kind == 1 && (mode & 4);
+    const bool fmad = (kind == 1 || kind == 3) && (mode & 4);
     const std::string gkey = std::to_string(p->n) + "|" + std::to_string(p->np) + "|" + ne.str() + (fmad ? "|fast|" : "|parity|") + p->user_src;
     {
         std::lock_guard<std::mutex> gg(g_cache_mu);
@@ -227,9 +227,9 @@ static unsigned persistent_blocks(const Kernel& k, unsigned long long ntraj) {
     return (unsigned)(want < cap ? (want ? want : 1) : cap);
 }
 
-bool launch_ode23s(Program* p, int pt, int mode, const deqk::AdaptParams& P, cudaStream_t st, std::string* err) {
+bool launch_ode23s(Program* p, int pt, int mode, bool fast, const deqk::AdaptParams& P, cudaStream_t st, std::string* err) {
     Kernel k;
-    if (!get_kernel(p, 3, 0, pt ? 1 : 0, mode & 3, &k, err)) return false;
+    if (!get_kernel(p, 3, 0, pt ? 1 : 0, (mode & 3) | (fast ? 4 : 0), &k, err)) return false;
     return launch(k, persistent_blocks(k, P.ntraj), P, st, err);
 }
 

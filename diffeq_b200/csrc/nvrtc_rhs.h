@@ -22,7 +22,7 @@ bool launch_fixed(Program* p, int tb, int per_traj_params, int all, const deqk::
                   std::string* err);
 
 // stiff solvers (stiff.cuh), n <= 3: ode23s with the MODE_* output kinds, oderosenbrock with which = 0 kr4 / 1 s4
-bool launch_ode23s(Program* p, int per_traj_params, int mode, const deqk::AdaptParams& P, cudaStream_t st, std::string* err);
+bool launch_ode23s(Program* p, int per_traj_params, int mode, bool fast, const deqk::AdaptParams& P, cudaStream_t st, std::string* err);
 bool launch_rosenbrock(Program* p, int which, int per_traj_params, int all, const deqk::FixedParams& P, cudaStream_t st,
                        std::string* err);
 

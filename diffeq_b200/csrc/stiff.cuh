@@ -61,6 +61,31 @@ __device__ __forceinline__ void na_lu_packed(double (&m)[N][N]) {
     }
 }
 
+// FAST arithmetic only: the same adjugate formulas with ONE reciprocal of the determinant instead of n^2 IEEE divisions.
+template <int N>
+__device__ __forceinline__ bool inverse_fast(const double (&m)[N][N], double (&o)[N][N]) {
+    static_assert(N >= 1 && N <= 3, "the stiff path carries n <= 3");
+    if constexpr (N == 1) {
+        if (m[0][0] == 0.0) return false;
+        o[0][0] = 1.0 / m[0][0];
+    } else if constexpr (N == 2) {
+        const double det = m[0][0] * m[1][1] - m[1][0] * m[0][1];
+        if (det == 0.0) return false;
+        const double r = 1.0 / det;
+        o[0][0] = m[1][1] * r; o[0][1] = -m[0][1] * r; o[1][0] = -m[1][0] * r; o[1][1] = m[0][0] * r;
+    } else {
+        const double c00 = m[1][1] * m[2][2] - m[2][1] * m[1][2], c01 = m[1][0] * m[2][2] - m[2][0] * m[1][2],
+                     c02 = m[1][0] * m[2][1] - m[2][0] * m[1][1];
+        const double det = m[0][0] * c00 - m[0][1] * c01 + m[0][2] * c02;
+        if (det == 0.0) return false;
+        const double r = 1.0 / det;
+        o[0][0] = c00 * r; o[0][1] = (m[0][2] * m[2][1] - m[2][2] * m[0][1]) * r; o[0][2] = (m[0][1] * m[1][2] - m[1][1] * m[0][2]) * r;
+        o[1][0] = -c01 * r; o[1][1] = (m[0][0] * m[2][2] - m[2][0] * m[0][2]) * r; o[1][2] = (m[0][2] * m[1][0] - m[1][2] * m[0][0]) * r;
+        o[2][0] = c02 * r; o[2][1] = (m[0][1] * m[2][0] - m[2][1] * m[0][0]) * r; o[2][2] = (m[0][0] * m[1][1] - m[1][0] * m[0][1]) * r;
+    }
+    return true;
+}
+
 template <int N>
 __device__ __forceinline__ bool na_try_inverse(const double (&m)[N][N], double (&o)[N][N]) {
     static_assert(N >= 1 && N <= 3, "the stiff path carries n <= 3 (closed-form try_inverse)");
@@ -90,7 +115,7 @@ __device__ __forceinline__ bool na_try_inverse(const double (&m)[N][N], double (
 
 // fdjacobian (problem.rs:903-926).  `ftx` = f(t, x): the reference evaluates it again at the top of fdjacobian; every
 // caller here already holds that very value (same t, same x, a deterministic f), so it is passed in.
-template <class F>
+template <class F, bool FAST = false>
 __device__ __forceinline__ void fdjacobian(double t, const double (&x)[F::N], const double (&ftx)[F::N], const double* prm,
                                            double (&J)[F::N][F::N]) {
     constexpr int N = F::N;
@@ -104,9 +129,24 @@ __device__ __forceinline__ void fdjacobian(double t, const double (&x)[F::N], co
         for (int d = 0; d < N; ++d) tmp[d] = x[d];
         tmp[c] += dxj;
         F::eval(t, tmp, yj, prm);
+        if (FAST) {
+            const double rdx = 1.0 / dxj;
 #pragma unroll
-        for (int r = 0; r < N; ++r) J[r][c] = (yj[r] - ftx[r]) / dxj;
+            for (int r = 0; r < N; ++r) J[r][c] = (yj[r] - ftx[r]) * rdx;
+        } else {
+#pragma unroll
+            for (int r = 0; r < N; ++r) J[r][c] = (yj[r] - ftx[r]) / dxj;
+        }
     }
+}
+
+// FAST arithmetic only: 2-norm by sqrt (what an LLVM-optimised build of the crate evaluates anyway)
+template <int N>
+__device__ __forceinline__ double norm2_fast(const double (&v)[N]) {
+    double s = 0.0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) s = __fma_rn(v[d], v[d], s);
+    return sqrt(s);
 }
 
 template <int N, class TT>
@@ -123,7 +163,10 @@ __device__ __forceinline__ double pnorm2(const double (&v)[N], int libm_folded, 
 // (tout, yout) stream, rows [t, y...], counting pass then writing pass.  The reference rescans the whole tspan on every
 // accepted step (:519); for a monotone tspan a cursor yields the same rows (capi.cu rejects a non-monotone one).
 // ---------------------------------------------------------------------------------------------------------------
-template <class F, bool PT, int MODE>
+// FAST (compiled in the -fmad=true objects only, deq_options.mode = DEQ_MODE_FAST): fused multiply-adds, one reciprocal per
+// inverse / Jacobian column instead of n^2 divisions, sqrt norms, the 17-instruction table pow for the step factor.  Same
+// formulas, results within the solver tolerance of PARITY (tests/test_gpu_stiff.py); no bit-parity claim.
+template <class F, bool PT, int MODE, bool FAST = false>
 __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
     constexpr int N = F::N;
     constexpr bool SOA = MODE == MODE_DENSE, REC = MODE == MODE_REC, ROWS = MODE != MODE_FINAL;
@@ -196,7 +239,7 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
                         for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt) * P.ntraj + traj] = y[d];
                     }
                     if (REC) emit(t, y);
-                    fdjacobian<F>(t, y, f0, prm, jac);                         // :454
+                    fdjacobian<F, FAST>(t, y, f0, prm, jac);                   // :454
                 }
             }
         }
@@ -230,7 +273,7 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) fdt[i] = (fdt[i] - f0[i]) * sc;
                 double winv[N][N];
-                if (!na_try_inverse<N>(w, winv)) {
+                if (!(FAST ? inverse_fast<N>(w, winv) : na_try_inverse<N>(w, winv))) {
                     fin = ST_INVALID_MATRIX; invalid = true;
                 } else {
                     double rhs[N], k1[N], k2[N], k3[N], f1[N], f2[N], ynew[N];
@@ -253,8 +296,9 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
                     double kerr[N];
 #pragma unroll
                     for (int i = 0; i < N; ++i) kerr[i] = (k1[i] - k2[i] * 2.) + k3[i];
-                    const double err = pnorm2<N>(kerr, P.libm_folded, T) * (fabs(h) / 6.);
-                    const double delta = fmax(fmax(pnorm2<N>(y, P.libm_folded, T), pnorm2<N>(ynew, P.libm_folded, T)) * reltol, abstol);
+                    const double err = (FAST ? norm2_fast<N>(kerr) : pnorm2<N>(kerr, P.libm_folded, T)) * (fabs(h) / 6.);
+                    const double delta = FAST ? fmax(fmax(norm2_fast<N>(y), norm2_fast<N>(ynew)) * reltol, abstol)
+                                              : fmax(fmax(pnorm2<N>(y, P.libm_folded, T), pnorm2<N>(ynew, P.libm_folded, T)) * reltol, abstol);
                     if (err <= delta) {
                         acc += 1;
                         if (ROWS) {
@@ -282,12 +326,13 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
                         t = tn;
 #pragma unroll
                         for (int i = 0; i < N; ++i) { y[i] = ynew[i]; f0[i] = f2[i]; }
-                        fdjacobian<F>(t, y, f0, prm, jac);                       // :549
+                        fdjacobian<F, FAST>(t, y, f0, prm, jac);                 // :549
                     } else {
                         rej += 1;
                     }
                     const double r = delta / err;
-                    h = fmin(P.maxstep, (deqm::pow_glibc(r, 1. / 3., T) * fabs(h)) * 0.8) * tdir;   // :552-553
+                    const double g = FAST ? deqm::pow_fast_pos(r, 1. / 3., T) : deqm::pow_glibc(r, 1. / 3., T);
+                    h = fmin(P.maxstep, (g * fabs(h)) * 0.8) * tdir;   // :552-553
                 }
             }
             if (fin != 0xff) {

@@ -72,7 +72,8 @@ typedef enum deq_output {
 /* Arithmetic of the adaptive kernels.  PARITY (default): every operation rounded and ordered as in the reference,
  * glibc-exact pow — results are bit-identical to the CPU restatement of the crate.  FAST: fused multiply-adds,
  * structurally-zero tableau entries skipped, one pow per step — identical accepted-step counts and final states
- * within 10 x rtol of PARITY on the BASELINE ensembles (tests/test_gpu_parity.py), ~2x the throughput. */
+ * within 10 x rtol of PARITY on the BASELINE ensembles (tests/test_gpu_parity.py), ~2x the throughput.  DEQ_ODE23S has a FAST
+ * flavour too (FMA, one reciprocal per inverse / Jacobian column, sqrt norms); the other methods always run PARITY. */
 typedef enum deq_mode { DEQ_MODE_PARITY = 0, DEQ_MODE_FAST = 1 } deq_mode;
 
 /* Optional single-precision state (north_star "optional f32 mode").  The reference cannot instantiate f32 (types.rs:262-278),

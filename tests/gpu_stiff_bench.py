@@ -9,7 +9,8 @@ T = float(sys.argv[2]) if len(sys.argv) > 2 else 20.0
 mu = np.geomspace(0.1, 1000.0, n)[:, None]
 y0 = np.tile([2.0, 0.0], (n, 1))
 prob = D.OdeProblem.builder().fun(D.Rhs.builtin(D.System.VanDerPol)).params(mu).init(y0).tspan([0.0, T]).build()
-for name, tset, extra in (("reference", 0, ()), ("textbook", 1, ()), ("reference_llvm_folded", 0, (D.Libm.LlvmFolded,))):
+for name, tset, extra in (("reference", 0, ()), ("textbook", 1, ()), ("reference_llvm_folded", 0, (D.Libm.LlvmFolded,)),
+                          ("textbook_fast_mode", 1, (D.Mode.Fast,)), ("reference_fast_mode", 0, (D.Mode.Fast,))):
     o = D.OdeOptionMap().insert(D.Reltol(1e-5), D.Abstol(1e-8), D.MaxSteps(20000), *extra)   # the reference variant loops forever on ~3 per million trajectories
     best = None
     for rep in range(3):
