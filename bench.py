@@ -274,7 +274,8 @@ def main():
         sp = D.OdeProblem.builder().fun(D.Rhs.builtin(D.System.VanDerPol)).params(mu).init(np.tile([2.0, 0.0], (ns, 1))).tspan([0.0, 20.0]).build()
         so = D.OdeOptionMap().insert(D.Reltol(1e-5), D.Abstol(1e-8), D.MaxSteps(20000))
         stiff = {"workload": "2^18 Van der Pol, mu = geomspace(0.1, 1000), y0 = [2, 0], tspan [0, 20], ode23s rtol 1e-5 atol 1e-8, max_steps 20000"}
-        for name, tset in (("reference", 0), ("textbook", 1)):
+        for name, tset, extra in (("reference", 0, ()), ("textbook", 1, ()), ("textbook_fast_mode", 1, (D.Mode.Fast,))):
+            so = D.OdeOptionMap().insert(D.Reltol(1e-5), D.Abstol(1e-8), D.MaxSteps(20000), *extra)
             sp.solve(D.Ode.Ode23s, so, tableau_set=tset, fetch=False)
             r = sp.solve(D.Ode.Ode23s, so, tableau_set=tset, fetch=False)
             att = r.totals["accepted"] + r.totals["rejected"]
