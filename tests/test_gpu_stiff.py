@@ -187,6 +187,13 @@ def test_ode23s_fast_mode_within_tolerance(deq):
         assert abs(int(f.accepted[ok].sum()) - int(a.accepted[ok].sum())) <= 2e-3 * int(a.accepted[ok].sum())
         if tset == 1:
             assert same.mean() >= 0.9 and np.quantile(dev, 0.99) <= 10.0
+    # the user-source (NVRTC) flavour of the fast kernel
+    rhs = deq.Rhs.from_source(USER_VDP, 2, 1)
+    pu = deq.OdeProblem.builder().fun(rhs).params(mu[::8]).init(y0[::8]).tspan([0.0, 20.0]).build()
+    fu = pu.solve(deq.Ode.Ode23s, deq.OdeOptionMap().insert(*base, deq.Mode.Fast), tableau_set=1)
+    au = pu.solve(deq.Ode.Ode23s, deq.OdeOptionMap().insert(*base), tableau_set=1)
+    du = np.max(np.abs(fu.final - au.final) / (np.abs(au.final) * rtol + atol), axis=1)
+    assert (fu.accepted == au.accepted).mean() >= 0.9 and np.quantile(du, 0.99) <= 10.0
 
 
 @pytest.mark.parametrize("which", ["kr4", "s4"])
