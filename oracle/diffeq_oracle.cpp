@@ -681,6 +681,115 @@ int solve_rosenbrock(const RosenbrockCoeffs& co, const double* y0, const double*
     return OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Allocation-faithful variant of oderk_adapt (problem.rs:193-358 with `Y = Vec<f64>`): the same arithmetic as solve_adapt,
+// but with the reference's memory behaviour — every state is a heap vector, `coeff.clone()` (:261), one `yi` clone and one
+// freshly returned `Vec` per stage (:722,733), `y` cloned from the output vector (:262), two clones in embedded_step
+// (:755,759), `ys.push(ytrial.clone())` into a growing Vec<Vec<f64>> (:321) — about 20 allocations per dopri5 step attempt.
+// Used only to report how the CPU baseline moves with the reference's allocation pattern (bench.py cpu_baseline);
+// results are bit-identical to solve_adapt (tests/test_oracle_cpu.py).  Points::All.
+// ------------------------------------------------------------------------------------------
+typedef std::vector<double> VecY;
+struct CoefficientPointV { VecY k, y; };
+
+template <int N, class F>
+inline VecY rhs_vec(double t, const VecY& y, const double* p) {
+    VecY out(N);
+    F::eval(t, y.data(), out.data(), p);
+    return out;
+}
+
+template <int N, class F>
+int solve_adapt_vec(const Tableau& tb, const double* y0p, const double* tspan_in, size_t nt, const double* p, const Opts& o,
+                    Counters& cnt, double* yfinal) {
+    if (!tb.adaptive) return ERR_WEIGHT_TYPE;
+    if (nt == 0) return OK;
+    const VecY y0(y0p, y0p + N);
+    double t = tspan_in[0];
+    const double tend = tspan_in[nt - 1];
+    const double minstep = o.has_minstep ? o.minstep : std::fabs(tend - t) / 1e18;
+    const double maxstep = o.has_maxstep ? o.maxstep : std::fabs(tend - t) / 2.5;
+    const double reltol = o.reltol, abstol = o.abstol;
+    const int order = tb.order_min;
+    double h, tdir, f0a[N];
+    hinit<N, F>(y0.data(), t, tend, order, reltol, abstol, p, h, tdir, f0a, o.libm_folded);
+    cnt.nfe += 2;
+    double dt;
+    if (o.initstep != 0.) {
+        if (std::fabs(signum(o.initstep) - tdir) < DBL_EPSILON) dt = o.initstep; else return ERR_INVALID_INITSTEP;
+    } else dt = h;
+    unsigned timeout = 0;
+    bool last_step = std::fabs(t + dt - tend) <= DBL_EPSILON;
+    std::vector<double> tout; tout.reserve(nt); tout.push_back(t);
+    std::vector<VecY> ys; ys.reserve(nt); ys.push_back(y0);
+    CoefficientPointV coeff{VecY(f0a, f0a + N), y0};
+    size_t it = 1;
+    uint64_t attempts = 0;
+    cnt.status = ST_DONE;
+    for (;;) {
+        if (o.max_steps && attempts >= o.max_steps) { cnt.status = ST_MAX_STEPS; break; }
+        ++attempts;
+        // calc_coefficients(btab, t, coeff.clone(), dt)
+        std::vector<CoefficientPointV> coeffs; coeffs.reserve(tb.S);
+        coeffs.push_back(coeff);
+        for (int row = 1; row < tb.S; ++row) {
+            VecY yi = coeffs[0].y;
+            for (int col = 0; col < row; ++col) {
+                const VecY& k = coeffs[col].k;
+                for (int d = 0; d < N; ++d) yi[d] += k[d] * (tb.a[row][col] * dt);
+            }
+            const double tn = t + tb.c[row] * dt;
+            VecY kn = rhs_vec<N, F>(tn, yi, p);
+            coeffs.push_back(CoefficientPointV{std::move(kn), std::move(yi)});
+        }
+        cnt.nfe += tb.S - 1;
+        const VecY y = ys[ys.size() - 1];
+        // embedded_step
+        VecY ytrial = y; for (int d = 0; d < N; ++d) ytrial[d] = 0.0;
+        VecY yerr = ytrial;
+        for (int s = 0; s < tb.S; ++s) {
+            const VecY& k = coeffs[s].k;
+            for (int d = 0; d < N; ++d) { ytrial[d] += k[d] * tb.b[s][0]; yerr[d] += k[d] * tb.b[s][1]; }
+        }
+        for (int d = 0; d < N; ++d) { yerr[d] = (ytrial[d] - yerr[d]) * dt; ytrial[d] = y[d] + (ytrial[d] * dt); }
+        double err, ndt; unsigned tmo;
+        stepsize_hw92<N>(dt, tdir, y.data(), ytrial.data(), yerr.data(), order, timeout, abstol, reltol, maxstep, err, ndt, tmo, o.libm_folded);
+        timeout = tmo;
+        if (err < 1.) {
+            cnt.accepted += 1;
+            const VecY& f0 = coeffs[0].k;
+            VecY f1;
+            if (tb.fsal) f1 = coeffs[tb.S - 1].k; else { f1 = rhs_vec<N, F>(t + dt, ytrial, p); cnt.nfe += 1; }
+            while (it < nt && tdir * t < tdir * tspan_in[it] && tdir * tspan_in[it] < tdir * (t + dt)) {
+                VecY yo(N);
+                hermite<N>(tspan_in[it], t, dt, y.data(), ytrial.data(), f0.data(), f1.data(), yo.data());
+                ys.push_back(std::move(yo));
+                tout.push_back(tspan_in[it]);
+                ++it;
+            }
+            ys.push_back(ytrial);
+            tout.push_back(t + dt);
+            coeff = CoefficientPointV{std::move(f1), std::move(ytrial)};
+            if (last_step) { cnt.t_reached = t + dt; break; }
+            t += dt;
+            dt = ndt;
+            if (tdir * (t + dt + dt / 100.) >= tdir * tend) { dt = tend - t; last_step = true; }
+        } else if (std::fabs(ndt) < minstep) {
+            cnt.status = ST_MINSTEP_BREAK; cnt.t_reached = t;
+            break;
+        } else {
+            cnt.rejected += 1;
+            last_step = false;
+            dt = ndt;
+            timeout = 5;
+        }
+    }
+    if (cnt.status == ST_MAX_STEPS) cnt.t_reached = t;
+    if (yfinal) for (int d = 0; d < N; ++d) yfinal[d] = ys.back()[d];
+    return OK;
+}
+
 template <class Fn>
 int dispatch_rhs(int rhs, Fn&& fn) {
     switch (rhs) {
@@ -793,6 +902,35 @@ int oracle_ensemble_adaptive(int method, int set, int rhs, size_t ntraj, const d
             if (t_reached) t_reached[i] = c.t_reached;
         }
         return rc_all;
+    });
+}
+
+// Ensemble, adaptive, allocation-faithful variant (solve_adapt_vec): final states + counters.
+int oracle_ensemble_adaptive_vec(int method, int set, int rhs, size_t ntraj, const double* y0, const double* params,
+                                 int params_per_traj, const double* tspan, size_t nt, const oracle_opts* o, int nthreads,
+                                 double* yfinal, uint32_t* accepted, uint32_t* rejected, uint32_t* nfe, uint8_t* status) {
+    if (!is_adapt(method)) return is_fixed(method) ? ERR_WEIGHT_TYPE : ERR_UNSUPPORTED;
+    Tableau tb; make_tableau(method, set, tb);
+    Opts op{o->reltol, o->abstol, o->has_minstep, o->minstep, o->has_maxstep, o->maxstep, o->initstep, 0, o->max_steps, o->libm_folded};
+    const int np = oracle_rhs_nparams(rhs);
+    return dispatch_rhs(rhs, [&](auto f) {
+        using F = decltype(f);
+        constexpr int N = F::N;
+#ifdef _OPENMP
+        if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long long i = 0; i < (long long)ntraj; ++i) {
+            Counters c; double yf[N] = {};
+            const double* p = params_per_traj ? params + (size_t)i * np : params;
+            solve_adapt_vec<N, F>(tb, y0 + (size_t)i * N, tspan, nt, p, op, c, yf);
+            if (yfinal) for (int d = 0; d < N; ++d) yfinal[(size_t)i * N + d] = yf[d];
+            if (accepted) accepted[i] = c.accepted;
+            if (rejected) rejected[i] = c.rejected;
+            if (nfe) nfe[i] = c.nfe;
+            if (status) status[i] = c.status;
+        }
+        return (int)OK;
     });
 }
 

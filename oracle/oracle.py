@@ -157,6 +157,23 @@ def ensemble_adaptive(method, rhs, params, y0, tspan, o=None, tset=REFERENCE, nt
     return dict(yfinal=yf, accepted=acc, rejected=rej, nfe=nfe, status=st, t_reached=tr)
 
 
+def ensemble_adaptive_vec(method, rhs, params, y0, tspan, o=None, tset=REFERENCE, nthreads=0):
+    """ensemble_adaptive with the reference's allocation pattern (heap vector per state, ~20 allocations per step attempt);
+    same bits, used to report how the CPU baseline depends on it."""
+    o = o or opts()
+    y0, tspan = _f64(y0), _f64(tspan)
+    ntraj, n = y0.shape
+    params, per = _ens_params(params, ntraj, rhs_nparams(rhs))
+    yf = np.empty((ntraj, n)); acc = np.empty(ntraj, np.uint32); rej = np.empty(ntraj, np.uint32)
+    nfe = np.empty(ntraj, np.uint32); st = np.empty(ntraj, np.uint8)
+    rc = lib().oracle_ensemble_adaptive_vec(method, tset, rhs, C.c_size_t(ntraj), _p(y0), _p(params), per, _p(tspan),
+                                            C.c_size_t(len(tspan)), C.byref(o), nthreads, _p(yf), _p(acc, C.c_uint32),
+                                            _p(rej, C.c_uint32), _p(nfe, C.c_uint32), _p(st, C.c_uint8))
+    if rc:
+        raise RuntimeError(f"oracle_ensemble_adaptive_vec rc={rc}")
+    return dict(yfinal=yf, accepted=acc, rejected=rej, nfe=nfe, status=st)
+
+
 def ensemble_dense(method, rhs, params, y0, tspan, o=None, tset=REFERENCE, nthreads=0):
     """Points::All filtered to the tspan times; out is SoA [n][nt][ntraj] (rows >= nvalid, except the last, are NaN)."""
     o = o or opts()

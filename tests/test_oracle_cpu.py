@@ -230,3 +230,18 @@ def test_reference_unit_tests_mirrored(oracle):
     assert J.tolist() == pyref.fdjacobian(pyref.lorenz([10.0, 28.0, 8.0 / 3.0]), 0.0, [0.1, 0.0, 0.0])
     exact = np.array([[-10.0, 10.0, 0.0], [28.0, -1.0, -0.1], [0.0, 0.1, -8.0 / 3.0]])   # analytic Jacobian at Y0
     assert np.allclose(J, exact, rtol=0, atol=2e-2)                      # "crude" indeed: dx = 1 % of x (or of 1 where x = 0)
+
+
+def test_allocation_faithful_variant_is_bit_identical(oracle):
+    """solve_adapt_vec (the reference's Vec<f64> / clone pattern) must not change a bit against solve_adapt."""
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    from diffeq_b200 import synth
+    y0 = synth.lorenz_ics(0, 300)
+    for method, tset, kw in ((oracle.ODE45, 0, {}), (oracle.ODE45FE, 0, dict(maxstep=0.05)), (oracle.ODE78, 1, dict(max_steps=500)),
+                             (oracle.ODE23, 0, dict(max_steps=300)), (oracle.ODE45, 0, dict(libm_folded=1, initstep=1e-3))):
+        o = oracle.opts(1e-7, 1e-9, **kw)
+        a = oracle.ensemble_adaptive(method, oracle.LORENZ, synth.LORENZ_PARAMS, y0, [0.0, 0.3, 1.0], o, tset)
+        b = oracle.ensemble_adaptive_vec(method, oracle.LORENZ, synth.LORENZ_PARAMS, y0, [0.0, 0.3, 1.0], o, tset)
+        for k in ("yfinal", "accepted", "rejected", "nfe", "status"):
+            assert np.array_equal(a[k], b[k], equal_nan=(k == "yfinal")), (method, k)
