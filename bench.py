@@ -296,7 +296,7 @@ def main():
 
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^20 trajectories (ncu --set full, profiles/r1_final_*_kernel_
     # ncu_full_summary.csv); it scales with the trajectory count, not with the step count
-    NCU_DRAM_BYTES = {"parity": 62.504448e6 + 14.322176e6, "fast": 62.857472e6 + 15.247360e6}
+    NCU_DRAM_BYTES = {"parity": 62.139648e6 + 16.999680e6, "fast": 62.736384e6 + 15.812608e6}
 
     def roofline(kernel_ms_list, steps_local, kernel_name, mode_note, traffic_key):
         kms = sum(kernel_ms_list) / len(kernel_ms_list)
