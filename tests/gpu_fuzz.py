@@ -1,0 +1,140 @@
+"""Probe (not a test): a long seeded differential campaign, CUDA path vs CPU oracle, bit for bit.  Covers what the unit tests
+cover, with many more random draws: explicit adaptive methods (all tableaus, both sets, Points::All / Specified, final / dense /
+ragged output, both libm flavours), fixed-step methods, ode23s and oderosenbrock.
+usage: python tests/gpu_fuzz.py [cases] [seed]"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import diffeq_b200 as D
+from diffeq_b200 import synth
+from oracle import oracle as O
+
+LOR = np.array([10.0, 28.0, 8.0 / 3.0])
+cases = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+rng = np.random.default_rng(seed)
+bad = 0
+t_start = time.time()
+
+
+def system(case, n):
+    name = ["Lorenz", "VanDerPol", "Pendulum"][int(rng.integers(0, 3))]
+    if name == "Lorenz":
+        return name, synth.lorenz_ics(case * 977, case * 977 + n), LOR
+    if name == "VanDerPol":
+        return name, np.tile([2.0, 0.0], (n, 1)) + rng.uniform(-1, 1, (n, 2)), 10.0 ** rng.uniform(-1, 1.5, (n, 1))
+    return name, synth.pendulum_ics(case * 977, case * 977 + n), np.array(synth.PENDULUM_PARAMS)
+
+
+def check(tag, pairs):
+    global bad
+    for name, a, b in pairs:
+        if not np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True):
+            bad += 1
+            print("MISMATCH", name, tag, flush=True)
+            return False
+    return True
+
+
+def grid(t0, span, npts, allow_dup=True):
+    g = np.sort(np.concatenate([[0.0, 1.0], rng.uniform(0, 1, max(npts - 2, 0))]))
+    if allow_dup and npts > 4 and rng.random() < 0.2:
+        g[2] = g[1]
+    return t0 + span * g
+
+
+for case in range(cases):
+    kind = rng.choice(["adapt", "adapt", "adapt", "fixed", "ode23s", "rosen"])
+    n = int(rng.integers(1, 150))
+    name, y0, params = system(case, n)
+    sysid, osys = getattr(D.System, name), getattr(O, name.upper())
+    t0 = float(rng.uniform(-2, 2))
+    span = float(10.0 ** rng.uniform(-2, 0.7))
+    prob = lambda ts: D.OdeProblem.builder().fun(D.Rhs.builtin(sysid)).params(params).init(y0).tspan(ts).build()  # noqa: E731
+    if kind == "fixed":
+        m = ["Feuler", "Heun", "Midpoint", "Ode4"][int(rng.integers(0, 4))]
+        ts = grid(t0, span, int(rng.integers(2, 60)))
+        ref = O.ensemble_fixed(getattr(O, m.upper()), osys, params, y0, ts)
+        sol = prob(ts).solve(getattr(D.Ode, m), D.OdeOptionMap().insert(D.Output.Tspan))
+        ok = check((case, kind, m, name, n), [("final", sol.final, ref)])
+        if ok:
+            one = O.solve_fixed(getattr(O, m.upper()), osys, params[0] if np.ndim(params) == 2 else params, y0[0], ts)
+            check((case, kind, m, name, "rows"), [("rows", sol.yout[0], one["yout"])])
+        continue
+    if kind == "rosen":
+        which = int(rng.integers(0, 2))
+        ts = grid(t0, span * 0.05, int(rng.integers(1, 40)))
+        ref = O.ensemble_rosenbrock(which, osys, params, y0, ts, want_all=True)
+        sol = prob(ts).solve(D.Ode.Ode4skr if which == 0 else D.Ode.Ode4ss, D.OdeOptionMap().insert(D.Output.Tspan))
+        m_ = np.arange(len(ts))[None, :] < sol.nvalid[:, None]
+        check((case, kind, which, name, n), [("status", sol.status, ref["status"]), ("final", sol.final, ref["yfinal"]),
+                                              ("rows", sol.yout[m_], ref["yall"][m_])])
+        continue
+    rtol, atol = 10.0 ** rng.uniform(-9, -3), 10.0 ** rng.uniform(-11, -4)
+    folded = int(rng.random() < 0.4)
+    kw = dict(max_steps=int(rng.choice([300, 1500, 4000])), libm_folded=folded)
+    o = D.OdeOptionMap().insert(D.Reltol(rtol), D.Abstol(atol), D.MaxSteps(kw["max_steps"]))
+    if folded:
+        o.insert(D.Libm.LlvmFolded)
+    backward = rng.random() < 0.15
+    if rng.random() < 0.3:
+        kw["maxstep"] = span / float(rng.integers(3, 30)); o.insert(D.Maxstep(kw["maxstep"]))
+    if rng.random() < 0.2:
+        kw["minstep"] = span * 10.0 ** rng.uniform(-6, -3); o.insert(D.Minstep(kw["minstep"]))
+    ts = grid(t0, span, int(rng.integers(2, 50)), allow_dup=(kind == "ode23s"))
+    if backward:
+        ts = ts[::-1].copy()
+    tdir = 1.0 if ts[-1] >= ts[0] else -1.0
+    if kind == "ode23s":
+        tset = int(rng.integers(0, 2))
+        pts = int(rng.random() < 0.4)
+        if rng.random() < 0.3:
+            kw["initstep"] = float(rng.choice([-1.0, 1.0]) * span * 10.0 ** rng.uniform(-5, -1)); o.insert(D.Initstep(kw["initstep"]))
+        kw["points"] = pts
+        o.insert(D.Points.Specified if pts else D.Points.All)
+        oo = O.opts(rtol, atol, **kw)
+        ref = O.ensemble_ode23s(osys, params, y0, ts, oo, tset=tset, dense=True)
+        p = prob(ts)
+        sol = p.solve(D.Ode.Ode23s, o, tableau_set=tset)
+        tag = (case, kind, name, n, tset, folded, pts, backward)
+        ok = check(tag, [(k, getattr(sol, k), ref[k]) for k in ("accepted", "rejected", "nfe", "status", "t_reached")] + [("final", sol.final, ref["yfinal"])])
+        if ok:
+            sa = p.solve(D.Ode.Ode23s, D.OdeOptionMap(o).insert(D.Output.All), tableau_set=tset)
+            i = int(rng.integers(0, n))
+            one = O.solve_ode23s(osys, params[i] if np.ndim(params) == 2 else params, y0[i], ts, oo, tset=tset)
+            tout, yout = sa.trajectory(i)
+            check(tag + ("stream", i), [("tout", tout, one["tout"]), ("yout", yout, one["yout"]), ("nrows", np.diff(sa.offsets).astype(np.uint32), ref["nrows"])])
+        continue
+    # explicit adaptive
+    m, tset = [("Ode45", 0), ("Ode45", 1), ("Ode45fe", 0), ("Ode23", 1), ("Ode23", 0), ("Ode21", 1), ("Ode21", 0), ("Ode78", 1), ("Ode78", 0)][int(rng.integers(0, 9))]
+    if rng.random() < 0.3:
+        kw["initstep"] = float(tdir * span * 10.0 ** rng.uniform(-5, -1)); o.insert(D.Initstep(kw["initstep"]))
+    pts = int(rng.random() < 0.25)
+    kw["points"] = pts
+    if pts:
+        o.insert(D.Points.Specified)
+    oo = O.opts(rtol, atol, **kw)
+    ref = O.ensemble_adaptive(getattr(O, m.upper()), osys, params, y0, ts, oo, tset)
+    p = prob(ts)
+    sol = p.solve(getattr(D.Ode, m), o, tableau_set=tset)
+    tag = (case, kind, m, tset, name, n, folded, pts, backward)
+    ok = check(tag, [(k, getattr(sol, k), ref[k]) for k in ("accepted", "rejected", "nfe", "status", "t_reached")] + [("final", sol.final, ref["yfinal"])])
+    if ok:
+        sa = p.solve(getattr(D.Ode, m), D.OdeOptionMap(o).insert(D.Output.All), tableau_set=tset)
+        i = int(rng.integers(0, n))
+        one = O.solve_adaptive(getattr(O, m.upper()), osys, params[i] if np.ndim(params) == 2 else params, y0[i], ts, oo, tset=tset)
+        tout, yout = sa.trajectory(i)
+        check(tag + ("stream", i), [("tout", tout, one["tout"]), ("yout", yout, one["yout"])])
+        if not pts and len(ts) >= 2:
+            for lay in (D.DenseLayout.SoA, D.DenseLayout.TrajMajor):
+                sd = p.solve(getattr(D.Ode, m), D.OdeOptionMap(o).insert(D.Output.Tspan, lay), tableau_set=tset)
+                rd = O.ensemble_dense(getattr(O, m.upper()), osys, params, y0, ts, oo, tset)
+                want = rd["out"].transpose(2, 1, 0)
+                msk = ~np.isnan(want) & ~np.isnan(sd.yout)   # rows the reference never emitted are unset on either side
+                check(tag + ("dense", int(lay)), [("nvalid", sd.nvalid, rd["nvalid"]), ("rows", sd.yout[msk], want[msk])])
+print(f"fuzz done: {cases} cases, seed {seed}, mismatches {bad}, {time.time() - t_start:.1f} s")
+sys.exit(1 if bad else 0)
