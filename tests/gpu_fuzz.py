@@ -1,7 +1,7 @@
 """Probe (not a test): a long seeded differential campaign, CUDA path vs CPU oracle, bit for bit.  Covers what the unit tests
 cover, with many more random draws: explicit adaptive methods (all tableaus, both sets, Points::All / Specified, final / dense /
 ragged output, both libm flavours), fixed-step methods, ode23s and oderosenbrock.
-usage: python tests/gpu_fuzz.py [cases] [seed]"""
+usage: python tests/gpu_fuzz.py [cases] [seed] [nvrtc]      (nvrtc: the systems come in as user CUDA source through NVRTC)"""
 import os
 import sys
 import time
@@ -17,6 +17,15 @@ LOR = np.array([10.0, 28.0, 8.0 / 3.0])
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 rng = np.random.default_rng(seed)
+USER = {
+    "Lorenz": (3, 3, "__device__ void rhs(double t, const double* v, double* d, const double* p) { const double x = v[0], y = v[1], z = v[2];"
+                     " d[0] = p[0] * (y - x); d[1] = x * (p[1] - z) - y; d[2] = x * y - p[2] * z; }"),
+    "VanDerPol": (2, 1, "__device__ void rhs(double t, const double* v, double* d, const double* p) { d[0] = v[1];"
+                        " d[1] = p[0] * (1.0 - v[0] * v[0]) * v[1] - v[0]; }"),
+    "Pendulum": (2, 3, "__device__ void rhs(double t, const double* v, double* d, const double* p) { d[0] = v[1];"
+                       " d[1] = -p[0] * v[1] - deq_sin(v[0]) + p[1] * deq_cos(p[2] * t); }"),
+}
+RHS = {k: D.Rhs.from_source(src, n, np_) for k, (n, np_, src) in USER.items()} if "nvrtc" in sys.argv[3:] else {}
 bad = 0
 t_start = time.time()
 
@@ -54,7 +63,7 @@ for case in range(cases):
     sysid, osys = getattr(D.System, name), getattr(O, name.upper())
     t0 = float(rng.uniform(-2, 2))
     span = float(10.0 ** rng.uniform(-2, 0.7))
-    prob = lambda ts: D.OdeProblem.builder().fun(D.Rhs.builtin(sysid)).params(params).init(y0).tspan(ts).build()  # noqa: E731
+    prob = lambda ts: D.OdeProblem.builder().fun(RHS.get(name) or D.Rhs.builtin(sysid)).params(params).init(y0).tspan(ts).build()  # noqa: E731
     if kind == "fixed":
         m = ["Feuler", "Heun", "Midpoint", "Ode4"][int(rng.integers(0, 4))]
         ts = grid(t0, span, int(rng.integers(2, 60)))
