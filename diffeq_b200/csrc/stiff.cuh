@@ -161,7 +161,8 @@ __device__ __forceinline__ double pnorm2(const double (&v)[N], int libm_folded, 
 // ode23s (problem.rs:409-557).  Persistent lanes re-filled from a global counter like adapt_kernel.  MODE_FINAL: loop
 // state at exit; MODE_DENSE: the rows the reference pushes for the tspan times, SoA [N][nt][ntraj]; MODE_REC: the full
 // (tout, yout) stream, rows [t, y...], counting pass then writing pass.  The reference rescans the whole tspan on every
-// accepted step (:519); for a monotone tspan a cursor yields the same rows (capi.cu rejects a non-monotone one).
+// accepted step (:519); for a monotone tspan a cursor yields the same rows while time moves with the direction of
+// integration, and the kernel falls back to the full scan when it does not (capi.cu rejects a non-monotone tspan).
 // ---------------------------------------------------------------------------------------------------------------
 // FAST (compiled in the -fmad=true objects only, deq_options.mode = DEQ_MODE_FAST): fused multiply-adds, one reciprocal per
 // inverse / Jacobian column instead of n^2 divisions, sqrt norms, the 17-instruction table pow for the step factor.  Same
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
     const double tdir = P.tdir, tfinal = P.tend, reltol = P.reltol, abstol = P.abstol;
     const uint32_t max_steps = P.max_steps == 0ull || P.max_steps > 0xffffffffull ? 0xffffffffu : (uint32_t)P.max_steps;
 
-    bool active = false, pool_empty = false;
+    bool active = false, pool_empty = false, disorder = false;
     unsigned long long traj = 0, it = 1, wpos = 0;
     double t = 0.0, h = 0.0, tlast = 0.0;
     double y[N], f0[N], jac[N][N], prm[F::NP ? F::NP : 1];
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
                     t = P.t0;
                     const double hh = P.use_initstep ? P.initstep : P.h0[traj];
                     h = tdir * fmin(fabs(hh), P.maxstep);                      // :443
-                    acc = 0; rej = 0; attempts = 0; it = 1; wpos = 0; nv = 1; tlast = t;
+                    acc = 0; rej = 0; attempts = 0; it = 1; wpos = 0; nv = 1; tlast = t; disorder = false;
                     if (SOA) {
 #pragma unroll
                         for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt) * P.ntraj + traj] = y[d];
@@ -302,24 +303,35 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
                     if (err <= delta) {
                         acc += 1;
                         if (ROWS) {
-                            while (it < P.nt) {                                  // :519-534
-                                const double tq = __ldg(P.tspan + it);
-                                if (tq <= t) { ++it; continue; }                 // can never satisfy `toi > t` again
-                                if (!(tq <= tn)) break;
-                                const double s = (tq - t) / h;
-                                const double c1 = (s * (1. - s)) / (1. - 2. * D);
-                                const double c2 = (s * (s - 2. * D)) / (1. - 2. * D);
-                                double ytmp[N];
+                            // :519-534 — the reference rescans the whole tspan after every accepted step for `toi > t && toi <=
+                            // t + h`, which needs h > 0.  A forward run that has always moved forward visits the grid in order: a
+                            // cursor.  Otherwise — the tiny correction step with h > 0 at the end of a BACKWARD run that
+                            // overshot tfinal, or any step after time once moved against the direction — the full scan.
+                            if (h > 0.) {
+                                const bool scan_all = tdir < 0. || disorder;
+                                unsigned long long q = scan_all ? 0ull : it;
+                                while (q < P.nt) {
+                                    const double tq = __ldg(P.tspan + q);
+                                    if (!(tq > t)) { ++q; continue; }            // in cursor mode: can never satisfy `toi > t` again
+                                    if (!(tq <= tn)) { if (scan_all) { ++q; continue; } break; }
+                                    const double s = (tq - t) / h;
+                                    const double c1 = (s * (1. - s)) / (1. - 2. * D);
+                                    const double c2 = (s * (s - 2. * D)) / (1. - 2. * D);
+                                    double ytmp[N];
 #pragma unroll
-                                for (int i = 0; i < N; ++i) ytmp[i] = y[i] + (k1[i] * c1 + k2[i] * c2) * h;
-                                if (SOA) {
+                                    for (int i = 0; i < N; ++i) ytmp[i] = y[i] + (k1[i] * c1 + k2[i] * c2) * h;
+                                    if (SOA) {
 #pragma unroll
-                                    for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt + it) * P.ntraj + traj] = ytmp[d];
-                                    nv = (uint32_t)it + 1u;
+                                        for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt + q) * P.ntraj + traj] = ytmp[d];
+                                        nv = (uint32_t)q + 1u;
+                                    }
+                                    if (REC) emit(tq, ytmp);
+                                    tlast = tq;
+                                    ++q;
                                 }
-                                if (REC) emit(tq, ytmp);
-                                tlast = tq;
-                                ++it;
+                                if (!scan_all) it = q;
+                            } else if (tdir > 0.) {
+                                disorder = true;   // a forward run stepped backwards (overshoot correction): grid order is lost
                             }
                             if (REC && !P.points_specified && fabs(tlast - tn) > DBL_EPSILON) { emit(tn, ynew); tlast = tn; }   // :536-542
                         }

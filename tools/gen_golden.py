@@ -261,6 +261,13 @@ def main_stiff():
     ode23s("ode23s_invalid_matrix", "Lorenz", [10.0, 0.0, -4.0], [0.0, 0.0, 0.0], ["list", 0.0, 10.0], [0.0, 10.0],
            initstep=float.fromhex("0x1.b504f333f9de6p-1"), maxstep=5.0)
     ode23s("ode23s_minstep_midrun", "VanDerPol", [1000.0], [2.0, 0.0], ["list", 0.0, 2000.0], [0.0, 2000.0], minstep=3e-4)
+    # backward run that overshoots tfinal by 8 ulp and returns with a tiny step h > 0: the full tspan rescan (problem.rs:519-521)
+    # then pushes the row for tfinal although the run is backward (found by tests/gpu_fuzz.py, seed 8 case 1987)
+    fh_ = float.fromhex
+    ode23s("ode23s_backward_overshoot_correction", "VanDerPol", [fh_("0x1.a989391c904bbp-1")],
+           [fh_("0x1.f9432062ca40fp+0"), fh_("-0x1.4b5804af8ef58p-2")], ["list", fh_("0x1.0a4941f00af94p+1"), fh_("-0x1.6f0d005933b00p-7")],
+           [fh_("0x1.0a4941f00af94p+1"), fh_("-0x1.6f0d005933b00p-7")], tset="textbook", reltol=fh_("0x1.3f0fbaf4e45fep-12"),
+           abstol=fh_("0x1.4adc292f2891ap-30"), maxstep=fh_("0x1.0bb84ef0642cfp-1"), initstep=fh_("-0x1.58b45d6392d05p-4"))
     ode23s("ode23s_zero_span", "Lorenz", LOR, [1.0, 2.0, 20.0], ["list", 1.0, 1.0], [1.0, 1.0])
     for which in ("kr4", "s4"):
         rosen(f"{which}_vdp", which, "VanDerPol", [5.0], [2.0, 0.0], ["linspace", 0.0, 0.39, 40], linspace(0.0, 0.39, 40))
