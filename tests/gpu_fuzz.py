@@ -50,6 +50,8 @@ def check(tag, pairs):
 
 
 def grid(t0, span, npts, allow_dup=True):
+    if npts < 2:
+        return np.array([t0])
     g = np.sort(np.concatenate([[0.0, 1.0], rng.uniform(0, 1, max(npts - 2, 0))]))
     if allow_dup and npts > 4 and rng.random() < 0.2:
         g[2] = g[1]
@@ -58,7 +60,7 @@ def grid(t0, span, npts, allow_dup=True):
 
 for case in range(cases):
     kind = rng.choice(["adapt", "adapt", "adapt", "fixed", "ode23s", "rosen"])
-    n = int(rng.integers(1, 150))
+    n = int(rng.integers(1, 150)) if rng.random() < 0.97 else int(rng.integers(1000, 6000))   # a few multi-CTA ensembles
     name, y0, params = system(case, n)
     sysid, osys = getattr(D.System, name), getattr(O, name.upper())
     t0 = float(rng.uniform(-2, 2))
@@ -86,7 +88,7 @@ for case in range(cases):
     rtol, atol = 10.0 ** rng.uniform(-9, -3), 10.0 ** rng.uniform(-11, -4)
     folded = int(rng.random() < 0.4)
     kw = dict(max_steps=int(rng.choice([300, 1500, 4000])), libm_folded=folded)
-    o = D.OdeOptionMap().insert(D.Reltol(rtol), D.Abstol(atol), D.MaxSteps(kw["max_steps"]))
+    o = D.OdeOptionMap().insert(D.Reltol(rtol), D.Abstol(atol), D.MaxSteps(kw["max_steps"]), D.Refill(int(rng.integers(0, 2))))
     if folded:
         o.insert(D.Libm.LlvmFolded)
     backward = rng.random() < 0.15
@@ -94,7 +96,9 @@ for case in range(cases):
         kw["maxstep"] = span / float(rng.integers(3, 30)); o.insert(D.Maxstep(kw["maxstep"]))
     if rng.random() < 0.2:
         kw["minstep"] = span * 10.0 ** rng.uniform(-6, -3); o.insert(D.Minstep(kw["minstep"]))
-    ts = grid(t0, span, int(rng.integers(2, 50)), allow_dup=(kind == "ode23s"))
+    ts = grid(t0, span, int(rng.integers(2, 50)) if rng.random() < 0.95 else 1)
+    if len(ts) < 2:
+        ts = ts[:1]
     if backward:
         ts = ts[::-1].copy()
     tdir = 1.0 if ts[-1] >= ts[0] else -1.0
@@ -117,6 +121,15 @@ for case in range(cases):
             one = O.solve_ode23s(osys, params[i] if np.ndim(params) == 2 else params, y0[i], ts, oo, tset=tset)
             tout, yout = sa.trajectory(i)
             check(tag + ("stream", i), [("tout", tout, one["tout"]), ("yout", yout, one["yout"]), ("nrows", np.diff(sa.offsets).astype(np.uint32), ref["nrows"])])
+            if len(ts) >= 2:
+                sd = p.solve(D.Ode.Ode23s, D.OdeOptionMap(o).insert(D.Output.Tspan), tableau_set=tset)
+                want = ref["out"].transpose(2, 1, 0)
+                msk = (np.arange(len(ts))[None, :] < ref["nvalid"][:, None]) & ~np.isnan(want[:, :, 0])
+                check(tag + ("dense",), [("nvalid", sd.nvalid, ref["nvalid"]), ("rows", sd.yout[msk], want[msk])])
+            if rng.random() < 0.2:
+                oh = D.OdeOptionMap(o).insert(D.ShardChunk(int(rng.choice([0, 1, 7, 64]))))
+                hs = D.solve_host_multi(RHS.get(name) or D.Rhs.builtin(sysid), y0, params, ts, D.Ode.Ode23s, oh, devices=[0] * int(rng.integers(1, 5)), tableau_set=tset)
+                check(tag + ("host",), [("final", hs["final"], ref["yfinal"]), ("accepted", hs["accepted"], ref["accepted"]), ("status", hs["status"], ref["status"])])
         continue
     # explicit adaptive
     m, tset = [("Ode45", 0), ("Ode45", 1), ("Ode45fe", 0), ("Ode23", 1), ("Ode23", 0), ("Ode21", 1), ("Ode21", 0), ("Ode78", 1), ("Ode78", 0)][int(rng.integers(0, 9))]
@@ -138,6 +151,10 @@ for case in range(cases):
         one = O.solve_adaptive(getattr(O, m.upper()), osys, params[i] if np.ndim(params) == 2 else params, y0[i], ts, oo, tset=tset)
         tout, yout = sa.trajectory(i)
         check(tag + ("stream", i), [("tout", tout, one["tout"]), ("yout", yout, one["yout"])])
+        if rng.random() < 0.15:
+            oh = D.OdeOptionMap(o).insert(D.ShardChunk(int(rng.choice([0, 1, 7, 64]))))
+            hs = D.solve_host_multi(RHS.get(name) or D.Rhs.builtin(sysid), y0, params, ts, getattr(D.Ode, m), oh, devices=[0] * int(rng.integers(1, 5)), tableau_set=tset)
+            check(tag + ("host",), [("final", hs["final"], ref["yfinal"]), ("accepted", hs["accepted"], ref["accepted"]), ("t_reached", hs["t_reached"], ref["t_reached"])])
         if not pts and len(ts) >= 2:
             for lay in (D.DenseLayout.SoA, D.DenseLayout.TrajMajor):
                 sd = p.solve(getattr(D.Ode, m), D.OdeOptionMap(o).insert(D.Output.Tspan, lay), tableau_set=tset)
