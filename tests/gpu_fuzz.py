@@ -62,6 +62,9 @@ for case in range(cases):
     kind = rng.choice(["adapt", "adapt", "adapt", "fixed", "ode23s", "rosen"])
     n = int(rng.integers(1, 150)) if rng.random() < 0.97 else int(rng.integers(1000, 6000))   # a few multi-CTA ensembles
     name, y0, params = system(case, n)
+    if rng.random() < 0.04:   # special values in the initial state: NaN, infinities, signed zeros, huge and tiny magnitudes
+        y0 = y0.copy()
+        y0[int(rng.integers(0, n)), int(rng.integers(0, y0.shape[1]))] = float(rng.choice([np.nan, np.inf, -np.inf, 0.0, -0.0, 1e300, -1e300, 1e-300, 5e-324]))
     sysid, osys = getattr(D.System, name), getattr(O, name.upper())
     t0 = float(rng.uniform(-2, 2))
     span = float(10.0 ** rng.uniform(-2, 0.7))
