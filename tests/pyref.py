@@ -19,6 +19,16 @@ _libm.exp10.argtypes = [ctypes.c_double]
 EPS = 2.220446049250313e-16
 
 
+def fdiv(a, b):
+    """IEEE-754 division (Python raises on a zero divisor)."""
+    try:
+        return a / b
+    except ZeroDivisionError:
+        if a != a or a == 0.0:
+            return math.nan
+        return math.copysign(math.inf, a) * math.copysign(1.0, b)
+
+
 def signum(x):
     return x if x != x else math.copysign(1.0, x)
 
@@ -329,7 +339,7 @@ def fdjacobian(f, t, x):
         tmp[c] += dxj
         yj = f(t, tmp)
         for r in range(n):
-            J[r][c] = (yj[r] - ftx[r]) / dxj
+            J[r][c] = fdiv(yj[r] - ftx[r], dxj)
     return J
 
 
@@ -401,7 +411,7 @@ def ode23s(f, y0, tspan, reltol=1e-5, abstol=1e-8, minstep=None, maxstep=None, i
             acc += 1
             for toi in tspan:
                 if toi > t and toi <= t + h:
-                    s = (toi - t) / h
+                    s = fdiv(toi - t, h)
                     tout.append(toi)
                     c1 = 1.0 * (s * (1.0 - s) / (1.0 - 2.0 * d))
                     c2 = 1.0 * (s * (s - 2.0 * d) / (1.0 - 2.0 * d))
@@ -454,7 +464,7 @@ def oderosenbrock(f, co, y0, tspan):
         ts = tspan[solstep]
         xs = list(x[solstep])
         dfdx = fdjacobian(f, ts, xs)
-        dg = 1.0 * (1.0 / (co["gamma"] * hs))
+        dg = 1.0 * fdiv(1.0, co["gamma"] * hs)
         jac = [[(dg if r == c else 0.0) - dfdx[r][c] for c in range(n)] for r in range(n)]
         jinv = na_try_inverse(jac)
         if jinv is None:
@@ -472,7 +482,7 @@ def oderosenbrock(f, co, y0, tspan):
                     df[dd] += g[j][dd] * co["c"][i][j]
             fx = f(ts + co["b"][i] * hs, [xs[dd] + dx[dd] for dd in range(n)])
             gv = na_gemv(jinv, fx)
-            gv = [gv[dd] + df[dd] * (1.0 / hs) for dd in range(n)]
+            gv = [gv[dd] + df[dd] * fdiv(1.0, hs) for dd in range(n)]
             for dd in range(n):
                 nx[dd] += gv[dd] * co["b"][i]
             g.append(gv)
