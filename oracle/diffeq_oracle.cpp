@@ -171,7 +171,7 @@ bool make_tableau(int method, int set, Tableau& t) {
 // ------------------------------------------------------------------------------------------
 // Built-in right-hand sides (the reference takes a closure F: Fn(f64,&Y)->Y, problem.rs:32-36).
 // ------------------------------------------------------------------------------------------
-enum Rhs { LORENZ = 0, VANDERPOL = 1, PENDULUM = 2 };
+enum Rhs { LORENZ = 0, VANDERPOL = 1, PENDULUM = 2, RING8 = 3, RING16 = 4 };
 
 struct LorenzF {  // problem.rs:989-1000: params = {sigma, rho, beta}
     static constexpr int N = 3;
@@ -180,6 +180,19 @@ struct LorenzF {  // problem.rs:989-1000: params = {sigma, rho, beta}
         d[0] = p[0] * (y - x);
         d[1] = x * (p[1] - z) - y;
         d[2] = x * y - p[2] * z;
+    }
+};
+// Test systems of larger dimension (not in the reference; they pin the generic-dimension NVRTC path of the product, whose user
+// source states the same expression): a ring of N logistic cells with diffusive coupling, params = {kappa, r},
+//   d_i = kappa * (y_{i+1} - y_i) + r * (y_i * (1 - y_{i-1}))   (indices mod N)
+template <int NN>
+struct RingF {
+    static constexpr int N = NN;
+    static inline void eval(double, const double* v, double* d, const double* p) {
+        for (int i = 0; i < NN; ++i) {
+            const int ip = (i + 1) % NN, im = (i + NN - 1) % NN;
+            d[i] = p[0] * (v[ip] - v[i]) + p[1] * (v[i] * (1.0 - v[im]));
+        }
     }
 };
 struct VdpF {  // x' = y, y' = mu (1 - x^2) y - x ; params = {mu}
@@ -796,6 +809,8 @@ int dispatch_rhs(int rhs, Fn&& fn) {
         case LORENZ: return fn(LorenzF());
         case VANDERPOL: return fn(VdpF());
         case PENDULUM: return fn(PendulumF());
+        case RING8: return fn(RingF<8>());
+        case RING16: return fn(RingF<16>());
         default: return ERR_UNSUPPORTED;
     }
 }
@@ -816,8 +831,8 @@ struct oracle_opts {
     int libm_folded;
 };
 
-int oracle_rhs_dim(int rhs) { return rhs == LORENZ ? 3 : (rhs == VANDERPOL || rhs == PENDULUM) ? 2 : -1; }
-int oracle_rhs_nparams(int rhs) { return rhs == LORENZ ? 3 : rhs == VANDERPOL ? 1 : rhs == PENDULUM ? 3 : -1; }
+int oracle_rhs_dim(int rhs) { return rhs == LORENZ ? 3 : (rhs == VANDERPOL || rhs == PENDULUM) ? 2 : rhs == RING8 ? 8 : rhs == RING16 ? 16 : -1; }
+int oracle_rhs_nparams(int rhs) { return rhs == LORENZ ? 3 : rhs == VANDERPOL ? 1 : rhs == PENDULUM ? 3 : (rhs == RING8 || rhs == RING16) ? 2 : -1; }
 
 // itertools_num::linspace as recalled (unpinned third-party): a + ((b-a)/(n-1))*i
 void oracle_linspace(double a, double b, size_t n, double* out) {

@@ -784,3 +784,56 @@ def test_device_resident_inputs_and_outputs(deq, oracle):
     pl = deq.OdeProblem.from_device(deq.Rhs.builtin(deq.System.Lorenz), d_l.data_ptr(), 500, [0.0, 1.0], params=LOR)
     rl = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, y0l, [0.0, 1.0])
     assert np.array_equal(pl.solve(deq.Ode.Ode45).final, rl["yfinal"])
+
+
+RING_SRC = r'''
+// ring of DEQ_USER_N logistic cells with diffusive coupling (the oracle's RingF): same expression, same order
+__device__ void rhs(double t, const double* v, double* d, const double* p) {
+#pragma unroll
+    for (int i = 0; i < DEQ_USER_N; ++i) {
+        const int ip = (i + 1) % DEQ_USER_N, im = (i + DEQ_USER_N - 1) % DEQ_USER_N;
+        d[i] = p[0] * (v[ip] - v[i]) + p[1] * (v[i] * (1.0 - v[im]));
+    }
+}
+'''
+
+
+@pytest.mark.parametrize("n", [8, 16])
+def test_generic_dimension_user_systems_bit_exact(deq, oracle, n):
+    """State dimension 8 and 16 (the `OdeType` impls of the reference reach 9-tuples and arbitrary Vecs, types.rs:138-278): the
+    generic-dimension NVRTC path against the oracle's ring system — adaptive (FSAL and 13-stage non-FSAL), fixed step, final
+    states, dense rows in both layouts and the ragged stream, all bit for bit."""
+    osys = oracle.RING8 if n == 8 else oracle.RING16
+    rng = np.random.default_rng(n)
+    m = 300
+    y0 = rng.uniform(0.1, 0.9, (m, n))
+    prm = np.column_stack([rng.uniform(0.1, 0.5, m), rng.uniform(0.5, 2.5, m)])
+    rhs = deq.Rhs.from_source(RING_SRC, n, 2)
+    assert rhs.dim == n
+    ts = deq.linspace(0.0, 4.0, 33)
+    prob = deq.OdeProblem.builder().fun(rhs).params(prm).init(y0).tspan(ts).build()
+    for method, tset, tol in ((deq.Ode.Ode45, 0, 1e-8), (deq.Ode.Ode78, 1, 1e-10), (deq.Ode.Ode45fe, 0, 1e-6)):
+        om = {deq.Ode.Ode45: oracle.ODE45, deq.Ode.Ode78: oracle.ODE78, deq.Ode.Ode45fe: oracle.ODE45FE}[method]
+        oo = oracle.opts(tol, tol)
+        base = (deq.Reltol(tol), deq.Abstol(tol))
+        ref = oracle.ensemble_adaptive(om, osys, prm, y0, ts, oo, tset)
+        sol = prob.solve(method, deq.OdeOptionMap().insert(*base), tableau_set=tset)
+        for k in ("accepted", "rejected", "nfe", "status", "t_reached"):
+            assert np.array_equal(getattr(sol, k), ref[k]), (method, k)
+        assert np.array_equal(sol.final, ref["yfinal"]), method
+        rd = oracle.ensemble_dense(om, osys, prm, y0, ts, oo, tset)
+        want = rd["out"].transpose(2, 1, 0)
+        for lay in (deq.DenseLayout.SoA, deq.DenseLayout.TrajMajor):
+            sd = prob.solve(method, deq.OdeOptionMap().insert(*base, deq.Output.Tspan, lay), tableau_set=tset)
+            assert np.array_equal(sd.nvalid, rd["nvalid"]) and np.array_equal(sd.yout, want), (method, lay)
+        sa = prob.solve(method, deq.OdeOptionMap().insert(*base, deq.Output.All), tableau_set=tset)
+        for i in (0, m - 1):
+            one = oracle.solve_adaptive(om, osys, prm[i], y0[i], ts, oo, tset=tset)
+            tout, yout = sa.trajectory(i)
+            assert np.array_equal(tout, one["tout"]) and np.array_equal(yout, one["yout"]), (method, i)
+    fx = prob.solve(deq.Ode.Ode4, deq.OdeOptionMap().insert(deq.Output.Tspan))
+    assert np.array_equal(fx.final, oracle.ensemble_fixed(oracle.ODE4, osys, prm, y0, ts))
+    assert np.array_equal(fx.yout[7], oracle.solve_fixed(oracle.ODE4, osys, prm[7], y0[7], ts)["yout"])
+    with pytest.raises(deq.OdeError) as e:       # the stiff path carries n <= 3
+        prob.solve(deq.Ode.Ode23s)
+    assert e.value.kind == "Unsupported"
