@@ -831,9 +831,11 @@ def test_generic_dimension_user_systems_bit_exact(deq, oracle, n):
             one = oracle.solve_adaptive(om, osys, prm[i], y0[i], ts, oo, tset=tset)
             tout, yout = sa.trajectory(i)
             assert np.array_equal(tout, one["tout"]) and np.array_equal(yout, one["yout"]), (method, i)
-    fx = prob.solve(deq.Ode.Ode4, deq.OdeOptionMap().insert(deq.Output.Tspan))
-    assert np.array_equal(fx.final, oracle.ensemble_fixed(oracle.ODE4, osys, prm, y0, ts))
-    assert np.array_equal(fx.yout[7], oracle.solve_fixed(oracle.ODE4, osys, prm[7], y0[7], ts)["yout"])
+    fx = prob.solve(deq.Ode.Ode4, deq.OdeOptionMap().insert(deq.Output.Tspan))      # RK4 at dt = 1/8 blows up for the stiffer cells:
+    rfx = oracle.ensemble_fixed(oracle.ODE4, osys, prm, y0, ts)                     # the overflow to NaN must match as well
+    assert np.array_equal(fx.final, rfx, equal_nan=True) and np.isfinite(rfx).all(axis=1).mean() > 0.5
+    for i in (3, 7):
+        assert np.array_equal(fx.yout[i], oracle.solve_fixed(oracle.ODE4, osys, prm[i], y0[i], ts)["yout"], equal_nan=True)
     with pytest.raises(deq.OdeError) as e:       # the stiff path carries n <= 3
         prob.solve(deq.Ode.Ode23s)
     assert e.value.kind == "Unsupported"
