@@ -25,13 +25,21 @@ USER = {
     "Pendulum": (2, 3, "__device__ void rhs(double t, const double* v, double* d, const double* p) { d[0] = v[1];"
                        " d[1] = -p[0] * v[1] - deq_sin(v[0]) + p[1] * deq_cos(p[2] * t); }"),
 }
-RHS = {k: D.Rhs.from_source(src, n, np_) for k, (n, np_, src) in USER.items()} if "nvrtc" in sys.argv[3:] else {}
+RING = ("__device__ void rhs(double t, const double* v, double* d, const double* p) {\n#pragma unroll\n for (int i = 0; i < DEQ_USER_N; ++i) {"
+        " const int ip = (i + 1) % DEQ_USER_N, im = (i + DEQ_USER_N - 1) % DEQ_USER_N; d[i] = p[0] * (v[ip] - v[i]) + p[1] * (v[i] * (1.0 - v[im])); } }")
+NVRTC = "nvrtc" in sys.argv[3:]
+if NVRTC:   # plus the oracle's ring systems of dimension 8 and 16 (explicit methods only: the stiff path carries n <= 3)
+    USER.update({"Ring8": (8, 2, RING), "Ring16": (16, 2, RING)})
+RHS = {k: D.Rhs.from_source(src, n, np_) for k, (n, np_, src) in USER.items()} if NVRTC else {}
 bad = 0
 t_start = time.time()
 
 
-def system(case, n):
-    name = ["Lorenz", "VanDerPol", "Pendulum"][int(rng.integers(0, 3))]
+def system(case, n, stiff=False):
+    name = ["Lorenz", "VanDerPol", "Pendulum", "Ring8", "Ring16"][int(rng.integers(0, 5 if (NVRTC and not stiff) else 3))]
+    if name.startswith("Ring"):
+        d = int(name[4:])
+        return name, rng.uniform(0.1, 0.9, (n, d)), np.column_stack([rng.uniform(0.1, 0.5, n), rng.uniform(0.5, 2.5, n)])
     if name == "Lorenz":
         return name, synth.lorenz_ics(case * 977, case * 977 + n), LOR
     if name == "VanDerPol":
@@ -68,11 +76,11 @@ def grid(t0, span, npts, allow_dup=True):
 for case in range(cases):
     kind = rng.choice(["adapt", "adapt", "adapt", "fixed", "ode23s", "rosen"])
     n = int(rng.integers(1, 150)) if rng.random() < 0.97 else int(rng.integers(1000, 6000))   # a few multi-CTA ensembles
-    name, y0, params = system(case, n)
+    name, y0, params = system(case, n, stiff=kind in ("ode23s", "rosen"))
     if rng.random() < 0.04:   # special values in the initial state: NaN, infinities, signed zeros, huge and tiny magnitudes
         y0 = y0.copy()
         y0[int(rng.integers(0, n)), int(rng.integers(0, y0.shape[1]))] = float(rng.choice([np.nan, np.inf, -np.inf, 0.0, -0.0, 1e300, -1e300, 1e-300, 5e-324]))
-    sysid, osys = getattr(D.System, name), getattr(O, name.upper())
+    sysid, osys = getattr(D.System, name, None), getattr(O, name.upper())
     t0 = float(rng.uniform(-2, 2))
     span = float(10.0 ** rng.uniform(-2, 0.7))
     prob = lambda ts: D.OdeProblem.builder().fun(RHS.get(name) or D.Rhs.builtin(sysid)).params(params).init(y0).tspan(ts).build()  # noqa: E731
