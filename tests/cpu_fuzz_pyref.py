@@ -37,13 +37,17 @@ def same(a, b):
 
 for case in range(cases):
     kind = rng.choice(["adapt", "adapt", "fixed", "ode23s", "rosen"])
-    sysname = ["Lorenz", "VanDerPol", "Pendulum"][int(rng.integers(0, 3))]
+    sysname = ["Lorenz", "VanDerPol", "Pendulum", "Ring8", "Ring16"][int(rng.integers(0, 3 if kind in ("ode23s", "rosen") else 5))]
     if sysname == "Lorenz":
         prm, y0, f = [10.0, 28.0, 8.0 / 3.0], rng.uniform([-20, -20, 0], [20, 20, 50]).tolist(), None
         f = pyref.lorenz(prm)
     elif sysname == "VanDerPol":
         prm, y0 = [float(10.0 ** rng.uniform(-1, 2.5))], (np.array([2.0, 0.0]) + rng.uniform(-1, 1, 2)).tolist()
         f = pyref.vanderpol(prm)
+    elif sysname.startswith("Ring"):
+        d = int(sysname[4:])
+        prm, y0 = [float(rng.uniform(0.1, 0.5)), float(rng.uniform(0.5, 2.5))], rng.uniform(0.1, 0.9, d).tolist()
+        f = pyref.ring(prm, d)
     else:
         prm, y0 = [0.5, 1.2, 2.0 / 3.0], rng.uniform([-3.1, -2], [3.1, 2]).tolist()
         f = pyref.pendulum(prm)

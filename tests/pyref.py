@@ -64,6 +64,12 @@ def pendulum(p):
     return lambda t, v: [v[1], -g * v[1] - math.sin(v[0]) + a * math.cos(w * t)]
 
 
+def ring(p, n):
+    """The oracle's RingF test system (dimension n): d_i = kappa (y_{i+1} - y_i) + r (y_i (1 - y_{i-1})), indices mod n."""
+    kappa, r = p
+    return lambda t, v: [kappa * (v[(i + 1) % n] - v[i]) + r * (v[i] * (1.0 - v[(i + n - 1) % n])) for i in range(n)]
+
+
 def is_fsal(tb):
     """runge_kutta.rs:185-193 (b.as_slice() is column-major: the first S entries are column 0)."""
     S = len(tb["c"])
