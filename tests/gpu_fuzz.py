@@ -1,7 +1,10 @@
 """Probe (not a test): a long seeded differential campaign, CUDA path vs CPU oracle, bit for bit.  Covers what the unit tests
 cover, with many more random draws: explicit adaptive methods (all tableaus, both sets, Points::All / Specified, final / dense /
 ragged output, both libm flavours), fixed-step methods, ode23s and oderosenbrock.
-usage: python tests/gpu_fuzz.py [cases] [seed] [nvrtc]      (nvrtc: the systems come in as user CUDA source through NVRTC)"""
+usage: python tests/gpu_fuzz.py [cases] [seed] [nvrtc] [fast]
+   nvrtc: the systems come in as user CUDA source through NVRTC
+   fast:  additionally run Mode.Fast on the adaptive cases and hold it to a sanity bar against the bit-exact result (it must
+          finish, keep every trajectory's exit status, and take a total number of step attempts within 2 %)"""
 import os
 import sys
 import time
@@ -28,6 +31,23 @@ USER = {
 RING = ("__device__ void rhs(double t, const double* v, double* d, const double* p) {\n#pragma unroll\n for (int i = 0; i < DEQ_USER_N; ++i) {"
         " const int ip = (i + 1) % DEQ_USER_N, im = (i + DEQ_USER_N - 1) % DEQ_USER_N; d[i] = p[0] * (v[ip] - v[i]) + p[1] * (v[i] * (1.0 - v[im])); } }")
 NVRTC = "nvrtc" in sys.argv[3:]
+FASTCHK = "fast" in sys.argv[3:]
+fast_stats = []
+
+
+def fast_check(tag, p, ode, o, tset, sol):
+    """Mode.Fast against the PARITY solution `sol` of the same problem (sanity bar, see the module docstring)."""
+    global bad
+    f = p.solve(ode, D.OdeOptionMap(o).insert(D.Mode.Fast), tableau_set=tset)
+    a0 = int(sol.accepted.sum(dtype=np.int64) + sol.rejected.sum(dtype=np.int64))
+    a1 = int(f.accepted.sum(dtype=np.int64) + f.rejected.sum(dtype=np.int64))
+    same_status = float((f.status == sol.status).mean())
+    fin = np.isfinite(sol.final).all(axis=1) & (sol.status == 0) & (f.status == 0)
+    dev = np.max(np.abs(f.final[fin] - sol.final[fin]) / (np.abs(sol.final[fin]) * float(o["Reltol"]) + float(o["Abstol"])), axis=1) if fin.any() else np.zeros(1)
+    fast_stats.append((same_status, abs(a1 - a0) / max(a0, 1), float(np.median(dev)), float(dev.max())))
+    if same_status < 0.9 or abs(a1 - a0) > 0.02 * a0 + 20:
+        bad += 1
+        print("FAST-MODE OUTLIER", tag, same_status, a0, a1, flush=True)
 if NVRTC:   # plus the oracle's ring systems of dimension 8 and 16 (explicit methods only: the stiff path carries n <= 3)
     USER.update({"Ring8": (8, 2, RING), "Ring16": (16, 2, RING)})
 RHS = {k: D.Rhs.from_source(src, n, np_) for k, (n, np_, src) in USER.items()} if NVRTC else {}
@@ -133,6 +153,8 @@ for case in range(cases):
         sol = p.solve(D.Ode.Ode23s, o, tableau_set=tset)
         tag = (case, kind, name, n, tset, folded, pts, backward)
         ok = check(tag, [(k, getattr(sol, k), ref[k]) for k in ("accepted", "rejected", "nfe", "status", "t_reached")] + [("final", sol.final, ref["yfinal"])])
+        if FASTCHK and not folded:
+            fast_check(tag, p, D.Ode.Ode23s, o, tset, sol)
         if ok:
             sa = p.solve(D.Ode.Ode23s, D.OdeOptionMap(o).insert(D.Output.All), tableau_set=tset)
             i = int(rng.integers(0, n))
@@ -163,6 +185,8 @@ for case in range(cases):
     sol = p.solve(getattr(D.Ode, m), o, tableau_set=tset)
     tag = (case, kind, m, tset, name, n, folded, pts, backward)
     ok = check(tag, [(k, getattr(sol, k), ref[k]) for k in ("accepted", "rejected", "nfe", "status", "t_reached")] + [("final", sol.final, ref["yfinal"])])
+    if FASTCHK and not pts and not folded and (m, tset) not in (("Ode23", 0), ("Ode21", 0), ("Ode78", 0)):   # not the collapsing reference tableaus
+        fast_check(tag, p, getattr(D.Ode, m), o, tset, sol)
     if ok:
         sa = p.solve(getattr(D.Ode, m), D.OdeOptionMap(o).insert(D.Output.All), tableau_set=tset)
         i = int(rng.integers(0, n))
@@ -180,5 +204,10 @@ for case in range(cases):
                 want = rd["out"].transpose(2, 1, 0)
                 msk = ~np.isnan(want) & ~np.isnan(sd.yout)   # rows the reference never emitted are unset on either side
                 check(tag + ("dense", int(lay)), [("nvalid", sd.nvalid, rd["nvalid"]), ("rows", sd.yout[msk], want[msk])])
+if fast_stats:
+    fs = np.array(fast_stats)
+    print(f"fast-mode sanity: {len(fs)} adaptive cases; same exit status mean {fs[:, 0].mean():.4f} min {fs[:, 0].min():.3f}; step-attempt total differs by "
+          f"mean {fs[:, 1].mean():.2e} max {fs[:, 1].max():.2e}; final-state deviation in units of (rtol |y| + atol): median of medians {np.median(fs[:, 2]):.2e}, "
+          f"median of maxima {np.median(fs[:, 3]):.2e}")
 print(f"fuzz done: {cases} cases, seed {seed}, mismatches {bad}, {time.time() - t_start:.1f} s")
 sys.exit(1 if bad else 0)
