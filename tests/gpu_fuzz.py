@@ -35,6 +35,10 @@ FASTCHK = "fast" in sys.argv[3:]
 fast_stats = []
 
 
+def p_y0(p, i):
+    return getattr(p, "_y0_dbg", [None])[i] if hasattr(p, "_y0_dbg") else None
+
+
 def fast_check(tag, p, ode, o, tset, sol):
     """Mode.Fast against the PARITY solution `sol` of the same problem (sanity bar, see the module docstring)."""
     global bad
@@ -48,6 +52,12 @@ def fast_check(tag, p, ode, o, tset, sol):
     if same_status < 0.9 or abs(a1 - a0) > 0.02 * a0 + 20:
         bad += 1
         print("FAST-MODE OUTLIER", tag, same_status, a0, a1, flush=True)
+        if os.environ.get("DEQ_FUZZ_VERBOSE"):
+            d = (f.accepted.astype(np.int64) + f.rejected) - (sol.accepted.astype(np.int64) + sol.rejected)
+            i = int(np.argmax(np.abs(d)))
+            print("   options", {k: (float(v) if isinstance(v, (float, np.floating)) else v) for k, v in o.items()}, "tspan", p.tspan[0], p.tspan[-1], len(p.tspan))
+            print("   per-trajectory attempt differences: nonzero", int((d != 0).sum()), "of", len(d), "largest at", i, "parity acc/rej", int(sol.accepted[i]), int(sol.rejected[i]),
+                  "fast acc/rej", int(f.accepted[i]), int(f.rejected[i]), "y0", p_y0(p, i), "final parity", sol.final[i], "fast", f.final[i], flush=True)
 if NVRTC:   # plus the oracle's ring systems of dimension 8 and 16 (explicit methods only: the stiff path carries n <= 3)
     USER.update({"Ring8": (8, 2, RING), "Ring16": (16, 2, RING)})
 RHS = {k: D.Rhs.from_source(src, n, np_) for k, (n, np_, src) in USER.items()} if NVRTC else {}
@@ -103,7 +113,10 @@ for case in range(cases):
     sysid, osys = getattr(D.System, name, None), getattr(O, name.upper())
     t0 = float(rng.uniform(-2, 2))
     span = float(10.0 ** rng.uniform(-2, 0.7))
-    prob = lambda ts: D.OdeProblem.builder().fun(RHS.get(name) or D.Rhs.builtin(sysid)).params(params).init(y0).tspan(ts).build()  # noqa: E731
+    def prob(ts):
+        pp = D.OdeProblem.builder().fun(RHS.get(name) or D.Rhs.builtin(sysid)).params(params).init(y0).tspan(ts).build()
+        pp._y0_dbg = y0
+        return pp
     if kind == "fixed":
         m = ["Feuler", "Heun", "Midpoint", "Ode4"][int(rng.integers(0, 4))]
         ts = grid(t0, span, int(rng.integers(2, 60)))
