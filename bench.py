@@ -297,6 +297,9 @@ def main():
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^20 trajectories (ncu --set full, profiles/r1_final_*_kernel_
     # ncu_full_summary.csv); it scales with the trajectory count, not with the step count
     NCU_DRAM_BYTES = {"parity": 62.139648e6 + 16.999680e6, "fast": 62.736384e6 + 15.812608e6}
+    # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed of the same captures: how busy the FP64 pipe is, whatever the
+    # instructions are worth in algorithmic FLOP (a non-fused multiply-add occupies it twice)
+    NCU_FP64_PIPE_ACTIVE_PCT = {"parity": 79.7, "fast": 74.3}
 
     def roofline(kernel_ms_list, steps_local, kernel_name, mode_note, traffic_key):
         kms = sum(kernel_ms_list) / len(kernel_ms_list)
@@ -304,6 +307,7 @@ def main():
         return {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if fp64_peak else None,
                 "traffic": NCU_DRAM_BYTES[traffic_key] * (ntraj / float(1 << 20)), "traffic_unit": "bytes per launch (DRAM, ncu)",
+                "fp64_pipe_active_pct_ncu": NCU_FP64_PIPE_ACTIVE_PCT[traffic_key],
                 "kernel": kernel_name,
                 "kernel_ms": kms, "flop_per_step": FLOP_PER_STEP, "arithmetic": mode_note,
                 "peak_source": "DFMA-stream microbenchmark measured in this run (deq_measure_fp64_peak); MEASURED_PEAKS.json "
