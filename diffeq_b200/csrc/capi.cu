@@ -434,7 +434,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         H.libm_folded = o.libm == DEQ_LIBM_LLVM_FOLDED;
         deqk::AdaptParams P{};
         P.y0 = e->d_y0; P.f0 = r->d_f0; P.h0 = r->d_h0; P.params = e->d_params; P.shared = e->shared;
-        P.tspan = e->d_tspan; P.nt = nt; P.ntraj = ntraj; P.t0 = t0; P.tend = tend; P.tdir = tdir;
+        P.tspan = e->d_tspan; P.nt = nt; P.ntraj = ntraj; P.t0 = t0; P.tend = tend; P.tdir = tdir; P.tdir_tend = tdir * tend;
         P.minstep = o.has_minstep ? o.minstep : std::fabs(tend - t0) / 1e18;   // problem.rs:219-221
         P.maxstep = o.has_maxstep ? o.maxstep : std::fabs(tend - t0) / 2.5;    // problem.rs:223-225
         P.reltol = o.reltol; P.abstol = o.abstol; P.initstep = o.initstep; P.use_initstep = o.initstep != 0.;

@@ -33,6 +33,7 @@ struct AdaptParams {
     unsigned long long nt;
     unsigned long long ntraj;
     double t0, tend, tdir, minstep, maxstep, reltol, abstol, initstep;
+    double tdir_tend;      // tdir * tend (one IEEE product, problem.rs:337), formed once on the host
     int use_initstep;
     int libm_folded;       // 0: pow(s, 0.5) as written (types.rs:115); 1: sqrt(s), what LLVM folds pow(x, 0.5) to
     int refill;            // 1: persistent lanes re-filled individually; 0: a warp takes 32 trajectories at a time

@@ -41,6 +41,15 @@ __device__ const double g_log_tab[256] = {DEQ_LOG_TAB_INIT};
 // per step attempt).  Not `const` on purpose, so the front end does not fold the values back into immediates.
 template <class TB>
 __constant__ deqt::Data<TB::S> c_tab = TB::data();
+// Controller constants with non-zero low words (as immediates they cost two UMOV issue slots each, every attempt).
+__constant__ double c_ctl[4] = {0.8, 0.2, 0.01, -0x1.c8ff7c79a9a20p-3 /* ln 0.8 */};
+// per tableau: 1/(order_min + 1) (the controller exponent, problem.rs:830) and -1/(2 (order_min + 1)) (FAST: applied to the
+// squared norm)
+template <class TB>
+__constant__ double c_pw[2] = {1. / (double)(TB::ORDER_MIN + 1), -0.5 / (double)(TB::ORDER_MIN + 1)};
+#define DEQ_C08 (deqk::c_ctl[0])
+#define DEQ_C02 (deqk::c_ctl[1])
+#define DEQ_C001 (deqk::c_ctl[2])
 
 // FAST mode: combined error weights b - b* (one FMA chain for the error estimate instead of two for p and q).
 template <int S_>
@@ -76,9 +85,11 @@ __device__ __forceinline__ void load_params(double* prm, const double* params, c
 // calc_coefficients (problem.rs:702-737): k[0] holds k0; fills k[1..S-1].
 // FAST = false: the reference's operation order, one rounding per * and +, zero coefficients multiplied through.
 // FAST = true : fused multiply-adds, structurally-zero coefficients skipped (results differ in the last bits).
+// `ylast` (may be nullptr) receives the argument of the last stage, y + dt * sum_j a[S-1][j] k_j: for a first-same-as-last
+// tableau that IS the new solution (a[S-1][j] == b[j]), so FAST mode does not evaluate the weighted sum a second time.
 template <class TB, class F, bool FAST>
 __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double dt, double (&k)[TB::S][F::N],
-                                       const double* prm) {
+                                       const double* prm, double* ylast = nullptr) {
     DEQ_TAB(TB);
     constexpr auto tbc = TB::data();
 #pragma unroll
@@ -102,32 +113,130 @@ __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double
         }
         const double tn = FAST ? __fma_rn(tb.c[row], dt, t) : t + tb.c[row] * dt;
         F::eval(tn, yi, k[row], prm);
+        if (row == TB::S - 1 && ylast) {
+#pragma unroll
+            for (int d = 0; d < F::N; ++d) ylast[d] = yi[d];
+        }
     }
 }
 
-// max(|a|, |b|) and min/max for operands that are known not to be NaN at the call site (a NaN trial state takes the
-// reject branch before the error scale is formed; accepted states are never NaN).  fmax()/fmin() lower to a DSETP plus
-// ~7 integer/select instructions on sm_100a because of their NaN rules; these compare-selects are 3 and return the same
-// value for every non-NaN input (f64::max / f64::min of the reference, problem.rs:827,833,836).
-__device__ __forceinline__ double max_abs_nonan(double a, double b) {
-    const double fa = fabs(a), fb = fabs(b);
-    return fa > fb ? fa : fb;
+// Keeps a rarely taken block out of line: an empty volatile asm cannot be speculated, so the compiler does not hoist the
+// block's (cheap-looking, but FP64-pipe) compares above the branch that guards it.
+#define DEQ_COLD_PATH() asm volatile("")
+
+// The operand of larger magnitude, for operands that are known not to be NaN at the call site (a NaN trial state takes the
+// reject branch before the error scale is used; accepted states are never NaN): |absmax_operand(a, b)| == max(|a|, |b|)
+// of the reference (problem.rs:827).  Written this way the absolute values are operand modifiers of the compare and of the
+// consuming multiply — fabs() of a double on its own is a DADD on sm_100a and holds the FP64 issue port for two cycles;
+// fmax() would add ~7 integer/select instructions of NaN plumbing.
+__device__ __forceinline__ double absmax_operand(double a, double b) { return fabs(a) > fabs(b) ? a : b; }
+// sel_max(c, x) == f64::max(c, x) when c is not NaN: a NaN x yields c, like the NaN-ignoring reference call
+// (problem.rs:833,836).  PTX setp/selp on purpose: from `x > c ? x : c` the compiler builds its fmax idiom (DSETP.MAX plus
+// NaN-quieting selects, ~10 instructions).
+__device__ __forceinline__ double sel_max(double c, double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("{ .reg .pred p; setp.gt.f64 p, %1, %2; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(x), "d"(c));
+    return r;
+#else
+    return x > c ? x : c;
+#endif
 }
-// sel_max(c, x) == f64::max(c, x) when c is not NaN: a NaN x yields c, like the NaN-ignoring reference call.
-__device__ __forceinline__ double sel_max(double c, double x) { return x > c ? x : c; }
-__device__ __forceinline__ double sel_min(double c, double x) { return x < c ? x : c; }
+__device__ __forceinline__ double sel_min(double c, double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("{ .reg .pred p; setp.lt.f64 p, %1, %2; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(x), "d"(c));
+    return r;
+#else
+    return x < c ? x : c;
+#endif
+}
+// `if timeout > 0 { new_dt = new_dt.min(dt) }` (problem.rs:835-837) as one predicated compare-select
+__device__ __forceinline__ double sel_min_if(double c, double x, unsigned cond) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("{ .reg .pred p, q; setp.ne.u32 q, %3, 0; setp.lt.and.f64 p, %1, %2, q; selp.f64 %0, %1, %2, p; }"
+        : "=d"(r) : "d"(x), "d"(c), "r"(cond));
+    return r;
+#else
+    return (cond && x < c) ? x : c;
+#endif
+}
+__device__ __forceinline__ uint32_t hi32(double x) { return (uint32_t)__double2hiint(x); }
 
 // dt / 100. (problem.rs:337) — bit-identical to the IEEE division, in three FP64 instructions instead of the generic
 // division sequence (MUFU seed + Newton steps + range checks, ~10 FP64 + 6 other instructions per accepted step).
 // q = RN(x * R), rem = x - 100 q (exact in an FMA), q' = RN(q + rem * R) with R = RN(1/100): the value before the last
 // rounding is within 2^-52 ulp of x/100, while x/100 itself can never be closer than 0.02 ulp to a rounding midpoint
 // (x - 100 (m + 1/2) ulp(q) is a non-zero multiple of 2 ulp(q)), so the rounding is the correct one.  Checked against
-// the hardware division on 1.1e9 random operands (0 mismatches).  Outside the guarded exponent range it divides.
+// the hardware division on 1.1e9 random operands (0 mismatches).  Outside the guarded exponent range (2^-900 <= |x| <
+// 2^900, tested on the high word with integer instructions) it divides.
 __device__ __forceinline__ double div100_exact(double x) {
-    const double ax = fabs(x);
-    if (!(ax > 0x1p-900 && ax < 0x1p900)) return x / 100.;
-    const double q = x * 0.01;
-    return __fma_rn(__fma_rn(-100.0, q, x), 0.01, q);
+    const double R = DEQ_C001;
+    const double q = x * R;
+    double r = __fma_rn(__fma_rn(-100.0, q, x), R, q);
+    if (((hi32(x) & 0x7fffffffu) - 0x07b00000u) >= (0x78300000u - 0x07b00000u)) { DEQ_COLD_PATH(); r = x / 100.; }
+    return r;
+}
+
+template <int S_>
+constexpr bool has_zero_weight(const deqt::Data<S_>& d) {
+    for (int s = 0; s < S_; ++s)
+        if (d.b[s][0] == 0.0 || d.b[s][1] == 0.0) return true;
+    return false;
+}
+
+// embedded_step (problem.rs:740-780): p = sum_s k_s b[s][0], q = sum_s k_s b[s][1] accumulated from 0.0 in stage order,
+// yerr = (p - q) dt, ytrial = y + p dt — every product and sum rounded once, like the reference.
+// The reference also adds the terms whose weight is zero.  Such a term is k * 0.0 = +-0 whenever k is finite, and adding
+// +-0 to p leaves every bit of p alone: p starts as +0.0 and a sum is -0.0 only if both operands are, so p is never -0.0
+// (the one value that x + 0.0 would change).  So the zero-weight terms are skipped when all the stage values they would
+// multiply are finite, which is decided without FP64 work: the high words of those doubles are added as floats (a double
+// that is inf, NaN or >= 2^1017 has a high word that reads as a float inf / NaN, and a float sum that overflows errs on
+// the safe side).  Otherwise — the trajectory is blowing up — the sums are formed exactly as written.
+template <class TB, int N>
+__device__ __forceinline__ void embedded_parity(const double (&k)[TB::S][N], const double (&ys)[N], double dt,
+                                                double (&ytrial)[N], double (&yerr)[N]) {
+    DEQ_TAB(TB);
+    constexpr auto tbc = TB::data();
+    constexpr int S = TB::S;
+    bool skip_ok = true;
+    if (has_zero_weight(tbc)) {
+        float m = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            if (tbc.b[s][0] == 0.0 || tbc.b[s][1] == 0.0) {
+#pragma unroll
+                for (int d = 0; d < N; ++d) m = m + fabsf(__int_as_float(__double2hiint(k[s][d])));
+            }
+        }
+        skip_ok = m < 3.0e38f;
+    }
+    double p[N], q[N];
+    if (skip_ok) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            p[d] = 0.0; q[d] = 0.0;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                if (tbc.b[s][0] != 0.0) p[d] = p[d] + k[s][d] * tb.b[s][0];
+                if (tbc.b[s][1] != 0.0) q[d] = q[d] + k[s][d] * tb.b[s][1];
+            }
+        }
+    } else {
+        DEQ_COLD_PATH();
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            p[d] = 0.0; q[d] = 0.0;
+#pragma unroll
+            for (int s = 0; s < S; ++s) { p[d] = p[d] + k[s][d] * tb.b[s][0]; q[d] = q[d] + k[s][d] * tb.b[s][1]; }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        yerr[d] = (p[d] - q[d]) * dt;
+        ytrial[d] = ys[d] + (p[d] * dt);
+    }
 }
 
 #ifndef DEQ_BURST
@@ -342,7 +451,6 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     constexpr bool REC = MODE == MODE_REC;        // ragged Points::All stream, counting pass or writing pass (P.rec_mode)
     constexpr bool ROWS = MODE != MODE_FINAL;     // the tspan cursor `it` is tracked
     DEQ_TAB(TB);
-    constexpr double PW = 1. / (double)(TB::ORDER_MIN + 1);
 
     __shared__ uint64_t s_exp[256];
     __shared__ double s_powlog[384];
@@ -361,22 +469,20 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     const double tdir = P.tdir, tend = P.tend, reltol = P.reltol, abstol = P.abstol;
     const uint32_t max_steps = P.max_steps == 0ull || P.max_steps > 0xffffffffull ? 0xffffffffu : (uint32_t)P.max_steps;
 
-    bool active = false;
-    bool pool_empty = false;
+    // 32-bit flags on purpose: the compiler packs `bool` locals into byte lanes of one register and pays a PRMT for every
+    // read and write of them inside the attempt loop
+    unsigned active = 0u, pool_empty = 0u;
     unsigned long long traj = 0;
     double t = 0.0, dt = 0.0;
     double cy[N], ck[N], prm[F::NP ? F::NP : 1];
     double yl[N];   // SPEC only: ys[ys.len() - 1], the last row of the output vector (dead code otherwise)
     unsigned timeout = 0;
-    bool last_step = false;
+    unsigned last_step = 0u;
     uint32_t acc = 0, rej = 0, attempts = 0;
     unsigned long long it = 1, wpos = 0, wbase = 0;
     unsigned long long tot_acc = 0, tot_rej = 0, tot_nfe = 0;
     double* const stage = s_stage_dyn;
     StageLane sl;
-#ifdef DEQ_FINALIZE_OUTSIDE
-    uint8_t finished = 0xff;
-#endif
 #pragma unroll
     for (int d = 0; d < N; ++d) { cy[d] = 0.0; ck[d] = 0.0; }
 #pragma unroll
@@ -391,12 +497,12 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + (unsigned long long)__popc(idle) >= P.ntraj) pool_empty = true;
+            if (base + (unsigned long long)__popc(idle) >= P.ntraj) pool_empty = 1u;
             if (!active) {
                 const unsigned long long my = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
                 if (my < P.ntraj) {
                     traj = my;
-                    active = true;
+                    active = 1u;
                     load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
 #pragma unroll
                     for (int d = 0; d < N; ++d) {
@@ -407,7 +513,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     t = P.t0;
                     dt = P.use_initstep ? P.initstep : P.h0[traj];
                     timeout = 0;
-                    last_step = fabs((t + dt) - tend) <= DBL_EPSILON;
+                    last_step = fabs((t + dt) - tend) <= DBL_EPSILON ? 1u : 0u;
                     acc = 0; rej = 0; attempts = 0; it = 1;
                     if (ROWS) {
                         if (SOA) {
@@ -441,176 +547,163 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
         for (int burst = 0; burst < BURST_ATTEMPTS && active; ++burst) {
             if (TM) stage_drain(stage, P.dense, sl, false);
             if (REC && P.rec_mode == REC_WRITE) stage_drain(stage, P.rec_rows, sl, false);
-            // one step attempt (loop body of problem.rs:260-352)
+            // one step attempt (loop body of problem.rs:260-352).  Everything after the stage evaluations is straight-line,
+            // predicated code: the lanes of a warp accept and reject independently, so a branchy accept / reject tail is executed
+            // on both sides by practically every warp anyway and only adds branch and convergence-barrier instructions.
+            // The max_steps guard is tested after the attempt (a trajectory that has used its budget and did not stop would
+            // be stopped at the top of the next iteration with exactly this state).
             uint8_t fin = 0xff;  // 0xff: keep going
-            if (attempts >= max_steps) {
-                fin = ST_MAX_STEPS;
-            } else {
+            {
                 ++attempts;
                 double k[S][N];
 #pragma unroll
                 for (int d = 0; d < N; ++d) k[0][d] = ck[d];
-                stages<TB, F, FAST>(t, cy, dt, k, prm);
                 double ytrial[N], yerr[N];
                 double ndt;
-                bool accept;
+                unsigned accu;   // the accept decision as an opaque integer: ONE FP64 compare, every later test is an integer one
+                const unsigned timeout_next = timeout - (timeout > 0u ? 1u : 0u);   // stepsize_hw92 :835-838
                 if (!FAST) {
+                    stages<TB, F, false>(t, cy, dt, k, prm);
                     // embedded_step :761-771  (y == cy under Points::All; the last output row under Points::Specified)
                     double ys[N];
 #pragma unroll
                     for (int d = 0; d < N; ++d) ys[d] = SPEC ? yl[d] : cy[d];
-#pragma unroll
-                    for (int d = 0; d < N; ++d) {
-                        double p = 0.0, q = 0.0;
-#pragma unroll
-                        for (int s = 0; s < S; ++s) { p = p + k[s][d] * tb.b[s][0]; q = q + k[s][d] * tb.b[s][1]; }
-                        yerr[d] = (p - q) * dt;
-                        ytrial[d] = ys[d] + (p * dt);
-                    }
+                    embedded_parity<TB, N>(k, ys, dt, ytrial, yerr);
                     // stepsize_hw92 :801-845.  The reference first scans the trial state for NaN (-> err = 10, dt *= 0.2,
                     // timeout = 5).  A NaN trial component makes the scaled error sum NaN as well, so the scan only has to
                     // run when the sum is NaN — one test on the hot path instead of N.
                     double ssum = 0.0;
 #pragma unroll
                     for (int d = 0; d < N; ++d) {
-                        const double e = yerr[d] / (max_abs_nonan(ys[d], ytrial[d]) * reltol + abstol);
+                        const double e = yerr[d] / (fabs(absmax_operand(ys[d], ytrial[d])) * reltol + abstol);
                         const double a = fabs(e);
                         ssum = ssum + a * a;
                     }
-                    bool isnan_trial = false;
-                    if (ssum != ssum) {
+                    double err = P.libm_folded ? sqrt(ssum) : deqm::pow_glibc_hot(ssum, 0.5, T);
+                    const double g = deqm::pow_glibc_hot(1.0 / err, c_pw<TB>[0], T) * DEQ_C08;
+                    double nd = sel_min(P.maxstep, (sel_max(DEQ_C02, g) * tdir) * dt);
+                    nd = sel_min_if(nd, dt, timeout);
+                    ndt = tdir * nd;
+                    if (hi32(ssum) >= 0x7ff00000u) {   // rare: inf or NaN; the reference's rule applies only to a NaN TRIAL STATE
+                        DEQ_COLD_PATH();
+                        bool isnan_trial = false;
 #pragma unroll
                         for (int d = 0; d < N; ++d) isnan_trial = isnan_trial || (ytrial[d] != ytrial[d]);
+                        if (isnan_trial) { err = 10.; ndt = 0.2 * dt; }   // stepsize_hw92 :814-822 (timeout = 5 follows from the reject)
                     }
-                    if (isnan_trial) {
-                        accept = false; ndt = 0.2 * dt; timeout = 5;   // err = 10
-                    } else {
-                        const double err = P.libm_folded ? sqrt(ssum) : deqm::pow_glibc(ssum, 0.5, T);
-                        const double g = deqm::pow_glibc(1.0 / err, PW, T) * 0.8;
-                        double nd = sel_min(P.maxstep, (sel_max(0.2, g) * tdir) * dt);
-                        if (timeout > 0) { nd = sel_min(nd, dt); timeout -= 1; }
-                        ndt = tdir * nd;
-                        accept = err < 1.;
-                    }
+                    accu = err < 1. ? 1u : 0u;
                 } else {
                     // FAST: same formulas with fused multiply-adds; zero weights skipped; error weights b - b* combined;
-                    // err < 1 decided on the squared norm; one pow for the step factor: (1/err)^PW = ssum^(-PW/2).
+                    // err < 1 decided on the squared norm; one pow for the step factor: 0.8 (1/err)^PW = exp(ln 0.8 - PW/2 ln ssum).
+                    // For a first-same-as-last tableau the argument of the last stage is the new solution itself.
                     constexpr auto tbc = TB::data();
+                    stages<TB, F, true>(t, cy, dt, k, prm, FSAL ? ytrial : nullptr);
 #pragma unroll
                     for (int d = 0; d < N; ++d) {
                         double p = 0.0, e = 0.0;
 #pragma unroll
                         for (int s = 0; s < S; ++s) {
-                            if (tbc.b[s][0] != 0.0) p = __fma_rn(k[s][d], tb.b[s][0], p);
+                            if (!FSAL && tbc.b[s][0] != 0.0) p = __fma_rn(k[s][d], tb.b[s][0], p);
                             if (tbc.b[s][0] - tbc.b[s][1] != 0.0) e = __fma_rn(k[s][d], c_errw<TB>.e[s], e);
                         }
                         yerr[d] = e * dt;
-                        ytrial[d] = __fma_rn(p, dt, cy[d]);
+                        if (!FSAL) ytrial[d] = __fma_rn(p, dt, cy[d]);
                     }
                     double ssum = 0.0;
 #pragma unroll
                     for (int d = 0; d < N; ++d) {
-                        const double e = yerr[d] * rcp_fast(__fma_rn(max_abs_nonan(cy[d], ytrial[d]), reltol, abstol));
+                        const double e = yerr[d] * rcp_fast(__fma_rn(fabs(absmax_operand(cy[d], ytrial[d])), reltol, abstol));
                         ssum = __fma_rn(e, e, ssum);
                     }
-                    if (ssum != ssum) {
-                        accept = false; ndt = 0.2 * dt; timeout = 5;
-                    } else {
-                        const double g = deqm::pow_fast_pos(ssum, -0.5 * PW, T) * 0.8;
-                        double nd = sel_min(P.maxstep, (sel_max(0.2, g) * tdir) * dt);
-                        if (timeout > 0) { nd = sel_min(nd, dt); timeout -= 1; }
-                        ndt = tdir * nd;
-                        accept = ssum < 1.;   // sqrt(ssum) < 1  <=>  ssum < 1
+                    const double g = deqm::pow_fast_pos(ssum, c_pw<TB>[1], T, c_ctl[3]);
+                    double nd = sel_min(P.maxstep, (sel_max(DEQ_C02, g) * tdir) * dt);
+                    nd = sel_min_if(nd, dt, timeout);
+                    ndt = tdir * nd;
+                    if (hi32(ssum) >= 0x7ff00000u) { DEQ_COLD_PATH(); if (ssum != ssum) ndt = 0.2 * dt; }
+                    accu = ssum < 1. ? 1u : 0u;   // sqrt(ssum) < 1  <=>  ssum < 1; false for NaN
+                }
+                asm("" : "+r"(accu));
+                const bool accept = accu != 0u;
+                const double tn = t + dt;   // (the row-emitting flavours need it before the state update)
+                if (!FSAL || ROWS) {
+                    // the parts of an accepted step that are real work: the extra right-hand side of a non-FSAL tableau
+                    // and the output rows.  Branchy on purpose; absent from the FSAL / final-state instantiations.
+                    if (accept) {
+                        if (!FSAL) F::eval(tn, ytrial, k[S - 1], prm);   // f1 overwrites the last stage (dead after the error estimate)
+                        double (&f1)[N] = k[S - 1];
+                        if (SPEC) {
+                            // Points::Specified :284-300 — every tspan point before t+dt, all remaining ones on the last step;
+                            // Hermite from the step's (lagging) y, each emitted row becomes the new last output row
+                            double y0s[N];
+#pragma unroll
+                            for (int d = 0; d < N; ++d) y0s[d] = yl[d];
+                            while (it < P.nt) {
+                                const double tq = __ldg(P.tspan + it);
+                                if (!(tdir * tq < tdir * tn || last_step != 0u)) break;
+                                const double theta = (tq - t) / dt;
+                                if (P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, tq);
+#pragma unroll
+                                for (int d = 0; d < N; ++d) {
+                                    const double v = (y0s[d] * (1. - theta) + ytrial[d] * theta) +
+                                                     ((ytrial[d] - y0s[d]) * (1. - 2. * theta) + k[0][d] * (theta - 1.) * dt +
+                                                      f1[d] * theta * dt) * theta * (theta - 1.);
+                                    if (P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, v);
+                                    yl[d] = v;
+                                }
+                                ++wpos;
+                                ++it;
+                            }
+                        } else if (ROWS) {
+                            // Points::All :303-319 — Hermite values at tspan points strictly inside (t, t+dt)
+                            while (it < P.nt) {
+                                const double tq = __ldg(P.tspan + it);
+                                if (!(tdir * t < tdir * tq && tdir * tq < tdir * tn)) break;
+                                const double theta = (tq - t) / dt;
+                                if (REC && P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, tq);
+#pragma unroll
+                                for (int d = 0; d < N; ++d) {
+                                    const double v = (cy[d] * (1. - theta) + ytrial[d] * theta) +
+                                                     ((ytrial[d] - cy[d]) * (1. - 2. * theta) + k[0][d] * (theta - 1.) * dt +
+                                                      f1[d] * theta * dt) * theta * (theta - 1.);
+                                    if (SOA) P.dense[((unsigned long long)d * P.nt + it) * P.ntraj + traj] = v;
+                                    else if (TM) stage_append(stage, P.dense, sl, v);
+                                    else if (REC && P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, v);
+                                }
+                                if (REC) ++wpos;
+                                ++it;
+                            }
+                            if (REC) {  // "also store every step taken" (problem.rs:320-322)
+                                if (P.rec_mode == REC_WRITE) {
+                                    stage_append(stage, P.rec_rows, sl, tn);
+#pragma unroll
+                                    for (int d = 0; d < N; ++d) stage_append(stage, P.rec_rows, sl, ytrial[d]);
+                                }
+                                ++wpos;
+                            }
+                        }
                     }
                 }
+                // ---- state update (problem.rs:324-351), predicated ----
                 if (accept) {
-                    acc += 1;
-                    double f1[N];
-                    if (FSAL) {
 #pragma unroll
-                        for (int d = 0; d < N; ++d) f1[d] = k[S - 1][d];
-                    } else {
-                        F::eval(t + dt, ytrial, f1, prm);
-                    }
-                    if (SPEC) {
-                        // Points::Specified :284-300 — every tspan point before t+dt, all remaining ones on the last step;
-                        // Hermite from the step's (lagging) y, each emitted row becomes the new last output row
-                        const double tn = t + dt;
-                        double y0s[N];
-#pragma unroll
-                        for (int d = 0; d < N; ++d) y0s[d] = yl[d];
-                        while (it < P.nt) {
-                            const double tq = __ldg(P.tspan + it);
-                            if (!(tdir * tq < tdir * tn || last_step)) break;
-                            const double theta = (tq - t) / dt;
-                            if (P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, tq);
-#pragma unroll
-                            for (int d = 0; d < N; ++d) {
-                                const double v = (y0s[d] * (1. - theta) + ytrial[d] * theta) +
-                                                 ((ytrial[d] - y0s[d]) * (1. - 2. * theta) + k[0][d] * (theta - 1.) * dt +
-                                                  f1[d] * theta * dt) * theta * (theta - 1.);
-                                if (P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, v);
-                                yl[d] = v;
-                            }
-                            ++wpos;
-                            ++it;
-                        }
-                    } else if (ROWS) {
-                        // Points::All :303-319 — Hermite values at tspan points strictly inside (t, t+dt)
-                        const double tn = t + dt;
-                        while (it < P.nt) {
-                            const double tq = __ldg(P.tspan + it);
-                            if (!(tdir * t < tdir * tq && tdir * tq < tdir * tn)) break;
-                            const double theta = (tq - t) / dt;
-                            if (REC && P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, tq);
-#pragma unroll
-                            for (int d = 0; d < N; ++d) {
-                                const double v = (cy[d] * (1. - theta) + ytrial[d] * theta) +
-                                                 ((ytrial[d] - cy[d]) * (1. - 2. * theta) + k[0][d] * (theta - 1.) * dt +
-                                                  f1[d] * theta * dt) * theta * (theta - 1.);
-                                if (SOA) P.dense[((unsigned long long)d * P.nt + it) * P.ntraj + traj] = v;
-                                else if (TM) stage_append(stage, P.dense, sl, v);
-                                else if (REC && P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, v);
-                            }
-                            if (REC) ++wpos;
-                            ++it;
-                        }
-                        if (REC) {  // "also store every step taken" (problem.rs:320-322)
-                            if (P.rec_mode == REC_WRITE) {
-                                stage_append(stage, P.rec_rows, sl, tn);
-#pragma unroll
-                                for (int d = 0; d < N; ++d) stage_append(stage, P.rec_rows, sl, ytrial[d]);
-                            }
-                            ++wpos;
-                        }
-                    }
-#pragma unroll
-                    for (int d = 0; d < N; ++d) { ck[d] = f1[d]; cy[d] = ytrial[d]; }
-                    t = t + dt;
-                    if (last_step) {
-                        fin = ST_DONE;   // t is t_reached
-                    } else {
-                        dt = ndt;
-                        if (tdir * ((t + dt) + (FAST ? dt * 0.01 : div100_exact(dt))) >= tdir * tend) { dt = tend - t; last_step = true; }
-                    }
-                } else if (fabs(ndt) < P.minstep) {
-                    fin = ST_MINSTEP_BREAK;
-                } else {
-                    rej += 1;
-                    last_step = false;
-                    dt = ndt;
-                    timeout = 5;
+                    for (int d = 0; d < N; ++d) { ck[d] = k[S - 1][d]; cy[d] = ytrial[d]; }
                 }
+                // end snap of an accepted, not-yet-last step: `if tdir*((t+dt) + dt/100) >= tdir*tend { dt = tend - t; last = true }`
+                // with the NEW t and dt (:336-340); evaluated for every lane, used by the accepting ones.  A trajectory stops
+                // on an accepted last step (DONE) or on a rejected step whose successor is below minstep (:342-344); whatever
+                // else is written to its step-size state in that attempt is dead.
+                const double dt100 = FAST ? ndt * DEQ_C001 : div100_exact(ndt);
+                if (accept) t = tn;
+                const bool snapped = accept && (tdir * ((t + ndt) + dt100) >= P.tdir_tend);
+                const bool stop = accept ? last_step != 0u : (fabs(ndt) < P.minstep);
+                dt = snapped ? tend - t : ndt;
+                last_step = snapped ? 1u : 0u;
+                timeout = accept ? timeout_next : 5u;
+                acc += accept ? 1u : 0u;
+                rej += (accept || stop) ? 0u : 1u;
+                if (stop || attempts >= max_steps) fin = !stop ? (uint8_t)ST_MAX_STEPS : accept ? (uint8_t)ST_DONE : (uint8_t)ST_MINSTEP_BREAK;
             }
-#ifdef DEQ_FINALIZE_OUTSIDE
-            if (fin != 0xff) { finished = fin; break; }
-        }
-        if (finished != 0xff) {
-            const uint8_t fin = finished;
-            finished = 0xff;
-#else
             if (fin != 0xff) {
-#endif
                 const uint32_t nfe = 2u + attempts * (uint32_t)(S - 1) + (FSAL ? 0u : acc);
 #pragma unroll
                 for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = SPEC ? yl[d] : cy[d];
@@ -631,13 +724,9 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     P.nvalid[traj] = (uint32_t)it;
                 }
                 tot_acc += acc; tot_rej += rej; tot_nfe += nfe;
-                active = false;
-#ifdef DEQ_FINALIZE_OUTSIDE
-        }
-#else
+                active = 0u;
             }
         }
-#endif
     }
     // ensemble totals: warp reduce, one atomic per warp
 #pragma unroll
