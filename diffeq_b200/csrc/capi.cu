@@ -116,6 +116,7 @@ struct deq_result {
     unsigned long long* d_scalars = nullptr;  // [0] work counter, [1..3] totals
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;  // both events were recorded
+    bool totals_pending = false;  // adapt_kernel solves: d_scalars[1..3] are summed from the counter arrays on first request
     uint64_t fixed_nfe_per_traj = 0;
 };
 
@@ -303,7 +304,7 @@ deq_options deq_options_default(void) {
     o.abstol = 1e-8;   // options.rs:289-293
     o.points = DEQ_POINTS_ALL;
     o.output = DEQ_OUT_FINAL;
-    o.refill = 1;
+    o.refill = 2;
     o.max_steps = 10000000ull;  // guard (extension): the reference can loop forever
     return o;
 }
@@ -500,6 +501,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
             CKR(cudaEventRecord(r->ev0, st));
         }
         CKR(cudaEventRecord(r->ev1, st));
+        r->totals_pending = !sk && o.precision == DEQ_PRECISION_F64;
     }
     r->timed = true;
     if (!o.async) CKR(cudaStreamSynchronize(st));
@@ -538,6 +540,10 @@ deq_status deq_result_counts(deq_result* r, uint32_t* accepted, uint32_t* reject
 deq_status deq_result_totals(deq_result* r, uint64_t* accepted, uint64_t* rejected, uint64_t* nfe) {
     if (!r) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
     unsigned long long h[4] = {0, 0, 0, 0};
+    if (r->totals_pending && r->ntraj) {
+        CK(deql::launch_sum_counts(r->d_acc, r->d_rej, r->d_nfe, r->ntraj, r->d_scalars + 1, r->stream));
+        r->totals_pending = false;
+    }
     if (r->d_scalars) {
         CK(cudaMemcpyAsync(h, r->d_scalars, sizeof(h), cudaMemcpyDeviceToHost, r->stream));
         CK(cudaStreamSynchronize(r->stream));

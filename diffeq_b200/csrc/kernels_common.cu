@@ -72,6 +72,34 @@ cudaError_t launch_test_log10(const double* x, double* out, unsigned long long n
     return cudaGetLastError();
 }
 
+// Ensemble totals of the per-trajectory counters (the Diagnostics the reference counts, problem.rs:957-970): a grid-stride
+// sum with a warp-shuffle reduction and one atomic per warp.  Runs after the solve, on demand (deq_result_totals), so the
+// adaptive kernel does not carry three 64-bit accumulators through its hot loop (six registers at the 128-register cap).
+// HBM-bound: 12 bytes per trajectory, ~2 us per 2^20 trajectories.
+__global__ void __launch_bounds__(256) sum_counts_kernel(const uint32_t* __restrict__ acc, const uint32_t* __restrict__ rej,
+                                                         const uint32_t* __restrict__ nfe, unsigned long long n,
+                                                         unsigned long long* __restrict__ totals) {
+    unsigned long long a = 0, r = 0, f = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        a += acc[i]; r += rej[i]; f += nfe[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o); r += __shfl_down_sync(0xffffffffu, r, o); f += __shfl_down_sync(0xffffffffu, f, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(totals + 0, a); atomicAdd(totals + 1, r); atomicAdd(totals + 2, f); }
+}
+cudaError_t launch_sum_counts(const uint32_t* acc, const uint32_t* rej, const uint32_t* nfe, unsigned long long n,
+                              unsigned long long* totals, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned long long want = (n + 255) / 256, cap = (unsigned long long)sms * 8;
+    sum_counts_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(acc, rej, nfe, n, totals);
+    return cudaGetLastError();
+}
+
 // DFMA stream: 8 independent accumulator chains per thread, 2 flop per FMA.  The result is written so the loop
 // cannot be removed.  Used to measure the chip's sustained FP64 rate (MEASURED_PEAKS.json has no FP64 figure).
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* sink, int iters) {

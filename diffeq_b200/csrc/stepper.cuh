@@ -434,6 +434,47 @@ __device__ __forceinline__ void stage_append(double* stage, double* out, StageLa
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Tail compaction: census of a CTA's live trajectories and, when they fit into fewer warps than currently hold them, a
+// repack through shared memory into the lowest lanes of the CTA.  Out of line on purpose: with the barriers inlined into the
+// persistent loop, ptxas hoists tableau constants into general registers and moves them back with R2UR in every attempt.
+// All warps of the CTA call it together (converged, at the top of the persistent loop).  `cnt` is one of two census
+// buffers, used alternately, so that a warp that is already in the next census cannot overwrite counts that a slower warp
+// is still reading.
+// ---------------------------------------------------------------------------------------------------------------
+template <int SLOTS>
+struct TailPack { double v[SLOTS]; unsigned active, total; };
+
+template <int SLOTS>
+__device__ __noinline__ TailPack<SLOTS> tail_census(TailPack<SLOTS> pk, double (*s_pack)[BLOCK], unsigned* cnt) {
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const unsigned am = __ballot_sync(0xffffffffu, pk.active != 0u);
+    if (lane == 0) cnt[wid] = __popc(am);
+    __syncthreads();
+    unsigned total = 0u, below = 0u, holders = 0u;
+#pragma unroll
+    for (unsigned w = 0; w < BLOCK / 32; ++w) {
+        const unsigned c = cnt[w];
+        total += c; holders += c ? 1u : 0u; below += w < wid ? c : 0u;
+    }
+    pk.total = total;
+    if (total != 0u && (total + 31u) / 32u < holders) {   // uniform over the CTA
+        if (pk.active) {
+            const unsigned slot = below + __popc(am & ((1u << lane) - 1u));
+#pragma unroll
+            for (int f = 0; f < SLOTS; ++f) s_pack[f][slot] = pk.v[f];
+        }
+        __syncthreads();
+        pk.active = threadIdx.x < total ? 1u : 0u;
+        if (pk.active) {
+#pragma unroll
+            for (int f = 0; f < SLOTS; ++f) pk.v[f] = s_pack[f][threadIdx.x];
+        }
+        __syncthreads();   // every slot is read before a later repack overwrites it
+    }
+    return pk;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // oderk_adapt (problem.rs:193-358), Points::All semantics.
 // ---------------------------------------------------------------------------------------------------------------
 // SPEC = Points::Specified (problem.rs:284-300), reproduced with its defect: the step starts from `y` re-read from the OUTPUT
@@ -457,7 +498,24 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     for (int i = threadIdx.x; i < 256; i += BLOCK) s_exp[i] = g_exp_tab[i];
     for (int i = threadIdx.x; i < 384; i += BLOCK) s_powlog[i] = g_powlog_tab[i];
     if (F::USES_SINCOS) deqm::sincos_stage();
+    // ---- tail compaction (the "periodic trajectory compaction" of the design) ----
+    // Once the work pool is empty a warp can only lose lanes: it keeps issuing full-width instructions for ever fewer live
+    // trajectories until its slowest lane is done (measured: 3.4 % of all warp-steps at 2^20 trajectories, and most of the run
+    // when the ensemble is only a wave or two).  From then on the CTA takes a census every TAIL_BURSTS bursts and, whenever
+    // its live trajectories fit into fewer warps than currently hold them, moves their state through shared memory into
+    // the lowest lanes of the CTA; emptied warps then only wait at the census barrier, and the issue slots they
+    // occupied go to the warps that still have work.  Scheduling only: a trajectory's arithmetic does not depend on the lane
+    // that runs it.  Final-state and SoA-dense flavours (the staged layouts keep per-lane rings in shared memory).
+    constexpr int PACK_SLOTS = 2 + 2 * N + (PT ? F::NP : 0) + 3 + (ROWS ? 1 : 0);
+    constexpr bool CAN_COMPACT = (MODE == MODE_FINAL || MODE == MODE_DENSE) && !SPEC && PACK_SLOTS <= 24;
+    constexpr int TAIL_BURSTS = 4;
+    __shared__ double s_pack[CAN_COMPACT ? PACK_SLOTS : 1][CAN_COMPACT ? BLOCK : 1];
+    __shared__ unsigned s_cnt[2][BLOCK / 32];
+    __shared__ unsigned s_tail;
+    if (threadIdx.x == 0) s_tail = 0u;
     __syncthreads();
+    const bool compacting = CAN_COMPACT && P.refill == 2;
+    unsigned tail_mode = 0u, census = 0u;
     // Shared-window base addresses, computed once and made opaque (volatile asm) so the compiler keeps them in registers
     // instead of re-deriving them from SR_CgaCtaId in front of every table lookup.
     unsigned exp_base = (unsigned)__cvta_generic_to_shared(s_exp), powlog_base = (unsigned)__cvta_generic_to_shared(s_powlog);
@@ -480,7 +538,6 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     unsigned last_step = 0u;
     uint32_t acc = 0, rej = 0, attempts = 0;
     unsigned long long it = 1, wpos = 0, wbase = 0;
-    unsigned long long tot_acc = 0, tot_rej = 0, tot_nfe = 0;
     double* const stage = s_stage_dyn;
     StageLane sl;
 #pragma unroll
@@ -490,61 +547,14 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
 #pragma unroll
     for (int j = 0; j < (F::NP ? F::NP : 1); ++j) prm[j] = 0.0;
 
-    for (;;) {
-        // ---- refill idle lanes from the global work counter (warp-aggregated) ----
-        const unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (idle != 0u && !pool_empty && (P.refill || idle == 0xffffffffu)) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + (unsigned long long)__popc(idle) >= P.ntraj) pool_empty = 1u;
-            if (!active) {
-                const unsigned long long my = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
-                if (my < P.ntraj) {
-                    traj = my;
-                    active = 1u;
-                    load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
-#pragma unroll
-                    for (int d = 0; d < N; ++d) {
-                        cy[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
-                        ck[d] = P.f0[(unsigned long long)d * P.ntraj + traj];
-                        if (SPEC) yl[d] = cy[d];
-                    }
-                    t = P.t0;
-                    dt = P.use_initstep ? P.initstep : P.h0[traj];
-                    timeout = 0;
-                    last_step = fabs((t + dt) - tend) <= DBL_EPSILON ? 1u : 0u;
-                    acc = 0; rej = 0; attempts = 0; it = 1;
-                    if (ROWS) {
-                        if (SOA) {
-#pragma unroll
-                            for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt) * P.ntraj + traj] = cy[d];
-                        } else if (TM) {  // staged trajectory-major stream: row 0 = y0
-                            sl.head = 0; sl.cnt = 0; sl.gpos = traj * P.nt * (unsigned long long)N;
-#pragma unroll
-                            for (int d = 0; d < N; ++d) stage_append(stage, P.dense, sl, cy[d]);
-                        } else {  // ragged Points::All stream, rows [t, y...] interleaved and staged: row 0 = (t0, y0)
-                            wpos = 0ull; wbase = 0ull;
-                            if (P.rec_mode == REC_WRITE) {
-                                sl.head = 0; sl.cnt = 0; sl.gpos = P.rec_offsets[traj] * (unsigned long long)(N + 1);
-                                stage_append(stage, P.rec_rows, sl, t);
-#pragma unroll
-                                for (int d = 0; d < N; ++d) stage_append(stage, P.rec_rows, sl, cy[d]);
-                            }
-                            ++wpos;
-                        }
-                    }
-                }
-            }
-        }
-        if (__ballot_sync(0xffffffffu, active) == 0u) break;
-
-        // ---- a burst of step attempts without any warp-level synchronisation: the refill check above costs ~20
-        // issue slots, which at one check per attempt was ~3 % of the kernel (FP64 instructions hold the issue port
-        // for two cycles on B200 and nothing co-issues, so every non-FP64 instruction is paid in full).  A lane that
-        // finishes inside a burst idles for at most BURST-1 attempts out of the ~10^3 its trajectory took. ----
+    // ---- a burst of step attempts without any warp-level synchronisation: the refill check above costs ~20
+    // issue slots, which at one check per attempt was ~3 % of the kernel (FP64 instructions hold the issue port
+    // for two cycles on B200 and nothing co-issues, so every non-FP64 instruction is paid in full).  A lane that
+    // finishes inside a burst idles for at most BURST-1 attempts out of the ~10^3 its trajectory took. ----
+    // (a lambda, expanded once in the persistent loop and once in the tail loop below)
+    auto run_bursts = [&](const int nburst) {
 #pragma unroll 1
-        for (int burst = 0; burst < BURST_ATTEMPTS && active; ++burst) {
+        for (int burst = 0; burst < nburst && active; ++burst) {
             if (TM) stage_drain(stage, P.dense, sl, false);
             if (REC && P.rec_mode == REC_WRITE) stage_drain(stage, P.rec_rows, sl, false);
             // one step attempt (loop body of problem.rs:260-352).  Everything after the stage evaluations is straight-line,
@@ -723,21 +733,111 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     }
                     P.nvalid[traj] = (uint32_t)it;
                 }
-                tot_acc += acc; tot_rej += rej; tot_nfe += nfe;
                 active = 0u;
             }
         }
-    }
-    // ensemble totals: warp reduce, one atomic per warp
+    };
+
+    for (;;) {
+        // ---- refill idle lanes from the global work counter (warp-aggregated) ----
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle != 0u && !pool_empty && (P.refill || idle == 0xffffffffu)) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(P.work_counter, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + (unsigned long long)__popc(idle) >= P.ntraj) pool_empty = 1u;
+            if (!active) {
+                const unsigned long long my = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
+                if (my < P.ntraj) {
+                    traj = my;
+                    active = 1u;
+                    load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        tot_acc += __shfl_down_sync(0xffffffffu, tot_acc, o);
-        tot_rej += __shfl_down_sync(0xffffffffu, tot_rej, o);
-        tot_nfe += __shfl_down_sync(0xffffffffu, tot_nfe, o);
+                    for (int d = 0; d < N; ++d) {
+                        cy[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
+                        ck[d] = P.f0[(unsigned long long)d * P.ntraj + traj];
+                        if (SPEC) yl[d] = cy[d];
+                    }
+                    t = P.t0;
+                    dt = P.use_initstep ? P.initstep : P.h0[traj];
+                    timeout = 0;
+                    last_step = fabs((t + dt) - tend) <= DBL_EPSILON ? 1u : 0u;
+                    acc = 0; rej = 0; attempts = 0; it = 1;
+                    if (ROWS) {
+                        if (SOA) {
+#pragma unroll
+                            for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt) * P.ntraj + traj] = cy[d];
+                        } else if (TM) {  // staged trajectory-major stream: row 0 = y0
+                            sl.head = 0; sl.cnt = 0; sl.gpos = traj * P.nt * (unsigned long long)N;
+#pragma unroll
+                            for (int d = 0; d < N; ++d) stage_append(stage, P.dense, sl, cy[d]);
+                        } else {  // ragged Points::All stream, rows [t, y...] interleaved and staged: row 0 = (t0, y0)
+                            wpos = 0ull; wbase = 0ull;
+                            if (P.rec_mode == REC_WRITE) {
+                                sl.head = 0; sl.cnt = 0; sl.gpos = P.rec_offsets[traj] * (unsigned long long)(N + 1);
+                                stage_append(stage, P.rec_rows, sl, t);
+#pragma unroll
+                                for (int d = 0; d < N; ++d) stage_append(stage, P.rec_rows, sl, cy[d]);
+                            }
+                            ++wpos;
+                        }
+                    }
+                }
+            }
+        }
+        if (compacting) {
+            // the pool is known to be empty by some warp of this CTA: every warp moves on to the tail loop
+            if (pool_empty) *(volatile unsigned*)&s_tail = 1u;
+            if (*(volatile unsigned*)&s_tail) { tail_mode = 1u; break; }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) break;
+        run_bursts(BURST_ATTEMPTS);
     }
-    if (lane == 0) {
-        atomicAdd(P.totals + 0, tot_acc); atomicAdd(P.totals + 1, tot_rej); atomicAdd(P.totals + 2, tot_nfe);
+    if constexpr (CAN_COMPACT) {
+      if (tail_mode) {
+        for (;;) {
+            // ---- census of the CTA's live trajectories; repack when they fit into fewer warps (tail_census, out of line) ----
+            TailPack<PACK_SLOTS> pk;
+            {
+                int f = 0;
+                pk.v[f++] = t; pk.v[f++] = dt;
+#pragma unroll
+                for (int d = 0; d < N; ++d) { pk.v[f++] = cy[d]; pk.v[f++] = ck[d]; }
+                if (PT) {
+#pragma unroll
+                    for (int j = 0; j < F::NP; ++j) pk.v[f++] = prm[j];
+                }
+                pk.v[f++] = __longlong_as_double((long long)traj);
+                pk.v[f++] = __hiloint2double((int)acc, (int)rej);
+                pk.v[f++] = __hiloint2double((int)attempts, (int)(timeout | (last_step << 16)));
+                if (ROWS) pk.v[f++] = __longlong_as_double((long long)it);
+                pk.active = active;
+            }
+            pk = tail_census(pk, s_pack, s_cnt[census & 1u]);
+            ++census;
+            if (pk.total == 0u) break;                    // uniform over the CTA: every warp leaves together
+            {
+                int f = 0;
+                t = pk.v[f++]; dt = pk.v[f++];
+#pragma unroll
+                for (int d = 0; d < N; ++d) { cy[d] = pk.v[f++]; ck[d] = pk.v[f++]; }
+                if (PT) {
+#pragma unroll
+                    for (int j = 0; j < F::NP; ++j) prm[j] = pk.v[f++];
+                }
+                traj = (unsigned long long)__double_as_longlong(pk.v[f++]);
+                const double ar = pk.v[f++], at = pk.v[f++];
+                acc = (uint32_t)__double2hiint(ar); rej = (uint32_t)__double2loint(ar);
+                attempts = (uint32_t)__double2hiint(at);
+                timeout = (unsigned)__double2loint(at) & 0xffffu; last_step = ((unsigned)__double2loint(at) >> 16) & 1u;
+                if (ROWS) it = (unsigned long long)__double_as_longlong(pk.v[f++]);
+                active = pk.active;
+            }
+            run_bursts(BURST_ATTEMPTS * TAIL_BURSTS);
+        }
+      }
     }
+    // (ensemble totals are summed from the per-trajectory counters afterwards: sum_counts_kernel)
 }
 
 }  // namespace deqk

@@ -118,7 +118,8 @@ typedef struct deq_options {
     int output;          /* deq_output, default DEQ_OUT_FINAL */
     uint64_t max_steps;  /* extension: stop a trajectory after this many step attempts; default 10^7, 0 = unlimited
                           (the reference has no guard and can loop forever: broken tableaus, backward runs) */
-    int refill;          /* 1 (default): persistent lanes refilled individually; 0: static warp assignment */
+    int refill;          /* scheduling of the adaptive kernels (never changes a result): 2 (default) persistent lanes refilled
+                            individually + tail compaction once the pool is empty; 1: lane refill only; 0: static warp assignment */
     int async;           /* 0 (default): deq_solve returns after the GPU finished; 1: returns after enqueueing */
     int mode;            /* deq_mode, default DEQ_MODE_PARITY (adaptive methods only; fixed-step is always parity) */
     int precision;       /* deq_precision, default DEQ_PRECISION_F64 */

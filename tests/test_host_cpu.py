@@ -194,4 +194,4 @@ def test_binding_struct_layout_matches_library(deq):
     import ctypes as C
     assert deq.lib().deq_abi_options_size() == C.sizeof(deq._Options)
     o = deq.lib().deq_options_default()
-    assert (o.max_steps, o.refill, o.mode, o.precision, o.libm, o.dense_layout, o.output) == (10_000_000, 1, 0, 0, 0, 0, 0)
+    assert (o.max_steps, o.refill, o.mode, o.precision, o.libm, o.dense_layout, o.output) == (10_000_000, 2, 0, 0, 0, 0, 0)
