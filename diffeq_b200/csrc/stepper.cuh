@@ -795,6 +795,8 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     }
     if constexpr (CAN_COMPACT) {
       if (tail_mode) {
+        // a lane that never ran a trajectory has not loaded the ensemble-wide parameters yet; it may receive one now
+        if (!PT) load_params<F, PT>(prm, P.params, P.shared, 0ull, P.ntraj);
         for (;;) {
             // ---- census of the CTA's live trajectories; repack when they fit into fewer warps (tail_census, out of line) ----
             TailPack<PACK_SLOTS> pk;
