@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--ntraj", type=int, default=NTRAJ_PER_GPU, help="trajectories per GPU (default 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=65536)
+    ap.add_argument("--strong-log2", type=int, nargs="*", default=[20, 23, 26],
+                    help="BASELINE config 5: total trajectory counts (log2) of the strong-scaling sweep")
     return ap.parse_args()
 
 
@@ -53,8 +55,11 @@ def config_dict(args, world):
                         "tspan=[0,10], Points::All final state + step counters",
             "trajectories_per_gpu": args.ntraj, "trajectories_total": args.ntraj * world, "tspan": TSPAN,
             "rtol": RTOL, "atol": ATOL, "method": "Ode45/dopri5", "parallelism": f"ensemble-sharded x{world}",
-            "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
-            "kernel_mode": "parity (no FMA contraction, bit-exact vs oracle)"}
+            "l2": "flushed between timed steps (256 MiB memset outside the event pairs)"}
+
+
+KERNEL_MODE = ("headline = Mode.Parity, the library default: no FMA contraction, glibc-exact pow, bit-identical to the CPU oracle "
+               "(tests/test_gpu_parity.py); fast_mode = opt-in Mode.Fast (FMA, zero-skipping, one pow per step)")
 
 
 class ClockSampler:
@@ -122,7 +127,7 @@ def run_reference(args, rank, world):
     this image) with all host threads, each step a bounded sample of the workload.  Rank 0 only."""
     if rank != 0:
         return
-    sample = 16384
+    sample = 65536   # BASELINE.md 2: at least 65 536 trajectories per timed step
     for _ in range(args.warmup):
         cpu_reference_run(2048)
     steps_total, t_total, cores = 0, 0.0, 1
@@ -136,7 +141,8 @@ def run_reference(args, rank, world):
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1),
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                      "data": "synthetic", "config": config_dict(args, world), "cpu_baseline": desc,
+                      "data": "synthetic", "config": config_dict(args, world), "kernel_mode": "reference CPU path (oracle port)",
+                      "cpu_baseline": desc,
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                       "gpu_launches": 0}), flush=True)
 
@@ -153,7 +159,7 @@ def main():
     import torch
     import torch.distributed as dist
     import diffeq_b200 as D
-    from diffeq_b200 import synth
+    from diffeq_b200 import sharding, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (diffeq_b200 has no CPU fallback)")
@@ -217,16 +223,22 @@ def main():
     fold_ms, fold_steps, fold_kernel_ms, _, tot_fold = device_arm(opts_fold)
     # full-size parity property: both arithmetic modes must take exactly the same accepted / rejected steps, and the
     # final states must agree within the north-star tolerance (10 x rtol)
-    f_fast = prob.solve(D.Ode.Ode45, opts_fast).final
-    f_par = prob.solve(D.Ode.Ode45, opts_par).final
+    s_fast = prob.solve(D.Ode.Ode45, opts_fast)
+    s_par = prob.solve(D.Ode.Ode45, opts_par)
+    f_fast, f_par = s_fast.final, s_par.final
+    same_counts = (s_fast.accepted == s_par.accepted) & (s_fast.rejected == s_par.rejected)
     dev_units = np.max(np.abs(f_fast - f_par) / (np.abs(f_par) * RTOL + ATOL), axis=1)
-    mode_check = {"step_totals_identical": bool(tot_fast == tot_par), "accepted": tot_par["accepted"], "rejected": tot_par["rejected"],
+    mode_check = {"fraction_of_trajectories_with_identical_accepted_and_rejected_counts": float(same_counts.mean()),
+                  "trajectories_with_different_counts": int((~same_counts).sum()),
+                  "step_totals_identical": bool(tot_fast == tot_par), "accepted": tot_par["accepted"], "rejected": tot_par["rejected"],
                   "final_state_deviation_fast_vs_parity_in_units_of_(rtol*|y|+atol)": {
                       "median": float(np.median(dev_units)), "p99": float(np.quantile(dev_units, 0.99)),
                       "p99.99": float(np.quantile(dev_units, 0.9999)), "max": float(dev_units.max()),
                       "fraction_within_10": float((dev_units <= 10.0).mean())},
                   "note": "Lorenz trajectories that pass close to the saddle at the origin amplify ANY rounding difference by up to "
-                          "~1e10 within T=10, so only bit-identical arithmetic (parity mode) reproduces them to 10 x rtol"}
+                          "~1e10 within T=10, so only bit-identical arithmetic (parity mode) reproduces them to 10 x rtol; against a "
+                          "high-precision solution FAST is as accurate as PARITY (tests/test_gpu_parity.py::test_fast_mode_accuracy_against_truth)"}
+    del s_fast, s_par
 
     # ---------------- end-to-end arms (host buffers through the public API) ----------------
     h_y0 = torch.from_numpy(y0).pin_memory()
@@ -255,19 +267,124 @@ def main():
     h2d = y0.nbytes + 8 * len(TSPAN) + 8 * 3
     d2h = h_final.numel() * 8 + h_acc.numel() * 4 + h_rej.numel() * 4
 
-    # ---------------- final gather of the sharded final states (the only inter-GPU traffic the path needs) ----------------
-    gather_ms = None
-    if distributed:
-        from diffeq_b200 import sharding
-        loc = torch.from_numpy(f_par).cuda()
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        parts = sharding.gather_final(dist, loc, device="cuda")
-        g1.record(stream)
+    # CPU-side rendezvous for the sections below in which some ranks must stay off their GPU (an NCCL barrier is a kernel that
+    # spins on the device of every waiting rank)
+    cpu_group = dist.new_group(backend="gloo") if distributed else None
+
+    def cpu_barrier():
         torch.cuda.synchronize()
-        gather_ms = g0.elapsed_time(g1)
-        assert sum(p.shape[0] for p in parts) == ntraj * world and torch.equal(parts[rank], loc)
+        if distributed:
+            dist.barrier(group=cpu_group)
+
+    # ---------------- final gather of the sharded final states to rank 0 (the only inter-GPU traffic the path needs) ----------------
+    final_gather = None
+    if distributed:
+        loc = torch.from_numpy(f_par).cuda()
+        bufs = [torch.empty_like(loc) for _ in range(world)] if rank == 0 else None
+        for _ in range(3):   # warm the communicator: the first collective on it pays the lazy NCCL connection set-up
+            dist.gather(loc, bufs, dst=0)
+        barrier()
+        times = []
+        for _ in range(5):
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            dist.gather(loc, bufs, dst=0)
+            g1.record(stream)
+            torch.cuda.synchronize()
+            times.append(g0.elapsed_time(g1))
+        tg = torch.tensor([min(times)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            assert torch.equal(bufs[0], loc) and all(b.shape == loc.shape for b in bufs)
+            moved = loc.numel() * 8 * (world - 1)
+            final_gather = {"ms": float(tg.item()), "bytes_into_rank0": moved, "GB_per_s": moved / (float(tg.item()) * 1e-3) / 1e9,
+                            "what": f"dist.gather (NCCL send/recv) of {world} x {loc.numel() * 8 / 2**20:.0f} MiB final states to rank 0, "
+                                    "communicator warmed, best of 5, max over ranks"}
+        del loc, bufs
+
+    # ---------------- BASELINE config 5: strong scaling, 2^20 .. 2^26 trajectories IN TOTAL over the N ranks ----------------
+    def timed_solve(problem, opts, reps):
+        problem.solve(D.Ode.Ode45, opts, fetch=False)
+        best, steps_ = None, 0
+        for _ in range(reps):
+            flush.zero_()
+            sol = problem.solve(D.Ode.Ode45, opts, fetch=False)
+            steps_ = sol.totals["accepted"] + sol.totals["rejected"]
+            best = sol.kernel_ms if best is None else min(best, sol.kernel_ms)
+        return best, steps_
+
+    strong = []
+    for lg in args.strong_log2:
+        total = 1 << lg
+        b, e = sharding.shard_range(total, rank, world)
+        ys = synth.lorenz_ics(b, e)
+        ps = D.OdeProblem.builder().fun(rhs).params(synth.LORENZ_PARAMS).init(ys).tspan(TSPAN).build()
+        barrier()
+        ms, st = timed_solve(ps, opts_par, 2 if lg <= 23 else 1)
+        msf, stf = timed_solve(ps, opts_fast, 2 if lg <= 23 else 1)
+        # end to end: pinned host shard -> deq_solve_host -> host results
+        hy = torch.from_numpy(ys).pin_memory()
+        ho = {"final": torch.empty((e - b, 3), dtype=torch.float64).pin_memory().numpy(),
+              "accepted": torch.empty(e - b, dtype=torch.int32).pin_memory().numpy().view(np.uint32),
+              "rejected": torch.empty(e - b, dtype=torch.int32).pin_memory().numpy().view(np.uint32)}
+        D.solve_host_multi(rhs, hy.numpy(), synth.LORENZ_PARAMS, TSPAN, D.Ode.Ode45, opts_par, out=ho)
+        barrier()
+        t0 = time.perf_counter()
+        D.solve_host_multi(rhs, hy.numpy(), synth.LORENZ_PARAMS, TSPAN, D.Ode.Ode45, opts_par, out=ho)
+        torch.cuda.synchronize()
+        e2e_local = time.perf_counter() - t0
+        del ps, hy, ho
+        tt = torch.tensor([ms, msf, e2e_local * 1e3], dtype=torch.float64, device="cuda")
+        cc = torch.tensor([st, stf], dtype=torch.float64, device="cuda")
+        if distributed:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        entry = {"trajectories_total": total, "trajectories_per_gpu": e - b, "n_gpus": world,
+                 "parity_steps_per_s": cc[0].item() / (tt[0].item() * 1e-3), "parity_ms": tt[0].item(),
+                 "fast_steps_per_s": cc[1].item() / (tt[1].item() * 1e-3), "fast_ms": tt[1].item(),
+                 "e2e_parity_steps_per_s": cc[0].item() / (tt[2].item() * 1e-3), "e2e_parity_ms": tt[2].item()}
+        if distributed:
+            # the same total on ONE GPU (rank 0 alone; the others wait on the CPU): efficiency = t(1) / (N t(N))
+            cpu_barrier()
+            if rank == 0:
+                y1 = synth.lorenz_ics(0, total)
+                p1 = D.OdeProblem.builder().fun(rhs).params(synth.LORENZ_PARAMS).init(y1).tspan(TSPAN).build()
+                del y1
+                ms1, _ = timed_solve(p1, opts_par, 1)
+                ms1f, _ = timed_solve(p1, opts_fast, 1)
+                del p1
+                entry.update({"one_gpu_parity_ms": ms1, "one_gpu_fast_ms": ms1f,
+                              "parity_efficiency_vs_1_gpu": ms1 / (world * entry["parity_ms"]),
+                              "fast_efficiency_vs_1_gpu": ms1f / (world * entry["fast_ms"])})
+            cpu_barrier()
+        strong.append(entry)
+
+    # ---------------- the in-library multi-GPU path (what a Rust host calls): ONE process, deq_solve_host over all N devices ----------------
+    in_library = None
+    if distributed:
+        cpu_barrier()
+        if rank == 0:
+            n_all = ntraj * world
+            hy = torch.from_numpy(synth.lorenz_ics(0, n_all)).pin_memory()
+            ho = {"final": torch.empty((n_all, 3), dtype=torch.float64).pin_memory().numpy(),
+                  "accepted": torch.empty(n_all, dtype=torch.int32).pin_memory().numpy().view(np.uint32),
+                  "rejected": torch.empty(n_all, dtype=torch.int32).pin_memory().numpy().view(np.uint32)}
+            devs = list(range(world))
+            for _ in range(2):
+                D.solve_host_multi(rhs, hy.numpy(), synth.LORENZ_PARAMS, TSPAN, D.Ode.Ode45, opts_par, devices=devs, out=ho)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                D.solve_host_multi(rhs, hy.numpy(), synth.LORENZ_PARAMS, TSPAN, D.Ode.Ode45, opts_par, devices=devs, out=ho)
+            dt_lib = (time.perf_counter() - t0) / reps
+            st_lib = int(ho["accepted"].sum(dtype=np.int64) + ho["rejected"].sum(dtype=np.int64))
+            ok = bool(np.array_equal(ho["final"][:ntraj], f_par))   # rank 0's shard: same bits as the rank-per-GPU solve
+            in_library = {"steps_per_s": st_lib / dt_lib, "ms_per_call": dt_lib * 1e3, "trajectories": n_all, "devices": devs,
+                          "first_shard_bit_identical_to_rank0_solve": ok,
+                          "what": "deq_solve_host(devices = 0..N-1) called by ONE process on pinned host buffers (H2D + solve + D2H of "
+                                  "every shard inside the call, one host thread and stream per device); compare with e2e.value"}
+            del hy, ho
+        cpu_barrier()
 
     # ---------------- stiff path, informational: ode23s on a Van der Pol stiffness sweep ----------------
     stiff = None
@@ -294,20 +411,35 @@ def main():
     dev_ms_max, e2e_s_max, wall_max, fast_ms_max, e2e_fast_s_max, fold_ms_max = t.tolist()
     steps_all, e2e_steps_all, fast_steps_all, e2e_fast_steps_all, fold_steps_all = c.tolist()
 
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^20 trajectories (ncu --set full, profiles/r1_final_*_kernel_
-    # ncu_full_summary.csv); it scales with the trajectory count, not with the step count
-    NCU_DRAM_BYTES = {"parity": 62.139648e6 + 16.999680e6, "fast": 62.736384e6 + 15.812608e6}
-    # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed of the same captures: how busy the FP64 pipe is, whatever the
-    # instructions are worth in algorithmic FLOP (a non-fused multiply-add occupies it twice)
-    NCU_FP64_PIPE_ACTIVE_PCT = {"parity": 79.7, "fast": 74.3}
+    def ncu_summary(key):
+        """dram__bytes_read.sum + dram__bytes_write.sum and the FP64-pipe utilisation of ONE launch of the kernel at 2^20
+        trajectories, read from the committed `ncu --set full` summary of this round (tools/ncu_summary.py); traffic scales
+        with the trajectory count, not with the step count.  None if the summary is absent."""
+        path = os.path.join(ROOT, "profiles", "r2_%s_kernel_ncu_full_summary.csv" % key)
+        out = {"traffic": None, "fp64_pipe_active_pct_ncu": None, "ncu_summary": None}
+        if not os.path.exists(path):
+            return out
+        vals, scale = {}, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for line in open(path):
+            parts = [c.strip().strip('"') for c in line.rstrip("\n").split('","')]
+            if len(parts) == 3:
+                try:
+                    vals[parts[0]] = float(parts[2]) * scale.get(parts[1], 1.0)
+                except ValueError:
+                    pass
+        rd, wr = vals.get("dram__bytes_read.sum"), vals.get("dram__bytes_write.sum")
+        out["ncu_summary"] = os.path.relpath(path, ROOT)
+        if rd is not None and wr is not None:
+            out["traffic"] = (rd + wr) * (ntraj / float(1 << 20))
+        out["fp64_pipe_active_pct_ncu"] = vals.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed")
+        return out
 
     def roofline(kernel_ms_list, steps_local, kernel_name, mode_note, traffic_key):
         kms = sum(kernel_ms_list) / len(kernel_ms_list)
         achieved = (steps_local / args.steps) * FLOP_PER_STEP / (kms * 1e-3) / 1e12
         return {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if fp64_peak else None,
-                "traffic": NCU_DRAM_BYTES[traffic_key] * (ntraj / float(1 << 20)), "traffic_unit": "bytes per launch (DRAM, ncu)",
-                "fp64_pipe_active_pct_ncu": NCU_FP64_PIPE_ACTIVE_PCT[traffic_key],
+                **ncu_summary(traffic_key), "traffic_unit": "bytes per launch (DRAM, from the committed ncu summary named in ncu_summary)",
                 "kernel": kernel_name,
                 "kernel_ms": kms, "flop_per_step": FLOP_PER_STEP, "arithmetic": mode_note,
                 "peak_source": "DFMA-stream microbenchmark measured in this run (deq_measure_fp64_peak); MEASURED_PEAKS.json "
@@ -317,14 +449,12 @@ def main():
 
     if rank == 0:
         cfg = config_dict(args, world)
-        cfg["kernel_mode"] = ("headline = Mode.Parity, the library default: no FMA contraction, glibc-exact pow, bit-identical to the CPU "
-                              "oracle (tests/test_gpu_parity.py); fast_mode = opt-in Mode.Fast (FMA, zero-skipping, one pow per step)")
         par_note = ("no FMA allowed (the reference never fuses a*b+c): every multiply-add costs two FP64 issue slots, so at most 50 % "
                     "of the DFMA peak is reachable by construction in this mode")
         out = {
             "metric": METRIC, "value": steps_all / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "kernel_mode": KERNEL_MODE,
             "e2e": {"value": e2e_steps_all / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s_max / args.steps},
             "gpu_launches": 2 * args.steps,
@@ -343,7 +473,7 @@ def main():
                         "exp10 in hinit; DESIGN.md 4.1) — one pow per step instead of two"},
             "mode_check": mode_check,
             "stiff_ode23s": stiff,
-            "final_gather_ms": gather_ms,
+            "strong_scaling": strong, "solve_host_in_library": in_library, "final_gather": final_gather,
             "clocks": clocks, "wall_s_timed_region": wall_max,
         }
         if not args.no_cpu_baseline:
