@@ -229,4 +229,79 @@ DEQ_HD double cos_glibc(double x, const ST& tab) {
     return (n & 2) ? -r : r;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// sin(xs) and cos(xc) in ONE straight-line evaluation (the right-hand side of the driven pendulum needs exactly this pair
+// thirteen times per step attempt of Fehlberg 7(8)).  Same operations in the same order as sin_glibc / cos_glibc above for
+// each argument — verified bit for bit on the host against the running libm (tests/cpp/math_check.cpp) — but shaped for the
+// GPU's issue port (every instruction, FP64 or not, costs at least one issue slot):
+//   * one range test for the pair: both arguments in [2^-26, 105414350) (resp. 2^-27 for cos); anything else goes through
+//     the two general routines;
+//   * `if (x <= 0) dx = -dx` (do_sin) and `if (x < 0) dx = -dx` (do_cos) are a sign transfer, an XOR on the high word
+//     instead of a compare and two selects each.  The two conditions differ only for x == +-0, and there the result does
+//     not depend on the sign of dx: do_sin returns its Taylor branch (which reads the original dx) for |x| < 0.126, and
+//     do_cos at table entry 0 (sn = ssn = 0) multiplies every odd power of dx by zero;
+//   * negations by (n & 2) are XORs on the sign bit instead of an FP64 negate and two selects.
+// ---------------------------------------------------------------------------------------------------------------
+DEQ_HD double xor_sign_(double v, uint64_t signbit_source) {   // v with its sign flipped iff bit 63 of signbit_source is set
+    return asf64(asu64(v) ^ (signbit_source & 0x8000000000000000ULL));
+}
+
+template <class ST>
+DEQ_HD double sincos_dual2(double a, double da, bool want_cos, const ST& tab) {
+    const double ax = fabs(a);
+    const double u = ax + sc::big_();
+    const double xr = ax - (u - sc::big_());
+    const int k = (int)(uint32_t)asu64(u) * 4;
+    const double sn = tab.at(k), ssn = tab.at(k + 1), cs = tab.at(k + 2), ccs = tab.at(k + 3);
+    const double dx = xor_sign_(da, asu64(a));
+    // do_sin flavour
+    const double xxs = xr * xr;
+    const double ss = xr + fma_(xr * xxs, fma_(xxs, sc::sn5_(), sc::sn3_()), dx);
+    const double csn = fma_(xr, dx, xxs * fma_(xxs, fma_(xxs, sc::cs6_(), sc::cs4_()), sc::cs2_()));
+    const double rs = copysign_(sn + fma_(ss, cs, fma_(-csn, sn, fma_(ss, ccs, ssn))), a);
+    // do_cos flavour
+    const double xc = xr + dx;
+    const double xxc = xc * xc;
+    const double sc_ = fma_(xc * xxc, fma_(xxc, sc::sn5_(), sc::sn3_()), xc);
+    const double cc = xxc * fma_(xxc, fma_(xxc, sc::cs6_(), sc::cs4_()), sc::cs2_());
+    const double rc = cs + fma_(-sc_, sn, fma_(-cc, cs, fma_(-sc_, ssn, ccs)));
+    const double rt = taylor_sin(a, da);   // do_sin's small-argument branch
+    return want_cos ? rc : (ax < 0.126 ? rt : rs);
+}
+
+template <class ST>
+DEQ_HD void sin_cos_glibc(double xs, double xc, const ST& tab, double& so, double& co) {
+    const uint32_t ks = (uint32_t)(asu64(xs) >> 32) & 0x7fffffffu, kc = (uint32_t)(asu64(xc) >> 32) & 0x7fffffffu;
+    if ((ks - 0x3e500000u) >= (0x419921FBu - 0x3e500000u) || (kc - 0x3e400000u) >= (0x419921FBu - 0x3e400000u)) {
+        so = sin_glibc(xs, tab);
+        co = cos_glibc(xc, tab);
+        return;
+    }
+    {   // __sin
+        const bool ra = ks < 0x3feb6000u, rb = ks < 0x400368fdu;
+        double a, da;
+        int n = reduce_sincos(xs, a, da);
+        const double ab = sc::hp0_() - fabs(xs);
+        a = ra ? xs : rb ? ab : a;
+        da = ra ? 0.0 : rb ? sc::hp1_() : da;
+        n = ra ? 0 : rb ? 1 : n;
+        const double r = sincos_dual2(a, da, (n & 1) != 0, tab);
+        // middle range (taken through do_cos): copysign(r, x); otherwise negate in quadrants 2 and 3
+        so = (rb && !ra) ? copysign_(r, xs) : xor_sign_(r, (uint64_t)(n & 2) << 62);
+    }
+    {   // __cos
+        const bool ra = kc < 0x3feb6000u, rb = kc < 0x400368fdu;
+        double a, da;
+        int n = reduce_sincos(xc, a, da) + 1;
+        const double y = sc::hp0_() - fabs(xc);
+        const double ab = y + sc::hp1_();
+        const double dab = (y - ab) + sc::hp1_();
+        a = ra ? xc : rb ? ab : a;
+        da = ra ? 0.0 : rb ? dab : da;
+        n = ra ? 1 : rb ? 0 : n;
+        const double r = sincos_dual2(a, da, (n & 1) != 0, tab);
+        co = xor_sign_(r, (uint64_t)(n & 2) << 62);
+    }
+}
+
 }  // namespace deqm

@@ -60,7 +60,22 @@ int main(int argc, char** argv) {
         volatile double vx = x;
         if (!same(sin(vx), deqm::sin_glibc(x, ST))) { if (bad < 5) printf("sin x=%a\n", x); ++bad; }
         if (!same(cos(vx), deqm::cos_glibc(x, ST))) { if (bad < 5) printf("cos x=%a\n", x); ++bad; }
+        // the fused pair (pendulum right-hand side): sin of this argument, cos of the previous one
+        static double xprev = 0.3;
+        volatile double vp = xprev;
+        double fs, fc;
+        deqm::sin_cos_glibc(x, xprev, ST, fs, fc);
+        if (!same(sin(vx), fs) || !same(cos(vp), fc)) { if (bad < 5) printf("sin_cos pair xs=%a xc=%a\n", x, xprev); ++bad; }
+        xprev = x;
     }
+    for (double x : {0.0, -0.0, 0.126, -0.126, 0.855469, -0.855469, 2.426265, -2.426265, 105414349.0, 1e-300, 3.141592653589793, 1.5707963267948966,
+                     0x1p-26, 0x1p-27, 0x1.fffffffffffffp-27, 0x1.fffffffffffffp-28, 0.7853981633974483, 2.356194490192345, (double)INFINITY})
+        for (double z : {0.0, -0.0, 0.126, 0.855469, 2.426265, 105414349.0, 1e-300, 6.283185307179586, 4.71238898038469, (double)INFINITY}) {
+            volatile double vx = x, vz = z;
+            double fs, fc;
+            deqm::sin_cos_glibc(x, z, ST, fs, fc);
+            if (!same(sin(vx), fs) || !same(cos(vz), fc)) { printf("sin_cos pair special xs=%a xc=%a\n", x, z); ++bad; }
+        }
     for (double x : {0.0, -0.0, 0.126, -0.126, 0.855469, 2.426265, 105414349.0, 1e-300, 3.141592653589793, 1.5707963267948966, (double)INFINITY}) {
         volatile double vx = x;
         if (!same(sin(vx), deqm::sin_glibc(x, ST)) || !same(cos(vx), deqm::cos_glibc(x, ST))) { printf("sincos special x=%a\n", x); ++bad; }

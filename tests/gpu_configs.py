@@ -29,7 +29,7 @@ if which in ("3", "all"):
     y0, mu = synth.vdp_sweep(0, N, N)
     ts = D.linspace(0.0, 20.0, 1000)
     p = D.OdeProblem.builder().fun(D.Rhs.builtin(D.System.VanDerPol)).params(mu).init(y0).tspan(ts).build()
-    for mode, refill in ((D.Mode.Parity, 1), (D.Mode.Parity, 0), (D.Mode.Fast, 1)):
+    for mode, refill in ((D.Mode.Parity, 2), (D.Mode.Parity, 1), (D.Mode.Fast, 2)):
         o = D.OdeOptionMap().insert(D.Reltol(1e-6), D.Abstol(1e-8), D.Output.Tspan, mode, D.Refill(refill))
         for rep in range(2):
             s = p.solve(D.Ode.Ode45fe, o, fetch=False)

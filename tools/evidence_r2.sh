@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 TAG=${1:-r2}
 timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_$TAG.log
 tail -3 gpurun_out/pytest_gpu_$TAG.log
-/usr/bin/time -v timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; grep -E "Elapsed|Maximum resident" gpurun_out/bench_$TAG.err
+SECONDS=0; timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$? wall=${SECONDS}s"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_$TAG.json 2> gpurun_out/bench_reference_$TAG.err; echo "ref rc=$?"
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --strong-log2"
 timeout 300 $B > gpurun_out/plain_$TAG.log 2>&1 && {
