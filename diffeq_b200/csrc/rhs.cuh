@@ -37,9 +37,12 @@ static __constant__ double c_trigk[16] = {
     -2.50507602534068634195e-08, 1.58969099521155010221e-10,
     4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07,
     2.08757232129817482790e-09, -1.13596475577881948265e-11};
+// (out of line: 26 inlined copies of the platform routines' range dispatch and Payne-Hanek call would quadruple the code of a
+// 13-stage kernel and spread its hot path over the instruction cache)
+static __device__ __noinline__ double deq_trig_slow(double x, int phase) { return phase ? cos(x) : sin(x); }
 static __device__ __forceinline__ double deq_trig_fast(double x, int phase) {
     const double* K = c_trigk;
-    if (!(fabs(x) < 1.0e5)) return phase ? cos(x) : sin(x);
+    if (!(fabs(x) < 1.0e5)) return deq_trig_slow(x, phase);
     double q = __fma_rn(x, K[0], 6755399441055744.0);
     const int n = __double2loint(q) + phase;
     q -= 6755399441055744.0;
