@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--ntraj", type=int, default=NTRAJ_PER_GPU, help="trajectories per GPU (default 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=65536)
+    ap.add_argument("--no-config3", action="store_true", help="skip the dense-output end-to-end section")
     ap.add_argument("--strong-log2", type=int, nargs="*", default=[20, 23, 26],
                     help="BASELINE config 5: total trajectory counts (log2) of the strong-scaling sweep")
     return ap.parse_args()
@@ -386,6 +387,52 @@ def main():
             del hy, ho
         cpu_barrier()
 
+    # ---------------- BASELINE config 3 end to end: dense rows to HOST buffers through deq_solve_host_dense ----------------
+    # (2^18 of the 2^22 trajectories: 4.2 GB of rows; the full 67 GB take the same per-byte time and need a 67 GB pinned buffer)
+    config3_e2e = None
+    if distributed:
+        cpu_barrier()
+    if rank == 0 and not args.no_config3:
+        n3, nt3 = 1 << 18, 1000
+        y3, mu3 = synth.vdp_sweep(0, n3, 1 << 22)
+        ts3 = D.linspace(0.0, 20.0, nt3)
+        vdp = D.Rhs.builtin(D.System.VanDerPol)
+        o3 = D.OdeOptionMap().insert(D.Reltol(1e-6), D.Abstol(1e-8), D.Output.Tspan, D.DenseLayout.TrajMajor)
+        h3 = {"final": torch.empty((n3, 2), dtype=torch.float64).pin_memory().numpy(),
+              "accepted": torch.empty(n3, dtype=torch.int32).pin_memory().numpy().view(np.uint32),
+              "rejected": torch.empty(n3, dtype=torch.int32).pin_memory().numpy().view(np.uint32),
+              "nvalid": torch.empty(n3, dtype=torch.int32).pin_memory().numpy().view(np.uint32),
+              "dense": torch.empty((n3, nt3, 2), dtype=torch.float64).pin_memory().numpy()}
+        hy3, hm3 = torch.from_numpy(y3).pin_memory().numpy(), torch.from_numpy(mu3).pin_memory().numpy()
+        nbytes = h3["dense"].nbytes
+        # the plain pinned device-to-host copy of the same bytes: the ceiling of this path
+        dsrc = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        hdst = torch.from_numpy(h3["dense"].view(np.uint8).reshape(-1))
+        hdst.copy_(dsrc); torch.cuda.synchronize()
+        t0 = time.perf_counter(); hdst.copy_(dsrc, non_blocking=True); torch.cuda.synchronize(); t_copy = time.perf_counter() - t0
+        del dsrc
+        # kernel alone (device-resident rows, trajectory-major like the host result)
+        p3 = D.OdeProblem.builder().fun(vdp).params(mu3).init(y3).tspan(ts3).build()
+        p3.solve(D.Ode.Ode45fe, o3, fetch=False)
+        k3 = p3.solve(D.Ode.Ode45fe, o3, fetch=False)
+        del p3
+        D.solve_host_multi(vdp, hy3, hm3, ts3, D.Ode.Ode45fe, o3, out=h3)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        D.solve_host_multi(vdp, hy3, hm3, ts3, D.Ode.Ode45fe, o3, out=h3)
+        t_e2e = time.perf_counter() - t0
+        steps3 = int(h3["accepted"].sum(dtype=np.int64) + h3["rejected"].sum(dtype=np.int64))
+        config3_e2e = {"workload": "configs[2] at 2^18 of its 2^22 trajectories: Van der Pol mu sweep, Ode45fe, rtol 1e-6, atol 1e-8, 1000 tspan rows "
+                                   "per trajectory to pinned HOST memory, trajectory-major [ntraj][1000][2]",
+                       "rows_bytes": nbytes, "e2e_ms": t_e2e * 1e3, "GB_per_s_to_host": nbytes / t_e2e / 1e9,
+                       "plain_pinned_d2h_ms": t_copy * 1e3, "plain_pinned_d2h_GB_per_s": nbytes / t_copy / 1e9,
+                       "kernel_only_ms": k3.kernel_ms, "steps_per_s_e2e": steps3 / t_e2e,
+                       "e2e_over_max_of_kernel_and_copy": t_e2e / max(t_copy, k3.kernel_ms * 1e-3),
+                       "what": "deq_solve_host_dense: chunks of ~128 MiB of rows, chunk i+1 integrates while chunk i travels to the host"}
+        del h3, hy3, hm3
+    if distributed:
+        cpu_barrier()
+
     # ---------------- stiff path, informational: ode23s on a Van der Pol stiffness sweep ----------------
     stiff = None
     if rank == 0:
@@ -473,7 +520,7 @@ def main():
                         "exp10 in hinit; DESIGN.md 4.1) — one pow per step instead of two"},
             "mode_check": mode_check,
             "stiff_ode23s": stiff,
-            "strong_scaling": strong, "solve_host_in_library": in_library, "final_gather": final_gather,
+            "config3_e2e": config3_e2e, "strong_scaling": strong, "solve_host_in_library": in_library, "final_gather": final_gather,
             "clocks": clocks, "wall_s_timed_region": wall_max,
         }
         if not args.no_cpu_baseline:

@@ -120,7 +120,7 @@ class _Options(C.Structure):
 ABI_SYMBOLS = [
     "deq_last_error_message", "deq_version", "deq_abi_options_size", "deq_rhs_builtin", "deq_rhs_from_source", "deq_rhs_dim",
     "deq_rhs_nparams", "deq_rhs_destroy", "deq_tspan_linspace", "deq_ensemble_create", "deq_ensemble_create_device",
-    "deq_ensemble_destroy", "deq_ensemble_ntraj", "deq_set_stream", "deq_set_device", "deq_get_device", "deq_solve_host", "deq_options_default", "deq_solve",
+    "deq_ensemble_destroy", "deq_ensemble_ntraj", "deq_set_stream", "deq_set_device", "deq_get_device", "deq_solve_host", "deq_solve_host_dense", "deq_options_default", "deq_solve",
     "deq_result_final", "deq_result_counts", "deq_result_totals", "deq_result_dense", "deq_result_all_offsets",
     "deq_result_all_copy", "deq_result_device_ptrs",
     "deq_result_trajectory", "deq_result_kernel_ms", "deq_result_destroy", "deq_tableau_get", "deq_rosenbrock_get", "deq_host_alloc",
@@ -160,6 +160,37 @@ def _f64(a):
 
 def _ptr(a, t=C.c_double):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def _check_shapes(rhs, y0, params):
+    """The C ABI reads ntraj * n state and nparams (or ntraj * nparams) parameter doubles through raw pointers: refuse
+    anything else here.  Returns (y0 [ntraj, n], params or None, params_per_traj)."""
+    y0 = _f64(y0)
+    if y0.ndim == 1:
+        y0 = y0[None, :]
+    if y0.ndim != 2 or y0.shape[1] != rhs.dim:
+        raise OdeError(10, f"state array has shape {y0.shape}, the right-hand side expects [ntraj, {rhs.dim}]")
+    npar = rhs.nparams
+    if npar == 0:
+        return np.ascontiguousarray(y0), None, 0
+    if params is None:
+        raise OdeError(1, "Required problem parameters must be initialized")
+    params = _f64(params)
+    if params.ndim == 1 and params.shape[0] == npar:
+        return np.ascontiguousarray(y0), params, 0
+    if params.ndim == 2 and params.shape == (y0.shape[0], npar):
+        return np.ascontiguousarray(y0), params, 1
+    raise OdeError(10, f"parameter array has shape {params.shape}, expected [{npar}] or [{y0.shape[0]}, {npar}]")
+
+
+def _out_array(out, key, shape, dtype):
+    """A caller-provided result array must be C-contiguous with the exact shape and an item size matching the C type."""
+    a = out.get(key) if out is not None else None
+    if a is None:
+        return None
+    if not a.flags["C_CONTIGUOUS"] or tuple(a.shape) != tuple(shape) or a.dtype.itemsize != np.dtype(dtype).itemsize:
+        raise OdeError(10, f"out[{key!r}] must be a C-contiguous {np.dtype(dtype).name} array of shape {tuple(shape)}")
+    return a
 
 
 def set_device(device):
@@ -354,10 +385,10 @@ class OdeProblem:
     def __init__(self, rhs, y0, tspan, params, single):
         self._rhs = rhs
         self._single = single
+        y0, params, per = _check_shapes(rhs, y0, params)
         self.ntraj, self.n = y0.shape
         self.tspan = tspan
         h = C.c_void_p()
-        per = int(params is not None and params.ndim == 2)
         _check(lib().deq_ensemble_create(rhs._h, C.c_size_t(self.ntraj), _ptr(y0), _ptr(params), per, _ptr(tspan),
                                          C.c_size_t(len(tspan)), C.byref(h)))
         self._h = h
@@ -416,8 +447,13 @@ class OdeProblem:
         if not fetch:
             return sol
         nt = len(self.tspan)
+        if nt == 0:   # problem.rs:211-214: an empty tspan yields an empty OdeSolution
+            sol.final = np.empty((0, self.n))
+            sol.tout = np.empty(0)
+            sol.yout = np.empty((self.ntraj, 0, self.n))
+            return sol
         sol.final = np.empty((self.ntraj, self.n))
-        if self.ntraj and not (nt == 0):
+        if self.ntraj:
             _check(L.deq_result_final(res, _ptr(sol.final)))
         if has_counts and nt > 0:
             sol.accepted = np.empty(self.ntraj, np.uint32); sol.rejected = np.empty(self.ntraj, np.uint32)
@@ -521,14 +557,10 @@ def solve_host(rhs, y0, params, tspan, ode, opts=None, out_final=None, out_accep
     tspan, integrates on the GPU, and copies the final states and step counters back into the given (ideally pinned)
     buffers.  Returns (final, accepted, rejected) — plus the device-reduced totals dict when return_totals is set."""
     L = lib()
-    y0 = _f64(y0)
-    if y0.ndim == 1:
-        y0 = y0[None, :]
+    y0, params, per = _check_shapes(rhs, y0, params)
     ntraj, n = y0.shape
-    params = _f64(params) if params is not None else None
     tspan = _f64(tspan)
     o = (opts if opts is not None else OdeOptionMap()).to_c()
-    per = int(params is not None and params.ndim == 2)
     adaptive = _traits(ode, tableau_set)[1]
     ens = C.c_void_p(); res = C.c_void_p()
     _check(L.deq_ensemble_create(rhs._h, C.c_size_t(ntraj), _ptr(y0), _ptr(params), per, _ptr(tspan),
@@ -564,22 +596,40 @@ def solve_host(rhs, y0, params, tspan, ode, opts=None, out_final=None, out_accep
 def solve_host_multi(rhs, y0, params, tspan, ode, opts=None, devices=None, tableau_set=TableauSet.Reference, out=None):
     """`deq_solve_host`: one C-ABI call on host buffers, sharded over `devices` (list of CUDA ordinals; None = current device)
     with one host thread per GPU inside the library.  Returns dict(final, accepted, rejected, nfe, status, t_reached); pass
-    `out` (a dict of preallocated, ideally pinned, arrays with those keys) to avoid allocating the results per call."""
+    `out` (a dict of preallocated, ideally pinned, arrays with those keys) to avoid allocating the results per call.
+    With `Output.Tspan` in `opts` the call is `deq_solve_host_dense`: the result also carries `dense` ([ntraj, ntspan, n] for
+    DenseLayout.TrajMajor on the explicit adaptive methods, else [n, ntspan, ntraj]) and `nvalid`; chunks of the ensemble are
+    integrated while earlier chunks travel to the host."""
     L = lib()
-    y0 = _f64(y0)
-    if y0.ndim == 1:
-        y0 = y0[None, :]
+    y0, params, per = _check_shapes(rhs, y0, params)
     ntraj, n = y0.shape
-    params = _f64(params) if params is not None else None
     tspan = _f64(tspan)
+    nt = len(tspan)
     o = (opts if opts is not None else OdeOptionMap()).to_c()
-    per = int(params is not None and params.ndim == 2)
     dev = (C.c_int * len(devices))(*devices) if devices else None
+    dense = o.output == Output.Tspan
+    adaptive, _, stiff = _traits(ode, tableau_set)
+    tm = dense and o.dense_layout == DenseLayout.TrajMajor and adaptive and not stiff
+    dshape = (ntraj, nt, n) if tm else (n, nt, ntraj)
     if out is None:
         out = dict(final=np.empty((ntraj, n)), accepted=np.zeros(ntraj, np.uint32), rejected=np.zeros(ntraj, np.uint32),
                    nfe=np.zeros(ntraj, np.uint32), status=np.zeros(ntraj, np.uint8), t_reached=np.zeros(ntraj))
-    _check(L.deq_solve_host(rhs._h, C.c_size_t(ntraj), _ptr(y0), _ptr(params), per, _ptr(tspan), C.c_size_t(len(tspan)), int(ode),
-                            int(tableau_set), C.byref(o), dev, len(devices) if devices else 0, _ptr(out["final"]),
-                            _ptr(out.get("accepted"), C.c_uint32), _ptr(out.get("rejected"), C.c_uint32), _ptr(out.get("nfe"), C.c_uint32),
-                            _ptr(out.get("status"), C.c_uint8), _ptr(out.get("t_reached"))))
+        if dense:
+            out["dense"] = np.empty(dshape)
+            out["nvalid"] = np.zeros(ntraj, np.uint32)
+    final = _out_array(out, "final", (ntraj, n), np.float64)
+    if final is None:
+        raise OdeError(10, "out['final'] is required")
+    args = [rhs._h, C.c_size_t(ntraj), _ptr(y0), _ptr(params), per, _ptr(tspan), C.c_size_t(nt), int(ode), int(tableau_set), C.byref(o),
+            dev, len(devices) if devices else 0, _ptr(final),
+            _ptr(_out_array(out, "accepted", (ntraj,), np.uint32), C.c_uint32), _ptr(_out_array(out, "rejected", (ntraj,), np.uint32), C.c_uint32),
+            _ptr(_out_array(out, "nfe", (ntraj,), np.uint32), C.c_uint32), _ptr(_out_array(out, "status", (ntraj,), np.uint8), C.c_uint8),
+            _ptr(_out_array(out, "t_reached", (ntraj,), np.float64))]
+    if dense:
+        d = _out_array(out, "dense", dshape, np.float64)
+        if d is None:
+            raise OdeError(10, "out['dense'] is required with Output.Tspan")
+        _check(L.deq_solve_host_dense(*args, _ptr(d), _ptr(_out_array(out, "nvalid", (ntraj,), np.uint32), C.c_uint32)))
+    else:
+        _check(L.deq_solve_host(*args))
     return out

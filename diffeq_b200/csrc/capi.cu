@@ -11,7 +11,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -93,6 +95,7 @@ struct deq_ensemble {
     std::vector<double> tspan;
     double* d_tspan = nullptr;
     bool has_tspan = false;
+    cudaStream_t stream = nullptr;   // the stream its device arrays were allocated (and are freed) on
 };
 
 struct deq_result {
@@ -122,27 +125,53 @@ struct deq_result {
 
 namespace {
 
+// Device memory comes from a LIBRARY-OWNED stream-ordered pool per device (not the device's default pool, which a
+// co-resident allocator such as torch's may be using): freed blocks stay cached up to kPoolKeepBytes, so repeated solves do
+// not pay cudaMalloc-class latencies for their ~150 MB of result arrays (with the default threshold of 0 every synchronize
+// hands the memory back to the driver: 91 ms instead of 42 ms per end-to-end step), while a freed multi-GB dense buffer is
+// returned to the driver at the next synchronisation point.
+constexpr unsigned long long kPoolKeepBytes = 2ull << 30;
+cudaMemPool_t pool_for_current_device() {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pools[dev]) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&pools[dev], &props) != cudaSuccess) { cudaGetLastError(); pools[dev] = nullptr; return nullptr; }
+        unsigned long long thr = kPoolKeepBytes;
+        cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    return pools[dev];
+}
+
 template <class T>
 cudaError_t dalloc(T** p, size_t count, cudaStream_t st) {
     *p = nullptr;
     if (count == 0) return cudaSuccess;
-    return cudaMallocAsync((void**)p, count * sizeof(T), st);
+    cudaMemPool_t pool = pool_for_current_device();
+    if (!pool) return cudaMallocAsync((void**)p, count * sizeof(T), st);
+    return cudaMallocFromPoolAsync((void**)p, count * sizeof(T), pool, st);
 }
 void dfree(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
 
-// Keep freed blocks cached in the stream-ordered pool (default release threshold is 0: every synchronize would hand
-// the memory back to the driver and the next solve would pay cudaMalloc-class latencies again).
-void ensure_pool() {
-    static thread_local int done_dev = -1;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_dev) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long thr = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-    done_dev = dev;
-}
+void ensure_pool() {}   // (kept for the call sites: the pool is created on first allocation)
+
+// Temporary device buffer that is released on every exit path (the CK macro returns early on errors).
+template <class T>
+struct TempBuf {
+    T* p = nullptr;
+    cudaStream_t st;
+    explicit TempBuf(cudaStream_t s) : st(s) {}
+    ~TempBuf() { dfree(p, st); }
+    TempBuf(const TempBuf&) = delete;
+    TempBuf& operator=(const TempBuf&) = delete;
+};
 
 // Block-cyclic shards of deq_solve_host: the rows of this shard are runs (start, length) of the caller's arrays.  While the
 // list is set, upload_soa treats its host pointer as the base of the FULL array and copies run by run, so no host-side
@@ -151,19 +180,19 @@ typedef std::vector<std::pair<size_t, size_t>> Runs;
 thread_local const Runs* g_runs = nullptr;
 
 deq_status upload_soa(const double* h_aos, size_t ntraj, int n, double** d_soa, cudaStream_t st) {
-    double* d_aos = nullptr;
-    CK(dalloc(&d_aos, ntraj * n, st));
+    TempBuf<double> aos(st);
+    CK(dalloc(&aos.p, ntraj * n, st));
     CK(dalloc(d_soa, ntraj * n, st));
     if (g_runs) {
         size_t w = 0;
         for (const auto& run : *g_runs) {
-            CK(cudaMemcpyAsync(d_aos + w * n, h_aos + run.first * n, run.second * n * sizeof(double), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(aos.p + w * n, h_aos + run.first * n, run.second * n * sizeof(double), cudaMemcpyHostToDevice, st));
             w += run.second;
         }
-    } else
-    CK(cudaMemcpyAsync(d_aos, h_aos, ntraj * n * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(deql::launch_transpose_to_soa(d_aos, *d_soa, ntraj, n, st));
-    dfree(d_aos, st);
+    } else {
+        CK(cudaMemcpyAsync(aos.p, h_aos, ntraj * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    CK(deql::launch_transpose_to_soa(aos.p, *d_soa, ntraj, n, st));
     return DEQ_OK;
 }
 
@@ -185,6 +214,7 @@ deq_status ensemble_common(const deq_rhs* rhs, size_t ntraj, const double* param
     e->ntraj = ntraj;
     e->per_traj = per_traj ? 1 : 0;
     cudaStream_t st = g_stream;
+    e->stream = st;
     if (rhs->np > 0) {
         if (!params) return fail(DEQ_ERR_UNINITIALIZED, "Required problem parameters must be initialized");
         if (per_traj) {
@@ -264,6 +294,7 @@ deq_status deq_ensemble_create(const deq_rhs* rhs, size_t ntraj, const double* y
     if (!tspan) return fail(DEQ_ERR_UNINITIALIZED, "Time span must be initialized");
     ensure_pool();
     deq_ensemble* e = new deq_ensemble();
+    e->stream = g_stream;
     deq_status s = upload_soa(y0, ntraj, rhs->n, &e->d_y0, g_stream);
     if (!s) s = ensemble_common(rhs, ntraj, params, params_per_traj, tspan, ntspan, false, e);
     if (s) { deq_ensemble_destroy(e); return s; }
@@ -288,9 +319,9 @@ deq_status deq_ensemble_create_device(const deq_rhs* rhs, size_t ntraj, const do
 
 void deq_ensemble_destroy(deq_ensemble* e) {
     if (!e) return;
-    if (e->own_y0) dfree(e->d_y0, g_stream);
-    if (e->own_params) dfree(e->d_params, g_stream);
-    dfree(e->d_tspan, g_stream);
+    if (e->own_y0) dfree(e->d_y0, e->stream);
+    if (e->own_params) dfree(e->d_params, e->stream);
+    dfree(e->d_tspan, e->stream);
     if (e->rhs.prog) deqn::release(e->rhs.prog);
     delete e;
 }
@@ -513,11 +544,10 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
 deq_status deq_result_final(deq_result* r, double* y) {
     if (!r || !y) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
     if (r->ntraj == 0) return DEQ_OK;
-    double* d_aos = nullptr;
-    CK(dalloc(&d_aos, r->ntraj * r->n, r->stream));
-    CK(deql::launch_transpose_to_aos(r->d_yfinal, d_aos, r->ntraj, r->n, r->stream));
-    CK(cudaMemcpyAsync(y, d_aos, r->ntraj * r->n * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
-    dfree(d_aos, r->stream);
+    TempBuf<double> aos(r->stream);
+    CK(dalloc(&aos.p, r->ntraj * r->n, r->stream));
+    CK(deql::launch_transpose_to_aos(r->d_yfinal, aos.p, r->ntraj, r->n, r->stream));
+    CK(cudaMemcpyAsync(y, aos.p, r->ntraj * r->n * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
     CK(cudaStreamSynchronize(r->stream));
     return DEQ_OK;
 }
@@ -654,16 +684,32 @@ void deq_result_destroy(deq_result* r) {
 
 // One-shot multi-GPU solve on host buffers: contiguous shards of the trajectory range, one host thread and one stream per
 // device, no inter-GPU traffic; every shard writes its slice of the caller's output arrays.
-deq_status deq_solve_host(const deq_rhs* rhs, size_t ntraj, const double* y0, const double* params, int params_per_traj,
+static deq_status solve_host_dense_impl(const deq_rhs* rhs, size_t ntraj, const double* y0, const double* params, int params_per_traj,
+                                       const double* tspan, size_t ntspan, int method, int tableau_set, const deq_options& o_in,
+                                       const std::vector<int>& devs, int cur, double* yfinal, uint32_t* accepted, uint32_t* rejected,
+                                       uint32_t* nfe, uint8_t* status, double* t_reached, double* dense, uint32_t* nvalid);
+
+static deq_status solve_host_impl(const deq_rhs* rhs, size_t ntraj, const double* y0, const double* params, int params_per_traj,
                           const double* tspan, size_t ntspan, int method, int tableau_set, const deq_options* opts,
                           const int* devices, int ndevices, double* yfinal, uint32_t* accepted, uint32_t* rejected,
-                          uint32_t* nfe, uint8_t* status, double* t_reached) {
+                          uint32_t* nfe, uint8_t* status, double* t_reached, double* dense, uint32_t* nvalid) {
     if (!rhs) return fail(DEQ_ERR_UNINITIALIZED, "Required problem must be initialized");
     if (!y0 && ntraj) return fail(DEQ_ERR_UNINITIALIZED, "Initial starting point must be initialized");
     if (!tspan) return fail(DEQ_ERR_UNINITIALIZED, "Time span must be initialized");
     if (!yfinal) return fail(DEQ_ERR_INVALID_ARG, "yfinal is NULL");
     deq_options o = opts ? *opts : deq_options_default();
-    if (o.output != DEQ_OUT_FINAL) return fail(DEQ_ERR_INVALID_ARG, "deq_solve_host returns final states and counters only");
+    if (dense) {
+        if (o.output != DEQ_OUT_TSPAN) return fail(DEQ_ERR_INVALID_ARG, "deq_solve_host_dense needs output = DEQ_OUT_TSPAN");
+        int cur0 = 0;
+        CK(cudaGetDevice(&cur0));
+        std::vector<int> dv;
+        if (devices && ndevices > 0) dv.assign(devices, devices + ndevices); else dv.push_back(cur0);
+        return solve_host_dense_impl(rhs, ntraj, y0, params, params_per_traj, tspan, ntspan, method, tableau_set, o, dv, cur0, yfinal,
+                                     accepted, rejected, nfe, status, t_reached, dense, nvalid);
+    }
+    if (o.output == DEQ_OUT_TSPAN) return fail(DEQ_ERR_INVALID_ARG, "deq_solve_host returns final states and counters; the tspan rows come from deq_solve_host_dense");
+    if (o.output != DEQ_OUT_FINAL)
+        return fail(DEQ_ERR_UNSUPPORTED, "DEQ_OUT_ALL has a data-dependent size (rows per trajectory): use deq_solve + deq_result_all_offsets / deq_result_all_copy");
     o.async = 0;
     int cur = 0;
     CK(cudaGetDevice(&cur));
@@ -679,6 +725,16 @@ deq_status deq_solve_host(const deq_rhs* rhs, size_t ntraj, const double* y0, co
     auto work = [&](size_t k) {
         auto bad = [&](deq_status s) { rc[k] = s; msg[k] = g_err; };
         if (cudaSetDevice(devs[k]) != cudaSuccess) { rc[k] = DEQ_ERR_CUDA; msg[k] = "cudaSetDevice failed"; cudaGetLastError(); return; }
+        // a worker thread owns a non-blocking stream for its shard (the calling thread keeps the stream it set with deq_set_stream)
+        struct OwnStream {
+            cudaStream_t st = nullptr; bool own = false;
+            ~OwnStream() { if (own) { cudaStreamSynchronize(st); cudaStreamDestroy(st); g_stream = nullptr; } }
+        } ws;
+        if (!(nd == 1 && devs[0] == cur)) {
+            if (cudaStreamCreateWithFlags(&ws.st, cudaStreamNonBlocking) != cudaSuccess) { rc[k] = DEQ_ERR_CUDA; msg[k] = "cudaStreamCreate failed"; cudaGetLastError(); return; }
+            ws.own = true;
+            g_stream = ws.st;
+        }
         const bool per = params && params_per_traj;
         // this shard's trajectories: one contiguous block, or (block-cyclic) the chunks k, k + nd, k + 2 nd, ... — copied run by
         // run straight between the caller's arrays and the device, in both directions
@@ -737,6 +793,122 @@ deq_status deq_solve_host(const deq_rhs* rhs, size_t ntraj, const double* y0, co
     return DEQ_OK;
 }
 
+deq_status deq_solve_host(const deq_rhs* rhs, size_t ntraj, const double* y0, const double* params, int params_per_traj,
+                          const double* tspan, size_t ntspan, int method, int tableau_set, const deq_options* opts,
+                          const int* devices, int ndevices, double* yfinal, uint32_t* accepted, uint32_t* rejected,
+                          uint32_t* nfe, uint8_t* status, double* t_reached) {
+    return solve_host_impl(rhs, ntraj, y0, params, params_per_traj, tspan, ntspan, method, tableau_set, opts, devices, ndevices, yfinal,
+                           accepted, rejected, nfe, status, t_reached, nullptr, nullptr);
+}
+
+deq_status deq_solve_host_dense(const deq_rhs* rhs, size_t ntraj, const double* y0, const double* params, int params_per_traj,
+                                const double* tspan, size_t ntspan, int method, int tableau_set, const deq_options* opts,
+                                const int* devices, int ndevices, double* yfinal, uint32_t* accepted, uint32_t* rejected,
+                                uint32_t* nfe, uint8_t* status, double* t_reached, double* dense, uint32_t* nvalid) {
+    if (!dense) return fail(DEQ_ERR_INVALID_ARG, "dense is NULL");
+    return solve_host_impl(rhs, ntraj, y0, params, params_per_traj, tspan, ntspan, method, tableau_set, opts, devices, ndevices, yfinal,
+                           accepted, rejected, nfe, status, t_reached, dense, nvalid);
+}
+
+// The dense-output flavour of deq_solve_host.  The trajectory range is cut into chunks (~128 MiB of rows each); chunk j goes
+// to device j % ndevices (a block-cyclic deal, which also balances parameter-sorted sweeps); every device thread keeps two
+// chunks in flight: while chunk i travels to the caller's buffer on the copy stream, chunk i + 1 is integrated on the
+// compute stream.  For ensembles with dense rows the PCIe link, not the kernel, is the bound (config 3: 16 KB of rows per
+// trajectory against ~12 ns of kernel time), so the measure of this path is how close it stays to a plain pinned copy.
+static deq_status solve_host_dense_impl(const deq_rhs* rhs, size_t ntraj, const double* y0, const double* params, int params_per_traj,
+                                       const double* tspan, size_t ntspan, int method, int tableau_set, const deq_options& o_in,
+                                       const std::vector<int>& devs, int cur, double* yfinal, uint32_t* accepted, uint32_t* rejected,
+                                       uint32_t* nfe, uint8_t* status, double* t_reached, double* dense, uint32_t* nvalid) {
+    deql::TableauInfo info;
+    int sk = 0, tb = -2;
+    if (deq_status ms = resolve_method(method, tableau_set, &tb, &sk, &info)) return ms;
+    if (ntspan == 0) return DEQ_OK;   // nothing to solve (problem.rs:211-214)
+    deq_options o = o_in;
+    o.async = 1;
+    const size_t nd = devs.size(), n = (size_t)rhs->n, np = (size_t)rhs->np;
+    const bool tm = o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR && info.adaptive && !sk;
+    const bool counts = info.adaptive || sk;
+    const bool per = params && params_per_traj;
+    const size_t row_bytes = n * ntspan * sizeof(double);   // dense bytes of one trajectory
+    size_t chunk = (size_t)(128u << 20) / (row_bytes ? row_bytes : 1);
+    if (const char* e = getenv("DEQ_HOST_CHUNK")) chunk = (size_t)strtoull(e, nullptr, 10);
+    chunk = std::max<size_t>(chunk / 1024 * 1024, 1024);
+    const size_t nchunks = (ntraj + chunk - 1) / chunk;
+    std::vector<deq_status> rc(nd, DEQ_OK);
+    std::vector<std::string> msg(nd);
+    auto work = [&](size_t k) {
+        if (cudaSetDevice(devs[k]) != cudaSuccess) { rc[k] = DEQ_ERR_CUDA; msg[k] = "cudaSetDevice failed"; cudaGetLastError(); return; }
+        cudaStream_t sc = nullptr, sx = nullptr;
+        const cudaStream_t caller_stream = g_stream;
+        struct Slot { deq_ensemble* ens = nullptr; deq_result* res = nullptr; double* d_aos = nullptr; cudaEvent_t computed = nullptr, copied = nullptr; bool busy = false; } slot[2];
+        deq_status s = DEQ_OK;
+        auto ck = [&](cudaError_t e_) { if (e_ != cudaSuccess && !s) { cudaGetLastError(); s = fail(DEQ_ERR_CUDA, cudaGetErrorString(e_)); } };
+        ck(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
+        ck(cudaStreamCreateWithFlags(&sx, cudaStreamNonBlocking));
+        for (auto& sl : slot) { ck(cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming)); ck(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming)); }
+        g_stream = sc;
+        auto retire = [&](Slot& sl) {
+            if (!sl.busy) return;
+            ck(cudaEventSynchronize(sl.copied));
+            dfree(sl.d_aos, sx); sl.d_aos = nullptr;
+            if (sl.res) deq_result_destroy(sl.res);
+            if (sl.ens) deq_ensemble_destroy(sl.ens);
+            sl.res = nullptr; sl.ens = nullptr; sl.busy = false;
+        };
+        size_t it = 0;
+        for (size_t j = k; j < nchunks && !s; j += nd, ++it) {
+            Slot& sl = slot[it & 1];
+            retire(sl);
+            const size_t b = j * chunk, cnt = std::min(chunk, ntraj - b);
+            s = deq_ensemble_create(rhs, cnt, y0 + b * n, per ? params + b * np : params, params_per_traj, tspan, ntspan, &sl.ens);
+            if (s) break;
+            s = deq_solve(sl.ens, method, tableau_set, &o, &sl.res);
+            if (s) break;
+            sl.busy = true;
+            deq_result* r = sl.res;
+            ck(cudaEventRecord(sl.computed, sc));
+            ck(cudaStreamWaitEvent(sx, sl.computed, 0));
+            // rows
+            if (tm) ck(cudaMemcpyAsync(dense + b * n * ntspan, r->d_dense, cnt * row_bytes, cudaMemcpyDeviceToHost, sx));
+            else ck(cudaMemcpy2DAsync(dense + b, ntraj * sizeof(double), r->d_dense, cnt * sizeof(double), cnt * sizeof(double), n * ntspan, cudaMemcpyDeviceToHost, sx));
+            if (nvalid) {
+                if (r->d_nvalid) ck(cudaMemcpyAsync(nvalid + b, r->d_nvalid, cnt * 4, cudaMemcpyDeviceToHost, sx));
+                else for (size_t i = 0; i < cnt; ++i) nvalid[b + i] = (uint32_t)ntspan;   // fixed-step methods write every row
+            }
+            // final states ([n][cnt] on the device -> [cnt][n]) and counters
+            ck(dalloc(&sl.d_aos, cnt * n, sx));
+            if (!s) ck(deql::launch_transpose_to_aos(r->d_yfinal, sl.d_aos, cnt, (int)n, sx));
+            ck(cudaMemcpyAsync(yfinal + b * n, sl.d_aos, cnt * n * sizeof(double), cudaMemcpyDeviceToHost, sx));
+            if (counts && r->d_acc) {
+                if (accepted) ck(cudaMemcpyAsync(accepted + b, r->d_acc, cnt * 4, cudaMemcpyDeviceToHost, sx));
+                if (rejected) ck(cudaMemcpyAsync(rejected + b, r->d_rej, cnt * 4, cudaMemcpyDeviceToHost, sx));
+                if (nfe) ck(cudaMemcpyAsync(nfe + b, r->d_nfe, cnt * 4, cudaMemcpyDeviceToHost, sx));
+                if (status) ck(cudaMemcpyAsync(status + b, r->d_status, cnt, cudaMemcpyDeviceToHost, sx));
+                if (t_reached) ck(cudaMemcpyAsync(t_reached + b, r->d_treached, cnt * 8, cudaMemcpyDeviceToHost, sx));
+            }
+            ck(cudaEventRecord(sl.copied, sx));
+        }
+        for (auto& sl : slot) retire(sl);
+        if (sc) { cudaStreamSynchronize(sc); }
+        g_stream = caller_stream;
+        for (auto& sl : slot) { if (sl.computed) cudaEventDestroy(sl.computed); if (sl.copied) cudaEventDestroy(sl.copied); }
+        if (sx) cudaStreamDestroy(sx);
+        if (sc) cudaStreamDestroy(sc);
+        if (s) { rc[k] = s; msg[k] = g_err; }
+    };
+    if (nd == 1 && devs[0] == cur) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t k = 0; k < nd; ++k) th.emplace_back(work, k);
+        for (auto& t : th) t.join();
+        cudaSetDevice(cur);
+    }
+    for (size_t k = 0; k < nd; ++k)
+        if (rc[k]) return fail(rc[k], "device " + std::to_string(devs[k]) + ": " + msg[k]);
+    return DEQ_OK;
+}
+
 deq_status deq_tableau_get(int method, int set, int* stages, double* a, double* b, double* c, int* adaptive,
                            int* order_min, int* fsal) {
     const int tb = tb_of(method, set);
@@ -776,13 +948,12 @@ void deq_host_free(void* p) { if (p) cudaFreeHost(p); }
 deq_status deq_test_pow(const double* x, const double* y, double* out, size_t n) {
     if (n == 0) return DEQ_OK;
     cudaStream_t st = g_stream;
-    double *dx = nullptr, *dy = nullptr, *dout = nullptr;
-    CK(dalloc(&dx, n, st)); CK(dalloc(&dy, n, st)); CK(dalloc(&dout, n, st));
-    CK(cudaMemcpyAsync(dx, x, n * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dy, y, n * 8, cudaMemcpyHostToDevice, st));
-    CK(deql::launch_test_pow(dx, dy, dout, n, st));
-    CK(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, st));
-    dfree(dx, st); dfree(dy, st); dfree(dout, st);
+    TempBuf<double> dx(st), dy(st), dout(st);
+    CK(dalloc(&dx.p, n, st)); CK(dalloc(&dy.p, n, st)); CK(dalloc(&dout.p, n, st));
+    CK(cudaMemcpyAsync(dx.p, x, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dy.p, y, n * 8, cudaMemcpyHostToDevice, st));
+    CK(deql::launch_test_pow(dx.p, dy.p, dout.p, n, st));
+    CK(cudaMemcpyAsync(out, dout.p, n * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return DEQ_OK;
 }
@@ -790,12 +961,11 @@ deq_status deq_test_pow(const double* x, const double* y, double* out, size_t n)
 deq_status deq_test_log10(const double* x, double* out, size_t n) {
     if (n == 0) return DEQ_OK;
     cudaStream_t st = g_stream;
-    double *dx = nullptr, *dout = nullptr;
-    CK(dalloc(&dx, n, st)); CK(dalloc(&dout, n, st));
-    CK(cudaMemcpyAsync(dx, x, n * 8, cudaMemcpyHostToDevice, st));
-    CK(deql::launch_test_log10(dx, dout, n, st));
-    CK(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, st));
-    dfree(dx, st); dfree(dout, st);
+    TempBuf<double> dx(st), dout(st);
+    CK(dalloc(&dx.p, n, st)); CK(dalloc(&dout.p, n, st));
+    CK(cudaMemcpyAsync(dx.p, x, n * 8, cudaMemcpyHostToDevice, st));
+    CK(deql::launch_test_log10(dx.p, dout.p, n, st));
+    CK(cudaMemcpyAsync(out, dout.p, n * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return DEQ_OK;
 }
@@ -808,24 +978,22 @@ deq_status deq_measure_fp64_peak(double* tflops, double* sm_clock_mhz_hint) {
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
     const int blocks = sms * 8, iters = 4096;
-    double* sink = nullptr;
-    CK(dalloc(&sink, (size_t)blocks * 256, st));
-    cudaEvent_t a, b;
-    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    TempBuf<double> sink(st);
+    CK(dalloc(&sink.p, (size_t)blocks * 256, st));
+    struct Events { cudaEvent_t a = nullptr, b = nullptr; ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } ev;
+    CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
-        CK(cudaEventRecord(a, st));
-        CK(deql::launch_dfma_peak(sink, iters, blocks, st));
-        CK(cudaEventRecord(b, st));
-        CK(cudaEventSynchronize(b));
+        CK(cudaEventRecord(ev.a, st));
+        CK(deql::launch_dfma_peak(sink.p, iters, blocks, st));
+        CK(cudaEventRecord(ev.b, st));
+        CK(cudaEventSynchronize(ev.b));
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, a, b));
+        CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
         const double fl = (double)blocks * 256.0 * iters * 64.0 * 2.0;
         const double tf = fl / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }
-    cudaEventDestroy(a); cudaEventDestroy(b);
-    dfree(sink, st);
     CK(cudaStreamSynchronize(st));
     *tflops = best;
     if (sm_clock_mhz_hint) *sm_clock_mhz_hint = khz / 1000.0;

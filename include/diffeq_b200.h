@@ -193,6 +193,18 @@ deq_status deq_solve_host(const deq_rhs* rhs, size_t ntraj, const double* y0, co
                           const int* devices, int ndevices, double* yfinal, uint32_t* accepted, uint32_t* rejected,
                           uint32_t* nfe, uint8_t* status, double* t_reached);
 
+/* deq_solve_host with the tspan rows (opts->output must be DEQ_OUT_TSPAN): `dense` is a host buffer in the layout
+ * opts->dense_layout names — TRAJ_MAJOR [ntraj][ntspan][n] (each trajectory's rows contiguous, the reference's Vec<Y> per
+ * problem; explicit adaptive methods) or SOA [n][ntspan][ntraj] — and nvalid[ntraj] (may be NULL) receives the number of
+ * leading rows the reference would have emitted.  The trajectory range is cut into chunks of ~128 MiB of rows that are dealt
+ * round-robin to the devices; each device integrates chunk i + 1 while chunk i travels to the host on a second stream, so the
+ * call runs at the speed of the slower of the two (for dense rows that is the host link: use pinned buffers, deq_host_alloc).
+ * DEQ_OUT_ALL is not offered on host buffers: its size is data dependent (use deq_solve + deq_result_all_*). */
+deq_status deq_solve_host_dense(const deq_rhs* rhs, size_t ntraj, const double* y0, const double* params, int params_per_traj,
+                                const double* tspan, size_t ntspan, int method, int tableau_set, const deq_options* opts,
+                                const int* devices, int ndevices, double* yfinal, uint32_t* accepted, uint32_t* rejected,
+                                uint32_t* nfe, uint8_t* status, double* t_reached, double* dense, uint32_t* nvalid);
+
 /* ---- result: replaces OdeSolution{tout,yout} (src/ode/solution.rs:22-29) + the Diagnostics the reference
  * counts but drops (problem.rs:957-970).  All getters synchronise with the solve first. ---- */
 deq_status deq_result_final(deq_result* res, double* y /* host [ntraj][n] */);

@@ -595,6 +595,8 @@ def test_in_library_multi_gpu_solve_host(deq, oracle):
     import torch
     from diffeq_b200 import synth
     ndev = torch.cuda.device_count()
+    if ndev < 2:
+        print("NOTE: only one GPU visible; devices = list(range(ndev)) degenerates to [0] (see test_multi_gpu_devices_list)")
     y0 = synth.lorenz_ics(0, 5003)
     o = deq.OdeOptionMap().insert(deq.Reltol(1e-8), deq.Abstol(1e-8))
     ref = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, y0, [0.0, 2.0], oracle.opts(1e-8, 1e-8))
@@ -617,6 +619,65 @@ def test_in_library_multi_gpu_solve_host(deq, oracle):
         out = deq.solve_host_multi(vd, yv, mu, [0.0, 10.0], deq.Ode.Ode45fe, oc, devices=[0] * 8 if ndev == 1 else list(range(ndev)))   # chunk 5000: seven empty shards
         assert np.array_equal(out["final"], rv["yfinal"]) and np.array_equal(out["accepted"], rv["accepted"]), chunk
         assert np.array_equal(out["nfe"], rv["nfe"]) and np.array_equal(out["t_reached"], rv["t_reached"]), chunk
+
+
+def test_solve_host_dense_rows_across_shards(deq, oracle, monkeypatch):
+    """deq_solve_host_dense: the tspan rows of an ensemble on host buffers, integrated chunk by chunk (several chunks per
+    device, several device threads — all visible GPUs, and three threads on GPU 0 for the partition invariance) while earlier
+    chunks travel to the host.  Slices of the result are compared with the oracle's dense output, the whole of it with the
+    handle API, in both layouts; a multi-GPU box exercises devices = 0..ndev-1."""
+    import torch
+    from diffeq_b200 import synth
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        print("NOTE: only one GPU visible; the multi-device path is exercised with several device threads on GPU 0")
+    n = 5003
+    y0, mu = synth.vdp_sweep(0, n, n)
+    ts = deq.linspace(0.0, 10.0, 101)
+    monkeypatch.setenv("DEQ_HOST_CHUNK", "1024")   # five chunks
+    vd = deq.Rhs.builtin(deq.System.VanDerPol)
+    slices = [slice(0, 40), slice(2030, 2070), slice(n - 40, n)]
+    refs = [oracle.ensemble_dense(oracle.ODE45FE, oracle.VANDERPOL, mu[sl], y0[sl], ts, oracle.opts(1e-6, 1e-8)) for sl in slices]
+    for layout in (deq.DenseLayout.SoA, deq.DenseLayout.TrajMajor):
+        o = deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8), deq.Output.Tspan, layout)
+        whole = deq.OdeProblem.builder().fun(vd).params(mu).init(y0).tspan(ts).build().solve(deq.Ode.Ode45fe, o)
+        for devices in ([0], list(range(ndev)), [0] * 3):
+            out = deq.solve_host_multi(vd, y0, mu, ts, deq.Ode.Ode45fe, o, devices=devices)
+            dense = out["dense"] if layout == deq.DenseLayout.TrajMajor else np.ascontiguousarray(out["dense"].transpose(2, 1, 0))   # [traj][row][comp]
+            assert np.array_equal(out["nvalid"], whole.nvalid) and np.array_equal(out["final"], whole.final), (layout, devices)
+            assert np.array_equal(out["accepted"], whole.accepted) and np.array_equal(out["t_reached"], whole.t_reached)
+            for sl, ref in zip(slices, refs):
+                want = ref["out"].transpose(2, 1, 0)   # oracle: SoA [n][nt][traj], NaN beyond nvalid (except the last row)
+                got = dense[sl].copy()
+                idx = np.arange(len(ts))[None, :]
+                invalid = (idx >= ref["nvalid"][:, None]) & (idx != len(ts) - 1)
+                got[invalid] = np.nan
+                assert np.array_equal(got, want, equal_nan=True), (layout, devices, sl)
+                assert np.array_equal(out["nvalid"][sl], ref["nvalid"])
+    # fixed-step rows and the stiff solver go through the same call (SoA rows)
+    ys = synth.lorenz_ics(0, 2500)
+    of = deq.OdeOptionMap().insert(deq.Output.Tspan)
+    fx = deq.solve_host_multi(deq.Rhs.builtin(deq.System.Lorenz), ys, LOR, deq.linspace(0.0, 0.5, 51), deq.Ode.Ode4, of, devices=[0, 0])
+    wf = deq.OdeProblem.builder().fun(deq.Rhs.builtin(deq.System.Lorenz)).params(LOR).init(ys).tspan(deq.linspace(0.0, 0.5, 51)).build().solve(deq.Ode.Ode4, of)
+    assert np.array_equal(np.ascontiguousarray(fx["dense"].transpose(2, 1, 0)), wf.yout) and np.array_equal(fx["final"], wf.final)
+    with pytest.raises(deq.OdeError):   # Output.All has a data-dependent size: handle API only
+        deq.solve_host_multi(vd, y0, mu, ts, deq.Ode.Ode45fe, deq.OdeOptionMap().insert(deq.Output.All))
+
+
+def test_multi_gpu_devices_list(deq, oracle):
+    """deq_solve_host(devices = 0..ndev-1) on a box with at least two GPUs: one process, one host thread and stream per device,
+    results identical to the oracle trajectory by trajectory.  Skipped (and recorded as such) on a single-GPU box."""
+    import torch
+    from diffeq_b200 import synth
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip(f"needs >= 2 GPUs, this box has {ndev}")
+    y0 = synth.lorenz_ics(0, 20011)
+    ref = oracle.ensemble_adaptive(oracle.ODE45, oracle.LORENZ, LOR, y0, [0.0, 2.0], oracle.opts(1e-8, 1e-8))
+    out = deq.solve_host_multi(deq.Rhs.builtin(deq.System.Lorenz), y0, LOR, [0.0, 2.0], deq.Ode.Ode45,
+                               deq.OdeOptionMap().insert(deq.Reltol(1e-8), deq.Abstol(1e-8)), devices=list(range(ndev)))
+    assert np.array_equal(out["final"], ref["yfinal"]) and np.array_equal(out["accepted"], ref["accepted"])
+    assert np.array_equal(out["rejected"], ref["rejected"]) and np.array_equal(out["status"], ref["status"])
 
 
 def test_golden_fixtures_through_the_cuda_path(deq):
