@@ -504,7 +504,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "kernel_mode": KERNEL_MODE,
             "e2e": {"value": e2e_steps_all / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s_max / args.steps},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": 3 * args.steps,   # per timed step: hinit_kernel, adapt_kernel, sum_counts_kernel (the step totals)
             "accepted_only_steps_per_s": (tot_par["accepted"] * world) / (dev_ms_max / args.steps * 1e-3),
             "roofline": roofline(kernel_ms, steps_done, "deqk::adapt_kernel<Dopri5<false>, Lorenz, false, MODE_FINAL, FAST=false>", par_note, "parity"),
             "fast_mode": {"value": fast_steps_all / (fast_ms_max * 1e-3), "unit": UNIT, "ms_per_step": fast_ms_max / args.steps,
