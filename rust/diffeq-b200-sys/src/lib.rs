@@ -69,6 +69,10 @@ extern "C" {
                           tspan: *const c_double, ntspan: usize, method: c_int, tableau_set: c_int, opts: *const deq_options,
                           devices: *const c_int, ndevices: c_int, yfinal: *mut c_double, accepted: *mut u32, rejected: *mut u32,
                           nfe: *mut u32, status: *mut u8, t_reached: *mut c_double) -> deq_status;
+    pub fn deq_solve_host_dense(rhs: *const deq_rhs, ntraj: usize, y0: *const c_double, params: *const c_double, params_per_traj: c_int,
+                                tspan: *const c_double, ntspan: usize, method: c_int, tableau_set: c_int, opts: *const deq_options,
+                                devices: *const c_int, ndevices: c_int, yfinal: *mut c_double, accepted: *mut u32, rejected: *mut u32,
+                                nfe: *mut u32, status: *mut u8, t_reached: *mut c_double, dense: *mut c_double, nvalid: *mut u32) -> deq_status;
     pub fn deq_result_final(res: *mut deq_result, y: *mut c_double) -> deq_status;
     pub fn deq_result_counts(res: *mut deq_result, accepted: *mut u32, rejected: *mut u32, nfe: *mut u32,
                              status: *mut u8, t_reached: *mut c_double) -> deq_status;

@@ -195,3 +195,84 @@ def test_binding_struct_layout_matches_library(deq):
     assert deq.lib().deq_abi_options_size() == C.sizeof(deq._Options)
     o = deq.lib().deq_options_default()
     assert (o.max_steps, o.refill, o.mode, o.precision, o.libm, o.dense_layout, o.output) == (10_000_000, 2, 0, 0, 0, 0, 0)
+
+
+# ---- the Rust -sys crate cannot be compiled in this image: keep it in step with the header mechanically ----
+def _c_type_to_rust(t):
+    t = " ".join(t.replace("*", " * ").split())
+    toks = t.split()
+    base_map = {"double": "c_double", "int": "c_int", "float": "c_float", "char": "c_char", "void": "c_void", "size_t": "usize",
+                "uint64_t": "u64", "uint32_t": "u32", "uint8_t": "u8", "deq_status": "deq_status", "deq_options": "deq_options",
+                "deq_rhs": "deq_rhs", "deq_ensemble": "deq_ensemble", "deq_result": "deq_result"}
+    const = False
+    if toks[0] == "const":
+        const, toks = True, toks[1:]
+    base, stars = base_map[toks[0]], toks[1:]
+    assert all(x == "*" for x in stars), t
+    out = base
+    for i, _ in enumerate(stars):
+        out = ("*const " if (const and i == 0) else "*mut ") + out
+    return out
+
+
+def _parse_header(text):
+    import re
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    fields = re.search(r"typedef struct deq_options \{(.*?)\} deq_options;", text, flags=re.S).group(1)
+    opts = []
+    for decl in fields.split(";"):
+        decl = decl.strip()
+        if decl:
+            ty, name = decl.rsplit(None, 1)
+            opts.append((name, _c_type_to_rust(ty)))
+    status = {m.group(1): int(m.group(2)) for m in re.finditer(r"(DEQ_(?:OK|ERR_\w+))\s*=\s*(\d+)", text)}
+    funcs = {}
+    for m in re.finditer(r"(?m)^\s*((?:const\s+)?\w+\s*\**)\s*(deq_\w+)\s*\(([^;{}]*)\)\s*;", text):
+        ret, name, args = m.group(1), m.group(2), " ".join(m.group(3).split())
+        alist = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                ty = re.sub(r"\b\w+$", "", a).strip() if not a.endswith("*") else a   # drop the parameter name
+                alist.append(_c_type_to_rust(ty))
+        funcs[name] = (None if ret.strip() == "void" else _c_type_to_rust(ret), alist)
+    return opts, status, funcs
+
+
+def _parse_rust_sys(text):
+    import re
+    body = re.search(r"pub struct deq_options \{(.*?)\n\}", text, flags=re.S).group(1)
+    opts = [(m.group(1).replace("r#", ""), m.group(2).strip()) for m in re.finditer(r"pub\s+([\w#]+)\s*:\s*([^,\n]+),", body)]
+    status = {m.group(1): int(m.group(2)) for m in re.finditer(r"pub const (DEQ_\w+): deq_status = (\d+);", text)}
+    funcs = {}
+    ext = re.search(r'extern "C" \{(.*)\n\}', text, flags=re.S).group(1)
+    for m in re.finditer(r"pub fn (deq_\w+)\s*\((.*?)\)\s*(?:->\s*([^;]+))?;", ext, flags=re.S):
+        name, args, ret = m.group(1), " ".join(m.group(2).split()), m.group(3)
+        alist = [a.split(":", 1)[1].strip() for a in args.split(",") if a.strip()]
+        funcs[name] = (ret.strip() if ret else None, alist)
+    return opts, status, funcs
+
+
+def test_rust_sys_crate_matches_the_header():
+    """rust/diffeq-b200-sys/src/lib.rs declares exactly the functions of include/diffeq_b200.h with the same argument and
+    return types, `#[repr(C)] deq_options` has the header's fields in the header's order, and the status codes agree — so the
+    crate a maintainer compiles (there is no Rust toolchain in this image) binds the ABI the tests exercise."""
+    hopts, hstatus, hfuncs = _parse_header(open(os.path.join(ROOT, "include", "diffeq_b200.h")).read())
+    ropts, rstatus, rfuncs = _parse_rust_sys(open(os.path.join(ROOT, "rust", "diffeq-b200-sys", "src", "lib.rs")).read())
+    assert len(hfuncs) >= 37 and len(hopts) == 17
+    assert ropts == hopts
+    assert rstatus == hstatus
+    assert sorted(rfuncs) == sorted(hfuncs), (sorted(set(hfuncs) - set(rfuncs)), sorted(set(rfuncs) - set(hfuncs)))
+    for name, sig in hfuncs.items():
+        assert rfuncs[name] == sig, (name, rfuncs[name], sig)
+    # the safe wrapper exposes the reference's per-method entry points (problem.rs:150-190) and the option kinds
+    wrapper = open(os.path.join(ROOT, "rust", "diffeq-b200", "src", "lib.rs")).read()
+    for fn in ("feuler", "heun", "midpoint", "ode4", "ode21", "ode23", "ode45", "ode45_dp", "ode45_fe", "ode78", "ode23s", "ode4s_kr", "ode4s_s",
+               "solve_host", "tspan_linspace"):
+        assert ("pub fn %s(" % fn) in wrapper, fn
+    for ty in ("enum Points", "enum Output", "enum Mode", "enum TableauSet", "enum DenseLayout", "fn flatten", "fn ptr_or_null"):
+        assert ty in wrapper, ty
+    # every sys function the wrapper calls exists in the header
+    import re
+    for used in set(re.findall(r"sys::(deq_\w+)\(", wrapper)):
+        assert used in hfuncs, used
