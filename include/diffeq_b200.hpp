@@ -147,10 +147,23 @@ inline OdeProblem OdeBuilder::build() {  // problem.rs:92-104
     if (!f_) throw OdeError(DEQ_ERR_UNINITIALIZED, "Required problem must be initialized");
     if (!has_y0_) throw OdeError(DEQ_ERR_UNINITIALIZED, "Initial starting point must be initialized");
     if (!has_t_) throw OdeError(DEQ_ERR_UNINITIALIZED, "Time span must be initialized");
+    // the C ABI reads ntraj * n state and nparams (or ntraj * nparams) parameter doubles through raw pointers: check the lengths here
+    const size_t n = (size_t)f_->dim(), np = (size_t)deq_rhs_nparams(f_->get()), ntraj = y0_.size();
     std::vector<double> flat;
-    for (auto& y : y0_) flat.insert(flat.end(), y.begin(), y.end());
+    flat.reserve(ntraj * n);
+    for (size_t i = 0; i < ntraj; ++i) {
+        if (y0_[i].size() != n) throw OdeError(DEQ_ERR_INVALID_ARG, "initial state " + std::to_string(i) + " has " + std::to_string(y0_[i].size()) + " components, the right-hand side expects " + std::to_string(n));
+        flat.insert(flat.end(), y0_[i].begin(), y0_[i].end());
+    }
+    int per_traj = 0;
+    if (np == 0) { if (!params_.empty()) throw OdeError(DEQ_ERR_INVALID_ARG, "the right-hand side takes no parameters"); }
+    else if (params_.empty()) throw OdeError(DEQ_ERR_UNINITIALIZED, "Required problem parameters must be initialized");
+    else if (params_.size() == np) per_traj = 0;
+    else if (params_.size() == np * ntraj) per_traj = 1;   // one row per trajectory, [ntraj][nparams]
+    else throw OdeError(DEQ_ERR_INVALID_ARG, std::to_string(params_.size()) + " parameters given, expected " + std::to_string(np) + " or " + std::to_string(np * ntraj));
     deq_ensemble* h = nullptr;
-    check(deq_ensemble_create(f_->get(), y0_.size(), flat.data(), params_.empty() ? nullptr : params_.data(), 0, tspan_.data(), tspan_.size(), &h));
+    check(deq_ensemble_create(f_->get(), ntraj, flat.empty() ? nullptr : flat.data(), params_.empty() ? nullptr : params_.data(), per_traj,
+                              tspan_.data(), tspan_.size(), &h));
     return OdeProblem(h, (size_t)f_->dim(), y0_.size(), tspan_);
 }
 
