@@ -258,8 +258,8 @@ deq_status deq_rhs_builtin(int system, deq_rhs** out) {
 
 deq_status deq_rhs_from_source(const char* cuda_src, int n, int nparams, deq_rhs** out) {
     if (!out || !cuda_src) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
-    if (n < 1 || n > 16 || nparams < 0 || nparams > deqk::MAX_NP)
-        return fail(DEQ_ERR_INVALID_ARG, "need 1 <= n <= 16 and 0 <= nparams <= 8");
+    if (n < 1 || n > deqk::MAX_N || nparams < 0 || nparams > deqk::MAX_NP)
+        return fail(DEQ_ERR_INVALID_ARG, "need 1 <= n <= 64 and 0 <= nparams <= 8");
     std::string err;
     deqn::Program* p = deqn::create(cuda_src, n, nparams, &err);
     if (!p) return fail(DEQ_ERR_NVRTC, err);

@@ -19,6 +19,7 @@ enum : uint8_t { ST_DONE = 0, ST_MINSTEP_BREAK = 1, ST_MAX_STEPS = 2,
 #endif
 constexpr int BLOCK = DEQ_BLOCK;
 constexpr int MAX_NP = 8;
+constexpr int MAX_N = 64;   // state dimension of user (NVRTC) systems: stage vectors live in registers up to 16, in local memory beyond
 
 struct SharedParams { double v[MAX_NP]; };
 

@@ -87,6 +87,9 @@ __device__ __forceinline__ void load_params(double* prm, const double* params, c
 // FAST = true : fused multiply-adds, structurally-zero coefficients skipped (results differ in the last bits).
 // `ylast` (may be nullptr) receives the argument of the last stage, y + dt * sum_j a[S-1][j] k_j: for a first-same-as-last
 // tableau that IS the new solution (a[S-1][j] == b[j]), so FAST mode does not evaluate the weighted sum a second time.
+// Loops over the state components are fully unrolled while the stage vectors fit the register file (N <= 16); for larger
+// systems they stay rolled — `#pragma unroll (N <= 16 ? N : 1)` — which puts the per-thread arrays (k[S][N], stage argument,
+// trial state) into local memory and keeps the code size independent of N.
 template <class TB, class F, bool FAST>
 __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double dt, double (&k)[TB::S][F::N],
                                        const double* prm, double* ylast = nullptr) {
@@ -94,27 +97,27 @@ __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double
     constexpr auto tbc = TB::data();
 #pragma unroll
     for (int row = 1; row < TB::S; ++row) {
+        // w_col = a[row][col] * dt first (one product per entry, like the reference), then every component accumulates its
+        // stage argument over col in order: component-outer, so that the large-system flavour (rolled component loop, stage
+        // vectors in local memory) touches each element once per row
+        double w[TB::S];
+#pragma unroll
+        for (int col = 0; col < row; ++col) w[col] = tb.a[row][col] * dt;
         double yi[F::N];
+#pragma unroll (F::N <= 16 ? F::N : 1)
+        for (int d = 0; d < F::N; ++d) {
+            double acc = y[d];
 #pragma unroll
-        for (int d = 0; d < F::N; ++d) yi[d] = y[d];
-#pragma unroll
-        for (int col = 0; col < row; ++col) {
-            if (FAST) {
-                if (tbc.a[row][col] != 0.0) {
-                    const double w = tb.a[row][col] * dt;
-#pragma unroll
-                    for (int d = 0; d < F::N; ++d) yi[d] = __fma_rn(k[col][d], w, yi[d]);
-                }
-            } else {
-                const double w = tb.a[row][col] * dt;
-#pragma unroll
-                for (int d = 0; d < F::N; ++d) yi[d] = yi[d] + k[col][d] * w;
+            for (int col = 0; col < row; ++col) {
+                if (FAST) { if (tbc.a[row][col] != 0.0) acc = __fma_rn(k[col][d], w[col], acc); }
+                else acc = acc + k[col][d] * w[col];
             }
+            yi[d] = acc;
         }
         const double tn = FAST ? __fma_rn(tb.c[row], dt, t) : t + tb.c[row] * dt;
         F::eval(tn, yi, k[row], prm);
         if (row == TB::S - 1 && ylast) {
-#pragma unroll
+#pragma unroll (F::N <= 16 ? F::N : 1)
             for (int d = 0; d < F::N; ++d) ylast[d] = yi[d];
         }
     }
@@ -206,7 +209,7 @@ __device__ __forceinline__ void embedded_parity(const double (&k)[TB::S][N], con
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             if (tbc.b[s][0] == 0.0 || tbc.b[s][1] == 0.0) {
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                 for (int d = 0; d < N; ++d) m = m + fabsf(__int_as_float(__double2hiint(k[s][d])));
             }
         }
@@ -214,7 +217,7 @@ __device__ __forceinline__ void embedded_parity(const double (&k)[TB::S][N], con
     }
     double p[N], q[N];
     if (skip_ok) {
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
         for (int d = 0; d < N; ++d) {
             p[d] = 0.0; q[d] = 0.0;
 #pragma unroll
@@ -225,14 +228,14 @@ __device__ __forceinline__ void embedded_parity(const double (&k)[TB::S][N], con
         }
     } else {
         DEQ_COLD_PATH();
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
         for (int d = 0; d < N; ++d) {
             p[d] = 0.0; q[d] = 0.0;
 #pragma unroll
             for (int s = 0; s < S; ++s) { p[d] = p[d] + k[s][d] * tb.b[s][0]; q[d] = q[d] + k[s][d] * tb.b[s][1]; }
         }
     }
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
     for (int d = 0; d < N; ++d) {
         yerr[d] = (p[d] - q[d]) * dt;
         ytrial[d] = ys[d] + (p[d] * dt);
@@ -271,10 +274,10 @@ __global__ void __launch_bounds__(BLOCK) fixed_kernel(const FixedParams P) {
     double prm[F::NP ? F::NP : 1];
     load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
     double y[N];
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
     for (int d = 0; d < N; ++d) y[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
     if (ALL) {
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
         for (int d = 0; d < N; ++d) P.yall[((unsigned long long)d * P.nt) * P.ntraj + traj] = y[d];
     }
     double tcur = P.nt ? __ldg(P.tspan) : 0.0;
@@ -286,16 +289,16 @@ __global__ void __launch_bounds__(BLOCK) fixed_kernel(const FixedParams P) {
         stages<TB, F, false>(tcur, y, dt, k, prm);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
             for (int d = 0; d < N; ++d) y[d] = y[d] + (k[s][d] * tb.b[s][0]) * dt;
         }
         if (ALL) {
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
             for (int d = 0; d < N; ++d) P.yall[((unsigned long long)d * P.nt + (i + 1)) * P.ntraj + traj] = y[d];
         }
         tcur = tnext;
     }
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
     for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = y[d];
 }
 
@@ -318,28 +321,28 @@ __global__ void __launch_bounds__(BLOCK) hinit_kernel(const HinitParams P) {
     double prm[F::NP ? F::NP : 1];
     load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
     double x0[N], f0[N];
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
     for (int d = 0; d < N; ++d) x0[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
     const double t0 = P.t0, tend = P.tend, reltol = P.reltol, abstol = P.abstol;
     const double diff = tend - t0;
     const double tdir = (diff != diff) ? diff : copysign(1.0, diff);  // f64::signum
     double norm = 0.0;
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
     for (int d = 0; d < N; ++d) { const double a = fabs(x0[d]); if (a > norm) norm = a; }
     const double tau = fmax(norm * reltol, 1.0 * abstol);
     const double d0 = norm / tau;
     F::eval(t0, x0, f0, prm);
     double nf0 = 0.0;
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
     for (int d = 0; d < N; ++d) { const double a = fabs(f0[d]); if (a > nf0) nf0 = a; }
     const double d1 = nf0 / tau;
     const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1.0e-6 : 0.01 * (d0 / d1);
     double x1[N], f1[N];
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
     for (int d = 0; d < N; ++d) x1[d] = x0[d] + (f0[d] * h0) * tdir;
     F::eval(t0 + tdir * h0, x1, f1, prm);
     double nf1 = 0.0;
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
     for (int d = 0; d < N; ++d) { const double a = fabs(f1[d] - f0[d]); if (a > nf1) nf1 = a; }
     const double d2 = nf1 / (tau * h0);
     const double m = fmax(d1, d2);
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(BLOCK) hinit_kernel(const HinitParams P) {
     }
     const double h = tdir * fmin(fmin(h1, 100. * h0), tdir * (tend - t0));
     P.h0[traj] = h;
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
     for (int d = 0; d < N; ++d) P.f0[(unsigned long long)d * P.ntraj + traj] = f0[d];
 }
 
@@ -540,9 +543,9 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     unsigned long long it = 1, wpos = 0, wbase = 0;
     double* const stage = s_stage_dyn;
     StageLane sl;
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
     for (int d = 0; d < N; ++d) { cy[d] = 0.0; ck[d] = 0.0; }
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
     for (int d = 0; d < N; ++d) yl[d] = 0.0;
 #pragma unroll
     for (int j = 0; j < (F::NP ? F::NP : 1); ++j) prm[j] = 0.0;
@@ -566,7 +569,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
             {
                 ++attempts;
                 double k[S][N];
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                 for (int d = 0; d < N; ++d) k[0][d] = ck[d];
                 double ytrial[N], yerr[N];
                 double ndt;
@@ -576,14 +579,14 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     stages<TB, F, false>(t, cy, dt, k, prm);
                     // embedded_step :761-771  (y == cy under Points::All; the last output row under Points::Specified)
                     double ys[N];
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                     for (int d = 0; d < N; ++d) ys[d] = SPEC ? yl[d] : cy[d];
                     embedded_parity<TB, N>(k, ys, dt, ytrial, yerr);
                     // stepsize_hw92 :801-845.  The reference first scans the trial state for NaN (-> err = 10, dt *= 0.2,
                     // timeout = 5).  A NaN trial component makes the scaled error sum NaN as well, so the scan only has to
                     // run when the sum is NaN — one test on the hot path instead of N.
                     double ssum = 0.0;
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                     for (int d = 0; d < N; ++d) {
                         const double e = yerr[d] / (fabs(absmax_operand(ys[d], ytrial[d])) * reltol + abstol);
                         const double a = fabs(e);
@@ -597,7 +600,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     if (hi32(ssum) >= 0x7ff00000u) {   // rare: inf or NaN; the reference's rule applies only to a NaN TRIAL STATE
                         DEQ_COLD_PATH();
                         bool isnan_trial = false;
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                         for (int d = 0; d < N; ++d) isnan_trial = isnan_trial || (ytrial[d] != ytrial[d]);
                         if (isnan_trial) { err = 10.; ndt = 0.2 * dt; }   // stepsize_hw92 :814-822 (timeout = 5 follows from the reject)
                     }
@@ -608,7 +611,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     // For a first-same-as-last tableau the argument of the last stage is the new solution itself.
                     constexpr auto tbc = TB::data();
                     stages<TB, F, true>(t, cy, dt, k, prm, FSAL ? ytrial : nullptr);
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                     for (int d = 0; d < N; ++d) {
                         double p = 0.0, e = 0.0;
 #pragma unroll
@@ -620,7 +623,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                         if (!FSAL) ytrial[d] = __fma_rn(p, dt, cy[d]);
                     }
                     double ssum = 0.0;
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                     for (int d = 0; d < N; ++d) {
                         const double e = yerr[d] * rcp_fast(__fma_rn(fabs(absmax_operand(cy[d], ytrial[d])), reltol, abstol));
                         ssum = __fma_rn(e, e, ssum);
@@ -645,14 +648,14 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                             // Points::Specified :284-300 — every tspan point before t+dt, all remaining ones on the last step;
                             // Hermite from the step's (lagging) y, each emitted row becomes the new last output row
                             double y0s[N];
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                             for (int d = 0; d < N; ++d) y0s[d] = yl[d];
                             while (it < P.nt) {
                                 const double tq = __ldg(P.tspan + it);
                                 if (!(tdir * tq < tdir * tn || last_step != 0u)) break;
                                 const double theta = (tq - t) / dt;
                                 if (P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, tq);
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                                 for (int d = 0; d < N; ++d) {
                                     const double v = (y0s[d] * (1. - theta) + ytrial[d] * theta) +
                                                      ((ytrial[d] - y0s[d]) * (1. - 2. * theta) + k[0][d] * (theta - 1.) * dt +
@@ -670,7 +673,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                                 if (!(tdir * t < tdir * tq && tdir * tq < tdir * tn)) break;
                                 const double theta = (tq - t) / dt;
                                 if (REC && P.rec_mode == REC_WRITE) stage_append(stage, P.rec_rows, sl, tq);
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                                 for (int d = 0; d < N; ++d) {
                                     const double v = (cy[d] * (1. - theta) + ytrial[d] * theta) +
                                                      ((ytrial[d] - cy[d]) * (1. - 2. * theta) + k[0][d] * (theta - 1.) * dt +
@@ -685,7 +688,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                             if (REC) {  // "also store every step taken" (problem.rs:320-322)
                                 if (P.rec_mode == REC_WRITE) {
                                     stage_append(stage, P.rec_rows, sl, tn);
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                                     for (int d = 0; d < N; ++d) stage_append(stage, P.rec_rows, sl, ytrial[d]);
                                 }
                                 ++wpos;
@@ -695,7 +698,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                 }
                 // ---- state update (problem.rs:324-351), predicated ----
                 if (accept) {
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                     for (int d = 0; d < N; ++d) { ck[d] = k[S - 1][d]; cy[d] = ytrial[d]; }
                 }
                 // end snap of an accepted, not-yet-last step: `if tdir*((t+dt) + dt/100) >= tdir*tend { dt = tend - t; last = true }`
@@ -715,16 +718,16 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
             }
             if (fin != 0xff) {
                 const uint32_t nfe = 2u + attempts * (uint32_t)(S - 1) + (FSAL ? 0u : acc);
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                 for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = SPEC ? yl[d] : cy[d];
                 P.accepted[traj] = acc; P.rejected[traj] = rej; P.nfe[traj] = nfe; P.status[traj] = fin; P.t_reached[traj] = t;
                 if (ROWS) {
                     if (SOA) {
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                         for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt + (P.nt - 1)) * P.ntraj + traj] = cy[d];
                     } else if (TM) {
                         stage_drain(stage, P.dense, sl, true);   // ends with a __syncwarp: the helpers' stores precede the row below
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                         for (int d = 0; d < N; ++d) P.dense[(traj * P.nt + (P.nt - 1)) * (unsigned long long)N + d] = cy[d];
                     } else if (REC && P.rec_mode == REC_COUNT) {
                         P.rec_counts[traj] = (uint32_t)(wpos - wbase);
@@ -752,7 +755,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     traj = my;
                     active = 1u;
                     load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                     for (int d = 0; d < N; ++d) {
                         cy[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
                         ck[d] = P.f0[(unsigned long long)d * P.ntraj + traj];
@@ -765,18 +768,18 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     acc = 0; rej = 0; attempts = 0; it = 1;
                     if (ROWS) {
                         if (SOA) {
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                             for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt) * P.ntraj + traj] = cy[d];
                         } else if (TM) {  // staged trajectory-major stream: row 0 = y0
                             sl.head = 0; sl.cnt = 0; sl.gpos = traj * P.nt * (unsigned long long)N;
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                             for (int d = 0; d < N; ++d) stage_append(stage, P.dense, sl, cy[d]);
                         } else {  // ragged Points::All stream, rows [t, y...] interleaved and staged: row 0 = (t0, y0)
                             wpos = 0ull; wbase = 0ull;
                             if (P.rec_mode == REC_WRITE) {
                                 sl.head = 0; sl.cnt = 0; sl.gpos = P.rec_offsets[traj] * (unsigned long long)(N + 1);
                                 stage_append(stage, P.rec_rows, sl, t);
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                                 for (int d = 0; d < N; ++d) stage_append(stage, P.rec_rows, sl, cy[d]);
                             }
                             ++wpos;
@@ -803,7 +806,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
             {
                 int f = 0;
                 pk.v[f++] = t; pk.v[f++] = dt;
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                 for (int d = 0; d < N; ++d) { pk.v[f++] = cy[d]; pk.v[f++] = ck[d]; }
                 if (PT) {
 #pragma unroll
@@ -821,7 +824,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
             {
                 int f = 0;
                 t = pk.v[f++]; dt = pk.v[f++];
-#pragma unroll
+#pragma unroll (N <= 16 ? N : 1)
                 for (int d = 0; d < N; ++d) { cy[d] = pk.v[f++]; ck[d] = pk.v[f++]; }
                 if (PT) {
 #pragma unroll

@@ -37,7 +37,7 @@
 namespace {
 
 constexpr int MAXS = 13;
-constexpr int MAXN = 16;
+constexpr int MAXN = 64;
 
 // ------------------------------------------------------------------------------------------
 // Tableaus (runge_kutta.rs:231-817).  `set` 0 = REFERENCE (bug-for-bug), 1 = TEXTBOOK.
@@ -171,7 +171,7 @@ bool make_tableau(int method, int set, Tableau& t) {
 // ------------------------------------------------------------------------------------------
 // Built-in right-hand sides (the reference takes a closure F: Fn(f64,&Y)->Y, problem.rs:32-36).
 // ------------------------------------------------------------------------------------------
-enum Rhs { LORENZ = 0, VANDERPOL = 1, PENDULUM = 2, RING8 = 3, RING16 = 4 };
+enum Rhs { LORENZ = 0, VANDERPOL = 1, PENDULUM = 2, RING8 = 3, RING16 = 4, RING32 = 5, RING64 = 6 };
 
 struct LorenzF {  // problem.rs:989-1000: params = {sigma, rho, beta}
     static constexpr int N = 3;
@@ -811,6 +811,8 @@ int dispatch_rhs(int rhs, Fn&& fn) {
         case PENDULUM: return fn(PendulumF());
         case RING8: return fn(RingF<8>());
         case RING16: return fn(RingF<16>());
+        case RING32: return fn(RingF<32>());
+        case RING64: return fn(RingF<64>());
         default: return ERR_UNSUPPORTED;
     }
 }
@@ -831,8 +833,8 @@ struct oracle_opts {
     int libm_folded;
 };
 
-int oracle_rhs_dim(int rhs) { return rhs == LORENZ ? 3 : (rhs == VANDERPOL || rhs == PENDULUM) ? 2 : rhs == RING8 ? 8 : rhs == RING16 ? 16 : -1; }
-int oracle_rhs_nparams(int rhs) { return rhs == LORENZ ? 3 : rhs == VANDERPOL ? 1 : rhs == PENDULUM ? 3 : (rhs == RING8 || rhs == RING16) ? 2 : -1; }
+int oracle_rhs_dim(int rhs) { return rhs == LORENZ ? 3 : (rhs == VANDERPOL || rhs == PENDULUM) ? 2 : rhs == RING8 ? 8 : rhs == RING16 ? 16 : rhs == RING32 ? 32 : rhs == RING64 ? 64 : -1; }
+int oracle_rhs_nparams(int rhs) { return rhs == LORENZ ? 3 : rhs == VANDERPOL ? 1 : rhs == PENDULUM ? 3 : (rhs >= RING8 && rhs <= RING64) ? 2 : -1; }
 
 // itertools_num::linspace as recalled (unpinned third-party): a + ((b-a)/(n-1))*i
 void oracle_linspace(double a, double b, size_t n, double* out) {

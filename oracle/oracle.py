@@ -19,7 +19,7 @@ _LIB = None
 # `Ode` enum order (mod.rs:14-26) + ODE21 extension
 FEULER, HEUN, MIDPOINT, ODE23, ODE23S, ODE4, ODE45, ODE45FE, ODE4SKR, ODE4SS, ODE78, ODE21 = range(12)
 LORENZ, VANDERPOL, PENDULUM = 0, 1, 2
-RING8, RING16 = 3, 4   # test systems of dimension 8 / 16 (ring of coupled logistic cells) for the generic-dimension path
+RING8, RING16, RING32, RING64 = 3, 4, 5, 6   # test systems of dimension 8 .. 64 (ring of coupled logistic cells) for the generic-dimension path
 REFERENCE, TEXTBOOK = 0, 1
 POINTS_ALL, POINTS_SPECIFIED = 0, 1
 ST_DONE, ST_MINSTEP_BREAK, ST_MAX_STEPS, ST_INVALID_MATRIX = 0, 1, 2, 3

@@ -586,7 +586,7 @@ def test_nvrtc_max_dimension_high_order(deq):
     fx = deq.OdeProblem.builder().fun(rhs).params([1.0]).init(y0[:3]).tspan(deq.linspace(0.0, T, 3001)).build().solve(deq.Ode.Ode4)
     np.testing.assert_allclose(fx.final, np.tile(want, (3, 1)), rtol=0, atol=1e-9)
     with pytest.raises(deq.OdeError):
-        deq.Rhs.from_source(src, 17, 1)       # beyond the supported state dimension
+        deq.Rhs.from_source(src, 65, 1)       # beyond the supported state dimension
 
 
 def test_in_library_multi_gpu_solve_host(deq, oracle):
@@ -888,12 +888,12 @@ __device__ void rhs(double t, const double* v, double* d, const double* p) {
 '''
 
 
-@pytest.mark.parametrize("n", [8, 16])
+@pytest.mark.parametrize("n", [8, 16, 32, 64])
 def test_generic_dimension_user_systems_bit_exact(deq, oracle, n):
     """State dimension 8 and 16 (the `OdeType` impls of the reference reach 9-tuples and arbitrary Vecs, types.rs:138-278): the
     generic-dimension NVRTC path against the oracle's ring system — adaptive (FSAL and 13-stage non-FSAL), fixed step, final
     states, dense rows in both layouts and the ragged stream, all bit for bit."""
-    osys = oracle.RING8 if n == 8 else oracle.RING16
+    osys = {8: oracle.RING8, 16: oracle.RING16, 32: oracle.RING32, 64: oracle.RING64}[n]   # beyond 16 the stage vectors live in local memory
     rng = np.random.default_rng(n)
     m = 300
     y0 = rng.uniform(0.1, 0.9, (m, n))
