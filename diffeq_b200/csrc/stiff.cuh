@@ -6,12 +6,13 @@
 //
 // Same parity contract as stepper.cuh: IEEE f64, -fmad=false, the reference's operation order.  The n x n linear
 // algebra of the reference goes through nalgebra 0.20 (DMatrix operators, lu(), try_inverse()); it is restated here for
-// n <= 3 with every matrix in registers (all indices are compile-time after unrolling):
+// n <= 8 with every matrix in registers or thread-local memory (all indices are compile-time after unrolling):
 //   * M * v             column-ordered accumulation  y = M[:,0] v0;  y = M[:,j] v_j + y
 //   * lu()              partial pivoting on the first largest |.|, multipliers a_ji * (1 / pivot), exactly-zero pivot
 //                       columns skipped; only the packed factors survive (`lu_internal()`), the permutation is dropped
-//   * try_inverse()     adjugate formulas for n = 1, 2, 3; a zero determinant is the reference's OdeError::InvalidMatrix
-//                       (per-trajectory status ST_INVALID_MATRIX here)
+//   * try_inverse()     adjugate formulas for n = 1, 2, 3, the 4x4 cofactor routine (do_inverse4) for n = 4, lu::try_invert_to
+//                       for n >= 5; a zero determinant / pivot is the reference's OdeError::InvalidMatrix (per-trajectory
+//                       status ST_INVALID_MATRIX here)
 // The reference inverts the PACKED LU matrix of W = I - h d J rather than W (problem.rs:469,481); that is what the
 // REFERENCE set reproduces.  P.true_inverse (TEXTBOOK set) inverts W itself — Shampine & Reichelt's method.
 #pragma once
@@ -61,10 +62,16 @@ __device__ __forceinline__ void na_lu_packed(double (&m)[N][N]) {
     }
 }
 
+template <int N>
+__device__ __forceinline__ bool na_try_inverse(const double (&m)[N][N], double (&o)[N][N]);
+
 // FAST arithmetic only: the same adjugate formulas with ONE reciprocal of the determinant instead of n^2 IEEE divisions.
 template <int N>
 __device__ __forceinline__ bool inverse_fast(const double (&m)[N][N], double (&o)[N][N]) {
-    static_assert(N >= 1 && N <= 3, "the stiff path carries n <= 3");
+    static_assert(N >= 1 && N <= 8, "the stiff path carries n <= 8");
+    if constexpr (N >= 4) {
+        return na_try_inverse<N>(m, o);   // same routines, contracted by the FAST translation unit's -fmad=true
+    } else
     if constexpr (N == 1) {
         if (m[0][0] == 0.0) return false;
         o[0][0] = 1.0 / m[0][0];
@@ -88,7 +95,82 @@ __device__ __forceinline__ bool inverse_fast(const double (&m)[N][N], double (&o
 
 template <int N>
 __device__ __forceinline__ bool na_try_inverse(const double (&m)[N][N], double (&o)[N][N]) {
-    static_assert(N >= 1 && N <= 3, "the stiff path carries n <= 3 (closed-form try_inverse)");
+    static_assert(N >= 1 && N <= 8, "the stiff path carries n <= 8");
+    if constexpr (N == 4) {
+        // `do_inverse4` (nalgebra 0.20 linalg/inverse.rs; MESA's gluInvertMatrix cofactor expansion) on the column-major slice
+        // f[k] = M[k % 4][k / 4]: products and sums left to right, det from the first row of cofactors, then every cofactor is
+        // MULTIPLIED by 1/det (the n <= 3 formulas divide)
+        double f[16], c[16];
+        _Pragma("unroll") for (int k = 0; k < 16; ++k) f[k] = m[k % 4][k / 4];
+        c[0] = f[5] * f[10] * f[15] - f[5] * f[11] * f[14] - f[9] * f[6] * f[15] + f[9] * f[7] * f[14] + f[13] * f[6] * f[11] - f[13] * f[7] * f[10];
+        c[1] = -f[1] * f[10] * f[15] + f[1] * f[11] * f[14] + f[9] * f[2] * f[15] - f[9] * f[3] * f[14] - f[13] * f[2] * f[11] + f[13] * f[3] * f[10];
+        c[2] = f[1] * f[6] * f[15] - f[1] * f[7] * f[14] - f[5] * f[2] * f[15] + f[5] * f[3] * f[14] + f[13] * f[2] * f[7] - f[13] * f[3] * f[6];
+        c[3] = -f[1] * f[6] * f[11] + f[1] * f[7] * f[10] + f[5] * f[2] * f[11] - f[5] * f[3] * f[10] - f[9] * f[2] * f[7] + f[9] * f[3] * f[6];
+        c[4] = -f[4] * f[10] * f[15] + f[4] * f[11] * f[14] + f[8] * f[6] * f[15] - f[8] * f[7] * f[14] - f[12] * f[6] * f[11] + f[12] * f[7] * f[10];
+        c[5] = f[0] * f[10] * f[15] - f[0] * f[11] * f[14] - f[8] * f[2] * f[15] + f[8] * f[3] * f[14] + f[12] * f[2] * f[11] - f[12] * f[3] * f[10];
+        c[6] = -f[0] * f[6] * f[15] + f[0] * f[7] * f[14] + f[4] * f[2] * f[15] - f[4] * f[3] * f[14] - f[12] * f[2] * f[7] + f[12] * f[3] * f[6];
+        c[7] = f[0] * f[6] * f[11] - f[0] * f[7] * f[10] - f[4] * f[2] * f[11] + f[4] * f[3] * f[10] + f[8] * f[2] * f[7] - f[8] * f[3] * f[6];
+        c[8] = f[4] * f[9] * f[15] - f[4] * f[11] * f[13] - f[8] * f[5] * f[15] + f[8] * f[7] * f[13] + f[12] * f[5] * f[11] - f[12] * f[7] * f[9];
+        c[9] = -f[0] * f[9] * f[15] + f[0] * f[11] * f[13] + f[8] * f[1] * f[15] - f[8] * f[3] * f[13] - f[12] * f[1] * f[11] + f[12] * f[3] * f[9];
+        c[10] = f[0] * f[5] * f[15] - f[0] * f[7] * f[13] - f[4] * f[1] * f[15] + f[4] * f[3] * f[13] + f[12] * f[1] * f[7] - f[12] * f[3] * f[5];
+        c[11] = -f[0] * f[5] * f[11] + f[0] * f[7] * f[9] + f[4] * f[1] * f[11] - f[4] * f[3] * f[9] - f[8] * f[1] * f[7] + f[8] * f[3] * f[5];
+        c[12] = -f[4] * f[9] * f[14] + f[4] * f[10] * f[13] + f[8] * f[5] * f[14] - f[8] * f[6] * f[13] - f[12] * f[5] * f[10] + f[12] * f[6] * f[9];
+        c[13] = f[0] * f[9] * f[14] - f[0] * f[10] * f[13] - f[8] * f[1] * f[14] + f[8] * f[2] * f[13] + f[12] * f[1] * f[10] - f[12] * f[2] * f[9];
+        c[14] = -f[0] * f[5] * f[14] + f[0] * f[6] * f[13] + f[4] * f[1] * f[14] - f[4] * f[2] * f[13] - f[12] * f[1] * f[6] + f[12] * f[2] * f[5];
+        c[15] = f[0] * f[5] * f[10] - f[0] * f[6] * f[9] - f[4] * f[1] * f[10] + f[4] * f[2] * f[9] + f[8] * f[1] * f[6] - f[8] * f[2] * f[5];
+        const double det = f[0] * c[0] + f[1] * c[4] + f[2] * c[8] + f[3] * c[12];
+        if (det == 0.0) return false;
+        const double inv_det = 1.0 / det;
+        _Pragma("unroll") for (int k = 0; k < 16; ++k) o[k % 4][k / 4] = c[k] * inv_det;
+    } else if constexpr (N >= 5) {
+        // `lu::try_invert_to` (nalgebra 0.20 linalg/lu.rs), what try_inverse does for n >= 5: Gaussian elimination with partial
+        // pivoting on a copy (first largest |.|, multipliers a_ji * (1/pivot), update a_jk = (-p_k) l_j + a_jk; a zero pivot fails),
+        // the row swaps applied to an identity `o`; then o <- L^-1 o (unit diagonal, forward, column by column) and o <- U^-1 o
+        // (backward: coeff = b_i / u_ii, b_j = (-coeff) u_ji + b_j for j < i)
+        double a[N][N];
+        _Pragma("unroll") for (int r = 0; r < N; ++r) {
+        _Pragma("unroll")     for (int cc = 0; cc < N; ++cc) { a[r][cc] = m[r][cc]; o[r][cc] = r == cc ? 1.0 : 0.0; }
+        }
+        bool ok = true;
+        _Pragma("unroll") for (int i = 0; i < N; ++i) {
+            int piv = i;
+            double best = fabs(a[i][i]);
+        _Pragma("unroll")     for (int r = i + 1; r < N; ++r) { const double v = fabs(a[r][i]); if (v > best) { best = v; piv = r; } }
+        _Pragma("unroll")     for (int r = i + 1; r < N; ++r) {
+                if (piv == r) {
+        _Pragma("unroll")             for (int cc = 0; cc < N; ++cc) {
+                        double tmp = a[i][cc]; a[i][cc] = a[r][cc]; a[r][cc] = tmp;
+                        tmp = o[i][cc]; o[i][cc] = o[r][cc]; o[r][cc] = tmp;
+                    }
+                }
+            }
+            const double diag = a[i][i];
+            if (diag == 0.0) ok = false;
+            const double inv = 1.0 / diag;
+        _Pragma("unroll")     for (int r = i + 1; r < N; ++r) a[r][i] = a[r][i] * inv;
+        _Pragma("unroll")     for (int k = i + 1; k < N; ++k) {
+                const double p = -a[i][k];
+        _Pragma("unroll")         for (int r = i + 1; r < N; ++r) a[r][k] = p * a[r][i] + a[r][k];
+            }
+        }
+        if (!ok) return false;   // (the reference returns at the first zero pivot; nothing computed after it is used)
+        _Pragma("unroll") for (int k = 0; k < N; ++k) {
+        _Pragma("unroll")     for (int i = 0; i + 1 < N; ++i) {
+                const double coeff = o[i][k] / 1.0;
+        _Pragma("unroll")         for (int r = i + 1; r < N; ++r) o[r][k] = (-coeff) * a[r][i] + o[r][k];
+            }
+        }
+        _Pragma("unroll") for (int k = 0; k < N; ++k) {
+        _Pragma("unroll")     for (int i = N - 1; i >= 0; --i) {
+                const double diag = a[i][i];
+                if (diag == 0.0) ok = false;
+                const double coeff = o[i][k] / diag;
+                o[i][k] = coeff;
+        _Pragma("unroll")         for (int r = 0; r < i; ++r) o[r][k] = (-coeff) * a[r][i] + o[r][k];
+            }
+        }
+        if (!ok) return false;
+    } else
     if constexpr (N == 1) {
         const double det = m[0][0];
         if (det == 0.0) return false;

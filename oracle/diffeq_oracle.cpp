@@ -171,7 +171,7 @@ bool make_tableau(int method, int set, Tableau& t) {
 // ------------------------------------------------------------------------------------------
 // Built-in right-hand sides (the reference takes a closure F: Fn(f64,&Y)->Y, problem.rs:32-36).
 // ------------------------------------------------------------------------------------------
-enum Rhs { LORENZ = 0, VANDERPOL = 1, PENDULUM = 2, RING8 = 3, RING16 = 4, RING32 = 5, RING64 = 6 };
+enum Rhs { LORENZ = 0, VANDERPOL = 1, PENDULUM = 2, RING8 = 3, RING16 = 4, RING32 = 5, RING64 = 6, CVDP2 = 7, CVDP3 = 8 };
 
 struct LorenzF {  // problem.rs:989-1000: params = {sigma, rho, beta}
     static constexpr int N = 3;
@@ -192,6 +192,20 @@ struct RingF {
         for (int i = 0; i < NN; ++i) {
             const int ip = (i + 1) % NN, im = (i + NN - 1) % NN;
             d[i] = p[0] * (v[ip] - v[i]) + p[1] * (v[i] * (1.0 - v[im]));
+        }
+    }
+};
+// Test systems for the stiff path beyond n = 3 (not in the reference; the product's user source states the same expression):
+// M Van der Pol oscillators in a ring, state (x_0, y_0, x_1, y_1, ...), params = {mu, kappa},
+//   x_i' = y_i,   y_i' = mu * (1 - x_i^2) * y_i - x_i + kappa * (x_{i+1} - x_i)
+template <int M>
+struct CoupledVdpF {
+    static constexpr int N = 2 * M;
+    static inline void eval(double, const double* v, double* d, const double* p) {
+        for (int i = 0; i < M; ++i) {
+            const double x = v[2 * i], y = v[2 * i + 1], xn = v[2 * ((i + 1) % M)];
+            d[2 * i] = y;
+            d[2 * i + 1] = p[0] * (1.0 - x * x) * y - x + p[1] * (xn - x);
         }
     }
 };
@@ -453,8 +467,8 @@ int solve_adapt(const Tableau& tb, const double* y0, const double* tspan, size_t
 //                                               multipliers l = a_ji * (1/pivot), update a_jk = (-p_k)*l_j + a_jk,
 //                                               a column whose pivot is exactly zero is skipped;
 //     `lu_internal()`                           the packed L\U matrix, permutation dropped;
-//   * `M.try_inverse()` (linalg/inverse.rs)     closed-form adjugate formulas for n = 1, 2, 3 — n >= 4 (4x4 cofactor
-//                                               routine / LU inverse) is not restated: the stiff path is n <= 3 here.
+//   * `M.try_inverse()` (linalg/inverse.rs)     closed-form adjugate formulas for n = 1, 2, 3; `do_inverse4` (the 4x4
+//                                               cofactor routine) for n = 4; `lu::try_invert_to` for n >= 5.
 // ==========================================================================================
 enum { ST_INVALID_MATRIX = 3 };
 
@@ -477,7 +491,83 @@ inline void na_lu_packed(double m[N][N]) {
 
 template <int N>
 inline bool na_try_inverse(const double m[N][N], double o[N][N]) {
-    static_assert(N >= 1 && N <= 3, "try_inverse restated for n <= 3");
+    if constexpr (N == 4) {
+        // `do_inverse4` (nalgebra 0.20 linalg/inverse.rs; MESA's gluInvertMatrix cofactor expansion) on the column-major slice
+        // f[k] = M[k % 4][k / 4]: products and sums left to right, det from the first row of cofactors, then every cofactor is
+        // MULTIPLIED by 1/det (the n <= 3 formulas divide)
+        double f[16], c[16];
+        for (int k = 0; k < 16; ++k) f[k] = m[k % 4][k / 4];
+        c[0] = f[5] * f[10] * f[15] - f[5] * f[11] * f[14] - f[9] * f[6] * f[15] + f[9] * f[7] * f[14] + f[13] * f[6] * f[11] - f[13] * f[7] * f[10];
+        c[1] = -f[1] * f[10] * f[15] + f[1] * f[11] * f[14] + f[9] * f[2] * f[15] - f[9] * f[3] * f[14] - f[13] * f[2] * f[11] + f[13] * f[3] * f[10];
+        c[2] = f[1] * f[6] * f[15] - f[1] * f[7] * f[14] - f[5] * f[2] * f[15] + f[5] * f[3] * f[14] + f[13] * f[2] * f[7] - f[13] * f[3] * f[6];
+        c[3] = -f[1] * f[6] * f[11] + f[1] * f[7] * f[10] + f[5] * f[2] * f[11] - f[5] * f[3] * f[10] - f[9] * f[2] * f[7] + f[9] * f[3] * f[6];
+        c[4] = -f[4] * f[10] * f[15] + f[4] * f[11] * f[14] + f[8] * f[6] * f[15] - f[8] * f[7] * f[14] - f[12] * f[6] * f[11] + f[12] * f[7] * f[10];
+        c[5] = f[0] * f[10] * f[15] - f[0] * f[11] * f[14] - f[8] * f[2] * f[15] + f[8] * f[3] * f[14] + f[12] * f[2] * f[11] - f[12] * f[3] * f[10];
+        c[6] = -f[0] * f[6] * f[15] + f[0] * f[7] * f[14] + f[4] * f[2] * f[15] - f[4] * f[3] * f[14] - f[12] * f[2] * f[7] + f[12] * f[3] * f[6];
+        c[7] = f[0] * f[6] * f[11] - f[0] * f[7] * f[10] - f[4] * f[2] * f[11] + f[4] * f[3] * f[10] + f[8] * f[2] * f[7] - f[8] * f[3] * f[6];
+        c[8] = f[4] * f[9] * f[15] - f[4] * f[11] * f[13] - f[8] * f[5] * f[15] + f[8] * f[7] * f[13] + f[12] * f[5] * f[11] - f[12] * f[7] * f[9];
+        c[9] = -f[0] * f[9] * f[15] + f[0] * f[11] * f[13] + f[8] * f[1] * f[15] - f[8] * f[3] * f[13] - f[12] * f[1] * f[11] + f[12] * f[3] * f[9];
+        c[10] = f[0] * f[5] * f[15] - f[0] * f[7] * f[13] - f[4] * f[1] * f[15] + f[4] * f[3] * f[13] + f[12] * f[1] * f[7] - f[12] * f[3] * f[5];
+        c[11] = -f[0] * f[5] * f[11] + f[0] * f[7] * f[9] + f[4] * f[1] * f[11] - f[4] * f[3] * f[9] - f[8] * f[1] * f[7] + f[8] * f[3] * f[5];
+        c[12] = -f[4] * f[9] * f[14] + f[4] * f[10] * f[13] + f[8] * f[5] * f[14] - f[8] * f[6] * f[13] - f[12] * f[5] * f[10] + f[12] * f[6] * f[9];
+        c[13] = f[0] * f[9] * f[14] - f[0] * f[10] * f[13] - f[8] * f[1] * f[14] + f[8] * f[2] * f[13] + f[12] * f[1] * f[10] - f[12] * f[2] * f[9];
+        c[14] = -f[0] * f[5] * f[14] + f[0] * f[6] * f[13] + f[4] * f[1] * f[14] - f[4] * f[2] * f[13] - f[12] * f[1] * f[6] + f[12] * f[2] * f[5];
+        c[15] = f[0] * f[5] * f[10] - f[0] * f[6] * f[9] - f[4] * f[1] * f[10] + f[4] * f[2] * f[9] + f[8] * f[1] * f[6] - f[8] * f[2] * f[5];
+        const double det = f[0] * c[0] + f[1] * c[4] + f[2] * c[8] + f[3] * c[12];
+        if (det == 0.0) return false;
+        const double inv_det = 1.0 / det;
+        for (int k = 0; k < 16; ++k) o[k % 4][k / 4] = c[k] * inv_det;
+        return true;
+    } else if constexpr (N >= 5) {
+        // `lu::try_invert_to` (nalgebra 0.20 linalg/lu.rs), what try_inverse does for n >= 5: Gaussian elimination with partial
+        // pivoting on a copy (first largest |.|, multipliers a_ji * (1/pivot), update a_jk = (-p_k) l_j + a_jk; a zero pivot fails),
+        // the row swaps applied to an identity `o`; then o <- L^-1 o (unit diagonal, forward, column by column) and o <- U^-1 o
+        // (backward: coeff = b_i / u_ii, b_j = (-coeff) u_ji + b_j for j < i)
+        double a[N][N];
+        for (int r = 0; r < N; ++r) {
+            for (int cc = 0; cc < N; ++cc) { a[r][cc] = m[r][cc]; o[r][cc] = r == cc ? 1.0 : 0.0; }
+        }
+        bool ok = true;
+        for (int i = 0; i < N; ++i) {
+            int piv = i;
+            double best = std::fabs(a[i][i]);
+            for (int r = i + 1; r < N; ++r) { const double v = std::fabs(a[r][i]); if (v > best) { best = v; piv = r; } }
+            for (int r = i + 1; r < N; ++r) {
+                if (piv == r) {
+                    for (int cc = 0; cc < N; ++cc) {
+                        double tmp = a[i][cc]; a[i][cc] = a[r][cc]; a[r][cc] = tmp;
+                        tmp = o[i][cc]; o[i][cc] = o[r][cc]; o[r][cc] = tmp;
+                    }
+                }
+            }
+            const double diag = a[i][i];
+            if (diag == 0.0) ok = false;
+            const double inv = 1.0 / diag;
+            for (int r = i + 1; r < N; ++r) a[r][i] = a[r][i] * inv;
+            for (int k = i + 1; k < N; ++k) {
+                const double p = -a[i][k];
+                for (int r = i + 1; r < N; ++r) a[r][k] = p * a[r][i] + a[r][k];
+            }
+        }
+        if (!ok) return false;   // (the reference returns at the first zero pivot; nothing computed after it is used)
+        for (int k = 0; k < N; ++k) {
+            for (int i = 0; i + 1 < N; ++i) {
+                const double coeff = o[i][k] / 1.0;
+                for (int r = i + 1; r < N; ++r) o[r][k] = (-coeff) * a[r][i] + o[r][k];
+            }
+        }
+        for (int k = 0; k < N; ++k) {
+            for (int i = N - 1; i >= 0; --i) {
+                const double diag = a[i][i];
+                if (diag == 0.0) ok = false;
+                const double coeff = o[i][k] / diag;
+                o[i][k] = coeff;
+                for (int r = 0; r < i; ++r) o[r][k] = (-coeff) * a[r][i] + o[r][k];
+            }
+        }
+        if (!ok) return false;
+        return true;
+    } else
     if constexpr (N == 1) {
         const double det = m[0][0];
         if (det == 0.0) return false;
@@ -813,6 +903,8 @@ int dispatch_rhs(int rhs, Fn&& fn) {
         case RING16: return fn(RingF<16>());
         case RING32: return fn(RingF<32>());
         case RING64: return fn(RingF<64>());
+        case CVDP2: return fn(CoupledVdpF<2>());
+        case CVDP3: return fn(CoupledVdpF<3>());
         default: return ERR_UNSUPPORTED;
     }
 }
@@ -833,8 +925,8 @@ struct oracle_opts {
     int libm_folded;
 };
 
-int oracle_rhs_dim(int rhs) { return rhs == LORENZ ? 3 : (rhs == VANDERPOL || rhs == PENDULUM) ? 2 : rhs == RING8 ? 8 : rhs == RING16 ? 16 : rhs == RING32 ? 32 : rhs == RING64 ? 64 : -1; }
-int oracle_rhs_nparams(int rhs) { return rhs == LORENZ ? 3 : rhs == VANDERPOL ? 1 : rhs == PENDULUM ? 3 : (rhs >= RING8 && rhs <= RING64) ? 2 : -1; }
+int oracle_rhs_dim(int rhs) { return rhs == LORENZ ? 3 : (rhs == VANDERPOL || rhs == PENDULUM) ? 2 : rhs == RING8 ? 8 : rhs == RING16 ? 16 : rhs == RING32 ? 32 : rhs == RING64 ? 64 : rhs == CVDP2 ? 4 : rhs == CVDP3 ? 6 : -1; }
+int oracle_rhs_nparams(int rhs) { return rhs == LORENZ ? 3 : rhs == VANDERPOL ? 1 : rhs == PENDULUM ? 3 : (rhs >= RING8 && rhs <= CVDP3) ? 2 : -1; }
 
 // itertools_num::linspace as recalled (unpinned third-party): a + ((b-a)/(n-1))*i
 void oracle_linspace(double a, double b, size_t n, double* out) {
@@ -1017,7 +1109,7 @@ int oracle_solve_ode23s(int set, int rhs, const double* params, const double* y0
     Opts op{o->reltol, o->abstol, o->has_minstep, o->minstep, o->has_maxstep, o->maxstep, o->initstep, o->points, o->max_steps, o->libm_folded};
     return dispatch_rhs(rhs, [&](auto f) {
         using F = decltype(f);
-        if constexpr (F::N > 3) return (int)ERR_UNSUPPORTED; else {
+        if constexpr (F::N > 8) return (int)ERR_UNSUPPORTED; else {
         Sink sink; sink.tout = tout; sink.yout = yout; sink.cap = cap; sink.N = F::N;
         Counters c;
         int rc = solve_ode23s<F::N, F>(y0, tspan, nt, params, op, set == 1, sink, c, yfinal);
@@ -1040,7 +1132,7 @@ int oracle_ensemble_ode23s(int set, int rhs, size_t ntraj, const double* y0, con
     return dispatch_rhs(rhs, [&](auto f) {
         using F = decltype(f);
         constexpr int N = F::N;
-        if constexpr (N > 3) return (int)ERR_UNSUPPORTED; else {
+        if constexpr (N > 8) return (int)ERR_UNSUPPORTED; else {
 #ifdef _OPENMP
         if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -1071,7 +1163,7 @@ int oracle_solve_rosenbrock(int which, int rhs, const double* params, const doub
     const RosenbrockCoeffs co = rosenbrock_coeffs(which);
     return dispatch_rhs(rhs, [&](auto f) {
         using F = decltype(f);
-        if constexpr (F::N > 3) return (int)ERR_UNSUPPORTED; else
+        if constexpr (F::N > 8) return (int)ERR_UNSUPPORTED; else
         return solve_rosenbrock<F::N, F>(co, y0, tspan, nt, params, yout, yfinal, status, nfe, rows);
     });
 }
@@ -1085,7 +1177,7 @@ int oracle_ensemble_rosenbrock(int which, int rhs, size_t ntraj, const double* y
     return dispatch_rhs(rhs, [&](auto f) {
         using F = decltype(f);
         constexpr int N = F::N;
-        if constexpr (N > 3) return (int)ERR_UNSUPPORTED; else {
+        if constexpr (N > 8) return (int)ERR_UNSUPPORTED; else {
 #ifdef _OPENMP
         if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif

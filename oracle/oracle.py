@@ -19,6 +19,7 @@ _LIB = None
 # `Ode` enum order (mod.rs:14-26) + ODE21 extension
 FEULER, HEUN, MIDPOINT, ODE23, ODE23S, ODE4, ODE45, ODE45FE, ODE4SKR, ODE4SS, ODE78, ODE21 = range(12)
 LORENZ, VANDERPOL, PENDULUM = 0, 1, 2
+CVDP2, CVDP3 = 7, 8   # 2 / 3 Van der Pol oscillators in a ring (dimension 4 / 6): the stiff path beyond the closed-form inverses
 RING8, RING16, RING32, RING64 = 3, 4, 5, 6   # test systems of dimension 8 .. 64 (ring of coupled logistic cells) for the generic-dimension path
 REFERENCE, TEXTBOOK = 0, 1
 POINTS_ALL, POINTS_SPECIFIED = 0, 1

@@ -70,6 +70,21 @@ def ring(p, n):
     return lambda t, v: [kappa * (v[(i + 1) % n] - v[i]) + r * (v[i] * (1.0 - v[(i + n - 1) % n])) for i in range(n)]
 
 
+def coupled_vdp(p, m):
+    """The oracle's CoupledVdpF test system (dimension 2 m): m Van der Pol oscillators in a ring, state (x_0, y_0, x_1, ...),
+    x_i' = y_i, y_i' = mu (1 - x_i^2) y_i - x_i + kappa (x_{i+1} - x_i)."""
+    mu, kappa = p
+
+    def f(t, v):
+        d = []
+        for i in range(m):
+            x, y, xn = v[2 * i], v[2 * i + 1], v[2 * ((i + 1) % m)]
+            d.append(y)
+            d.append(mu * (1.0 - x * x) * y - x + kappa * (xn - x))
+        return d
+    return f
+
+
 def is_fsal(tb):
     """runge_kutta.rs:185-193 (b.as_slice() is column-major: the first S entries are column 0)."""
     S = len(tb["c"])
@@ -269,7 +284,8 @@ def oderk_adapt(f, tb, y0, tspan, reltol=1e-5, abstol=1e-8, minstep=None, maxste
 #   * `M.lu()` (linalg/lu.rs): partial pivoting on the first largest |.| (icamax), multipliers = a_ji * (1/pivot),
 #     trailing update a_jk = (-p_k)*l_j + a_jk, columns with a zero pivot skipped; `lu_internal()` is the packed L\U
 #     matrix WITHOUT the permutation;
-#   * `M.try_inverse()` (linalg/inverse.rs): closed-form adjugate formulas for n = 1, 2, 3 (n >= 4 is not restated here).
+#   * `M.try_inverse()` (linalg/inverse.rs): closed-form adjugate formulas for n = 1, 2, 3; the 4x4 cofactor routine
+#     (`do_inverse4`) for n = 4; `lu::try_invert_to` for n >= 5.
 # ---------------------------------------------------------------------------------------------------------------------
 SQRT2 = math.sqrt(2.0)
 
@@ -319,7 +335,81 @@ def na_try_inverse(m):
         return [[minor_m12_m23 / det, (m13 * m32 - m33 * m12) / det, (m12 * m23 - m22 * m13) / det],
                 [-minor_m11_m23 / det, (m11 * m33 - m31 * m13) / det, (m13 * m21 - m23 * m11) / det],
                 [minor_m11_m22 / det, (m12 * m31 - m32 * m11) / det, (m11 * m22 - m21 * m12) / det]]
-    raise NotImplementedError("try_inverse for n >= 4")
+    if n == 4:
+        return _na_inverse4(m)
+    return _na_lu_invert(m)
+
+
+def _na_inverse4(mat):
+    """`do_inverse4` (nalgebra 0.20 linalg/inverse.rs): the cofactor expansion of MESA's gluInvertMatrix on the column-major
+    slice m[k] = M[k % 4][k / 4]; products left to right, sums left to right; det from the first row of cofactors; the
+    cofactors are then MULTIPLIED by 1/det (not divided, unlike the n <= 3 formulas)."""
+    m = [mat[k % 4][k // 4] for k in range(16)]
+    o = [0.0] * 16
+    o[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10]
+    o[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10]
+    o[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6]
+    o[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6]
+    o[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10]
+    o[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10]
+    o[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6]
+    o[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6]
+    o[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9]
+    o[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9]
+    o[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5]
+    o[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5]
+    o[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9]
+    o[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9]
+    o[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5]
+    o[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5]
+    det = m[0] * o[0] + m[1] * o[4] + m[2] * o[8] + m[3] * o[12]
+    if det == 0.0:
+        return None
+    inv_det = 1.0 / det
+    return [[o[c * 4 + r] * inv_det for c in range(4)] for r in range(4)]
+
+
+def _na_lu_invert(mat):
+    """`lu::try_invert_to` (nalgebra 0.20 linalg/lu.rs), what try_inverse does for n >= 5: Gaussian elimination with partial
+    pivoting on a copy (first largest |.|, multipliers a_ji * (1/pivot), update a_jk = (-p_k) l_j + a_jk; a zero pivot fails)
+    with the row swaps applied to an identity `out`; then out <- L^-1 out (unit diagonal, forward, column by column) and
+    out <- U^-1 out (backward: coeff = b_i / u_ii, b_j = (-coeff) u_ji + b_j for j < i)."""
+    n = len(mat)
+    m = [list(r) for r in mat]
+    out = [[1.0 if r == c else 0.0 for c in range(n)] for r in range(n)]
+    for i in range(n):
+        piv, best = i, abs(m[i][i])
+        for r in range(i + 1, n):
+            if abs(m[r][i]) > best:
+                best, piv = abs(m[r][i]), r
+        diag = m[piv][i]
+        if diag == 0.0:
+            return None
+        if piv != i:
+            out[i], out[piv] = out[piv], out[i]
+            m[i], m[piv] = m[piv], m[i]
+        inv = 1.0 / diag
+        for r in range(i + 1, n):
+            m[r][i] = m[r][i] * inv
+        for k in range(i + 1, n):
+            a = -m[i][k]
+            for r in range(i + 1, n):
+                m[r][k] = a * m[r][i] + m[r][k]
+    for k in range(n):          # solve_lower_triangular_with_diag_mut(out, 1.0)
+        for i in range(n - 1):
+            coeff = out[i][k] / 1.0
+            for r in range(i + 1, n):
+                out[r][k] = (-coeff) * m[r][i] + out[r][k]
+    for k in range(n):          # solve_upper_triangular_mut(out)
+        for i in range(n - 1, -1, -1):
+            diag = m[i][i]
+            if diag == 0.0:
+                return None
+            coeff = out[i][k] / diag
+            out[i][k] = coeff
+            for r in range(i):
+                out[r][k] = (-coeff) * m[r][i] + out[r][k]
+    return out
 
 
 def na_gemv(m, v):

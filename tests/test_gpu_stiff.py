@@ -278,9 +278,54 @@ def test_stiff_nvrtc_user_rhs(deq, oracle):
     assert abs(a.final[0, 0] - exact) < 1e-5
 
 
+USER_CVDP = r'''
+// DEQ_USER_N / 2 Van der Pol oscillators in a ring (the oracle's CoupledVdpF): same expression, same order
+__device__ void rhs(double t, const double* v, double* d, const double* p) {
+    const int M = DEQ_USER_N / 2;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        const double x = v[2 * i], y = v[2 * i + 1], xn = v[2 * ((i + 1) % M)];
+        d[2 * i] = y;
+        d[2 * i + 1] = p[0] * (1.0 - x * x) * y - x + p[1] * (xn - x);
+    }
+}
+'''
+
+
+@pytest.mark.parametrize("n", [4, 6])
+def test_stiff_beyond_closed_form_inverses(deq, oracle, n):
+    """n = 4 goes through nalgebra's 4x4 cofactor inverse (`do_inverse4`), n = 6 through its LU-based `try_inverse`
+    (problem.rs:481,588 on a DMatrix of any size): ode23s in both W-inverse variants (final states, counters, dense rows) and
+    both Rosenbrock coefficient sets against the oracle, bit for bit; the committed pyref goldens pin the oracle."""
+    osys = oracle.CVDP2 if n == 4 else oracle.CVDP3
+    rng = np.random.default_rng(n)
+    m = 150
+    y0 = rng.uniform(-2.0, 2.0, (m, n))
+    prm = np.column_stack([np.geomspace(0.5, 300.0, m), rng.uniform(0.0, 2.0, m)])
+    rhs = deq.Rhs.from_source(USER_CVDP, n, 2)
+    ts = deq.linspace(0.0, 12.0, 25)
+    prob = deq.OdeProblem.builder().fun(rhs).params(prm).init(y0).tspan(ts).build()
+    for tset in (0, 1):
+        oo = oracle.opts(1e-5, 1e-8, max_steps=20000)
+        ref = oracle.ensemble_ode23s(osys, prm, y0, ts, oo, tset=tset, dense=True)
+        sol = prob.solve(deq.Ode.Ode23s, deq.OdeOptionMap().insert(deq.MaxSteps(20000), deq.Output.Tspan), tableau_set=tset)
+        for k in ("accepted", "rejected", "nfe", "status", "t_reached"):
+            assert np.array_equal(getattr(sol, k), ref[k]), (tset, k)
+        assert np.array_equal(sol.final, ref["yfinal"], equal_nan=True), tset
+        assert np.array_equal(sol.nvalid, ref["nvalid"]) and np.array_equal(sol.yout, ref["out"].transpose(2, 1, 0), equal_nan=True), tset
+    assert (ref["status"] == 0).mean() > 0.9      # the textbook variant integrates the stiff end of the sweep
+    tr = np.linspace(0.0, 0.2, 21)
+    pr = deq.OdeProblem.builder().fun(rhs).params(prm).init(y0).tspan(tr).build()
+    for which, ode in ((oracle.KR4, deq.Ode.Ode4skr), (oracle.S4, deq.Ode.Ode4ss)):
+        rr = oracle.ensemble_rosenbrock(which, osys, prm, y0, tr, want_all=True)
+        sr = pr.solve(ode, deq.OdeOptionMap().insert(deq.Output.Tspan))
+        assert np.array_equal(sr.final, rr["yfinal"], equal_nan=True) and np.array_equal(sr.status, rr["status"]), which
+        assert np.array_equal(sr.yout[::37], rr["yall"][::37], equal_nan=True)
+
+
 def test_stiff_argument_checks(deq):
-    src = "__device__ void rhs(double t, const double* y, double* dy, const double* p) { for (int i = 0; i < 4; ++i) dy[i] = -y[i]; }"
-    p4 = deq.OdeProblem.builder().fun(deq.Rhs.from_source(src, 4, 0)).init([[1.0, 1.0, 1.0, 1.0]]).tspan([0.0, 1.0]).build()
+    src = "__device__ void rhs(double t, const double* y, double* dy, const double* p) { for (int i = 0; i < 9; ++i) dy[i] = -y[i]; }"
+    p4 = deq.OdeProblem.builder().fun(deq.Rhs.from_source(src, 9, 0)).init([[1.0] * 9]).tspan([0.0, 1.0]).build()   # the stiff path carries n <= 8
     for m in (deq.Ode.Ode23s, deq.Ode.Ode4skr, deq.Ode.Ode4ss):
         with pytest.raises(deq.OdeError) as e:
             p4.solve(m)

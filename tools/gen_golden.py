@@ -117,7 +117,8 @@ def linspace(a, b, n):
 
 METHOD_TAB = {"Feuler": "feuler", "Heun": "heun", "Midpoint": "midpoint", "Ode4": "rk4", "Ode21": "rk21", "Ode23": "rk23",
               "Ode45": "dopri5", "Ode45fe": "rk45", "Ode78": "feh78"}
-SYS = {"Lorenz": pyref.lorenz, "VanDerPol": pyref.vanderpol, "Pendulum": pyref.pendulum}
+SYS = {"Lorenz": pyref.lorenz, "VanDerPol": pyref.vanderpol, "Pendulum": pyref.pendulum,
+       "Cvdp2": lambda p: pyref.coupled_vdp(p, 2), "Cvdp3": lambda p: pyref.coupled_vdp(p, 3)}
 
 
 def main():
@@ -269,6 +270,16 @@ def main_stiff():
            [fh_("0x1.0a4941f00af94p+1"), fh_("-0x1.6f0d005933b00p-7")], tset="textbook", reltol=fh_("0x1.3f0fbaf4e45fep-12"),
            abstol=fh_("0x1.4adc292f2891ap-30"), maxstep=fh_("0x1.0bb84ef0642cfp-1"), initstep=fh_("-0x1.58b45d6392d05p-4"))
     ode23s("ode23s_zero_span", "Lorenz", LOR, [1.0, 2.0, 20.0], ["list", 1.0, 1.0], [1.0, 1.0])
+    # n = 4 (nalgebra's 4x4 cofactor inverse) and n = 6 (LU-based try_inverse): coupled Van der Pol oscillators
+    Y4, Y6 = [2.0, 0.0, -1.5, 0.5], [2.0, 0.0, -1.5, 0.5, 0.3, -1.0]
+    for tset in ("reference", "textbook"):
+        ode23s(f"ode23s_{tset}_cvdp2_mu5", "Cvdp2", [5.0, 0.7], Y4, ["list", 0.0, 10.0], [0.0, 10.0], tset=tset, max_steps=20000)
+        ode23s(f"ode23s_{tset}_cvdp3_mu5", "Cvdp3", [5.0, 0.7], Y6, ["list", 0.0, 10.0], [0.0, 10.0], tset=tset, max_steps=20000)
+    ode23s("ode23s_textbook_cvdp2_stiff_dense", "Cvdp2", [200.0, 1.5], Y4, ["linspace", 0.0, 100.0, 51], linspace(0.0, 100.0, 51), tset="textbook",
+           reltol=1e-6, abstol=1e-8)
+    ode23s("ode23s_textbook_cvdp3_stiff_dense", "Cvdp3", [200.0, 1.5], Y6, ["linspace", 0.0, 100.0, 51], linspace(0.0, 100.0, 51), tset="textbook",
+           reltol=1e-6, abstol=1e-8)
+    ode23s("ode23s_cvdp2_singular_w", "Cvdp2", [0.0, 0.0], [0.0, 0.0, 0.0, 0.0], ["list", 0.0, 1.0], [0.0, 1.0], tset="textbook", max_steps=200)
     for which in ("kr4", "s4"):
         rosen(f"{which}_vdp", which, "VanDerPol", [5.0], [2.0, 0.0], ["linspace", 0.0, 0.39, 40], linspace(0.0, 0.39, 40))
         rosen(f"{which}_lorenz", which, "Lorenz", LOR, [0.1, 0.0, 0.0], ["linspace", 0.0, 0.05, 51], linspace(0.0, 0.05, 51))
@@ -276,6 +287,8 @@ def main_stiff():
         rosen(f"{which}_invalid_matrix_step2", which, "Lorenz", [10.0, 0.0, -4.0], [0.0, 0.0, 0.0],
               ["list", 0.0, 0.25, 0.25 + 0.25 / ros[which]["gamma"], 9.0], [0.0, 0.25, 0.25 + 0.25 / ros[which]["gamma"], 9.0])
         rosen(f"{which}_single_point", which, "Lorenz", LOR, [0.1, 0.0, 0.0], ["list", 0.0], [0.0])
+        rosen(f"{which}_cvdp2", which, "Cvdp2", [5.0, 0.7], Y4, ["linspace", 0.0, 0.2, 21], linspace(0.0, 0.2, 21))
+        rosen(f"{which}_cvdp3", which, "Cvdp3", [5.0, 0.7], Y6, ["linspace", 0.0, 0.2, 21], linspace(0.0, 0.2, 21))
     json.dump({"rosenbrock_coeffs": {k: dict(gamma=hx(v["gamma"]), a=hx(v["a"]), b=hx(v["b"]), c=hx(v["c"])) for k, v in ros.items()},
                "cases": cases}, open(os.path.join(OUT, "stiff_cases.json"), "w"), indent=0)
     print(f"wrote {len(cases)} stiff cases to {OUT}")
