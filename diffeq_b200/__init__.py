@@ -124,7 +124,7 @@ ABI_SYMBOLS = [
     "deq_result_final", "deq_result_counts", "deq_result_totals", "deq_result_dense", "deq_result_all_offsets",
     "deq_result_all_copy", "deq_result_device_ptrs",
     "deq_result_trajectory", "deq_result_kernel_ms", "deq_result_destroy", "deq_tableau_get", "deq_rosenbrock_get", "deq_host_alloc",
-    "deq_host_free", "deq_test_pow", "deq_test_log10", "deq_measure_fp64_peak",
+    "deq_host_free", "deq_test_pow", "deq_test_log10", "deq_test_div", "deq_measure_fp64_peak",
 ]
 
 
@@ -191,6 +191,13 @@ def _out_array(out, key, shape, dtype):
     if not a.flags["C_CONTIGUOUS"] or tuple(a.shape) != tuple(shape) or a.dtype.itemsize != np.dtype(dtype).itemsize:
         raise OdeError(10, f"out[{key!r}] must be a C-contiguous {np.dtype(dtype).name} array of shape {tuple(shape)}")
     return a
+
+
+def test_div(seed, count):
+    """Device self-test of the controller's division / reciprocal sequences: (bit mismatches, results checked)."""
+    m, c = C.c_uint64(), C.c_uint64()
+    _check(lib().deq_test_div(C.c_uint64(seed), C.c_uint64(count), C.byref(m), C.byref(c)))
+    return m.value, c.value
 
 
 def set_device(device):

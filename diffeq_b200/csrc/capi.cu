@@ -958,6 +958,20 @@ deq_status deq_test_pow(const double* x, const double* y, double* out, size_t n)
     return DEQ_OK;
 }
 
+deq_status deq_test_div(uint64_t seed, uint64_t count, uint64_t* mismatches, uint64_t* checked) {
+    if (!mismatches || !checked) return fail(DEQ_ERR_INVALID_ARG, "NULL argument");
+    cudaStream_t st = g_stream;
+    TempBuf<unsigned long long> d(st);
+    CK(dalloc(&d.p, 2, st));
+    CK(cudaMemsetAsync(d.p, 0, 2 * sizeof(unsigned long long), st));
+    CK(deql::launch_test_div(seed, count, d.p, st));
+    unsigned long long h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, d.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *mismatches = h[0]; *checked = h[1];
+    return DEQ_OK;
+}
+
 deq_status deq_test_log10(const double* x, double* out, size_t n) {
     if (n == 0) return DEQ_OK;
     cudaStream_t st = g_stream;

@@ -100,6 +100,41 @@ cudaError_t launch_sum_counts(const uint32_t* acc, const uint32_t* rej, const ui
     return cudaGetLastError();
 }
 
+// Self-test of div_main / rcp_main (deq_math.cuh) against the IEEE operators: operand pairs from a counter hash — random
+// mantissas, exponents spread over the whole double range in a quarter of the cases and over the range the step-size
+// controller produces in the rest — compared bit for bit wherever the main-path flag stays clear.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256) test_div_kernel(unsigned long long seed, unsigned long long count, unsigned long long* out) {
+    unsigned long long mism = 0, fast = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long a = mix64(seed + 2 * i), b = mix64(seed + 2 * i + 1), c = mix64(a ^ b);
+        unsigned long long na = a, nb = b;
+        if (c & 3ull) {   // controller-like magnitudes: numerator 2^-60 .. 2^20, denominator 2^-40 .. 2^20
+            na = (a & 0x800fffffffffffffull) | ((unsigned long long)(1023 - 60 + (int)((c >> 8) % 80)) << 52);
+            nb = (b & 0x000fffffffffffffull) | ((unsigned long long)(1023 - 40 + (int)((c >> 20) % 60)) << 52);
+        }
+        const double n = __longlong_as_double((long long)na), d = __longlong_as_double((long long)nb);
+        bool bad = false;
+        const double q = deqm::div_main(n, d, bad);
+        if (!bad) { ++fast; if (__double_as_longlong(q) != __double_as_longlong(n / d)) ++mism; }
+        bool bad2 = false;
+        const double r = deqm::rcp_main(d, bad2);
+        if (!bad2) { ++fast; if (__double_as_longlong(r) != __double_as_longlong(1.0 / d)) ++mism; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mism += __shfl_down_sync(0xffffffffu, mism, o); fast += __shfl_down_sync(0xffffffffu, fast, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out + 0, mism); atomicAdd(out + 1, fast); }
+}
+cudaError_t launch_test_div(unsigned long long seed, unsigned long long count, unsigned long long* d_out, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    test_div_kernel<<<sms * 8, 256, 0, st>>>(seed, count, d_out);
+    return cudaGetLastError();
+}
+
 // DFMA stream: 8 independent accumulator chains per thread, 2 flop per FMA.  The result is written so the loop
 // cannot be removed.  Used to measure the chip's sustained FP64 rate (MEASURED_PEAKS.json has no FP64 figure).
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* sink, int iters) {

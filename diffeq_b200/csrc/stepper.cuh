@@ -90,7 +90,7 @@ __device__ __forceinline__ void load_params(double* prm, const double* params, c
 // Loops over the state components are fully unrolled while the stage vectors fit the register file (N <= 16); for larger
 // systems they stay rolled — `#pragma unroll (N <= 16 ? N : 1)` — which puts the per-thread arrays (k[S][N], stage argument,
 // trial state) into local memory and keeps the code size independent of N.
-template <class TB, class F, bool FAST>
+template <class TB, class F, bool FAST, bool SKIPZ = false>
 __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double dt, double (&k)[TB::S][F::N],
                                        const double* prm, double* ylast = nullptr) {
     DEQ_TAB(TB);
@@ -110,7 +110,7 @@ __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double
 #pragma unroll
             for (int col = 0; col < row; ++col) {
                 if (FAST) { if (tbc.a[row][col] != 0.0) acc = __fma_rn(k[col][d], w[col], acc); }
-                else acc = acc + k[col][d] * w[col];
+                else if (!SKIPZ || tbc.a[row][col] != 0.0) acc = acc + k[col][d] * w[col];
             }
             yi[d] = acc;
         }
@@ -120,6 +120,23 @@ __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double
 #pragma unroll (F::N <= 16 ? F::N : 1)
             for (int d = 0; d < F::N; ++d) ylast[d] = yi[d];
         }
+    }
+}
+
+// The stages exactly as the reference writes them (every zero coefficient multiplied through), behind a call: used by the rare
+// attempts in which the zero-skipping main path is not provably bit-neutral.  kbuf is [S][N] row-major, kbuf[0..N) = k0 on entry.
+template <class TB, class F>
+__device__ __noinline__ void stages_exact_cold(double t, const double* ybuf, double dt, double* kbuf, const double* pbuf) {
+    double y[F::N], k[TB::S][F::N], prm[F::NP ? F::NP : 1];
+#pragma unroll (F::N <= 16 ? F::N : 1)
+    for (int d = 0; d < F::N; ++d) { y[d] = ybuf[d]; k[0][d] = kbuf[d]; }
+#pragma unroll
+    for (int j = 0; j < (F::NP ? F::NP : 1); ++j) prm[j] = pbuf[j];
+    stages<TB, F, false, false>(t, y, dt, k, prm);
+#pragma unroll
+    for (int s = 1; s < TB::S; ++s) {
+#pragma unroll (F::N <= 16 ? F::N : 1)
+        for (int d = 0; d < F::N; ++d) kbuf[s * F::N + d] = k[s][d];
     }
 }
 
@@ -180,6 +197,14 @@ __device__ __forceinline__ double div100_exact(double x) {
     double r = __fma_rn(__fma_rn(-100.0, q, x), R, q);
     if (((hi32(x) & 0x7fffffffu) - 0x07b00000u) >= (0x78300000u - 0x07b00000u)) { DEQ_COLD_PATH(); r = x / 100.; }
     return r;
+}
+
+template <int S_>
+constexpr int zero_entries_of_a(const deqt::Data<S_>& d) {
+    int z = 0;
+    for (int r = 1; r < S_; ++r)
+        for (int c = 0; c < r; ++c) z += d.a[r][c] == 0.0 ? 1 : 0;
+    return z;
 }
 
 template <int S_>
@@ -576,7 +601,38 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                 unsigned accu;   // the accept decision as an opaque integer: ONE FP64 compare, every later test is an integer one
                 const unsigned timeout_next = timeout - (timeout > 0u ? 1u : 0u);   // stepsize_hw92 :835-838
                 if (!FAST) {
-                    stages<TB, F, false>(t, cy, dt, k, prm);
+                    // The reference also adds the stage terms whose coefficient a[row][col] is zero: k * (0 * dt) = +-0 for finite
+                    // k and dt, and x + (+-0) == x bit for bit unless x is -0.0 — which a partial sum y + ... can only be if y
+                    // itself is -0.0 (a sum is -0.0 only when both operands are).  So for tableaus with many structural zeros
+                    // (Fehlberg 7(8): 32 of 78 entries, 160 FP64 instructions per attempt for n = 2) the stages run without those
+                    // terms, and are re-run exactly as written in the rare attempt where a state component is -0.0 or a stage
+                    // value / the step is not finite (decided on high words: float adds and integer compares, no FP64 work).
+                    constexpr bool SKIPZ = zero_entries_of_a(TB::data()) >= 4;
+                    stages<TB, F, false, SKIPZ>(t, cy, dt, k, prm);
+                    if (SKIPZ) {
+                        float m = fabsf(__int_as_float(__double2hiint(dt)));
+                        bool negzero = false;
+#pragma unroll (N <= 16 ? N : 1)
+                        for (int d = 0; d < N; ++d) {
+                            negzero = negzero || (((unsigned)__double2hiint(cy[d]) ^ 0x80000000u) | (unsigned)__double2loint(cy[d])) == 0u;
+#pragma unroll
+                            for (int s2 = 0; s2 < S; ++s2) m = m + fabsf(__int_as_float(__double2hiint(k[s2][d])));
+                        }
+                        if (!(m < 3.0e38f) || negzero) {   // out of line: a second inlined copy of the stage code costs registers on the main path
+                            DEQ_COLD_PATH();
+                            double kbuf[S * N], ybuf[N], pbuf[F::NP ? F::NP : 1];
+#pragma unroll (N <= 16 ? N : 1)
+                            for (int d = 0; d < N; ++d) { ybuf[d] = cy[d]; kbuf[d] = k[0][d]; }
+#pragma unroll
+                            for (int j = 0; j < (F::NP ? F::NP : 1); ++j) pbuf[j] = prm[j];
+                            stages_exact_cold<TB, F>(t, ybuf, dt, kbuf, pbuf);
+#pragma unroll
+                            for (int s2 = 1; s2 < S; ++s2) {
+#pragma unroll (N <= 16 ? N : 1)
+                                for (int d = 0; d < N; ++d) k[s2][d] = kbuf[s2 * N + d];
+                            }
+                        }
+                    }
                     // embedded_step :761-771  (y == cy under Points::All; the last output row under Points::Specified)
                     double ys[N];
 #pragma unroll (N <= 16 ? N : 1)
@@ -585,25 +641,41 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     // stepsize_hw92 :801-845.  The reference first scans the trial state for NaN (-> err = 10, dt *= 0.2,
                     // timeout = 5).  A NaN trial component makes the scaled error sum NaN as well, so the scan only has to
                     // run when the sum is NaN — one test on the hot path instead of N.
+                    // Main path: every division, the reciprocal and both pow calls by their straight-line instruction sequences
+                    // (deq_math.cuh: div_main, rcp_main, pow_glibc_main), the out-of-range conditions OR-ed into ONE flag; if it
+                    // is set — or the error sum is inf / NaN — the block below re-evaluates the controller with the general
+                    // operators and routines.  Same bits either way; eight branch regions fewer per attempt on the main path.
+                    bool redo = false;
                     double ssum = 0.0;
 #pragma unroll (N <= 16 ? N : 1)
                     for (int d = 0; d < N; ++d) {
-                        const double e = yerr[d] / (fabs(absmax_operand(ys[d], ytrial[d])) * reltol + abstol);
+                        const double e = deqm::div_main(yerr[d], fabs(absmax_operand(ys[d], ytrial[d])) * reltol + abstol, redo);
                         const double a = fabs(e);
                         ssum = ssum + a * a;
                     }
-                    double err = P.libm_folded ? sqrt(ssum) : deqm::pow_glibc_hot(ssum, 0.5, T);
-                    const double g = deqm::pow_glibc_hot(1.0 / err, c_pw<TB>[0], T) * DEQ_C08;
+                    double err = P.libm_folded ? sqrt(ssum) : deqm::pow_glibc_main(ssum, 0.5, T, redo);
+                    double g = deqm::pow_glibc_main(deqm::rcp_main(err, redo), c_pw<TB>[0], T, redo) * DEQ_C08;
+                    redo = redo || hi32(ssum) >= 0x7ff00000u;
+                    bool isnan_trial = false;
+                    if (redo) {
+                        DEQ_COLD_PATH();
+                        ssum = 0.0;
+#pragma unroll (N <= 16 ? N : 1)
+                        for (int d = 0; d < N; ++d) {
+                            const double e = yerr[d] / (fabs(absmax_operand(ys[d], ytrial[d])) * reltol + abstol);
+                            const double a = fabs(e);
+                            ssum = ssum + a * a;
+                        }
+                        // the reference first scans the trial state for NaN (stepsize_hw92 :814-822): err = 10, dt *= 0.2, timeout = 5
+#pragma unroll (N <= 16 ? N : 1)
+                        for (int d = 0; d < N; ++d) isnan_trial = isnan_trial || (ytrial[d] != ytrial[d]);
+                        err = P.libm_folded ? sqrt(ssum) : deqm::pow_glibc_cold(ssum, 0.5, T);
+                        g = deqm::pow_glibc_cold(1.0 / err, c_pw<TB>[0], T) * DEQ_C08;
+                    }
                     double nd = sel_min(P.maxstep, (sel_max(DEQ_C02, g) * tdir) * dt);
                     nd = sel_min_if(nd, dt, timeout);
                     ndt = tdir * nd;
-                    if (hi32(ssum) >= 0x7ff00000u) {   // rare: inf or NaN; the reference's rule applies only to a NaN TRIAL STATE
-                        DEQ_COLD_PATH();
-                        bool isnan_trial = false;
-#pragma unroll (N <= 16 ? N : 1)
-                        for (int d = 0; d < N; ++d) isnan_trial = isnan_trial || (ytrial[d] != ytrial[d]);
-                        if (isnan_trial) { err = 10.; ndt = 0.2 * dt; }   // stepsize_hw92 :814-822 (timeout = 5 follows from the reject)
-                    }
+                    if (isnan_trial) { DEQ_COLD_PATH(); err = 10.; ndt = 0.2 * dt; }   // (timeout = 5 follows from the reject)
                     accu = err < 1. ? 1u : 0u;
                 } else {
                     // FAST: same formulas with fused multiply-adds; zero weights skipped; error weights b - b* combined;

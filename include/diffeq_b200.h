@@ -240,6 +240,9 @@ void deq_host_free(void* p);
 /* Device self-tests used by the parity suite: evaluate the library's pow / log10 on the GPU. */
 deq_status deq_test_pow(const double* x, const double* y, double* out, size_t n);
 deq_status deq_test_log10(const double* x, double* out, size_t n);
+/* The controller's straight-line division / reciprocal sequences against the IEEE operators on `count` hashed operand pairs:
+ * number of bit mismatches among the `checked` results whose main-path flag stayed clear (must be 0). */
+deq_status deq_test_div(uint64_t seed, uint64_t count, uint64_t* mismatches, uint64_t* checked);
 /* FP64 roofline denominator: sustained DFMA rate of this GPU in TFLOP/s (FMA = 2 flop). */
 deq_status deq_measure_fp64_peak(double* tflops, double* sm_clock_mhz_hint);
 

@@ -94,5 +94,6 @@ extern "C" {
     pub fn deq_host_free(p: *mut c_void);
     pub fn deq_test_pow(x: *const c_double, y: *const c_double, out: *mut c_double, n: usize) -> deq_status;
     pub fn deq_test_log10(x: *const c_double, out: *mut c_double, n: usize) -> deq_status;
+    pub fn deq_test_div(seed: u64, count: u64, mismatches: *mut u64, checked: *mut u64) -> deq_status;
     pub fn deq_measure_fp64_peak(tflops: *mut c_double, sm_clock_mhz_hint: *mut c_double) -> deq_status;
 }

@@ -100,6 +100,15 @@ def test_cfg2_dopri5_lorenz_ensemble_bit_exact(deq, oracle):
     assert sol.totals["nfe"] == int(ref["nfe"].sum())
 
 
+def test_controller_division_sequences_match_ieee(deq):
+    """div_main / rcp_main (the division and reciprocal of the step-size controller as straight-line instruction sequences,
+    one shared out-of-range flag) against the IEEE operators: 2^30 hashed operand pairs — the full double range and the
+    controller's magnitudes — bit for bit wherever the flag stays clear, and the flag stays clear on most of them."""
+    mism, checked = deq.test_div(0xD1F, 1 << 30)
+    assert mism == 0
+    assert checked > 1.2 * (1 << 30)
+
+
 def test_refill_and_static_scheduling_agree(deq, oracle):
     """Lane refill only changes which lane runs a trajectory, never its arithmetic (shard/schedule invariance)."""
     from diffeq_b200 import synth
