@@ -9,6 +9,14 @@
 // Domain: |x| < 105414350 (glibc's `reduce_sincos` range).  Larger arguments use glibc's Payne–Hanek `__branred`,
 // which is not replicated: they fall back to the platform sin/cos (documented loss of bit parity, never hit by the
 // built-in systems).
+// ---- third-party notice -------------------------------------------------------------------------------------------
+// The algorithms and the table restated in this file are those of the GNU C Library 2.39 (sysdeps/ieee754/dbl-64/s_sin.c,
+// sincostab.c, usncs.h, branred.c: the IBM Accurate Mathematical Library, written by International Business Machines Corp.).
+// Copyright (C) 2001-2024 Free Software Foundation, Inc.  The GNU C Library is free software, distributed under the terms
+// of the GNU Lesser General Public License, version 2.1 or (at your option) any later version
+// (https://www.gnu.org/licenses/lgpl-2.1.html).  This file is a derived work for the purpose of bit-compatibility with glibc
+// and is provided under the same terms, WITHOUT ANY WARRANTY.
+// --------------------------------------------------------------------------------------------------------------------
 #pragma once
 #include "deq_math.cuh"
 #include "deq_sincos_table.h"

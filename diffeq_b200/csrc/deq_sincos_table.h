@@ -1,6 +1,14 @@
 // deq_sincos_table.h — glibc 2.39 `__sincostab` (sysdeps/ieee754/dbl-64/sincostab.c, IBM Accurate Mathematical Library):
 // {sin(x_k), its low part, cos(x_k), its low part} for x_k = k/128, k = 0..109.  Read from the libm.so.6 of this image
 // by tools/gen_sincos_table.py; deq_sincos.cuh built on it is pinned against the running libm (tests/cpp/math_check.cpp).
+// ---- third-party notice -------------------------------------------------------------------------------------------
+// The algorithms and the table restated in this file are those of the GNU C Library 2.39 (sysdeps/ieee754/dbl-64/s_sin.c,
+// sincostab.c, usncs.h, branred.c: the IBM Accurate Mathematical Library, written by International Business Machines Corp.).
+// Copyright (C) 2001-2024 Free Software Foundation, Inc.  The GNU C Library is free software, distributed under the terms
+// of the GNU Lesser General Public License, version 2.1 or (at your option) any later version
+// (https://www.gnu.org/licenses/lgpl-2.1.html).  This file is a derived work for the purpose of bit-compatibility with glibc
+// and is provided under the same terms, WITHOUT ANY WARRANTY.
+// --------------------------------------------------------------------------------------------------------------------
 #pragma once
 #define DEQ_SINCOSTAB_INIT \
     0x0.0p+0, 0x0.0p+0, 0x1.0000000000000p+0, 0x0.0p+0, \
