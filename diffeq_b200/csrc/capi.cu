@@ -477,7 +477,11 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         P.true_inverse = sk && tableau_set == DEQ_TABLEAU_TEXTBOOK; P.points_specified = o.points == DEQ_POINTS_SPECIFIED;
         const int mode = spec ? (int)deqk::MODE_REC_SPEC   // a final-state request runs its counting pass only
                          : want_all ? (int)deqk::MODE_REC
-                         : want_dense ? (o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR ? (int)deqk::MODE_DENSE_TM : (int)deqk::MODE_DENSE) : (int)deqk::MODE_FINAL;
+                         : want_dense ? (o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR ? (int)deqk::MODE_DENSE_TM
+                                         // SoA rows: the row-synchronous kernel (coalesced for any trajectory order) unless the caller
+                                         // asks for the lane-refill kernel (refill == 1), the stiff solver or the f32 flavour
+                                         : (!sk && o.precision == DEQ_PRECISION_F64 && o.refill != 1) ? (int)deqk::MODE_DENSE_ROWS : (int)deqk::MODE_DENSE)
+                         : (int)deqk::MODE_FINAL;
         P.rec_mode = deqk::REC_COUNT;
         r->traj_major = want_dense && o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR;
         P.rec_counts = r->d_rec_counts;

@@ -78,8 +78,22 @@ static cudaError_t launch_adapt_t(const deqk::AdaptParams& P, int grid_blocks, c
     }
 }
 
+template <class F, bool PT>
+static cudaError_t launch_adapt_rows_t(const deqk::AdaptParams& P, int grid_blocks, cudaStream_t st) {
+    if constexpr (TB::ADAPTIVE) {
+        auto kernel = deqk::adapt_rows_kernel<TB, F, PT, kFast>;
+        const int grid = grid_blocks > 0 ? grid_blocks : persistent_grid(kernel, P.ntraj);
+        kernel<<<grid, deqk::BLOCK, 0, st>>>(P);
+        return cudaGetLastError();
+    } else {
+        (void)P; (void)grid_blocks; (void)st;
+        return cudaErrorInvalidValue;
+    }
+}
+
 template <class F>
 static cudaError_t launch_adapt_f(int pt, int mode, const deqk::AdaptParams& P, int grid_blocks, cudaStream_t st) {
+    if (mode == deqk::MODE_DENSE_ROWS) return pt ? launch_adapt_rows_t<F, true>(P, grid_blocks, st) : launch_adapt_rows_t<F, false>(P, grid_blocks, st);
     switch (mode * 2 + (pt ? 1 : 0)) {
         case deqk::MODE_FINAL * 2: return launch_adapt_t<F, false, deqk::MODE_FINAL>(P, grid_blocks, st);
         case deqk::MODE_FINAL * 2 + 1: return launch_adapt_t<F, true, deqk::MODE_FINAL>(P, grid_blocks, st);

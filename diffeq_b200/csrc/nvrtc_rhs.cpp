@@ -148,17 +148,18 @@ static bool get_kernel(Program* p, int kind, int tb, int pt, int mode, Kernel* o
     else if (kind == 1) ne << "&deqk::adapt_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode & 3) << ", "
                            << ((mode & 4) ? "true" : "false") << ", " << ((mode & 8) ? "true" : "false") << ">";
     else if (kind == 2) ne << "&deqk::fixed_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << (mode ? "true" : "false") << ">";
+    else if (kind == 5) ne << "&deqk::adapt_rows_kernel<" << tb_type(tb) << ", DeqUserRhs, " << b << ", " << ((mode & 4) ? "true" : "false") << ">";
     else if (kind == 3) ne << "&deqk::ode23s_kernel<DeqUserRhs, " << b << ", " << (mode & 3) << ", " << ((mode & 4) ? "true" : "false") << ">";
     else ne << "&deqk::rosenbrock_kernel<" << (tb == 0 ? "deqk::Kr4" : "deqk::S4") << ", DeqUserRhs, " << b << ", " << (mode ? "true" : "false") << ">";
     Kernel k;
-    const bool fmad = (kind == 1 || kind == 3) && (mode & 4);
+    const bool fmad = (kind == 1 || kind == 3 || kind == 5) && (mode & 4);
     const std::string gkey = std::to_string(p->n) + "|" + std::to_string(p->np) + "|" + ne.str() + (fmad ? "|fast|" : "|parity|") + p->user_src;
     {
         std::lock_guard<std::mutex> gg(g_cache_mu);
         auto git = g_cache.find(gkey);
         if (git != g_cache.end()) { p->cache[key] = git->second; *out = git->second; return true; }
     }
-    if (!compile(p, ne.str(), fmad, &k, err, kind >= 3)) return false;
+    if (!compile(p, ne.str(), fmad, &k, err, kind == 3 || kind == 4)) return false;
     {
         std::lock_guard<std::mutex> gg(g_cache_mu);
         g_cache[gkey] = k;
@@ -195,9 +196,15 @@ bool launch_hinit(Program* p, int pt, const deqk::HinitParams& P, cudaStream_t s
     return launch(k, (unsigned)((P.ntraj + deqk::BLOCK - 1) / deqk::BLOCK), P, st, err);
 }
 
+static unsigned persistent_blocks(const Kernel& k, unsigned long long ntraj);
+
 bool launch_adapt(Program* p, int tb, int pt, int mode, bool fast, const deqk::AdaptParams& P, cudaStream_t st,
                   std::string* err) {
     Kernel k;
+    if (mode == deqk::MODE_DENSE_ROWS) {   // row-synchronous SoA dense kernel
+        if (!get_kernel(p, 5, tb, pt ? 1 : 0, fast ? 4 : 0, &k, err)) return false;
+        return launch(k, persistent_blocks(k, P.ntraj), P, st, err);
+    }
     const bool spec = mode == deqk::MODE_REC_SPEC;   // Points::Specified flavour of MODE_REC
     if (spec) mode = deqk::MODE_REC;
     if (!get_kernel(p, 1, tb, pt ? 1 : 0, (mode & 3) | (fast ? 4 : 0) | (spec ? 8 : 0), &k, err)) return false;

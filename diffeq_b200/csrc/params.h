@@ -9,6 +9,8 @@ namespace deqk {
 enum : int { MODE_FINAL = 0, MODE_DENSE = 1, MODE_DENSE_TM = 2, MODE_REC = 3 };   // kernel template parameter
 // launcher-level id of the Points::Specified flavour: adapt_kernel<..., MODE_REC, FAST = false, SPEC = true>
 enum : int { MODE_REC_SPEC = 4 };
+// launcher-level id of the row-synchronous SoA dense kernel (adapt_rows_kernel): same output as MODE_DENSE, any trajectory order
+enum : int { MODE_DENSE_ROWS = 5 };
 // the two passes of a MODE_REC kernel (the reference's full ragged Points::All stream): count rows, then write them
 enum : int { REC_COUNT = 1, REC_WRITE = 2 };
 enum : uint8_t { ST_DONE = 0, ST_MINSTEP_BREAK = 1, ST_MAX_STEPS = 2,

@@ -462,6 +462,131 @@ __device__ __forceinline__ void stage_append(double* stage, double* out, StageLa
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The arithmetic of ONE step attempt (problem.rs:261-283: calc_coefficients, embedded_step, stepsize_hw92), shared by the
+// persistent-lane kernel and the row-synchronous dense kernel: from (t, dt, cy, ck) to the stage values k, the trial state,
+// the proposed next step `ndt` and the accept decision `accu` (1 / 0).  `yl` is read by the Points::Specified flavour only.
+// ---------------------------------------------------------------------------------------------------------------
+template <class TB, class F, bool FAST, bool SPEC, class TT>
+__device__ __forceinline__ void attempt_math(const AdaptParams& P, const TT& T, double t, double dt, const double (&cy)[F::N],
+                                             const double (&ck)[F::N], const double (&yl)[F::N], const double* prm, unsigned timeout,
+                                             double tdir, double reltol, double abstol, double (&k)[TB::S][F::N],
+                                             double (&ytrial)[F::N], double& ndt, unsigned& accu) {
+    constexpr int N = F::N, S = TB::S;
+    constexpr bool FSAL = deqt::fsal_of(TB::data());
+    DEQ_TAB(TB);
+#pragma unroll (N <= 16 ? N : 1)
+    for (int d = 0; d < N; ++d) k[0][d] = ck[d];
+    double yerr[N];
+    if (!FAST) {
+        // The reference also adds the stage terms whose coefficient a[row][col] is zero: k * (0 * dt) = +-0 for finite
+        // k and dt, and x + (+-0) == x bit for bit unless x is -0.0 — which a partial sum y + ... can only be if y
+        // itself is -0.0 (a sum is -0.0 only when both operands are).  So for tableaus with many structural zeros
+        // (Fehlberg 7(8): 32 of 78 entries, 160 FP64 instructions per attempt for n = 2) the stages run without those
+        // terms, and are re-run exactly as written in the rare attempt where a state component is -0.0 or a stage
+        // value / the step is not finite (decided on high words: float adds and integer compares, no FP64 work).
+        constexpr bool SKIPZ = zero_entries_of_a(TB::data()) >= 4;
+        stages<TB, F, false, SKIPZ>(t, cy, dt, k, prm);
+        if (SKIPZ) {
+            float m = fabsf(__int_as_float(__double2hiint(dt)));
+            bool negzero = false;
+#pragma unroll (N <= 16 ? N : 1)
+            for (int d = 0; d < N; ++d) {
+                negzero = negzero || (((unsigned)__double2hiint(cy[d]) ^ 0x80000000u) | (unsigned)__double2loint(cy[d])) == 0u;
+#pragma unroll
+                for (int s2 = 0; s2 < S; ++s2) m = m + fabsf(__int_as_float(__double2hiint(k[s2][d])));
+            }
+            if (!(m < 3.0e38f) || negzero) {   // out of line: a second inlined copy of the stage code costs registers on the main path
+                DEQ_COLD_PATH();
+                double kbuf[S * N], ybuf[N], pbuf[F::NP ? F::NP : 1];
+#pragma unroll (N <= 16 ? N : 1)
+                for (int d = 0; d < N; ++d) { ybuf[d] = cy[d]; kbuf[d] = k[0][d]; }
+#pragma unroll
+                for (int j = 0; j < (F::NP ? F::NP : 1); ++j) pbuf[j] = prm[j];
+                stages_exact_cold<TB, F>(t, ybuf, dt, kbuf, pbuf);
+#pragma unroll
+                for (int s2 = 1; s2 < S; ++s2) {
+#pragma unroll (N <= 16 ? N : 1)
+                    for (int d = 0; d < N; ++d) k[s2][d] = kbuf[s2 * N + d];
+                }
+            }
+        }
+        // embedded_step :761-771  (y == cy under Points::All; the last output row under Points::Specified)
+        double ys[N];
+#pragma unroll (N <= 16 ? N : 1)
+        for (int d = 0; d < N; ++d) ys[d] = SPEC ? yl[d] : cy[d];
+        embedded_parity<TB, N>(k, ys, dt, ytrial, yerr);
+        // stepsize_hw92 :801-845.  The reference first scans the trial state for NaN (-> err = 10, dt *= 0.2,
+        // timeout = 5).  A NaN trial component makes the scaled error sum NaN as well, so the scan only has to
+        // run when the sum is NaN — one test on the hot path instead of N.
+        // Main path: every division, the reciprocal and both pow calls by their straight-line instruction sequences
+        // (deq_math.cuh: div_main, rcp_main, pow_glibc_main), the out-of-range conditions OR-ed into ONE flag; if it
+        // is set — or the error sum is inf / NaN — the block below re-evaluates the controller with the general
+        // operators and routines.  Same bits either way; eight branch regions fewer per attempt on the main path.
+        bool redo = false;
+        double ssum = 0.0;
+#pragma unroll (N <= 16 ? N : 1)
+        for (int d = 0; d < N; ++d) {
+            const double e = deqm::div_main(yerr[d], fabs(absmax_operand(ys[d], ytrial[d])) * reltol + abstol, redo);
+            const double a = fabs(e);
+            ssum = ssum + a * a;
+        }
+        double err = P.libm_folded ? sqrt(ssum) : deqm::pow_glibc_main(ssum, 0.5, T, redo);
+        double g = deqm::pow_glibc_main(deqm::rcp_main(err, redo), c_pw<TB>[0], T, redo) * DEQ_C08;
+        redo = redo || hi32(ssum) >= 0x7ff00000u;
+        bool isnan_trial = false;
+        if (redo) {
+            DEQ_COLD_PATH();
+            ssum = 0.0;
+#pragma unroll (N <= 16 ? N : 1)
+            for (int d = 0; d < N; ++d) {
+                const double e = yerr[d] / (fabs(absmax_operand(ys[d], ytrial[d])) * reltol + abstol);
+                const double a = fabs(e);
+                ssum = ssum + a * a;
+            }
+            // the reference first scans the trial state for NaN (stepsize_hw92 :814-822): err = 10, dt *= 0.2, timeout = 5
+#pragma unroll (N <= 16 ? N : 1)
+            for (int d = 0; d < N; ++d) isnan_trial = isnan_trial || (ytrial[d] != ytrial[d]);
+            err = P.libm_folded ? sqrt(ssum) : deqm::pow_glibc_cold(ssum, 0.5, T);
+            g = deqm::pow_glibc_cold(1.0 / err, c_pw<TB>[0], T) * DEQ_C08;
+        }
+        double nd = sel_min(P.maxstep, (sel_max(DEQ_C02, g) * tdir) * dt);
+        nd = sel_min_if(nd, dt, timeout);
+        ndt = tdir * nd;
+        if (isnan_trial) { DEQ_COLD_PATH(); err = 10.; ndt = 0.2 * dt; }   // (timeout = 5 follows from the reject)
+        accu = err < 1. ? 1u : 0u;
+    } else {
+        // FAST: same formulas with fused multiply-adds; zero weights skipped; error weights b - b* combined;
+        // err < 1 decided on the squared norm; one pow for the step factor: 0.8 (1/err)^PW = exp(ln 0.8 - PW/2 ln ssum).
+        // For a first-same-as-last tableau the argument of the last stage is the new solution itself.
+        constexpr auto tbc = TB::data();
+        stages<TB, F, true>(t, cy, dt, k, prm, FSAL ? ytrial : nullptr);
+#pragma unroll (N <= 16 ? N : 1)
+        for (int d = 0; d < N; ++d) {
+            double p = 0.0, e = 0.0;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                if (!FSAL && tbc.b[s][0] != 0.0) p = __fma_rn(k[s][d], tb.b[s][0], p);
+                if (tbc.b[s][0] - tbc.b[s][1] != 0.0) e = __fma_rn(k[s][d], c_errw<TB>.e[s], e);
+            }
+            yerr[d] = e * dt;
+            if (!FSAL) ytrial[d] = __fma_rn(p, dt, cy[d]);
+        }
+        double ssum = 0.0;
+#pragma unroll (N <= 16 ? N : 1)
+        for (int d = 0; d < N; ++d) {
+            const double e = yerr[d] * rcp_fast(__fma_rn(fabs(absmax_operand(cy[d], ytrial[d])), reltol, abstol));
+            ssum = __fma_rn(e, e, ssum);
+        }
+        const double g = deqm::pow_fast_pos(ssum, c_pw<TB>[1], T, c_ctl[3]);
+        double nd = sel_min(P.maxstep, (sel_max(DEQ_C02, g) * tdir) * dt);
+        nd = sel_min_if(nd, dt, timeout);
+        ndt = tdir * nd;
+        if (hi32(ssum) >= 0x7ff00000u) { DEQ_COLD_PATH(); if (ssum != ssum) ndt = 0.2 * dt; }
+        accu = ssum < 1. ? 1u : 0u;   // sqrt(ssum) < 1  <=>  ssum < 1; false for NaN
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Tail compaction: census of a CTA's live trajectories and, when they fit into fewer warps than currently hold them, a
 // repack through shared memory into the lowest lanes of the CTA.  Out of line on purpose: with the barriers inlined into the
 // persistent loop, ptxas hoists tableau constants into general registers and moves them back with R2UR in every attempt.
@@ -519,7 +644,6 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     constexpr bool TM = MODE == MODE_DENSE_TM;    // tspan rows, [ntraj][nt][N], staged through shared memory
     constexpr bool REC = MODE == MODE_REC;        // ragged Points::All stream, counting pass or writing pass (P.rec_mode)
     constexpr bool ROWS = MODE != MODE_FINAL;     // the tspan cursor `it` is tracked
-    DEQ_TAB(TB);
 
     __shared__ uint64_t s_exp[256];
     __shared__ double s_powlog[384];
@@ -593,120 +717,11 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
             uint8_t fin = 0xff;  // 0xff: keep going
             {
                 ++attempts;
-                double k[S][N];
-#pragma unroll (N <= 16 ? N : 1)
-                for (int d = 0; d < N; ++d) k[0][d] = ck[d];
-                double ytrial[N], yerr[N];
+                double k[S][N], ytrial[N];
                 double ndt;
                 unsigned accu;   // the accept decision as an opaque integer: ONE FP64 compare, every later test is an integer one
                 const unsigned timeout_next = timeout - (timeout > 0u ? 1u : 0u);   // stepsize_hw92 :835-838
-                if (!FAST) {
-                    // The reference also adds the stage terms whose coefficient a[row][col] is zero: k * (0 * dt) = +-0 for finite
-                    // k and dt, and x + (+-0) == x bit for bit unless x is -0.0 — which a partial sum y + ... can only be if y
-                    // itself is -0.0 (a sum is -0.0 only when both operands are).  So for tableaus with many structural zeros
-                    // (Fehlberg 7(8): 32 of 78 entries, 160 FP64 instructions per attempt for n = 2) the stages run without those
-                    // terms, and are re-run exactly as written in the rare attempt where a state component is -0.0 or a stage
-                    // value / the step is not finite (decided on high words: float adds and integer compares, no FP64 work).
-                    constexpr bool SKIPZ = zero_entries_of_a(TB::data()) >= 4;
-                    stages<TB, F, false, SKIPZ>(t, cy, dt, k, prm);
-                    if (SKIPZ) {
-                        float m = fabsf(__int_as_float(__double2hiint(dt)));
-                        bool negzero = false;
-#pragma unroll (N <= 16 ? N : 1)
-                        for (int d = 0; d < N; ++d) {
-                            negzero = negzero || (((unsigned)__double2hiint(cy[d]) ^ 0x80000000u) | (unsigned)__double2loint(cy[d])) == 0u;
-#pragma unroll
-                            for (int s2 = 0; s2 < S; ++s2) m = m + fabsf(__int_as_float(__double2hiint(k[s2][d])));
-                        }
-                        if (!(m < 3.0e38f) || negzero) {   // out of line: a second inlined copy of the stage code costs registers on the main path
-                            DEQ_COLD_PATH();
-                            double kbuf[S * N], ybuf[N], pbuf[F::NP ? F::NP : 1];
-#pragma unroll (N <= 16 ? N : 1)
-                            for (int d = 0; d < N; ++d) { ybuf[d] = cy[d]; kbuf[d] = k[0][d]; }
-#pragma unroll
-                            for (int j = 0; j < (F::NP ? F::NP : 1); ++j) pbuf[j] = prm[j];
-                            stages_exact_cold<TB, F>(t, ybuf, dt, kbuf, pbuf);
-#pragma unroll
-                            for (int s2 = 1; s2 < S; ++s2) {
-#pragma unroll (N <= 16 ? N : 1)
-                                for (int d = 0; d < N; ++d) k[s2][d] = kbuf[s2 * N + d];
-                            }
-                        }
-                    }
-                    // embedded_step :761-771  (y == cy under Points::All; the last output row under Points::Specified)
-                    double ys[N];
-#pragma unroll (N <= 16 ? N : 1)
-                    for (int d = 0; d < N; ++d) ys[d] = SPEC ? yl[d] : cy[d];
-                    embedded_parity<TB, N>(k, ys, dt, ytrial, yerr);
-                    // stepsize_hw92 :801-845.  The reference first scans the trial state for NaN (-> err = 10, dt *= 0.2,
-                    // timeout = 5).  A NaN trial component makes the scaled error sum NaN as well, so the scan only has to
-                    // run when the sum is NaN — one test on the hot path instead of N.
-                    // Main path: every division, the reciprocal and both pow calls by their straight-line instruction sequences
-                    // (deq_math.cuh: div_main, rcp_main, pow_glibc_main), the out-of-range conditions OR-ed into ONE flag; if it
-                    // is set — or the error sum is inf / NaN — the block below re-evaluates the controller with the general
-                    // operators and routines.  Same bits either way; eight branch regions fewer per attempt on the main path.
-                    bool redo = false;
-                    double ssum = 0.0;
-#pragma unroll (N <= 16 ? N : 1)
-                    for (int d = 0; d < N; ++d) {
-                        const double e = deqm::div_main(yerr[d], fabs(absmax_operand(ys[d], ytrial[d])) * reltol + abstol, redo);
-                        const double a = fabs(e);
-                        ssum = ssum + a * a;
-                    }
-                    double err = P.libm_folded ? sqrt(ssum) : deqm::pow_glibc_main(ssum, 0.5, T, redo);
-                    double g = deqm::pow_glibc_main(deqm::rcp_main(err, redo), c_pw<TB>[0], T, redo) * DEQ_C08;
-                    redo = redo || hi32(ssum) >= 0x7ff00000u;
-                    bool isnan_trial = false;
-                    if (redo) {
-                        DEQ_COLD_PATH();
-                        ssum = 0.0;
-#pragma unroll (N <= 16 ? N : 1)
-                        for (int d = 0; d < N; ++d) {
-                            const double e = yerr[d] / (fabs(absmax_operand(ys[d], ytrial[d])) * reltol + abstol);
-                            const double a = fabs(e);
-                            ssum = ssum + a * a;
-                        }
-                        // the reference first scans the trial state for NaN (stepsize_hw92 :814-822): err = 10, dt *= 0.2, timeout = 5
-#pragma unroll (N <= 16 ? N : 1)
-                        for (int d = 0; d < N; ++d) isnan_trial = isnan_trial || (ytrial[d] != ytrial[d]);
-                        err = P.libm_folded ? sqrt(ssum) : deqm::pow_glibc_cold(ssum, 0.5, T);
-                        g = deqm::pow_glibc_cold(1.0 / err, c_pw<TB>[0], T) * DEQ_C08;
-                    }
-                    double nd = sel_min(P.maxstep, (sel_max(DEQ_C02, g) * tdir) * dt);
-                    nd = sel_min_if(nd, dt, timeout);
-                    ndt = tdir * nd;
-                    if (isnan_trial) { DEQ_COLD_PATH(); err = 10.; ndt = 0.2 * dt; }   // (timeout = 5 follows from the reject)
-                    accu = err < 1. ? 1u : 0u;
-                } else {
-                    // FAST: same formulas with fused multiply-adds; zero weights skipped; error weights b - b* combined;
-                    // err < 1 decided on the squared norm; one pow for the step factor: 0.8 (1/err)^PW = exp(ln 0.8 - PW/2 ln ssum).
-                    // For a first-same-as-last tableau the argument of the last stage is the new solution itself.
-                    constexpr auto tbc = TB::data();
-                    stages<TB, F, true>(t, cy, dt, k, prm, FSAL ? ytrial : nullptr);
-#pragma unroll (N <= 16 ? N : 1)
-                    for (int d = 0; d < N; ++d) {
-                        double p = 0.0, e = 0.0;
-#pragma unroll
-                        for (int s = 0; s < S; ++s) {
-                            if (!FSAL && tbc.b[s][0] != 0.0) p = __fma_rn(k[s][d], tb.b[s][0], p);
-                            if (tbc.b[s][0] - tbc.b[s][1] != 0.0) e = __fma_rn(k[s][d], c_errw<TB>.e[s], e);
-                        }
-                        yerr[d] = e * dt;
-                        if (!FSAL) ytrial[d] = __fma_rn(p, dt, cy[d]);
-                    }
-                    double ssum = 0.0;
-#pragma unroll (N <= 16 ? N : 1)
-                    for (int d = 0; d < N; ++d) {
-                        const double e = yerr[d] * rcp_fast(__fma_rn(fabs(absmax_operand(cy[d], ytrial[d])), reltol, abstol));
-                        ssum = __fma_rn(e, e, ssum);
-                    }
-                    const double g = deqm::pow_fast_pos(ssum, c_pw<TB>[1], T, c_ctl[3]);
-                    double nd = sel_min(P.maxstep, (sel_max(DEQ_C02, g) * tdir) * dt);
-                    nd = sel_min_if(nd, dt, timeout);
-                    ndt = tdir * nd;
-                    if (hi32(ssum) >= 0x7ff00000u) { DEQ_COLD_PATH(); if (ssum != ssum) ndt = 0.2 * dt; }
-                    accu = ssum < 1. ? 1u : 0u;   // sqrt(ssum) < 1  <=>  ssum < 1; false for NaN
-                }
+                attempt_math<TB, F, FAST, SPEC>(P, T, t, dt, cy, ck, yl, prm, timeout, tdir, reltol, abstol, k, ytrial, ndt, accu);
                 asm("" : "+r"(accu));
                 const bool accept = accu != 0u;
                 const double tn = t + dt;   // (the row-emitting flavours need it before the state update)
@@ -915,6 +930,148 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
       }
     }
     // (ensemble totals are summed from the per-trajectory counters afterwards: sum_counts_kernel)
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-synchronous dense output: the tspan rows of oderk_adapt (problem.rs:303-319) in the SoA layout [N][nt][ntraj] with
+// fully coalesced stores for ensembles in ANY order.
+//
+// In the persistent-lane kernel every lane emits its rows inside its own accepted steps; a warp's stores land in one row
+// only while its lanes advance together (a parameter-sorted sweep).  On a permuted sweep every lane sits in a different
+// row: 32 single-sector stores per instruction, a partial-sector read-modify-write in L2 for each of them (ncu: 65 GB
+// written + 61 GB read for 17 GB of rows, 84 ms instead of 12 ms at 2^20 trajectories), and the emission loop diverges
+// (20 of 32 lanes active).  Here a warp owns 32 CONSECUTIVE trajectories and walks the output rows together: row r is
+// emitted by the whole warp at once — one 256-byte store per component — as soon as every lane's last accepted step
+// reaches past tspan[r]; lanes that are not there yet take step attempts while the others wait, holding the Hermite data
+// of their last accepted step (its start state and slope; the end state and slope are the current ones).  The warp thus
+// advances in TIME, not in step count; the number of attempts it executes is that of its slowest lane, like the static
+// assignment of the other kernel.  Same arithmetic per trajectory (attempt_math, the reference's Hermite formula and
+// row conditions, `nvalid` quirk included): results are bit-identical to MODE_DENSE.
+// ---------------------------------------------------------------------------------------------------------------
+template <class TB, class F, bool PT, bool FAST>
+__global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_rows_kernel(const AdaptParams P) {
+    constexpr int N = F::N, S = TB::S;
+    constexpr bool FSAL = deqt::fsal_of(TB::data());
+    __shared__ uint64_t s_exp[256];
+    __shared__ double s_powlog[384];
+    for (int i = threadIdx.x; i < 256; i += BLOCK) s_exp[i] = g_exp_tab[i];
+    for (int i = threadIdx.x; i < 384; i += BLOCK) s_powlog[i] = g_powlog_tab[i];
+    if (F::USES_SINCOS) deqm::sincos_stage();
+    __syncthreads();
+    unsigned exp_base = (unsigned)__cvta_generic_to_shared(s_exp), powlog_base = (unsigned)__cvta_generic_to_shared(s_powlog);
+    asm volatile("mov.u32 %0, %0;" : "+r"(exp_base));
+    asm volatile("mov.u32 %0, %0;" : "+r"(powlog_base));
+    const deqm::SmemTables T{exp_base, powlog_base, 0u};
+
+    const unsigned lane = threadIdx.x & 31u;
+    const double tdir = P.tdir, tend = P.tend, reltol = P.reltol, abstol = P.abstol;
+    const uint32_t max_steps = P.max_steps == 0ull || P.max_steps > 0xffffffffull ? 0xffffffffu : (uint32_t)P.max_steps;
+    const unsigned long long nt = P.nt;
+
+    for (;;) {
+        // ---- the next block of 32 consecutive trajectories ----
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(P.work_counter, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= P.ntraj) break;
+        const unsigned long long traj = base + lane;
+        const bool live = traj < P.ntraj;
+        double cy[N], ck[N], yl[N], prm[F::NP ? F::NP : 1];
+        double y0v[N], f0v[N];           // start state and slope of the last accepted step (its end: cy, ck)
+        double t = P.t0, dt = 0.0, t0v = P.t0, dt0v = 0.0;
+        unsigned timeout = 0u, last_step = 0u, done = live ? 0u : 1u, have_iv = 0u;
+        uint32_t acc = 0, rej = 0, attempts = 0;
+        unsigned long long it = 1;
+        uint8_t status = ST_DONE;
+#pragma unroll (N <= 16 ? N : 1)
+        for (int d = 0; d < N; ++d) { cy[d] = 0.0; ck[d] = 0.0; yl[d] = 0.0; y0v[d] = 0.0; f0v[d] = 0.0; }
+#pragma unroll
+        for (int j = 0; j < (F::NP ? F::NP : 1); ++j) prm[j] = 0.0;
+        if (live) {
+            load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
+#pragma unroll (N <= 16 ? N : 1)
+            for (int d = 0; d < N; ++d) {
+                cy[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
+                ck[d] = P.f0[(unsigned long long)d * P.ntraj + traj];
+                P.dense[((unsigned long long)d * nt) * P.ntraj + traj] = cy[d];   // row 0 = y0
+            }
+            dt = P.use_initstep ? P.initstep : P.h0[traj];
+            last_step = fabs((t + dt) - tend) <= DBL_EPSILON ? 1u : 0u;
+        }
+        unsigned long long r = 1;   // warp-uniform row cursor; rows 1 .. nt-2 are Hermite rows, row nt-1 is the final state
+        for (;;) {
+            // ---- emit every row the whole warp is ready for ----
+            while (r + 1 < nt) {
+                const double tq = __ldg(P.tspan + r);
+                bool emit = false, wait = false;
+                if (live && it == r) {   // (it < r: this lane has stopped emitting — a step end hit a tspan point exactly — or its run ended early)
+                    const bool after_start = have_iv && tdir * t0v < tdir * tq;
+                    if (after_start && tdir * tq < tdir * t) emit = true;          // strictly inside the last accepted step
+                    else if (!done && (!have_iv || after_start)) wait = true;     // not reached yet: step first
+                }
+                if (__any_sync(0xffffffffu, wait)) break;
+                if (emit) {
+                    const double theta = (tq - t0v) / dt0v;
+#pragma unroll (N <= 16 ? N : 1)
+                    for (int d = 0; d < N; ++d) {
+                        const double v = (y0v[d] * (1. - theta) + cy[d] * theta) +
+                                         ((cy[d] - y0v[d]) * (1. - 2. * theta) + f0v[d] * (theta - 1.) * dt0v +
+                                          ck[d] * theta * dt0v) * theta * (theta - 1.);
+                        P.dense[((unsigned long long)d * nt + r) * P.ntraj + traj] = v;
+                    }
+                    ++it;
+                }
+                ++r;
+            }
+            // ---- one attempt for the lanes that have not reached row r (or emit nothing any more) and are not finished ----
+            bool need = live && !done;
+            if (need && it == r && r + 1 < nt && have_iv) {
+                const double tq = __ldg(P.tspan + r);
+                if (tdir * t0v < tdir * tq && tdir * tq < tdir * t) need = false;   // holds a row the warp has not emitted yet
+            }
+            if (!__any_sync(0xffffffffu, need)) break;
+            if (need) {
+                ++attempts;
+                double k[S][N], ytrial[N];
+                double ndt;
+                unsigned accu;
+                const unsigned timeout_next = timeout - (timeout > 0u ? 1u : 0u);
+                attempt_math<TB, F, FAST, false>(P, T, t, dt, cy, ck, yl, prm, timeout, tdir, reltol, abstol, k, ytrial, ndt, accu);
+                const bool accept = accu != 0u;
+                const double tn = t + dt;
+                if (accept) {
+                    if (!FSAL) F::eval(tn, ytrial, k[S - 1], prm);
+#pragma unroll (N <= 16 ? N : 1)
+                    for (int d = 0; d < N; ++d) { y0v[d] = cy[d]; f0v[d] = ck[d]; cy[d] = ytrial[d]; ck[d] = k[S - 1][d]; }
+                    t0v = t; dt0v = dt; have_iv = 1u;
+                    t = tn;
+                }
+                const double dt100 = FAST ? ndt * DEQ_C001 : div100_exact(ndt);
+                const bool snapped = accept && (tdir * ((t + ndt) + dt100) >= P.tdir_tend);
+                const bool stop = accept ? last_step != 0u : (fabs(ndt) < P.minstep);
+                dt = snapped ? tend - t : ndt;
+                last_step = snapped ? 1u : 0u;
+                timeout = accept ? timeout_next : 5u;
+                acc += accept ? 1u : 0u;
+                rej += (accept || stop) ? 0u : 1u;
+                if (stop || attempts >= max_steps) {
+                    status = !stop ? (uint8_t)ST_MAX_STEPS : accept ? (uint8_t)ST_DONE : (uint8_t)ST_MINSTEP_BREAK;
+                    done = 1u;
+                }
+            }
+        }
+        // ---- the block is finished: final states, counters, the end point as the last row (problem.rs:320-322) ----
+        if (live) {
+            const uint32_t nfe = 2u + attempts * (uint32_t)(S - 1) + (FSAL ? 0u : acc);
+#pragma unroll (N <= 16 ? N : 1)
+            for (int d = 0; d < N; ++d) {
+                P.yfinal[(unsigned long long)d * P.ntraj + traj] = cy[d];
+                P.dense[((unsigned long long)d * nt + (nt - 1)) * P.ntraj + traj] = cy[d];
+            }
+            P.accepted[traj] = acc; P.rejected[traj] = rej; P.nfe[traj] = nfe; P.status[traj] = status; P.t_reached[traj] = t;
+            P.nvalid[traj] = (uint32_t)it;
+        }
+    }
 }
 
 }  // namespace deqk

@@ -1,5 +1,5 @@
 """Probe (not a test): the four dense-output flavours of config 3 at 2^20 trajectories, one launch each after a warm-up
-(launch order for ncu: sorted SoA, sorted TrajMajor, permuted SoA, permuted TrajMajor; every second adapt_kernel launch is the timed one)."""
+(per order: SoA row-synchronous kernel, staged trajectory-major, SoA lane-refill kernel; every second launch is the timed one)."""
 import json, sys
 import numpy as np
 sys.path.insert(0, ".")
@@ -11,10 +11,10 @@ ts = D.linspace(0.0, 20.0, 1000)
 perm = np.random.default_rng(0).permutation(N)
 for name, m in (("sorted", mu), ("permuted", mu[perm].copy())):
     p = D.OdeProblem.builder().fun(D.Rhs.builtin(D.System.VanDerPol)).params(m).init(y0).tspan(ts).build()
-    for lay in (0, 1):
-        o = D.OdeOptionMap().insert(D.Reltol(1e-6), D.Abstol(1e-8), D.Output.Tspan, D.DenseLayout(lay))
+    for lay, refill in ((0, 2), (1, 2), (0, 1)):   # SoA row-synchronous kernel, staged trajectory-major, SoA lane-refill kernel
+        o = D.OdeOptionMap().insert(D.Reltol(1e-6), D.Abstol(1e-8), D.Output.Tspan, D.DenseLayout(lay), D.Refill(refill))
         for rep in range(2):
             s = p.solve(D.Ode.Ode45fe, o, fetch=False)
-        print(json.dumps({"order": name, "layout": D.DenseLayout(lay).name, "kernel_ms": round(s.kernel_ms, 3), "steps": s.totals["accepted"] + s.totals["rejected"],
+        print(json.dumps({"order": name, "layout": D.DenseLayout(lay).name, "refill": refill, "kernel_ms": round(s.kernel_ms, 3), "steps": s.totals["accepted"] + s.totals["rejected"],
                           "GBps": N * 1000 * 2 * 8 / (s.kernel_ms * 1e-3) / 1e9}), flush=True)
     del p

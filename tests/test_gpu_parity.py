@@ -169,6 +169,44 @@ def test_vdp_dense_output_matches_oracle(deq, oracle):
     assert np.array_equal(sol.accepted, ref["accepted"])
 
 
+@pytest.mark.parametrize("order", ["sorted", "permuted"])
+def test_soa_dense_rows_any_order(deq, oracle, order):
+    """SoA dense rows from the row-synchronous kernel (default: a warp owns 32 consecutive trajectories and emits each row
+    together) and from the lane-refill kernel (Refill(1): every lane emits inside its own steps), on a parameter sweep in
+    sorted and in randomly permuted order: both equal the oracle bit for bit — rows, nvalid, counters, final states — for the
+    forward run, a backward run, a tspan whose points are hit exactly by step ends (the reference stops emitting there),
+    an early stop (max_steps) and the FSAL / non-FSAL tableaus."""
+    from diffeq_b200 import synth
+    n = 1037
+    y0, mu = synth.vdp_sweep(0, n, n)
+    if order == "permuted":
+        perm = np.random.default_rng(7).permutation(n)
+        mu = mu[perm].copy()
+    cases = [("Ode45fe", 0, deq.linspace(0.0, 20.0, 200), 1e-6, dict()),
+             ("Ode45", 1, deq.linspace(0.0, 6.0, 61), 1e-6, dict()),                       # FSAL
+             ("Ode45fe", 0, deq.linspace(3.0, -2.0, 41), 1e-6, dict(max_steps=400)),       # backward (the reference runs away after a rejection)
+             ("Ode23", 1, np.arange(9) * 0.25, 0.5, dict(initstep=0.25, maxstep=0.25)),    # step ends fall exactly on tspan points
+             ("Ode45fe", 0, deq.linspace(0.0, 20.0, 50), 1e-6, dict(max_steps=60))]        # trajectories stop early
+    quirk = False
+    for method, tset, ts, tol, kw in cases:
+        atol = 1e-8 if tol < 0.1 else tol
+        oo = oracle.opts(tol, atol, **kw)
+        ref = oracle.ensemble_dense(getattr(oracle, method.upper()), oracle.VANDERPOL, mu, y0, ts, oo, tset)
+        want = ref["out"].transpose(2, 1, 0)
+        for refill in (2, 1, 0):
+            o = deq.OdeOptionMap().insert(deq.Reltol(tol), deq.Abstol(atol), deq.Output.Tspan, deq.Refill(refill))
+            if "max_steps" in kw: o.insert(deq.MaxSteps(kw["max_steps"]))
+            if "initstep" in kw: o.insert(deq.Initstep(kw["initstep"]), deq.Maxstep(kw["maxstep"]))
+            sol = _problem(deq, deq.System.VanDerPol, mu, y0, ts).solve(getattr(deq.Ode, method), o, tableau_set=tset)
+            assert np.array_equal(sol.nvalid, ref["nvalid"]), (method, refill)
+            assert np.array_equal(sol.yout, want, equal_nan=True), (method, refill)
+            assert np.array_equal(sol.accepted, ref["accepted"]) and np.array_equal(sol.rejected, ref["rejected"]), (method, refill)
+            assert np.array_equal(sol.status, ref["status"]), (method, refill)
+        quirk = quirk or bool(((ref["nvalid"] < len(ts) - 1) & (ref["status"] == 0)).any())
+    assert quirk                        # some complete run stopped emitting because a step end hit a tspan point exactly
+    assert (ref["nvalid"] < 50).any()   # the early-stop case really leaves rows unwritten
+
+
 def test_pendulum_feh78_textbook_bit_exact(deq, oracle):
     """BASELINE config 4 at oracle-sized N.  The pendulum calls sin/cos; the device evaluates glibc's algorithm
     (deq_sincos.cuh), so even at rtol = atol = 1e-12 every count and every final state equals the oracle's."""

@@ -13,3 +13,6 @@
 #define HOT_MODE deqk::MODE_FINAL
 #endif
 template __global__ void deqk::adapt_kernel<HOT_TB, HOT_SYS, false, HOT_MODE, HOT_FAST, false>(const deqk::AdaptParams);
+#ifdef HOT_ROWS
+template __global__ void deqk::adapt_rows_kernel<deqt::Rk45, deqr::VanDerPol, true, HOT_FAST>(const deqk::AdaptParams);
+#endif
