@@ -475,7 +475,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
         P.t_reached = r->d_treached; P.dense = r->d_dense; P.nvalid = r->d_nvalid;
         P.work_counter = r->d_scalars; P.totals = r->d_scalars + 1;
         P.true_inverse = sk && tableau_set == DEQ_TABLEAU_TEXTBOOK; P.points_specified = o.points == DEQ_POINTS_SPECIFIED;
-        const int mode = spec ? (int)deqk::MODE_REC_SPEC   // a final-state request runs its counting pass only
+        int mode = spec ? (int)deqk::MODE_REC_SPEC   // a final-state request runs its counting pass only
                          : want_all ? (int)deqk::MODE_REC
                          : want_dense ? (o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR ? (int)deqk::MODE_DENSE_TM
                                          // SoA rows: the row-synchronous kernel (coalesced for any trajectory order) unless the caller
@@ -528,6 +528,17 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
             std::string err;
             if (e->rhs.kind == 0) CKR(deql::launch_hinit(e->rhs.sys, e->per_traj, H, st));
             else if (!deqn::launch_hinit(e->rhs.prog, e->per_traj, H, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
+            if (mode == (int)deqk::MODE_DENSE_ROWS && o.refill == 2 && o.initstep == 0.) {
+                // SoA rows, choice left open: neighbours that start alike (a parameter-sorted sweep) advance together, and the
+                // lane-refill kernel's own stores coalesce (and it keeps its lanes busier); otherwise the row-synchronous kernel
+                unsigned long long hc[2] = {0, 0};
+                CKR(cudaMemsetAsync(r->d_scalars + 1, 0, 2 * sizeof(unsigned long long), st));
+                CKR(deql::launch_coherence(r->d_h0, ntraj, r->d_scalars + 1, st));
+                CKR(cudaMemcpyAsync(hc, r->d_scalars + 1, sizeof(hc), cudaMemcpyDeviceToHost, st));
+                CKR(cudaStreamSynchronize(st));
+                CKR(cudaMemsetAsync(r->d_scalars + 1, 0, 2 * sizeof(unsigned long long), st));
+                if (hc[1] > 0 && (double)hc[0] <= 0.02 * (double)hc[1]) mode = (int)deqk::MODE_DENSE;
+            }
             CKR(cudaEventRecord(r->ev0, st));
             const int rc = launch_adapt(&err);
             if (rc == 1) return bail(DEQ_ERR_CUDA);

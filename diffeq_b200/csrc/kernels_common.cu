@@ -135,6 +135,31 @@ cudaError_t launch_test_div(unsigned long long seed, unsigned long long count, u
     return cudaGetLastError();
 }
 
+// How alike are neighbouring trajectories?  Fraction-of-pairs statistic on the first step sizes hinit produced: pairs (i, i + 1)
+// inside a 32-block whose h0 differ by more than 1/16.  A parameter-sorted sweep has (almost) none; an ensemble in arbitrary
+// order has most.  deq_solve uses it to pick the SoA dense kernel (lane-refill for coherent neighbours, row-synchronous
+// otherwise) when the caller leaves the choice open.  HBM-bound: reads 8 bytes per trajectory.
+__global__ void __launch_bounds__(256) coherence_kernel(const double* __restrict__ h0, unsigned long long n, unsigned long long* __restrict__ out) {
+    unsigned long long differ = 0, pairs = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        if ((i & 31ull) == 31ull) continue;
+        const double a = h0[i], b = h0[i + 1];
+        ++pairs;
+        if (!(fabs(a - b) <= 0.0625 * fabs(a))) ++differ;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { differ += __shfl_down_sync(0xffffffffu, differ, o); pairs += __shfl_down_sync(0xffffffffu, pairs, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out + 0, differ); atomicAdd(out + 1, pairs); }
+}
+cudaError_t launch_coherence(const double* h0, unsigned long long n, unsigned long long* d_out, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned long long want = (n + 255) / 256, cap = (unsigned long long)sms * 8;
+    coherence_kernel<<<(unsigned)(want < cap ? (want ? want : 1) : cap), 256, 0, st>>>(h0, n, d_out);
+    return cudaGetLastError();
+}
+
 // DFMA stream: 8 independent accumulator chains per thread, 2 flop per FMA.  The result is written so the loop
 // cannot be removed.  Used to measure the chip's sustained FP64 rate (MEASURED_PEAKS.json has no FP64 figure).
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* sink, int iters) {

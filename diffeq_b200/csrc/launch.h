@@ -49,6 +49,7 @@ cudaError_t launch_transpose_to_soa(const double* d_aos, double* d_soa, unsigned
 cudaError_t launch_transpose_to_aos(const double* d_soa, double* d_aos, unsigned long long ntraj, int n, cudaStream_t st);
 cudaError_t launch_sum_counts(const uint32_t* acc, const uint32_t* rej, const uint32_t* nfe, unsigned long long n,
                               unsigned long long* totals, cudaStream_t st);
+cudaError_t launch_coherence(const double* h0, unsigned long long n, unsigned long long* d_out, cudaStream_t st);
 cudaError_t launch_test_div(unsigned long long seed, unsigned long long count, unsigned long long* d_out, cudaStream_t st);
 cudaError_t launch_test_pow(const double* x, const double* y, double* out, unsigned long long n, cudaStream_t st);
 cudaError_t launch_test_log10(const double* x, double* out, unsigned long long n, cudaStream_t st);

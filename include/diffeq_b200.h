@@ -94,10 +94,13 @@ typedef enum deq_precision { DEQ_PRECISION_F64 = 0, DEQ_PRECISION_F32 = 1 } deq_
  * determined without a Rust toolchain, so both are provided, each bit-exact against the oracle in the same flavour. */
 typedef enum deq_libm { DEQ_LIBM_AS_WRITTEN = 0, DEQ_LIBM_LLVM_FOLDED = 1 } deq_libm;
 
-/* Memory layout of DEQ_OUT_TSPAN (adaptive methods).  SOA [n][ntspan][ntraj]: by default a warp owns 32 consecutive
- * trajectories and emits the rows together (one 256-byte store per component and row, whatever the order of the ensemble);
- * with refill = 1 every lane emits inside its own steps, which coalesces only when neighbouring trajectories advance
- * together (parameter-sorted sweeps).  TRAJ_MAJOR [ntraj][ntspan][n] is one contiguous stream per trajectory —
+/* Memory layout of DEQ_OUT_TSPAN (adaptive methods).  SOA [n][ntspan][ntraj] is written by one of two kernels: in the
+ * lane-refill kernel (refill = 1) every lane emits inside its own steps, which coalesces only while neighbouring
+ * trajectories advance together (parameter-sorted sweeps: the fastest choice there); in the row-synchronous kernel
+ * (refill = 0) a warp owns 32 consecutive trajectories and emits each row together — one 256-byte store per component and
+ * row whatever the order of the ensemble, at the price of lanes waiting for each other.  refill = 2 (default) decides after
+ * the initial-step pass: if neighbouring trajectories start with (almost) equal steps the lane-refill kernel runs,
+ * otherwise the row-synchronous one.  The output is bit-identical either way.  TRAJ_MAJOR [ntraj][ntspan][n] is one contiguous stream per trajectory —
  * the reference's Vec<Y> shape — written through per-lane shared-memory staging with cooperative 128-byte stores; it is
  * the fast choice for ensembles in arbitrary order (6x on a permuted Van der Pol sweep). */
 typedef enum deq_dense_layout { DEQ_LAYOUT_SOA = 0, DEQ_LAYOUT_TRAJ_MAJOR = 1 } deq_dense_layout;

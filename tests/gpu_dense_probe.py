@@ -11,7 +11,7 @@ ts = D.linspace(0.0, 20.0, 1000)
 perm = np.random.default_rng(0).permutation(N)
 for name, m in (("sorted", mu), ("permuted", mu[perm].copy())):
     p = D.OdeProblem.builder().fun(D.Rhs.builtin(D.System.VanDerPol)).params(m).init(y0).tspan(ts).build()
-    for lay, refill in ((0, 2), (1, 2), (0, 1)):   # SoA row-synchronous kernel, staged trajectory-major, SoA lane-refill kernel
+    for lay, refill in ((0, 2), (0, 0), (0, 1), (1, 2)):   # SoA auto, SoA row-synchronous kernel, SoA lane-refill kernel, staged trajectory-major
         o = D.OdeOptionMap().insert(D.Reltol(1e-6), D.Abstol(1e-8), D.Output.Tspan, D.DenseLayout(lay), D.Refill(refill))
         for rep in range(2):
             s = p.solve(D.Ode.Ode45fe, o, fetch=False)
