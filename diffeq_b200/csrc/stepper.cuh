@@ -418,6 +418,10 @@ __device__ __forceinline__ double& stage_ref(double* stage, unsigned col, unsign
 // item i = element (i % LINE) of the (i / LINE)-th pending lane, so 32 lanes write two full lines per iteration with three
 // shuffles and no vote inside the loop.
 __device__ __forceinline__ void stage_drain(double* stage, double* out, StageLane& s, bool all) {
+#ifdef DEQ_TM_DIRECT
+    (void)stage; (void)out; (void)s; (void)all;
+    return;
+#endif
     const unsigned am = __activemask();
     const unsigned lane = threadIdx.x & 31u;
     __syncwarp(am);  // the owners' appends are visible to the helpers
@@ -452,6 +456,11 @@ __device__ __forceinline__ void stage_drain(double* stage, double* out, StageLan
 }
 
 __device__ __forceinline__ void stage_append(double* stage, double* out, StageLane& s, double v) {
+#ifdef DEQ_TM_DIRECT   // experiment: every lane streams its own rows with plain 8-byte stores (L2 merges the sectors)
+    (void)stage;
+    out[s.gpos++] = v;
+    return;
+#endif
     const unsigned lane = threadIdx.x & 31u;
     if (s.cnt == (unsigned)STAGE_COLS) {  // ring full inside one step (many tspan points per step): the owner drains a line alone
         for (unsigned e = 0; e < (unsigned)STAGE_LINE; ++e) out[s.gpos + e] = stage_ref(stage, (s.head + e) & (STAGE_COLS - 1), lane);
@@ -661,6 +670,10 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     constexpr int PACK_SLOTS = 2 + 2 * N + (PT ? F::NP : 0) + 3 + (ROWS ? 1 : 0);
     constexpr bool CAN_COMPACT = (MODE == MODE_FINAL || MODE == MODE_DENSE) && !SPEC && PACK_SLOTS <= 24;
     constexpr int TAIL_BURSTS = 4;
+    // attempts between two refill checks: a check costs ~25 issue slots, an attempt of a 13-stage tableau with a transcendental
+    // right-hand side ~6000 — and such runs are short (config 4: ~75 attempts per trajectory), so idling up to BURST - 1 attempts
+    // after a trajectory ends would cost several per cent there
+    constexpr int BURST = S >= 10 ? 2 : BURST_ATTEMPTS;
     __shared__ double s_pack[CAN_COMPACT ? PACK_SLOTS : 1][CAN_COMPACT ? BLOCK : 1];
     __shared__ unsigned s_cnt[2][BLOCK / 32];
     __shared__ unsigned s_tail;
@@ -881,7 +894,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
             if (*(volatile unsigned*)&s_tail) { tail_mode = 1u; break; }
         }
         if (__ballot_sync(0xffffffffu, active) == 0u) break;
-        run_bursts(BURST_ATTEMPTS);
+        run_bursts(BURST);
     }
     if constexpr (CAN_COMPACT) {
       if (tail_mode) {
@@ -925,7 +938,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                 if (ROWS) it = (unsigned long long)__double_as_longlong(pk.v[f++]);
                 active = pk.active;
             }
-            run_bursts(BURST_ATTEMPTS * TAIL_BURSTS);
+            run_bursts(BURST * TAIL_BURSTS);
         }
       }
     }
