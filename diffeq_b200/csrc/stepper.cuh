@@ -418,10 +418,6 @@ __device__ __forceinline__ double& stage_ref(double* stage, unsigned col, unsign
 // item i = element (i % LINE) of the (i / LINE)-th pending lane, so 32 lanes write two full lines per iteration with three
 // shuffles and no vote inside the loop.
 __device__ __forceinline__ void stage_drain(double* stage, double* out, StageLane& s, bool all) {
-#ifdef DEQ_TM_DIRECT
-    (void)stage; (void)out; (void)s; (void)all;
-    return;
-#endif
     const unsigned am = __activemask();
     const unsigned lane = threadIdx.x & 31u;
     __syncwarp(am);  // the owners' appends are visible to the helpers
@@ -456,11 +452,6 @@ __device__ __forceinline__ void stage_drain(double* stage, double* out, StageLan
 }
 
 __device__ __forceinline__ void stage_append(double* stage, double* out, StageLane& s, double v) {
-#ifdef DEQ_TM_DIRECT   // experiment: every lane streams its own rows with plain 8-byte stores (L2 merges the sectors)
-    (void)stage;
-    out[s.gpos++] = v;
-    return;
-#endif
     const unsigned lane = threadIdx.x & 31u;
     if (s.cnt == (unsigned)STAGE_COLS) {  // ring full inside one step (many tspan points per step): the owner drains a line alone
         for (unsigned e = 0; e < (unsigned)STAGE_LINE; ++e) out[s.gpos + e] = stage_ref(stage, (s.head + e) & (STAGE_COLS - 1), lane);
