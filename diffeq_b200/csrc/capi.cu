@@ -826,7 +826,7 @@ deq_status deq_solve_host_dense(const deq_rhs* rhs, size_t ntraj, const double* 
 }
 
 // The dense-output flavour of deq_solve_host.  The trajectory range is cut into chunks (~128 MiB of rows each); chunk j goes
-// to device j % ndevices (a block-cyclic deal, which also balances parameter-sorted sweeps); every device thread keeps two
+// to device j % ndevices (a block-cyclic deal, which also balances parameter-sorted sweeps); every device thread keeps three
 // chunks in flight: while chunk i travels to the caller's buffer on the copy stream, chunk i + 1 is integrated on the
 // compute stream.  For ensembles with dense rows the PCIe link, not the kernel, is the bound (config 3: 16 KB of rows per
 // trajectory against ~12 ns of kernel time), so the measure of this path is how close it stays to a plain pinned copy.
@@ -840,6 +840,7 @@ static deq_status solve_host_dense_impl(const deq_rhs* rhs, size_t ntraj, const 
     if (ntspan == 0) return DEQ_OK;   // nothing to solve (problem.rs:211-214)
     deq_options o = o_in;
     o.async = 1;
+    if (o.refill == 2) o.refill = 0;   // SoA rows: no per-chunk coherence probe (a host round trip); the kernel time hides behind the copies anyway
     const size_t nd = devs.size(), n = (size_t)rhs->n, np = (size_t)rhs->np;
     const bool tm = o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR && info.adaptive && !sk;
     const bool counts = info.adaptive || sk;
@@ -855,7 +856,7 @@ static deq_status solve_host_dense_impl(const deq_rhs* rhs, size_t ntraj, const 
         if (cudaSetDevice(devs[k]) != cudaSuccess) { rc[k] = DEQ_ERR_CUDA; msg[k] = "cudaSetDevice failed"; cudaGetLastError(); return; }
         cudaStream_t sc = nullptr, sx = nullptr;
         const cudaStream_t caller_stream = g_stream;
-        struct Slot { deq_ensemble* ens = nullptr; deq_result* res = nullptr; double* d_aos = nullptr; cudaEvent_t computed = nullptr, copied = nullptr; bool busy = false; } slot[2];
+        struct Slot { deq_ensemble* ens = nullptr; deq_result* res = nullptr; double* d_aos = nullptr; cudaEvent_t computed = nullptr, copied = nullptr; bool busy = false; } slot[3];   // three chunks in flight: computed / travelling / being set up
         deq_status s = DEQ_OK;
         auto ck = [&](cudaError_t e_) { if (e_ != cudaSuccess && !s) { cudaGetLastError(); s = fail(DEQ_ERR_CUDA, cudaGetErrorString(e_)); } };
         ck(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
@@ -872,7 +873,7 @@ static deq_status solve_host_dense_impl(const deq_rhs* rhs, size_t ntraj, const 
         };
         size_t it = 0;
         for (size_t j = k; j < nchunks && !s; j += nd, ++it) {
-            Slot& sl = slot[it & 1];
+            Slot& sl = slot[it % 3];
             retire(sl);
             const size_t b = j * chunk, cnt = std::min(chunk, ntraj - b);
             s = deq_ensemble_create(rhs, cnt, y0 + b * n, per ? params + b * np : params, params_per_traj, tspan, ntspan, &sl.ens);
