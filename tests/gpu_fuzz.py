@@ -142,7 +142,7 @@ for case in range(cases):
     rtol, atol = 10.0 ** rng.uniform(-9, -3), 10.0 ** rng.uniform(-11, -4)
     folded = int(rng.random() < 0.4)
     kw = dict(max_steps=int(rng.choice([300, 1500, 4000])), libm_folded=folded)
-    o = D.OdeOptionMap().insert(D.Reltol(rtol), D.Abstol(atol), D.MaxSteps(kw["max_steps"]), D.Refill(int(rng.integers(0, 2))))
+    o = D.OdeOptionMap().insert(D.Reltol(rtol), D.Abstol(atol), D.MaxSteps(kw["max_steps"]), D.Refill(int(rng.integers(0, 3))))   # static / lane refill / + tail compaction and the dense-kernel choice
     if folded:
         o.insert(D.Libm.LlvmFolded)
     backward = rng.random() < 0.15
