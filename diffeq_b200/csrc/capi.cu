@@ -12,7 +12,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -172,6 +174,63 @@ struct TempBuf {
     TempBuf(const TempBuf&) = delete;
     TempBuf& operator=(const TempBuf&) = delete;
 };
+
+// Host threads of the multi-device calls.  A fresh std::thread pays the CUDA runtime's per-thread set-up on its first call
+// (milliseconds, every call); the workers here are created once, stay bound to their device between calls and keep a
+// non-blocking stream of their own.  One multi-device call uses the pool at a time (a second concurrent caller spawns plain
+// threads); the pool is leaked on purpose at process exit (its threads sleep on a condition variable).
+class WorkerPool {
+public:
+    // runs fn(k, stream_of_worker_k) for k = 0..n-1 concurrently, worker k on device devs[k]; returns false if the pool is busy
+    bool run(const std::vector<int>& devs, const std::function<void(size_t, cudaStream_t)>& fn) {
+        std::unique_lock<std::mutex> busy(busy_, std::try_to_lock);
+        if (!busy.owns_lock()) return false;
+        while (workers_.size() < devs.size()) workers_.push_back(new Worker());
+        for (size_t k = 0; k < devs.size(); ++k) workers_[k]->post(devs[k], k, &fn);
+        for (size_t k = 0; k < devs.size(); ++k) workers_[k]->wait();
+        return true;
+    }
+private:
+    struct Worker {
+        std::thread th;
+        std::mutex m;
+        std::condition_variable cv;
+        const std::function<void(size_t, cudaStream_t)>* job = nullptr;
+        size_t index = 0;
+        int want_dev = -1, cur_dev = -1;
+        bool pending = false, finished = false;
+        cudaStream_t st = nullptr;
+        Worker() { th = std::thread([this] { loop(); }); th.detach(); }
+        void post(int dev, size_t k, const std::function<void(size_t, cudaStream_t)>* fn) {
+            std::lock_guard<std::mutex> lk(m);
+            want_dev = dev; index = k; job = fn; pending = true; finished = false;
+            cv.notify_all();
+        }
+        void wait() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [this] { return finished; }); }
+        void loop() {
+            for (;;) {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [this] { return pending; });
+                pending = false;
+                const auto* fn = job; const size_t k = index; const int dev = want_dev;
+                lk.unlock();
+                if (dev != cur_dev) {   // (re)bind: device and a stream on it
+                    if (st) { cudaSetDevice(cur_dev); cudaStreamDestroy(st); st = nullptr; }
+                    cur_dev = -1;
+                    if (cudaSetDevice(dev) == cudaSuccess && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess) cur_dev = dev;
+                    else { cudaGetLastError(); st = nullptr; }
+                }
+                (*fn)(k, cur_dev == dev ? st : nullptr);
+                lk.lock();
+                finished = true;
+                cv.notify_all();
+            }
+        }
+    };
+    std::mutex busy_;
+    std::vector<Worker*> workers_;
+};
+WorkerPool& worker_pool() { static WorkerPool* p = new WorkerPool(); return *p; }
 
 // Block-cyclic shards of deq_solve_host: the rows of this shard are runs (start, length) of the caller's arrays.  While the
 // list is set, upload_soa treats its host pointer as the base of the FULL array and copies run by run, so no host-side
@@ -737,17 +796,22 @@ static deq_status solve_host_impl(const deq_rhs* rhs, size_t ntraj, const double
     std::vector<deq_status> rc(nd, DEQ_OK);
     std::vector<std::string> msg(nd);
     const size_t chunk = (nd > 1 && o.shard_chunk > 0) ? (size_t)o.shard_chunk : 0;
-    auto work = [&](size_t k) {
+    auto work = [&](size_t k, cudaStream_t pool_stream) {
         auto bad = [&](deq_status s) { rc[k] = s; msg[k] = g_err; };
         if (cudaSetDevice(devs[k]) != cudaSuccess) { rc[k] = DEQ_ERR_CUDA; msg[k] = "cudaSetDevice failed"; cudaGetLastError(); return; }
-        // a worker thread owns a non-blocking stream for its shard (the calling thread keeps the stream it set with deq_set_stream)
+        // a worker thread runs its shard on a non-blocking stream of its own — the pool worker's persistent one, or a temporary one
+        // (the calling thread keeps the stream it set with deq_set_stream)
         struct OwnStream {
-            cudaStream_t st = nullptr; bool own = false;
-            ~OwnStream() { if (own) { cudaStreamSynchronize(st); cudaStreamDestroy(st); g_stream = nullptr; } }
+            cudaStream_t st = nullptr; bool own = false, bound = false;
+            ~OwnStream() { if (own) { cudaStreamSynchronize(st); cudaStreamDestroy(st); } if (bound) g_stream = nullptr; }
         } ws;
         if (!(nd == 1 && devs[0] == cur)) {
-            if (cudaStreamCreateWithFlags(&ws.st, cudaStreamNonBlocking) != cudaSuccess) { rc[k] = DEQ_ERR_CUDA; msg[k] = "cudaStreamCreate failed"; cudaGetLastError(); return; }
-            ws.own = true;
+            if (pool_stream) ws.st = pool_stream;
+            else {
+                if (cudaStreamCreateWithFlags(&ws.st, cudaStreamNonBlocking) != cudaSuccess) { rc[k] = DEQ_ERR_CUDA; msg[k] = "cudaStreamCreate failed"; cudaGetLastError(); return; }
+                ws.own = true;
+            }
+            ws.bound = true;
             g_stream = ws.st;
         }
         const bool per = params && params_per_traj;
@@ -796,11 +860,13 @@ static deq_status solve_host_impl(const deq_rhs* rhs, size_t ntraj, const double
         deq_ensemble_destroy(ens);
     };
     if (nd == 1 && devs[0] == cur) {
-        work(0);
+        work(0, nullptr);
     } else {
-        std::vector<std::thread> th;
-        for (size_t k = 0; k < nd; ++k) th.emplace_back(work, k);
-        for (auto& t : th) t.join();
+        if (!worker_pool().run(devs, work)) {   // pool in use by a concurrent call: plain threads
+            std::vector<std::thread> th;
+            for (size_t k = 0; k < nd; ++k) th.emplace_back(work, k, (cudaStream_t) nullptr);
+            for (auto& t : th) t.join();
+        }
         cudaSetDevice(cur);
     }
     for (size_t k = 0; k < nd; ++k)

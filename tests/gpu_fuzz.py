@@ -93,6 +93,12 @@ def check(tag, pairs):
         if not ok_:
             bad += 1
             print("MISMATCH", name, tag, flush=True)
+            try:   # keep the inputs of the failing case for analysis on the CPU
+                os.makedirs("gpurun_out", exist_ok=True)
+                np.savez(os.path.join("gpurun_out", "fuzz_fail_%d_%d_%s.npz" % (seed, tag[0], name)), got=a, want=b, tag=np.array(repr(tag)),
+                         **{k: np.asarray(v) for k, v in CUR.items()})
+            except Exception as e:   # noqa: BLE001
+                print("could not save the failing case:", e, flush=True)
             return False
     return True
 
@@ -106,6 +112,7 @@ def grid(t0, span, npts, allow_dup=True):
     return t0 + span * g
 
 
+CUR = {}
 for case in range(cases):
     kind = rng.choice(["adapt", "adapt", "adapt", "fixed", "ode23s", "rosen"])
     n = int(rng.integers(1, 150)) if rng.random() < 0.97 else int(rng.integers(1000, 6000))   # a few multi-CTA ensembles
@@ -196,6 +203,8 @@ for case in range(cases):
     if pts:
         o.insert(D.Points.Specified)
     oo = O.opts(rtol, atol, **kw)
+    CUR = dict(y0=y0, params=params, ts=ts, rtol=rtol, atol=atol, method=m, tset=tset, system=name, opt_keys=list(kw.keys()),
+               opt_vals=[float(v) for v in kw.values()], refill=int(o["Refill"]) if "Refill" in o else -1)
     ref = O.ensemble_adaptive(getattr(O, m.upper()), osys, params, y0, ts, oo, tset)
     p = prob(ts)
     sol = p.solve(getattr(D.Ode, m), o, tableau_set=tset)
