@@ -6,9 +6,10 @@
 // of 4 % of the trajectories.  With these replicas the built-in pendulum is bit-identical to the CPU oracle.
 // Every fused multiply-add is explicit (placement from GCC 13's -mfma contraction of the published source, verified
 // bit-for-bit against the running libm: tests/cpp/math_check.cpp); compile with -fmad=false / -ffp-contract=off.
-// Domain: |x| < 105414350 (glibc's `reduce_sincos` range).  Larger arguments use glibc's Payne–Hanek `__branred`,
-// which is not replicated: they fall back to the platform sin/cos (documented loss of bit parity, never hit by the
-// built-in systems).
+// Domain: every double.  |x| < 105414350 is glibc's `reduce_sincos` range; larger finite arguments go through `branred`
+// below, glibc's Payne–Hanek style reduction against 1800 bits of 2/pi (branred.c; the libm of this image runs it WITHOUT
+// fused multiply-adds — the one copy in libm.so.6 is plain SSE2 — so it is written with separate roundings); inf / NaN
+// give x / x.
 // ---- third-party notice -------------------------------------------------------------------------------------------
 // The algorithms and the table restated in this file are those of the GNU C Library 2.39 (sysdeps/ieee754/dbl-64/s_sin.c,
 // sincostab.c, usncs.h, branred.c: the IBM Accurate Mathematical Library, written by International Business Machines Corp.).
@@ -82,6 +83,87 @@ DEQ_HD double copysign_(double a, double b) {
     return asf64((asu64(a) & 0x7fffffffffffffffULL) | (asu64(b) & 0x8000000000000000ULL));
 }
 
+// ---- branred.c: x = n*pi/2 + (a + aa) for |x| >= 105414350 -------------------------------------------------------------
+// toverp[i] = the i-th 24-bit digit of 2/pi.  The argument is scaled by 2^-600 and split into two 26-bit halves; each half is
+// multiplied by the six digits of 2/pi that matter at its magnitude (scaled by `gor` = 2^(576 - 24k)), the integer parts are
+// taken off with the 1.5 * 2^52 trick, and the fractional parts are summed in double-double.  Every operation is one IEEE
+// rounding in glibc's order.  Cold path (a state of 1e8 rad and more): out of line on the device.
+#define DEQ_TOVERP_INIT \
+    10680707.0, 7228996.0, 1387004.0, 2578385.0, 16069853.0, 12639074.0, 9804092.0, 4427841.0, 16666979.0, 11263675.0, \
+    12935607.0, 2387514.0, 4345298.0, 14681673.0, 3074569.0, 13734428.0, 16653803.0, 1880361.0, 10960616.0, 8533493.0, \
+    3062596.0, 8710556.0, 7349940.0, 6258241.0, 3772886.0, 3769171.0, 3798172.0, 8675211.0, 12450088.0, 3874808.0, \
+    9961438.0, 366607.0, 15675153.0, 9132554.0, 7151469.0, 3571407.0, 2607881.0, 12013382.0, 4155038.0, 6285869.0, \
+    7677882.0, 13102053.0, 15825725.0, 473591.0, 9065106.0, 15363067.0, 6271263.0, 9264392.0, 5636912.0, 4652155.0, \
+    7056368.0, 13614112.0, 10155062.0, 1944035.0, 9527646.0, 15080200.0, 6658437.0, 6231200.0, 6832269.0, 16767104.0, \
+    5075751.0, 3212806.0, 1398474.0, 7579849.0, 6349435.0, 12618859.0, 4703257.0, 12806093.0, 14477321.0, 2786137.0, \
+    12875403.0, 9837734.0, 14528324.0, 13719321.0, 343717.0
+#if !defined(__CUDA_ARCH__)
+namespace host_tables { static const double toverp_tab[75] = {DEQ_TOVERP_INIT}; }
+#endif
+#if defined(__CUDACC__)
+static __device__ const double g_toverp_tab[75] = {DEQ_TOVERP_INIT};
+#endif
+DEQ_HD double toverp_at(int i) {
+#if defined(__CUDA_ARCH__)
+    return g_toverp_tab[i];
+#else
+    return host_tables::toverp_tab[i];
+#endif
+}
+
+DEQ_HD void branred_half(double xh, double& b, double& bb, double& sum_out) {
+    const double big = 0x1.8p52, big1 = 0x1.8p54, tm24 = 0x1p-24;
+    int k = (int)((asu64(xh) >> 52) & 2047u);
+    k = (k - 450) / 24;
+    if (k < 0) k = 0;
+    double gor = asf64(asu64(0x1p576) - ((uint64_t)(k * 24) << 52));
+    double r[6];
+    for (int i = 0; i < 6; ++i) { r[i] = xh * toverp_at(k + i) * gor; gor = gor * tm24; }
+    double sum = 0.0, s, t = 0.0;
+    for (int i = 0; i < 3; ++i) { s = (r[i] + big) - big; sum = sum + s; r[i] = r[i] - s; }
+    for (int i = 0; i < 6; ++i) t = t + r[5 - i];
+    bb = (((((r[0] - t) + r[1]) + r[2]) + r[3]) + r[4]) + r[5];
+    s = (t + big) - big;
+    sum = sum + s;
+    t = t - s;
+    b = t + bb;
+    bb = (t - b) + bb;
+    s = (sum + big1) - big1;
+    sum_out = sum - s;
+}
+
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+int branred(double x, double& a, double& aa) {
+    const double split = 134217729.0;   // 2^27 + 1
+    x = x * 0x1p-600;
+    double t = x * split;
+    const double x1 = t - (t - x), x2 = x - x1;
+    double b1, bb1, sum1, b2, bb2, sum2;
+    branred_half(x1, b1, bb1, sum1);
+    branred_half(x2, b2, bb2, sum2);
+    double sum = sum1 + sum2;
+    double b = b1 + b2;
+    double bb = (fabs(b1) > fabs(b2)) ? (b1 - b) + b2 : (b2 - b) + b1;
+    if (b > 0.5) { b = b - 1.0; sum = sum + 1.0; }
+    else if (b < -0.5) { b = b + 1.0; sum = sum - 1.0; }
+    double s = b + (bb + bb1 + bb2);
+    t = ((b - s) + bb) + (bb1 + bb2);
+    b = s * split;
+    const double t1 = b - (b - s), t2 = s - t1;
+    b = s * 0x1.921FB54442D18p0;   // (branred.h: mp1 + mp2 == hp0 exactly; its mp2 is not the mp2 of reduce_sincos)
+    bb = (((t1 * 0x1.921FB58p0 - b) + t1 * -0x1.DDE974p-27) + t2 * 0x1.921FB58p0) +
+         (t2 * -0x1.DDE974p-27 + s * 0x1.1A62633145C07p-54 + t * 0x1.921FB54442D18p0);
+    s = b + bb;
+    t = (b - s) + bb;
+    a = s;
+    aa = t;
+    return ((int)sum) & 3;
+}
+
 // TAYLOR_SIN(xx, x, dx)
 DEQ_HD double taylor_sin(double x, double dx) {
     const double xx = x * x;
@@ -145,6 +227,15 @@ DEQ_HD double do_sincos(double a, double da, int n, const ST& tab) {
     return (n & 2) ? -r : r;
 }
 
+// |x| >= 105414350 (s_sin.c: `n = __branred (x, &a, &da); retval = do_sincos (a, da, n)`, n + 1 for the cosine), inf / NaN.
+template <class ST>
+DEQ_HD double sincos_large(double x, int quadrant_offset, const ST& tab) {
+    if (((uint32_t)(asu64(x) >> 32) & 0x7fffffffu) >= 0x7ff00000u) return x / x;
+    double a, da;
+    const int n = branred(x, a, da);
+    return do_sincos(a, da, n + quadrant_offset, tab);
+}
+
 // do_sin and do_cos evaluated side by side and selected: every lane of a warp runs the same instruction stream whatever
 // quadrant its argument fell into (on the GPU the two-way branch cost a warp both paths anyway, plus the divergence
 // bookkeeping).  Each flavour's arithmetic is exactly glibc's do_sin / do_cos above, the small-argument Taylor branch of
@@ -187,7 +278,7 @@ template <class ST>
 DEQ_HD double sin_glibc(double x, const ST& tab) {
     const uint32_t k = (uint32_t)(asu64(x) >> 32) & 0x7fffffffu;
     if (k < 0x3e500000u) return x;
-    if (k >= 0x419921FBu) return sin(x);  // outside reduce_sincos' range (see header)
+    if (k >= 0x419921FBu) return sincos_large(x, 0, tab);  // outside reduce_sincos' range: branred, or x / x for inf and NaN
     double a, da;
     int n;
 #ifdef DEQ_SINCOS_BRANCHY
@@ -212,7 +303,7 @@ template <class ST>
 DEQ_HD double cos_glibc(double x, const ST& tab) {
     const uint32_t k = (uint32_t)(asu64(x) >> 32) & 0x7fffffffu;
     if (k < 0x3e400000u) return 1.0;
-    if (k >= 0x419921FBu) return cos(x);
+    if (k >= 0x419921FBu) return sincos_large(x, 1, tab);
     double a, da;
     int n;
 #ifdef DEQ_SINCOS_BRANCHY

@@ -1002,10 +1002,13 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_rows_kernel(const
             dt = P.use_initstep ? P.initstep : P.h0[traj];
             last_step = fabs((t + dt) - tend) <= DBL_EPSILON ? 1u : 0u;
         }
-        unsigned long long r = 1;   // warp-uniform row cursor; rows 1 .. nt-2 are Hermite rows, row nt-1 is the final state
+        unsigned long long r = 1;   // warp-uniform row cursor; rows 1 .. nt-2 are Hermite rows, row nt-1 is the final state (counted only)
         for (;;) {
             // ---- emit every row the whole warp is ready for ----
-            while (r + 1 < nt) {
+            // (row nt-1 takes part as well: its VALUE is the final state, written below, but the reference's emission loop
+            // (problem.rs:303-319) also counts tspan[nt-1] when the last step ends a rounding error past it — `t + (tend - t)` need
+            // not be `tend` — or when a user initstep overshoots the end: `nvalid` then reads nt)
+            while (r < nt) {
                 const double tq = __ldg(P.tspan + r);
                 bool emit = false, wait = false;
                 if (live && it == r) {   // (it < r: this lane has stopped emitting — a step end hit a tspan point exactly — or its run ended early)
@@ -1015,13 +1018,15 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_rows_kernel(const
                 }
                 if (__any_sync(0xffffffffu, wait)) break;
                 if (emit) {
-                    const double theta = (tq - t0v) / dt0v;
+                    if (r + 1 < nt) {
+                        const double theta = (tq - t0v) / dt0v;
 #pragma unroll (N <= 16 ? N : 1)
-                    for (int d = 0; d < N; ++d) {
-                        const double v = (y0v[d] * (1. - theta) + cy[d] * theta) +
-                                         ((cy[d] - y0v[d]) * (1. - 2. * theta) + f0v[d] * (theta - 1.) * dt0v +
-                                          ck[d] * theta * dt0v) * theta * (theta - 1.);
-                        P.dense[((unsigned long long)d * nt + r) * P.ntraj + traj] = v;
+                        for (int d = 0; d < N; ++d) {
+                            const double v = (y0v[d] * (1. - theta) + cy[d] * theta) +
+                                             ((cy[d] - y0v[d]) * (1. - 2. * theta) + f0v[d] * (theta - 1.) * dt0v +
+                                              ck[d] * theta * dt0v) * theta * (theta - 1.);
+                            P.dense[((unsigned long long)d * nt + r) * P.ntraj + traj] = v;
+                        }
                     }
                     ++it;
                 }
@@ -1029,7 +1034,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_rows_kernel(const
             }
             // ---- one attempt for the lanes that have not reached row r (or emit nothing any more) and are not finished ----
             bool need = live && !done;
-            if (need && it == r && r + 1 < nt && have_iv) {
+            if (need && it == r && r < nt && have_iv) {
                 const double tq = __ldg(P.tspan + r);
                 if (tdir * t0v < tdir * tq && tdir * tq < tdir * t) need = false;   // holds a row the warp has not emitted yet
             }

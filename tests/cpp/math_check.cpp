@@ -80,6 +80,24 @@ int main(int argc, char** argv) {
         volatile double vx = x;
         if (!same(sin(vx), deqm::sin_glibc(x, ST)) || !same(cos(vx), deqm::cos_glibc(x, ST))) { printf("sincos special x=%a\n", x); ++bad; }
     }
+    // huge arguments: glibc's __branred (|x| >= 105414350), every binade up to DBL_MAX, and the range boundary
+    for (long i = 0; i < n; ++i) {
+        const uint64_t r = rnd();
+        const uint64_t e = 0x419u + (r >> 52) % (0x7ffu - 0x419u);
+        double x = deqm::asf64((r & 0x800fffffffffffffULL) | (e << 52));
+        if (i % 16 == 0) x = (u01() * 2 - 1) * 4e8;
+        if (i % 1000 == 1) x = 105414350.0 + (double)(i % 7) - 3.0;
+        volatile double vx = x;
+        if (!same(sin(vx), deqm::sin_glibc(x, ST))) { if (bad < 5) printf("sin huge x=%a glibc=%a mine=%a\n", x, sin(vx), deqm::sin_glibc(x, ST)); ++bad; }
+        if (!same(cos(vx), deqm::cos_glibc(x, ST))) { if (bad < 5) printf("cos huge x=%a\n", x); ++bad; }
+    }
+    for (double x : {1e300, -1e300, 1e22, 0x1.fffffffffffffp1023, -0x1.fffffffffffffp1023, 105414350.0, 105414357.85197645, 0x1.921fb54442d18p+600,
+                     (double)INFINITY, -(double)INFINITY, (double)NAN}) {
+        volatile double vx = x;
+        double fs, fc;
+        deqm::sin_cos_glibc(x, x, ST, fs, fc);
+        if (!same(sin(vx), deqm::sin_glibc(x, ST)) || !same(cos(vx), deqm::cos_glibc(x, ST)) || !same(sin(vx), fs) || !same(cos(vx), fc)) { printf("sincos huge special x=%a\n", x); ++bad; }
+    }
     // FAST-mode step factor: relative error of pow_fast_pos against libm (not bit-exact by design)
     double worst = 0.0;
     for (long i = 0; i < n; ++i) {
