@@ -236,6 +236,46 @@ DEQ_HD double sincos_large(double x, int quadrant_offset, const ST& tab) {
     return do_sincos(a, da, n + quadrant_offset, tab);
 }
 
+DEQ_HD double xor_sign_(double v, uint64_t signbit_source) {   // v with its sign flipped iff bit 63 of signbit_source is set
+    return asf64(asu64(v) ^ (signbit_source & 0x8000000000000000ULL));
+}
+
+// do_sin OR do_cos through ONE instruction stream: the operands are selected, not the results (17 FP64 operations instead of
+// 13 + 13 for the two flavours side by side; the small-argument Taylor branch of do_sin is still evaluated alongside).
+// With (A, AA, B, BB) = (sn, ssn, cs, ccs) for the sine and (cs, ccs, sn, ssn) for the cosine both results are
+//     A + fma(s', B, fma(-c, A, fma(s', BB, AA)))            s' = s (sine), -s (cosine)
+// and with X = xr (sine), xr + dx (cosine), xx = X X, P = fma(xx, sn5, sn3), C = xx fma(xx, fma(xx, cs6, cs4), cs2):
+//     sine:   s = xr + fma(X xx, P, dx),   c = fma(xr, dx, C)
+//     cosine: s =      fma(X xx, P, X),    c = C
+// The cosine's forms are obtained from the sine's instructions bit for bit: s = -0.0 + f (x + -0.0 == x for EVERY x, -0.0
+// and +0.0 included) and c = fma(xr, 0.0, C) (xr is finite, so the product is +-0, and C >= +0 is not changed by adding it:
+// C is xx >= +0 times a polynomial close to 1/2).  dx is da with the sign of a transferred on (see sincos_dual2 below for why
+// `x <= 0` and `x < 0` of do_sin / do_cos need not be told apart).
+template <class ST>
+DEQ_HD double sincos_unified(double a, double da, bool want_cos, const ST& tab) {
+    const double ax = fabs(a);
+    const double u = ax + sc::big_();
+    const double xr = ax - (u - sc::big_());
+    const int k = (int)(uint32_t)asu64(u) * 4;
+    const int ka = want_cos ? k + 2 : k, kb = want_cos ? k : k + 2;
+    const double A = tab.at(ka), AA = tab.at(ka + 1), B = tab.at(kb), BB = tab.at(kb + 1);
+    const double dx = xor_sign_(da, asu64(a));
+    const double xc = xr + dx;
+    const double X = want_cos ? xc : xr;
+    const double xx = X * X;
+    const double P = fma_(xx, sc::sn5_(), sc::sn3_());
+    const double C = xx * fma_(xx, fma_(xx, sc::cs6_(), sc::cs4_()), sc::cs2_());
+    const double f = fma_(X * xx, P, want_cos ? xc : dx);
+    const double s = (want_cos ? -0.0 : xr) + f;
+    const double c = fma_(xr, want_cos ? 0.0 : dx, C);
+    const double sp = xor_sign_(s, want_cos ? 0x8000000000000000ULL : 0ULL);
+    const double res = A + fma_(sp, B, fma_(-c, A, fma_(sp, BB, AA)));
+    const double rt = taylor_sin(a, da);   // do_sin's small-argument branch (reads the original da)
+    // sine: copysign(res, a), or the Taylor value for |a| < 0.126; cosine: res
+    const double rs = ax < 0.126 ? rt : copysign_(res, a);
+    return want_cos ? res : rs;
+}
+
 // do_sin and do_cos evaluated side by side and selected: every lane of a warp runs the same instruction stream whatever
 // quadrant its argument fell into (on the GPU the two-way branch cost a warp both paths anyway, plus the divergence
 // bookkeeping).  Each flavour's arithmetic is exactly glibc's do_sin / do_cos above, the small-argument Taylor branch of
@@ -294,9 +334,15 @@ DEQ_HD double sin_glibc(double x, const ST& tab) {
     da = ra ? 0.0 : rb ? sc::hp1_() : da;
     n = ra ? 0 : rb ? 1 : n;
 #endif
+#ifdef DEQ_SINCOS_BRANCHY
     const double r = sincos_dual(a, da, n, tab);
     if (from_cos) return copysign_(r, x);
     return (n & 2) ? -r : r;
+#else
+    const double r = sincos_unified(a, da, (n & 1) != 0, tab);
+    // middle range (taken through do_cos): copysign(r, x); otherwise negate in quadrants 2 and 3
+    return from_cos ? copysign_(r, x) : xor_sign_(r, (uint64_t)(n & 2) << 62);
+#endif
 }
 
 template <class ST>
@@ -324,8 +370,12 @@ DEQ_HD double cos_glibc(double x, const ST& tab) {
     da = ra ? 0.0 : rb ? dab : da;
     n = ra ? 1 : rb ? 0 : n;
 #endif
+#ifdef DEQ_SINCOS_BRANCHY
     const double r = sincos_dual(a, da, n, tab);
     return (n & 2) ? -r : r;
+#else
+    return xor_sign_(sincos_unified(a, da, (n & 1) != 0, tab), (uint64_t)(n & 2) << 62);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -341,9 +391,6 @@ DEQ_HD double cos_glibc(double x, const ST& tab) {
 //     do_cos at table entry 0 (sn = ssn = 0) multiplies every odd power of dx by zero;
 //   * negations by (n & 2) are XORs on the sign bit instead of an FP64 negate and two selects.
 // ---------------------------------------------------------------------------------------------------------------
-DEQ_HD double xor_sign_(double v, uint64_t signbit_source) {   // v with its sign flipped iff bit 63 of signbit_source is set
-    return asf64(asu64(v) ^ (signbit_source & 0x8000000000000000ULL));
-}
 
 template <class ST>
 DEQ_HD double sincos_dual2(double a, double da, bool want_cos, const ST& tab) {
@@ -384,7 +431,7 @@ DEQ_HD void sin_cos_glibc(double xs, double xc, const ST& tab, double& so, doubl
         a = ra ? xs : rb ? ab : a;
         da = ra ? 0.0 : rb ? sc::hp1_() : da;
         n = ra ? 0 : rb ? 1 : n;
-        const double r = sincos_dual2(a, da, (n & 1) != 0, tab);
+        const double r = sincos_unified(a, da, (n & 1) != 0, tab);
         // middle range (taken through do_cos): copysign(r, x); otherwise negate in quadrants 2 and 3
         so = (rb && !ra) ? copysign_(r, xs) : xor_sign_(r, (uint64_t)(n & 2) << 62);
     }
@@ -398,7 +445,7 @@ DEQ_HD void sin_cos_glibc(double xs, double xc, const ST& tab, double& so, doubl
         a = ra ? xc : rb ? ab : a;
         da = ra ? 0.0 : rb ? dab : da;
         n = ra ? 1 : rb ? 0 : n;
-        const double r = sincos_dual2(a, da, (n & 1) != 0, tab);
+        const double r = sincos_unified(a, da, (n & 1) != 0, tab);
         co = xor_sign_(r, (uint64_t)(n & 2) << 62);
     }
 }

@@ -147,6 +147,14 @@ struct Pendulum {
         d[0] = w;
         d[1] = -p[0] * w - sc.s + p[1] * sc.c;
     }
+    // the time-only term on its own (stepper.cuh `stages`: evaluated once per distinct stage time)
+    static constexpr int NG = 1;
+    DEQ_RHS_HD static void forcing(double t, double* g, const double* p) { g[0] = deq_cos(p[2] * t); }
+    DEQ_RHS_HD static void eval_g(double, const double* v, double* d, const double* p, const double* g) {
+        const double w = v[1];
+        d[0] = w;
+        d[1] = -p[0] * w - deq_sin(v[0]) + p[1] * g[0];
+    }
     DEQ_RHS_HD static void eval_r(float t, const float* v, float* d, const float* p) {
         const float th = v[0], w = v[1];
         d[0] = w;

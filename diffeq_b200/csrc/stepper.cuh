@@ -90,11 +90,36 @@ __device__ __forceinline__ void load_params(double* prm, const double* params, c
 // Loops over the state components are fully unrolled while the stage vectors fit the register file (N <= 16); for larger
 // systems they stay rolled — `#pragma unroll (N <= 16 ? N : 1)` — which puts the per-thread arrays (k[S][N], stage argument,
 // trial state) into local memory and keeps the code size independent of N.
-template <class TB, class F, bool FAST, bool SKIPZ = false>
+// Time-only terms of the right-hand side ("forcing": cos(Omega t) of the driven pendulum).  A functor that declares
+//   static constexpr int NG;  forcing(t, g[NG], p);  eval_g(t, y, dy, p, g)     with eval(t, y, dy, p) == eval_g(.., forcing(t))
+// has them evaluated once per DISTINCT stage time: rows with equal c see the same bits of t + c dt, hence the same forcing
+// (Fehlberg 7(8): c3 = c7 = 1/6, c10 = c12 = 1 — and the extra right-hand side of an accepted step sits at t + dt as well),
+// and a row with c = 0 sees the forcing at t, which the previous accepted step left behind (`gcur`; CARRY flavours only).
+// 13 sin + 9 cos per attempt of config 4 instead of 13 + 13; same bits, because nothing is evaluated at different operands.
+template <class F, class = void>
+struct ng_of { static constexpr int value = 0; };
+template <class F>
+struct ng_of<F, decltype((void)F::NG)> { static constexpr int value = F::NG; };
+
+template <int S_>
+constexpr bool has_c_row(const deqt::Data<S_>& d, double c) {
+    for (int r = 1; r < S_; ++r)
+        if (d.c[r] == c) return true;
+    return false;
+}
+// carry the forcing at the current time across attempts: only when the tableau re-visits t (a c = 0 row) and an accepted
+// step's end (a c = 1 row) comes for free
+template <class TB, class F>
+constexpr bool carries_forcing() { return ng_of<F>::value > 0 && has_c_row(TB::data(), 0.0) && has_c_row(TB::data(), 1.0); }
+
+template <class TB, class F, bool FAST, bool SKIPZ = false, bool CARRY = false>
 __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double dt, double (&k)[TB::S][F::N],
-                                       const double* prm, double* ylast = nullptr) {
+                                       const double* prm, double* ylast = nullptr, const double* gcur = nullptr,
+                                       double* gend = nullptr) {
     DEQ_TAB(TB);
     constexpr auto tbc = TB::data();
+    constexpr int NG = ng_of<F>::value;
+    double g[TB::S][NG ? NG : 1];
 #pragma unroll
     for (int row = 1; row < TB::S; ++row) {
         // w_col = a[row][col] * dt first (one product per entry, like the reference), then every component accumulates its
@@ -115,7 +140,28 @@ __device__ __forceinline__ void stages(double t, const double (&y)[F::N], double
             yi[d] = acc;
         }
         const double tn = FAST ? __fma_rn(tb.c[row], dt, t) : t + tb.c[row] * dt;
-        F::eval(tn, yi, k[row], prm);
+        if constexpr (NG > 0) {
+            int src = row;   // the first row with this c (resolved at compile time once the row loop is unrolled)
+#pragma unroll
+            for (int r2 = row - 1; r2 >= 1; --r2)
+                if (tbc.c[r2] == tbc.c[row]) src = r2;
+            if (CARRY && tbc.c[row] == 0.0) {
+#pragma unroll
+                for (int j = 0; j < NG; ++j) g[row][j] = gcur[j];
+            } else if (src == row) {
+                F::forcing(tn, g[row], prm);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NG; ++j) g[row][j] = g[src][j];
+            }
+            F::eval_g(tn, yi, k[row], prm, g[row]);
+            if (gend && tbc.c[row] == 1.0) {
+#pragma unroll
+                for (int j = 0; j < NG; ++j) gend[j] = g[row][j];
+            }
+        } else {
+            F::eval(tn, yi, k[row], prm);
+        }
         if (row == TB::S - 1 && ylast) {
 #pragma unroll (F::N <= 16 ? F::N : 1)
             for (int d = 0; d < F::N; ++d) ylast[d] = yi[d];
@@ -470,9 +516,11 @@ template <class TB, class F, bool FAST, bool SPEC, class TT>
 __device__ __forceinline__ void attempt_math(const AdaptParams& P, const TT& T, double t, double dt, const double (&cy)[F::N],
                                              const double (&ck)[F::N], const double (&yl)[F::N], const double* prm, unsigned timeout,
                                              double tdir, double reltol, double abstol, double (&k)[TB::S][F::N],
-                                             double (&ytrial)[F::N], double& ndt, unsigned& accu) {
+                                             double (&ytrial)[F::N], double& ndt, unsigned& accu,
+                                             const double* cg = nullptr, double* gend = nullptr) {
     constexpr int N = F::N, S = TB::S;
     constexpr bool FSAL = deqt::fsal_of(TB::data());
+    constexpr bool CARRY = carries_forcing<TB, F>();   // cg: forcing at t (in), gend: forcing at t + dt (out)
     DEQ_TAB(TB);
 #pragma unroll (N <= 16 ? N : 1)
     for (int d = 0; d < N; ++d) k[0][d] = ck[d];
@@ -485,10 +533,12 @@ __device__ __forceinline__ void attempt_math(const AdaptParams& P, const TT& T, 
         // terms, and are re-run exactly as written in the rare attempt where a state component is -0.0 or a stage
         // value / the step is not finite (decided on high words: float adds and integer compares, no FP64 work).
         constexpr bool SKIPZ = zero_entries_of_a(TB::data()) >= 4;
-        stages<TB, F, false, SKIPZ>(t, cy, dt, k, prm);
+        // (the carried forcing stands for the one at t + 0 * dt: the same bits unless dt is not finite or t is -0.0, which the
+        // guard below sends to the exact path as well — hence carried in the guarded flavour only)
+        stages<TB, F, false, SKIPZ, SKIPZ && CARRY>(t, cy, dt, k, prm, nullptr, cg, gend);
         if (SKIPZ) {
             float m = fabsf(__int_as_float(__double2hiint(dt)));
-            bool negzero = false;
+            bool negzero = CARRY && (((unsigned)__double2hiint(t) ^ 0x80000000u) | (unsigned)__double2loint(t)) == 0u;
 #pragma unroll (N <= 16 ? N : 1)
             for (int d = 0; d < N; ++d) {
                 negzero = negzero || (((unsigned)__double2hiint(cy[d]) ^ 0x80000000u) | (unsigned)__double2loint(cy[d])) == 0u;
@@ -559,7 +609,7 @@ __device__ __forceinline__ void attempt_math(const AdaptParams& P, const TT& T, 
         // err < 1 decided on the squared norm; one pow for the step factor: 0.8 (1/err)^PW = exp(ln 0.8 - PW/2 ln ssum).
         // For a first-same-as-last tableau the argument of the last stage is the new solution itself.
         constexpr auto tbc = TB::data();
-        stages<TB, F, true>(t, cy, dt, k, prm, FSAL ? ytrial : nullptr);
+        stages<TB, F, true, false, CARRY>(t, cy, dt, k, prm, FSAL ? ytrial : nullptr, cg, gend);
 #pragma unroll (N <= 16 ? N : 1)
         for (int d = 0; d < N; ++d) {
             double p = 0.0, e = 0.0;
@@ -658,7 +708,10 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     // the lowest lanes of the CTA; emptied warps then only wait at the census barrier, and the issue slots they
     // occupied go to the warps that still have work.  Scheduling only: a trajectory's arithmetic does not depend on the lane
     // that runs it.  Final-state and SoA-dense flavours (the staged layouts keep per-lane rings in shared memory).
-    constexpr int PACK_SLOTS = 2 + 2 * N + (PT ? F::NP : 0) + 3 + (ROWS ? 1 : 0);
+    constexpr int NG = ng_of<F>::value;
+    constexpr bool CARRY = carries_forcing<TB, F>();   // forcing at the current time, kept across attempts (see stages)
+    constexpr bool GEND = NG > 0 && has_c_row(TB::data(), 1.0);   // the stages leave the forcing at t + dt behind
+    constexpr int PACK_SLOTS = 2 + 2 * N + (PT ? F::NP : 0) + 3 + (ROWS ? 1 : 0) + (CARRY ? NG : 0);
     constexpr bool CAN_COMPACT = (MODE == MODE_FINAL || MODE == MODE_DENSE) && !SPEC && PACK_SLOTS <= 24;
     constexpr int TAIL_BURSTS = 4;
     // attempts between two refill checks: a check costs ~25 issue slots, an attempt of a 13-stage tableau with a transcendental
@@ -690,6 +743,9 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
     double t = 0.0, dt = 0.0;
     double cy[N], ck[N], prm[F::NP ? F::NP : 1];
     double yl[N];   // SPEC only: ys[ys.len() - 1], the last row of the output vector (dead code otherwise)
+    double cg[NG ? NG : 1];   // CARRY only: forcing at t
+#pragma unroll
+    for (int j = 0; j < (NG ? NG : 1); ++j) cg[j] = 0.0;
     unsigned timeout = 0;
     unsigned last_step = 0u;
     uint32_t acc = 0, rej = 0, attempts = 0;
@@ -725,7 +781,9 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                 double ndt;
                 unsigned accu;   // the accept decision as an opaque integer: ONE FP64 compare, every later test is an integer one
                 const unsigned timeout_next = timeout - (timeout > 0u ? 1u : 0u);   // stepsize_hw92 :835-838
-                attempt_math<TB, F, FAST, SPEC>(P, T, t, dt, cy, ck, yl, prm, timeout, tdir, reltol, abstol, k, ytrial, ndt, accu);
+                double gend[NG ? NG : 1];
+                attempt_math<TB, F, FAST, SPEC>(P, T, t, dt, cy, ck, yl, prm, timeout, tdir, reltol, abstol, k, ytrial, ndt, accu,
+                                                cg, GEND ? gend : nullptr);
                 asm("" : "+r"(accu));
                 const bool accept = accu != 0u;
                 const double tn = t + dt;   // (the row-emitting flavours need it before the state update)
@@ -733,7 +791,10 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     // the parts of an accepted step that are real work: the extra right-hand side of a non-FSAL tableau
                     // and the output rows.  Branchy on purpose; absent from the FSAL / final-state instantiations.
                     if (accept) {
-                        if (!FSAL) F::eval(tn, ytrial, k[S - 1], prm);   // f1 overwrites the last stage (dead after the error estimate)
+                        if (!FSAL) {   // f1 overwrites the last stage (dead after the error estimate)
+                            if constexpr (GEND) F::eval_g(tn, ytrial, k[S - 1], prm, gend);
+                            else F::eval(tn, ytrial, k[S - 1], prm);
+                        }
                         double (&f1)[N] = k[S - 1];
                         if (SPEC) {
                             // Points::Specified :284-300 — every tspan point before t+dt, all remaining ones on the last step;
@@ -791,6 +852,10 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                 if (accept) {
 #pragma unroll (N <= 16 ? N : 1)
                     for (int d = 0; d < N; ++d) { ck[d] = k[S - 1][d]; cy[d] = ytrial[d]; }
+                    if constexpr (CARRY) {
+#pragma unroll
+                        for (int j = 0; j < NG; ++j) cg[j] = gend[j];
+                    }
                 }
                 // end snap of an accepted, not-yet-last step: `if tdir*((t+dt) + dt/100) >= tdir*tend { dt = tend - t; last = true }`
                 // with the NEW t and dt (:336-340); evaluated for every lane, used by the accepting ones.  A trajectory stops
@@ -853,6 +918,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                         if (SPEC) yl[d] = cy[d];
                     }
                     t = P.t0;
+                    if constexpr (CARRY) F::forcing(t, cg, prm);
                     dt = P.use_initstep ? P.initstep : P.h0[traj];
                     timeout = 0;
                     last_step = fabs((t + dt) - tend) <= DBL_EPSILON ? 1u : 0u;
@@ -907,6 +973,10 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                 pk.v[f++] = __hiloint2double((int)acc, (int)rej);
                 pk.v[f++] = __hiloint2double((int)attempts, (int)(timeout | (last_step << 16)));
                 if (ROWS) pk.v[f++] = __longlong_as_double((long long)it);
+                if (CARRY) {
+#pragma unroll
+                    for (int j = 0; j < NG; ++j) pk.v[f++] = cg[j];
+                }
                 pk.active = active;
             }
             pk = tail_census(pk, s_pack, s_cnt[census & 1u]);
@@ -927,6 +997,10 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                 attempts = (uint32_t)__double2hiint(at);
                 timeout = (unsigned)__double2loint(at) & 0xffffu; last_step = ((unsigned)__double2loint(at) >> 16) & 1u;
                 if (ROWS) it = (unsigned long long)__double_as_longlong(pk.v[f++]);
+                if (CARRY) {
+#pragma unroll
+                    for (int j = 0; j < NG; ++j) cg[j] = pk.v[f++];
+                }
                 active = pk.active;
             }
             run_bursts(BURST * TAIL_BURSTS);
@@ -982,6 +1056,12 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_rows_kernel(const
         const bool live = traj < P.ntraj;
         double cy[N], ck[N], yl[N], prm[F::NP ? F::NP : 1];
         double y0v[N], f0v[N];           // start state and slope of the last accepted step (its end: cy, ck)
+        constexpr int NG = ng_of<F>::value;
+        constexpr bool CARRY = carries_forcing<TB, F>();
+        constexpr bool GEND = NG > 0 && has_c_row(TB::data(), 1.0);
+        double cg[NG ? NG : 1];
+#pragma unroll
+        for (int j = 0; j < (NG ? NG : 1); ++j) cg[j] = 0.0;
         double t = P.t0, dt = 0.0, t0v = P.t0, dt0v = 0.0;
         unsigned timeout = 0u, last_step = 0u, done = live ? 0u : 1u, have_iv = 0u;
         uint32_t acc = 0, rej = 0, attempts = 0;
@@ -999,6 +1079,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_rows_kernel(const
                 ck[d] = P.f0[(unsigned long long)d * P.ntraj + traj];
                 P.dense[((unsigned long long)d * nt) * P.ntraj + traj] = cy[d];   // row 0 = y0
             }
+            if constexpr (CARRY) F::forcing(t, cg, prm);
             dt = P.use_initstep ? P.initstep : P.h0[traj];
             last_step = fabs((t + dt) - tend) <= DBL_EPSILON ? 1u : 0u;
         }
@@ -1045,11 +1126,20 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_rows_kernel(const
                 double ndt;
                 unsigned accu;
                 const unsigned timeout_next = timeout - (timeout > 0u ? 1u : 0u);
-                attempt_math<TB, F, FAST, false>(P, T, t, dt, cy, ck, yl, prm, timeout, tdir, reltol, abstol, k, ytrial, ndt, accu);
+                double gend[NG ? NG : 1];
+                attempt_math<TB, F, FAST, false>(P, T, t, dt, cy, ck, yl, prm, timeout, tdir, reltol, abstol, k, ytrial, ndt, accu,
+                                                 cg, GEND ? gend : nullptr);
                 const bool accept = accu != 0u;
                 const double tn = t + dt;
                 if (accept) {
-                    if (!FSAL) F::eval(tn, ytrial, k[S - 1], prm);
+                    if (!FSAL) {
+                        if constexpr (GEND) F::eval_g(tn, ytrial, k[S - 1], prm, gend);
+                        else F::eval(tn, ytrial, k[S - 1], prm);
+                    }
+                    if constexpr (CARRY) {
+#pragma unroll
+                        for (int j = 0; j < NG; ++j) cg[j] = gend[j];
+                    }
 #pragma unroll (N <= 16 ? N : 1)
                     for (int d = 0; d < N; ++d) { y0v[d] = cy[d]; f0v[d] = ck[d]; cy[d] = ytrial[d]; ck[d] = k[S - 1][d]; }
                     t0v = t; dt0v = dt; have_iv = 1u;
