@@ -587,6 +587,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
             std::string err;
             if (e->rhs.kind == 0) CKR(deql::launch_hinit(e->rhs.sys, e->per_traj, H, st));
             else if (!deqn::launch_hinit(e->rhs.prog, e->per_traj, H, st, &err)) return bail(fail(DEQ_ERR_NVRTC, err));
+            bool launched = false, ev0_recorded = false;
             if (mode == (int)deqk::MODE_DENSE_ROWS && o.refill == 2 && o.initstep == 0.) {
                 // SoA rows, choice left open: neighbours that start alike (a parameter-sorted sweep) advance together, and the
                 // lane-refill kernel's own stores coalesce (and it keeps its lanes busier); otherwise the row-synchronous kernel
@@ -597,11 +598,42 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
                 CKR(cudaStreamSynchronize(st));
                 CKR(cudaMemsetAsync(r->d_scalars + 1, 0, 2 * sizeof(unsigned long long), st));
                 if (hc[1] > 0 && (double)hc[0] <= 0.02 * (double)hc[1]) mode = (int)deqk::MODE_DENSE;
+                else if (ntraj >= 64 && ntraj < 0x7fffffffull && !getenv("DEQ_NO_SORTED_DENSE")) {
+                    // Not coherent as given.  Sorted by first step size it may be (a parameter sweep handed over in arbitrary order
+                    // is): then the lane-refill kernel runs the work items in that order, its row stores coalesce again — columns in
+                    // the order of the work items, and an in-place pass through an L2-sized scratch puts the columns back where the
+                    // caller expects them (HBM-bound, each byte about once in each direction; no second copy of the rows — config 3
+                    // is 67 GB).  The timed region starts here: sort, kernel and column permutation.
+                    CKR(cudaEventRecord(r->ev0, st));
+                    ev0_recorded = true;
+                    TempBuf<uint32_t> order(st), inv(st);
+                    TempBuf<double> hs(st), rows(st);
+                    TempBuf<char> scratch(st);
+                    const size_t sb = deql::sort_by_h0_scratch_bytes(ntraj);
+                    CKR(dalloc(&order.p, ntraj, st)); CKR(dalloc(&inv.p, ntraj, st)); CKR(dalloc(&hs.p, ntraj, st)); CKR(dalloc(&scratch.p, sb, st));
+                    CKR(deql::launch_sort_by_h0(r->d_h0, ntraj, order.p, inv.p, hs.p, scratch.p, sb, st));
+                    CKR(deql::launch_coherence(hs.p, ntraj, r->d_scalars + 1, st));
+                    CKR(cudaMemcpyAsync(hc, r->d_scalars + 1, sizeof(hc), cudaMemcpyDeviceToHost, st));
+                    CKR(cudaStreamSynchronize(st));
+                    CKR(cudaMemsetAsync(r->d_scalars + 1, 0, 2 * sizeof(unsigned long long), st));
+                    if (hc[1] > 0 && (double)hc[0] <= 0.02 * (double)hc[1]) {
+                        CKR(dalloc(&rows.p, 2 * deql::permute_rows_batch(ntraj) * ntraj, st));
+                        P.order = order.p;
+                        mode = (int)deqk::MODE_DENSE;
+                        const int rc = launch_adapt(&err);
+                        if (rc == 1) return bail(DEQ_ERR_CUDA);
+                        if (rc == 2) return bail(fail(DEQ_ERR_NVRTC, err));
+                        CKR(deql::launch_permute_rows_inplace(r->d_dense, inv.p, (unsigned long long)n * nt, ntraj, rows.p, st));
+                        launched = true;
+                    }
+                }
             }
-            CKR(cudaEventRecord(r->ev0, st));
-            const int rc = launch_adapt(&err);
-            if (rc == 1) return bail(DEQ_ERR_CUDA);
-            if (rc == 2) return bail(fail(DEQ_ERR_NVRTC, err));
+            if (!launched) {
+                if (!ev0_recorded) CKR(cudaEventRecord(r->ev0, st));
+                const int rc = launch_adapt(&err);
+                if (rc == 1) return bail(DEQ_ERR_CUDA);
+                if (rc == 2) return bail(fail(DEQ_ERR_NVRTC, err));
+            }
         } else {
             CKR(cudaEventRecord(r->ev0, st));
         }

@@ -3,6 +3,7 @@
 // Compiled with -fmad=false like every parity translation unit.
 #include "stepper.cuh"
 #include "launch.h"
+#include <cub/device/device_radix_sort.cuh>
 
 namespace deql {
 
@@ -157,6 +158,104 @@ cudaError_t launch_coherence(const double* h0, unsigned long long n, unsigned lo
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned long long want = (n + 255) / 256, cap = (unsigned long long)sms * 8;
     coherence_kernel<<<(unsigned)(want < cap ? (want ? want : 1) : cap), 256, 0, st>>>(h0, n, d_out);
+    return cudaGetLastError();
+}
+
+// ---- first-step ordering (the sorted SoA dense path of deq_solve) --------------------------------------------------------
+// An ensemble in arbitrary order defeats the lane-refill kernel's row stores (every lane sits in its own output row).  Sorted by
+// the size of the first step hinit chose — a cheap stand-in for "how fast does this trajectory move" — neighbours advance alike
+// again (for a parameter sweep the order IS the sweep).  Keys are the bit patterns of |h0| (monotone for non-negative
+// doubles; NaN sorts last), values the trajectory indices: one CUB radix sort, 12 bytes per trajectory.
+__global__ void __launch_bounds__(256) sort_keys_kernel(const double* __restrict__ h0, unsigned long long n, unsigned long long* __restrict__ keys,
+                                                        uint32_t* __restrict__ vals) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = (unsigned long long)__double_as_longlong(h0[i]) & 0x7fffffffffffffffull;
+    vals[i] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(256) invert_order_kernel(const uint32_t* __restrict__ order, unsigned long long n, uint32_t* __restrict__ inv) {
+    const unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) inv[order[s]] = (uint32_t)s;
+}
+static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+static size_t cub_sort_bytes(unsigned long long n) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)n);
+    return b;
+}
+size_t sort_by_h0_scratch_bytes(unsigned long long n) { return align256(n * 8) + align256(n * 4) + align256(cub_sort_bytes(n)); }
+cudaError_t launch_sort_by_h0(const double* h0, unsigned long long n, uint32_t* order, uint32_t* inv, double* h0_sorted,
+                              void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    if (n > 0x7fffffffull || scratch_bytes < sort_by_h0_scratch_bytes(n)) return cudaErrorInvalidValue;
+    char* p = (char*)scratch;
+    unsigned long long* keys = (unsigned long long*)p; p += align256(n * 8);
+    uint32_t* vals = (uint32_t*)p; p += align256(n * 4);
+    size_t cb = cub_sort_bytes(n);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    sort_keys_kernel<<<grid, 256, 0, st>>>(h0, n, keys, vals);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs((void*)p, cb, (const unsigned long long*)keys, (unsigned long long*)h0_sorted,
+                                                    (const uint32_t*)vals, order, (int)n, 0, 64, st);
+    if (e != cudaSuccess) return e;
+    invert_order_kernel<<<grid, 256, 0, st>>>(order, n, inv);
+    return cudaGetLastError();
+}
+
+// Columns back into caller order, IN PLACE: rows[q][j] <- rows[q][inv[j]] for nrows rows of ntraj doubles.  A row cannot be
+// permuted in place directly (a gather reads what a neighbour overwrites), and a second copy of the rows may not fit (config 3
+// is 67 GB), so the rows travel in batches through a small scratch that stays in L2: launch i gathers batch i out of scratch
+// (i & 1) back into its rows — coalesced writes, scattered reads that hit L2 — and copies batch i + 1 into the other scratch
+// (coalesced both ways).  DRAM sees each byte about once in each direction; the scratch is 2 x batch_rows x ntraj doubles.
+__global__ void __launch_bounds__(256) permute_batch_kernel(double* __restrict__ rows, const uint32_t* __restrict__ inv, unsigned long long ntraj,
+                                                            unsigned long long chunks, unsigned long long g_row0, unsigned long long g_nrows,
+                                                            const double* __restrict__ g_scratch, unsigned long long c_row0,
+                                                            unsigned long long c_nrows, double* __restrict__ c_scratch) {
+    const unsigned long long g_items = g_nrows * chunks, c_items = c_nrows * chunks;
+    for (unsigned long long b = blockIdx.x; b < g_items + c_items; b += gridDim.x) {
+        const bool gather = b < g_items;
+        const unsigned long long bb = gather ? b : b - g_items;
+        const unsigned long long q = bb / chunks, j0 = (bb % chunks) * 1024ull;
+        if (gather) {
+            const double* s = g_scratch + q * ntraj;
+            double* d = rows + (g_row0 + q) * ntraj;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned long long j = j0 + (unsigned long long)u * 256 + threadIdx.x;
+                if (j < ntraj) d[j] = s[inv[j]];
+            }
+        } else {
+            const double* s = rows + (c_row0 + q) * ntraj;
+            double* d = c_scratch + q * ntraj;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned long long j = j0 + (unsigned long long)u * 256 + threadIdx.x;
+                if (j < ntraj) d[j] = s[j];
+            }
+        }
+    }
+}
+unsigned long long permute_rows_batch(unsigned long long ntraj) {
+    const unsigned long long b = (24ull << 20) / (ntraj * 8ull ? ntraj * 8ull : 1ull);   // ~24 MB per scratch half: both halves and the rows in flight fit L2
+    return b < 1 ? 1 : (b > 64 ? 64 : b);
+}
+cudaError_t launch_permute_rows_inplace(double* rows, const uint32_t* inv, unsigned long long nrows, unsigned long long ntraj, double* scratch,
+                                        cudaStream_t st) {
+    if (nrows == 0 || ntraj == 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned long long B = permute_rows_batch(ntraj), chunks = (ntraj + 1023) / 1024, nb = (nrows + B - 1) / B;
+    const unsigned long long cap = (unsigned long long)sms * 8;
+    double* half[2] = {scratch, scratch + B * ntraj};
+    auto rows_of = [&](unsigned long long i) { return i + 1 < nb ? B : nrows - i * B; };
+    auto launch = [&](unsigned long long g0, unsigned long long gn, const double* gs, unsigned long long c0, unsigned long long cn, double* cs) {
+        const unsigned long long want = (gn + cn) * chunks;
+        permute_batch_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(rows, inv, ntraj, chunks, g0, gn, gs, c0, cn, cs);
+    };
+    launch(0, 0, nullptr, 0, rows_of(0), half[0]);
+    for (unsigned long long i = 0; i < nb; ++i)
+        launch(i * B, rows_of(i), half[i & 1], (i + 1) * B, i + 1 < nb ? rows_of(i + 1) : 0, half[(i + 1) & 1]);
     return cudaGetLastError();
 }
 

@@ -50,6 +50,16 @@ cudaError_t launch_transpose_to_aos(const double* d_soa, double* d_aos, unsigned
 cudaError_t launch_sum_counts(const uint32_t* acc, const uint32_t* rej, const uint32_t* nfe, unsigned long long n,
                               unsigned long long* totals, cudaStream_t st);
 cudaError_t launch_coherence(const double* h0, unsigned long long n, unsigned long long* d_out, cudaStream_t st);
+// first-step ordering of an ensemble (deq_solve's sorted SoA dense path): order[s] = index of the trajectory with the s-th smallest
+// |h0|, inv = its inverse, h0_sorted[s] = |h0[order[s]]|; scratch of sort_by_h0_scratch_bytes(n) bytes
+size_t sort_by_h0_scratch_bytes(unsigned long long n);
+cudaError_t launch_sort_by_h0(const double* h0, unsigned long long n, uint32_t* order, uint32_t* inv, double* h0_sorted,
+                              void* scratch, size_t scratch_bytes, cudaStream_t st);
+// rows[q][j] <- rows[q][inv[j]] in place for nrows rows of ntraj doubles (columns back from sorted to caller order), through a
+// scratch of 2 * permute_rows_batch(ntraj) * ntraj doubles that stays in L2
+unsigned long long permute_rows_batch(unsigned long long ntraj);
+cudaError_t launch_permute_rows_inplace(double* rows, const uint32_t* inv, unsigned long long nrows, unsigned long long ntraj, double* scratch,
+                                        cudaStream_t st);
 cudaError_t launch_test_div(unsigned long long seed, unsigned long long count, unsigned long long* d_out, cudaStream_t st);
 cudaError_t launch_test_pow(const double* x, const double* y, double* out, unsigned long long n, cudaStream_t st);
 cudaError_t launch_test_log10(const double* x, double* out, unsigned long long n, cudaStream_t st);

@@ -55,6 +55,11 @@ struct AdaptParams {
     // ode23s only (stiff.cuh)
     int true_inverse;      // TEXTBOOK set: invert W = I - h d J itself, not its packed LU factors (problem.rs:469,481)
     int points_specified;  // Points::Specified: MODE_REC rows are the tspan points only (problem.rs:536)
+    // MODE_DENSE only (lane-refill SoA rows): work item s integrates trajectory order[s] — inputs are read from, and the
+    // per-trajectory results written to, index order[s], while its dense rows go to COLUMN s of `dense` (a scratch buffer that
+    // capi.cu un-permutes afterwards).  nullptr: identity.  Used to run an ensemble in the order of its first step sizes, so
+    // that neighbouring lanes advance alike and their row stores coalesce (see deq_solve).
+    const uint32_t* order;
 };
 
 struct HinitParams {
