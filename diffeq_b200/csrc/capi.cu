@@ -617,7 +617,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
                     CKR(cudaStreamSynchronize(st));
                     CKR(cudaMemsetAsync(r->d_scalars + 1, 0, 2 * sizeof(unsigned long long), st));
                     if (hc[1] > 0 && (double)hc[0] <= 0.02 * (double)hc[1]) {
-                        CKR(dalloc(&rows.p, 2 * deql::permute_rows_batch(ntraj) * ntraj, st));
+                        CKR(dalloc(&rows.p, 2 * deql::permute_rows_batch(ntraj) * ntraj + 1, st));   // + the barrier word of the persistent permutation kernel
                         P.order = order.p;
                         mode = (int)deqk::MODE_DENSE;
                         const int rc = launch_adapt(&err);

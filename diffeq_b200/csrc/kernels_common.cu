@@ -3,6 +3,7 @@
 // Compiled with -fmad=false like every parity translation unit.
 #include "stepper.cuh"
 #include "launch.h"
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace deql {
@@ -207,55 +208,90 @@ cudaError_t launch_sort_by_h0(const double* h0, unsigned long long n, uint32_t* 
 // is 67 GB), so the rows travel in batches through a small scratch that stays in L2: launch i gathers batch i out of scratch
 // (i & 1) back into its rows — coalesced writes, scattered reads that hit L2 — and copies batch i + 1 into the other scratch
 // (coalesced both ways).  DRAM sees each byte about once in each direction; the scratch is 2 x batch_rows x ntraj doubles.
-__global__ void __launch_bounds__(256) permute_batch_kernel(double* __restrict__ rows, const uint32_t* __restrict__ inv, unsigned long long ntraj,
-                                                            unsigned long long chunks, unsigned long long g_row0, unsigned long long g_nrows,
-                                                            const double* __restrict__ g_scratch, unsigned long long c_row0,
-                                                            unsigned long long c_nrows, double* __restrict__ c_scratch) {
-    const unsigned long long g_items = g_nrows * chunks, c_items = c_nrows * chunks;
-    for (unsigned long long b = blockIdx.x; b < g_items + c_items; b += gridDim.x) {
-        const bool gather = b < g_items;
-        const unsigned long long bb = gather ? b : b - g_items;
-        const unsigned long long q = bb / chunks, j0 = (bb % chunks) * 1024ull;
-        if (gather) {
-            const double* s = g_scratch + q * ntraj;
-            double* d = rows + (g_row0 + q) * ntraj;
+// One persistent launch: phase i gathers batch i and copies batch i + 1; the phases are separated by a grid-wide barrier (all
+// CTAs are co-resident: the grid is sized from the occupancy query), which costs ~2 us against ~5 us of launch latency and the
+// ramp-up / drain of 668 separate launches at 2^20 trajectories.  Scratch reads bypass L1 (__ldcg): other SMs wrote the data
+// earlier in this same launch.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned nblocks, unsigned& generation) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++generation;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*(volatile unsigned*)counter < generation * nblocks) {}
+        __threadfence();
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(256) permute_persistent_kernel(double* rows, const uint32_t* __restrict__ inv, unsigned long long ntraj,
+                                                                 unsigned long long chunks, unsigned long long nrows, unsigned long long B,
+                                                                 double* scratch, unsigned* barrier) {
+    const unsigned long long nb = (nrows + B - 1) / B;
+    unsigned generation = 0;
+    for (unsigned long long ph = 0; ph <= nb; ++ph) {   // phase ph: gather batch ph - 1, copy batch ph
+        const unsigned long long g_row0 = ph ? (ph - 1) * B : 0, g_nrows = ph ? (ph < nb ? B : nrows - (nb - 1) * B) : 0;
+        const unsigned long long c_row0 = ph * B, c_nrows = ph < nb ? (ph + 1 < nb ? B : nrows - ph * B) : 0;
+        const double* g_scratch = scratch + ((ph + 1) & 1ull) * B * ntraj;   // batch ph - 1 was copied into half (ph - 1) & 1
+        double* c_scratch = scratch + (ph & 1ull) * B * ntraj;
+        const unsigned long long g_items = g_nrows * chunks, c_items = c_nrows * chunks;
+        for (unsigned long long b = blockIdx.x; b < g_items + c_items; b += gridDim.x) {
+            const bool gather = b < g_items;
+            const unsigned long long bb = gather ? b : b - g_items;
+            const unsigned long long q = bb / chunks, j0 = (bb % chunks) * 1024ull;
+            if (gather) {
+                const double* s = g_scratch + q * ntraj;
+                double* d = rows + (g_row0 + q) * ntraj;
+                double v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const unsigned long long j = j0 + (unsigned long long)u * 256 + threadIdx.x;
-                if (j < ntraj) d[j] = s[inv[j]];
-            }
-        } else {
-            const double* s = rows + (c_row0 + q) * ntraj;
-            double* d = c_scratch + q * ntraj;
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned long long j = j0 + (unsigned long long)u * 256 + threadIdx.x;
+                    if (j < ntraj) v[u] = __ldcg(s + inv[j]);
+                }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const unsigned long long j = j0 + (unsigned long long)u * 256 + threadIdx.x;
-                if (j < ntraj) d[j] = s[j];
+                for (int u = 0; u < 4; ++u) {   // streaming stores: the finished rows must not push the scratch out of L2
+                    const unsigned long long j = j0 + (unsigned long long)u * 256 + threadIdx.x;
+                    if (j < ntraj) __stcs(d + j, v[u]);
+                }
+            } else {
+                const double* s = rows + (c_row0 + q) * ntraj;
+                double* d = c_scratch + q * ntraj;
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned long long j = j0 + (unsigned long long)u * 256 + threadIdx.x;
+                    if (j < ntraj) v[u] = __ldcs(s + j);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned long long j = j0 + (unsigned long long)u * 256 + threadIdx.x;
+                    if (j < ntraj) d[j] = v[u];
+                }
             }
         }
+        if (ph < nb) grid_barrier(barrier, gridDim.x, generation);
     }
 }
 unsigned long long permute_rows_batch(unsigned long long ntraj) {
-    const unsigned long long b = (24ull << 20) / (ntraj * 8ull ? ntraj * 8ull : 1ull);   // ~24 MB per scratch half: both halves and the rows in flight fit L2
+    if (const char* e = getenv("DEQ_PERM_BATCH")) return strtoull(e, nullptr, 10) ? strtoull(e, nullptr, 10) : 1;
+    const unsigned long long b = (48ull << 20) / (ntraj * 8ull ? ntraj * 8ull : 1ull);   // ~48 MB per scratch half (measured best of 16 .. 96 MB at 2^20 trajectories: fewer barriers against L2 pressure)
     return b < 1 ? 1 : (b > 64 ? 64 : b);
 }
+// scratch: 2 * permute_rows_batch(ntraj) * ntraj doubles, followed by one zeroed 32-bit word (the barrier counter)
 cudaError_t launch_permute_rows_inplace(double* rows, const uint32_t* inv, unsigned long long nrows, unsigned long long ntraj, double* scratch,
                                         cudaStream_t st) {
     if (nrows == 0 || ntraj == 0) return cudaSuccess;
-    int dev = 0, sms = 148;
+    int dev = 0, sms = 148, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned long long B = permute_rows_batch(ntraj), chunks = (ntraj + 1023) / 1024, nb = (nrows + B - 1) / B;
-    const unsigned long long cap = (unsigned long long)sms * 8;
-    double* half[2] = {scratch, scratch + B * ntraj};
-    auto rows_of = [&](unsigned long long i) { return i + 1 < nb ? B : nrows - i * B; };
-    auto launch = [&](unsigned long long g0, unsigned long long gn, const double* gs, unsigned long long c0, unsigned long long cn, double* cs) {
-        const unsigned long long want = (gn + cn) * chunks;
-        permute_batch_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(rows, inv, ntraj, chunks, g0, gn, gs, c0, cn, cs);
-    };
-    launch(0, 0, nullptr, 0, rows_of(0), half[0]);
-    for (unsigned long long i = 0; i < nb; ++i)
-        launch(i * B, rows_of(i), half[i & 1], (i + 1) * B, i + 1 < nb ? rows_of(i + 1) : 0, half[(i + 1) & 1]);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, permute_persistent_kernel, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const unsigned long long B = permute_rows_batch(ntraj), chunks = (ntraj + 1023) / 1024;
+    unsigned* barrier = (unsigned*)(scratch + 2 * B * ntraj);
+    e = cudaMemsetAsync(barrier, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    const unsigned long long cap = (unsigned long long)sms * (unsigned long long)per_sm, want = 2 * B * chunks;
+    permute_persistent_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(rows, inv, ntraj, chunks, nrows, B, scratch, barrier);
     return cudaGetLastError();
 }
 

@@ -56,7 +56,7 @@ size_t sort_by_h0_scratch_bytes(unsigned long long n);
 cudaError_t launch_sort_by_h0(const double* h0, unsigned long long n, uint32_t* order, uint32_t* inv, double* h0_sorted,
                               void* scratch, size_t scratch_bytes, cudaStream_t st);
 // rows[q][j] <- rows[q][inv[j]] in place for nrows rows of ntraj doubles (columns back from sorted to caller order), through a
-// scratch of 2 * permute_rows_batch(ntraj) * ntraj doubles that stays in L2
+// scratch of 2 * permute_rows_batch(ntraj) * ntraj + 1 doubles (the batches stay in L2; the last word is a barrier counter)
 unsigned long long permute_rows_batch(unsigned long long ntraj);
 cudaError_t launch_permute_rows_inplace(double* rows, const uint32_t* inv, unsigned long long nrows, unsigned long long ntraj, double* scratch,
                                         cudaStream_t st);

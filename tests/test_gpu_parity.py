@@ -207,6 +207,32 @@ def test_soa_dense_rows_any_order(deq, oracle, order):
     assert (ref["nvalid"] < 50).any()   # the early-stop case really leaves rows unwritten
 
 
+def test_soa_dense_rows_sorted_by_first_step_large(deq, oracle):
+    """A sweep handed over in random order, 70 001 trajectories: the sorted SoA path of deq_solve (work items ordered by first
+    step size, lane-refill kernel through the order table, columns put back in place in several batches) — rows, nvalid, counters
+    and final states equal the oracle's, for a ragged trajectory count, forward and with an early stop (rows left unwritten)."""
+    from diffeq_b200 import synth
+    n = 70001
+    y0, mu = synth.vdp_sweep(0, n, n)
+    perm = np.random.default_rng(11).permutation(n)
+    mu = mu[perm].copy()
+    for ts, kw in ((deq.linspace(0.0, 2.0, 14), dict()), (deq.linspace(0.0, 6.0, 9), dict(max_steps=40))):
+        oo = oracle.opts(1e-6, 1e-8, **kw)
+        ref = oracle.ensemble_dense(oracle.ODE45FE, oracle.VANDERPOL, mu, y0, ts, oo, 0)
+        want = ref["out"].transpose(2, 1, 0)
+        o = deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8), deq.Output.Tspan)
+        if "max_steps" in kw: o.insert(deq.MaxSteps(kw["max_steps"]))
+        sol = _problem(deq, deq.System.VanDerPol, mu, y0, ts).solve(deq.Ode.Ode45fe, o)
+        assert np.array_equal(sol.nvalid, ref["nvalid"])
+        msk = np.arange(len(ts))[None, :] < np.maximum(ref["nvalid"], 1)[:, None]
+        msk[:, -1] = True
+        assert np.array_equal(sol.yout[msk], want[msk])
+        assert np.array_equal(sol.accepted, ref["accepted"]) and np.array_equal(sol.rejected, ref["rejected"])
+        assert np.array_equal(sol.status, ref["status"])
+        assert np.array_equal(sol.final, want[:, -1, :])
+    assert (ref["nvalid"] < 8).any()
+
+
 def test_pendulum_feh78_textbook_bit_exact(deq, oracle):
     """BASELINE config 4 at oracle-sized N.  The pendulum calls sin/cos; the device evaluates glibc's algorithm
     (deq_sincos.cuh), so even at rtol = atol = 1e-12 every count and every final state equals the oracle's."""
