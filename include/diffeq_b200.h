@@ -99,10 +99,12 @@ typedef enum deq_libm { DEQ_LIBM_AS_WRITTEN = 0, DEQ_LIBM_LLVM_FOLDED = 1 } deq_
  * trajectories advance together (parameter-sorted sweeps: the fastest choice there); in the row-synchronous kernel
  * (refill = 0) a warp owns 32 consecutive trajectories and emits each row together — one 256-byte store per component and
  * row whatever the order of the ensemble, at the price of lanes waiting for each other.  refill = 2 (default) decides after
- * the initial-step pass: if neighbouring trajectories start with (almost) equal steps the lane-refill kernel runs,
- * otherwise the row-synchronous one.  The output is bit-identical either way.  TRAJ_MAJOR [ntraj][ntspan][n] is one contiguous stream per trajectory —
+ * the initial-step pass: if neighbouring trajectories start with (almost) equal steps the lane-refill kernel runs; if they do
+ * once the ensemble is SORTED by first step size (a sweep handed over in arbitrary order), the lane-refill kernel runs the
+ * trajectories in that order and the columns are permuted back in place afterwards; otherwise the row-synchronous kernel.
+ * The output is bit-identical in every case.  TRAJ_MAJOR [ntraj][ntspan][n] is one contiguous stream per trajectory —
  * the reference's Vec<Y> shape — written through per-lane shared-memory staging with cooperative 128-byte stores; it is
- * the fast choice for ensembles in arbitrary order (6x on a permuted Van der Pol sweep). */
+ * the layout for ensembles in arbitrary order that are not sweeps in disguise (random initial states). */
 typedef enum deq_dense_layout { DEQ_LAYOUT_SOA = 0, DEQ_LAYOUT_TRAJ_MAJOR = 1 } deq_dense_layout;
 
 /* Per-trajectory completion code (the reference returns Ok(partial) silently in the first two cases). */

