@@ -98,7 +98,13 @@ static bool compile(Program* p, const std::string& name_expr, bool fmad, Kernel*
         << (stiff ? "#include \"stiff.cuh\"\n" : "#include \"stepper.cuh\"\n")
         << "struct DeqUserRhs {\n  static constexpr int N = DEQ_USER_N, NP = DEQ_USER_NP;\n"
         << "  static constexpr bool USES_SINCOS = true;  // user code may call deq_sin / deq_cos (3.5 KB of shared memory)\n"
-        << "  __device__ __forceinline__ static void eval(double t, const double* y, double* dy, const double* p) { rhs(t, y, dy, p); }\n};\n";
+        << "  __device__ __forceinline__ static void eval(double t, const double* y, double* dy, const double* p) { rhs(t, y, dy, p); }\n"
+        // optional: time-only terms evaluated once per distinct stage time (stepper.cuh `stages`).  The user source defines
+        // DEQ_USER_NG and two more functions, and promises rhs(t, y, dy, p) == rhs_g(t, y, dy, p, g) with g = forcing(t, ., p).
+        << "#ifdef DEQ_USER_NG\n  static constexpr int NG = DEQ_USER_NG;\n"
+        << "  __device__ __forceinline__ static void forcing(double t, double* g, const double* p) { ::forcing(t, g, p); }\n"
+        << "  __device__ __forceinline__ static void eval_g(double t, const double* y, double* dy, const double* p, const double* g) { rhs_g(t, y, dy, p, g); }\n"
+        << "#endif\n};\n";
     nvrtcProgram prog = nullptr;
     nvrtcResult rc = rt->CreateProgram(&prog, src.str().c_str(), "deq_user_program.cu", kNumSrc, kSrcTexts, kSrcNames);
     if (rc) { if (err) *err = std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc); return false; }

@@ -326,6 +326,48 @@ def test_nvrtc_user_rhs_matches_oracle(deq, oracle):
     assert np.array_equal(sd.nvalid, rd["nvalid"]) and np.array_equal(sd.yout[m], want[m])
 
 
+USER_PENDULUM_FORCING = """
+#define DEQ_USER_NG 1
+__device__ void forcing(double t, double* g, const double* p) { g[0] = deq_cos(p[2] * t); }
+__device__ void rhs_g(double t, const double* v, double* d, const double* p, const double* g) {
+    d[0] = v[1]; d[1] = -p[0] * v[1] - deq_sin(v[0]) + p[1] * g[0]; }
+__device__ void rhs(double t, const double* v, double* d, const double* p) {
+    d[0] = v[1]; d[1] = -p[0] * v[1] - deq_sin(v[0]) + p[1] * deq_cos(p[2] * t); }
+"""
+
+
+def test_nvrtc_user_rhs_with_time_only_forcing(deq, oracle):
+    """A user right-hand side may declare its time-only terms (DEQ_USER_NG, forcing, rhs_g): the stepper evaluates them once per
+    distinct stage time (rows of equal c, the end of an accepted step, the carried value at c = 0).  Same bits as the oracle,
+    which evaluates cos(Omega t) at every stage: Fehlberg 7(8) (both coefficient sets: duplicate c rows, a c = 0 row), RK4
+    (c1 = c2), dopri5 (FSAL), dense rows, backward, and a -0.0 start time (the carried value must not be used there)."""
+    from diffeq_b200 import synth
+    rhs = deq.Rhs.from_source(USER_PENDULUM_FORCING, 2, 3)
+    P = list(synth.PENDULUM_PARAMS)
+    y0 = synth.pendulum_ics(0, 333)
+    for method, tset, ts, tol in (("Ode78", 1, [0.0, 10.0], 1e-12), ("Ode78", 0, [0.0, 3.0], 1e-7), ("Ode45", 0, [0.0, 10.0], 1e-9),
+                                  ("Ode78", 1, [-0.0, 4.0], 1e-10), ("Ode78", 1, [2.0, -1.0], 1e-9)):
+        # (bounded: the reference's own Fehlberg 7(8) coefficients collapse the step size, and a backward run never ends — DESIGN.md §6)
+        kw = dict(max_steps=300 if (ts[1] < ts[0] or tset == 0 and method == "Ode78") else 5000)
+        o = deq.OdeOptionMap().insert(deq.Reltol(tol), deq.Abstol(tol), deq.MaxSteps(kw["max_steps"]))
+        sol = deq.OdeProblem.builder().fun(rhs).params(P).init(y0).tspan(ts).build().solve(getattr(deq.Ode, method), o, tableau_set=tset)
+        ref = oracle.ensemble_adaptive(getattr(oracle, method.upper()), oracle.PENDULUM, P, y0, ts, oracle.opts(tol, tol, **kw), tset)
+        for k in ("accepted", "rejected", "nfe", "status"):
+            assert np.array_equal(getattr(sol, k), ref[k]), (method, tset, ts, k)
+        assert np.array_equal(sol.final, ref["yfinal"], equal_nan=True), (method, tset, ts)
+    ts = deq.linspace(0.0, 5.0, 41)
+    fx = deq.OdeProblem.builder().fun(rhs).params(P).init(y0).tspan(ts).build().solve(deq.Ode.Ode4, deq.OdeOptionMap().insert(deq.Output.Tspan))
+    assert np.array_equal(fx.final, oracle.ensemble_fixed(oracle.ODE4, oracle.PENDULUM, P, y0, ts))
+    tsd = deq.linspace(0.0, 6.0, 25)
+    for lay in (deq.DenseLayout.SoA, deq.DenseLayout.TrajMajor):
+        sd = deq.OdeProblem.builder().fun(rhs).params(P).init(y0).tspan(tsd).build().solve(
+            deq.Ode.Ode78, deq.OdeOptionMap().insert(deq.Reltol(1e-9), deq.Abstol(1e-9), deq.Output.Tspan, lay), tableau_set=1)
+        rd = oracle.ensemble_dense(oracle.ODE78, oracle.PENDULUM, P, y0, tsd, oracle.opts(1e-9, 1e-9), 1)
+        want = rd["out"].transpose(2, 1, 0)
+        m = ~np.isnan(want) & ~np.isnan(sd.yout)
+        assert np.array_equal(sd.nvalid, rd["nvalid"]) and np.array_equal(sd.yout[m], want[m])
+
+
 def test_nvrtc_same_source_reuses_compiled_kernel(deq):
     """A second deq_rhs from the same source (the first one already destroyed) hits the process-wide kernel cache:
     same results, and the second solve is not slowed by a recompile."""
