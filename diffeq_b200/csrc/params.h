@@ -55,10 +55,10 @@ struct AdaptParams {
     // ode23s only (stiff.cuh)
     int true_inverse;      // TEXTBOOK set: invert W = I - h d J itself, not its packed LU factors (problem.rs:469,481)
     int points_specified;  // Points::Specified: MODE_REC rows are the tspan points only (problem.rs:536)
-    // MODE_DENSE only (lane-refill SoA rows): work item s integrates trajectory order[s] — inputs are read from, and the
-    // per-trajectory results written to, index order[s], while its dense rows go to COLUMN s of `dense` (a scratch buffer that
-    // capi.cu un-permutes afterwards).  nullptr: identity.  Used to run an ensemble in the order of its first step sizes, so
-    // that neighbouring lanes advance alike and their row stores coalesce (see deq_solve).
+    // MODE_DENSE / MODE_DENSE_TM (lane-refill kernels): work item s integrates trajectory order[s] — inputs are read from, and
+    // the per-trajectory results written to, index order[s].  SoA: its dense rows go to COLUMN s of `dense` (capi.cu permutes
+    // the columns back afterwards); trajectory-major: they go straight to the stream of trajectory order[s].  nullptr: identity.
+    // Used to run an ensemble in the order of its first step sizes, so that neighbouring lanes advance alike (see deq_solve).
     const uint32_t* order;
 };
 

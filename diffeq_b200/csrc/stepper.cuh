@@ -908,8 +908,8 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
             }
             if (fin != 0xff) {
                 const uint32_t nfe = 2u + attempts * (uint32_t)(S - 1) + (FSAL ? 0u : acc);
-                unsigned long long dst = traj;   // where this work item's results go (AdaptParams::order); its dense rows stay in column `traj`
-                if (SOA && P.order) dst = P.order[traj];
+                unsigned long long dst = traj;   // where this work item's results go (AdaptParams::order); its SoA dense rows stay in column `traj`
+                if ((SOA || TM) && P.order) dst = P.order[traj];
 #pragma unroll (N <= 16 ? N : 1)
                 for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + dst] = SPEC ? yl[d] : cy[d];
                 P.accepted[dst] = acc; P.rejected[dst] = rej; P.nfe[dst] = nfe; P.status[dst] = fin; P.t_reached[dst] = t;
@@ -920,7 +920,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     } else if (TM) {
                         stage_drain(stage, P.dense, sl, true);   // ends with a __syncwarp: the helpers' stores precede the row below
 #pragma unroll (N <= 16 ? N : 1)
-                        for (int d = 0; d < N; ++d) P.dense[(traj * P.nt + (P.nt - 1)) * (unsigned long long)N + d] = cy[d];
+                        for (int d = 0; d < N; ++d) P.dense[(dst * P.nt + (P.nt - 1)) * (unsigned long long)N + d] = cy[d];
                     } else if (REC && P.rec_mode == REC_COUNT) {
                         P.rec_counts[traj] = (uint32_t)(wpos - wbase);
                     } else if (REC) {
@@ -947,7 +947,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
                     traj = my;
                     active = 1u;
                     unsigned long long src = my;   // where this work item's inputs live (AdaptParams::order)
-                    if (SOA && P.order) src = P.order[my];
+                    if ((SOA || TM) && P.order) src = P.order[my];
                     load_params<F, PT>(prm, P.params, P.shared, src, P.ntraj);
 #pragma unroll (N <= 16 ? N : 1)
                     for (int d = 0; d < N; ++d) {
@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(BLOCK, DEQ_MIN_BLOCKS) adapt_kernel(const Adap
 #pragma unroll (N <= 16 ? N : 1)
                             for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt) * P.ntraj + traj] = cy[d];
                         } else if (TM) {  // staged trajectory-major stream: row 0 = y0
-                            sl.head = 0; sl.cnt = 0; sl.gpos = traj * P.nt * (unsigned long long)N;
+                            sl.head = 0; sl.cnt = 0; sl.gpos = src * P.nt * (unsigned long long)N;   // (the stream of trajectory order[s]: no column permutation afterwards)
 #pragma unroll (N <= 16 ? N : 1)
                             for (int d = 0; d < N; ++d) stage_append(stage, P.dense, sl, cy[d]);
                         } else {  // ragged Points::All stream, rows [t, y...] interleaved and staged: row 0 = (t0, y0)

@@ -104,7 +104,8 @@ typedef enum deq_libm { DEQ_LIBM_AS_WRITTEN = 0, DEQ_LIBM_LLVM_FOLDED = 1 } deq_
  * trajectories in that order and the columns are permuted back in place afterwards; otherwise the row-synchronous kernel.
  * The output is bit-identical in every case.  TRAJ_MAJOR [ntraj][ntspan][n] is one contiguous stream per trajectory —
  * the reference's Vec<Y> shape — written through per-lane shared-memory staging with cooperative 128-byte stores; it is
- * the layout for ensembles in arbitrary order that are not sweeps in disguise (random initial states). */
+ * the layout for ensembles in arbitrary order (a sweep in disguise is dispatched in first-step order here too, and needs no
+ * permutation afterwards: every stream is written where it belongs). */
 typedef enum deq_dense_layout { DEQ_LAYOUT_SOA = 0, DEQ_LAYOUT_TRAJ_MAJOR = 1 } deq_dense_layout;
 
 /* Per-trajectory completion code (the reference returns Ok(partial) silently in the first two cases). */
