@@ -220,16 +220,17 @@ def test_soa_dense_rows_sorted_by_first_step_large(deq, oracle):
         oo = oracle.opts(1e-6, 1e-8, **kw)
         ref = oracle.ensemble_dense(oracle.ODE45FE, oracle.VANDERPOL, mu, y0, ts, oo, 0)
         want = ref["out"].transpose(2, 1, 0)
-        o = deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8), deq.Output.Tspan)
-        if "max_steps" in kw: o.insert(deq.MaxSteps(kw["max_steps"]))
-        sol = _problem(deq, deq.System.VanDerPol, mu, y0, ts).solve(deq.Ode.Ode45fe, o)
-        assert np.array_equal(sol.nvalid, ref["nvalid"])
-        msk = np.arange(len(ts))[None, :] < np.maximum(ref["nvalid"], 1)[:, None]
-        msk[:, -1] = True
-        assert np.array_equal(sol.yout[msk], want[msk])
-        assert np.array_equal(sol.accepted, ref["accepted"]) and np.array_equal(sol.rejected, ref["rejected"])
-        assert np.array_equal(sol.status, ref["status"])
-        assert np.array_equal(sol.final, want[:, -1, :])
+        for lay in (deq.DenseLayout.SoA, deq.DenseLayout.TrajMajor):   # (trajectory-major: same dispatch, rows written straight to their streams)
+            o = deq.OdeOptionMap().insert(deq.Reltol(1e-6), deq.Abstol(1e-8), deq.Output.Tspan, lay)
+            if "max_steps" in kw: o.insert(deq.MaxSteps(kw["max_steps"]))
+            sol = _problem(deq, deq.System.VanDerPol, mu, y0, ts).solve(deq.Ode.Ode45fe, o)
+            assert np.array_equal(sol.nvalid, ref["nvalid"]), int(lay)
+            msk = np.arange(len(ts))[None, :] < np.maximum(ref["nvalid"], 1)[:, None]
+            msk[:, -1] = True
+            assert np.array_equal(sol.yout[msk], want[msk]), int(lay)
+            assert np.array_equal(sol.accepted, ref["accepted"]) and np.array_equal(sol.rejected, ref["rejected"]), int(lay)
+            assert np.array_equal(sol.status, ref["status"]), int(lay)
+            assert np.array_equal(sol.final, want[:, -1, :]), int(lay)
     assert (ref["nvalid"] < 8).any()
 
 
