@@ -626,7 +626,17 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
                         const int rc = launch_adapt(&err);
                         if (rc == 1) return bail(DEQ_ERR_CUDA);
                         if (rc == 2) return bail(fail(DEQ_ERR_NVRTC, err));
-                        if (!probe_tm) CKR(deql::launch_permute_rows_inplace(r->d_dense, inv.p, (unsigned long long)n * nt, ntraj, rows.p, st));
+                        if (!probe_tm) {
+                            if (ntraj >= 65536 && !getenv("DEQ_SIMPLE_PERMUTE")) {   // two coalesced stages (plan: 8 bytes per trajectory, built once)
+                                TempBuf<char> plan(st), pscratch(st);
+                                CKR(dalloc(&plan.p, deql::permute_plan_bytes(ntraj), st));
+                                CKR(dalloc(&pscratch.p, deql::permute_plan_scratch_bytes(ntraj), st));
+                                CKR(deql::launch_permute_plan(order.p, ntraj, plan.p, pscratch.p, st));
+                                CKR(deql::launch_permute_rows_staged(r->d_dense, plan.p, (unsigned long long)n * nt, ntraj, rows.p, st));
+                            } else {
+                                CKR(deql::launch_permute_rows_inplace(r->d_dense, inv.p, (unsigned long long)n * nt, ntraj, rows.p, st));
+                            }
+                        }
                         P.order = nullptr;
                         launched = true;
                     }

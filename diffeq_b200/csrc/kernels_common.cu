@@ -295,6 +295,131 @@ cudaError_t launch_permute_rows_inplace(double* rows, const uint32_t* inv, unsig
     return cudaGetLastError();
 }
 
+// ---- the same in-place permutation with every global access coalesced (ensembles of 2^16 trajectories and more) ------------
+// The gather above moves 8 bytes per 32-byte sector it touches and is bound by the rate of scattered requests.  One permutation
+// serves ALL rows, so it is factored once per solve:  slot s --(stage 1)--> intermediate position m(s) --(stage 2)--> column
+// order[s], where m is the stable rank of s under the key order[s] / 1024.  `order` being a permutation, destination bucket b
+// (columns [1024 b, 1024 b + 1024)) owns exactly the intermediate positions with the same numbers, so
+//   stage 2 is a permutation INSIDE each 1024-element block: read contiguous, shuffle in shared memory, write contiguous;
+//   stage 1 moves a chunk of 8192 consecutive slots (64 KB, staged in shared memory) to ~1024 runs of consecutive intermediate
+//           positions (8 doubles on average at 2^20 trajectories), written in ascending order of m (list M1; L1 = the slot
+//           inside the chunk that each position takes its value from).
+// Plan: two stable radix sorts and three index kernels, 8 bytes of indices per trajectory (L2-resident while the rows stream
+// through).  Measured in isolation (tools/micro/perm_bench.cu, profiles/r2_microbench_column_permutation.txt): 3.4 ms per 500
+// rows of 2^20 columns against 4.5 ms for the gather form; batching, scratch and barrier as above.
+constexpr int PERM_CH = 8192, PERM_BK = 1024, PERM_NT = 512;
+__global__ void __launch_bounds__(256) perm_keys_a_kernel(const uint32_t* __restrict__ order, unsigned long long n, uint32_t* __restrict__ keys,
+                                                          uint32_t* __restrict__ vals) {
+    const unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) { keys[s] = order[s] / PERM_BK; vals[s] = (uint32_t)s; }
+}
+__global__ void __launch_bounds__(256) perm_keys_b_kernel(const uint32_t* __restrict__ s1, const uint32_t* __restrict__ order, unsigned long long n,
+                                                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint16_t* __restrict__ d2) {
+    const unsigned long long m = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < n) { keys[m] = s1[m] / PERM_CH; vals[m] = (uint32_t)m; d2[m] = (uint16_t)(order[s1[m]] % PERM_BK); }
+}
+__global__ void __launch_bounds__(256) perm_l1_kernel(const uint32_t* __restrict__ s1, const uint32_t* __restrict__ m1, unsigned long long n,
+                                                      uint16_t* __restrict__ l1) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) l1[i] = (uint16_t)(s1[m1[i]] % PERM_CH);
+}
+static size_t cub_sort32_bytes(unsigned long long n) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    return b;
+}
+// plan = M1 [n] u32 | L1 [n] u16 | D2 [n] u16 ; scratch for building it: 4 u32 arrays + CUB's
+size_t permute_plan_bytes(unsigned long long n) { return align256(n * 4) + 2 * align256(n * 2); }
+size_t permute_plan_scratch_bytes(unsigned long long n) { return 4 * align256(n * 4) + align256(cub_sort32_bytes(n)); }
+cudaError_t launch_permute_plan(const uint32_t* order, unsigned long long n, void* plan, void* scratch, cudaStream_t st) {
+    if (n == 0 || n > 0x7fffffffull) return cudaErrorInvalidValue;
+    char* p = (char*)scratch;
+    uint32_t* keys = (uint32_t*)p; p += align256(n * 4);
+    uint32_t* vals = (uint32_t*)p; p += align256(n * 4);
+    uint32_t* keys_out = (uint32_t*)p; p += align256(n * 4);
+    uint32_t* s1 = (uint32_t*)p; p += align256(n * 4);
+    size_t cb = cub_sort32_bytes(n);
+    char* q = (char*)plan;
+    uint32_t* m1 = (uint32_t*)q; q += align256(n * 4);
+    uint16_t* l1 = (uint16_t*)q; q += align256(n * 2);
+    uint16_t* d2 = (uint16_t*)q;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    perm_keys_a_kernel<<<grid, 256, 0, st>>>(order, n, keys, vals);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs((void*)p, cb, (const uint32_t*)keys, keys_out, (const uint32_t*)vals, s1, (int)n, 0, 32, st);
+    if (e != cudaSuccess) return e;
+    perm_keys_b_kernel<<<grid, 256, 0, st>>>(s1, order, n, keys, vals, d2);
+    e = cub::DeviceRadixSort::SortPairs((void*)p, cb, (const uint32_t*)keys, keys_out, (const uint32_t*)vals, m1, (int)n, 0, 32, st);
+    if (e != cudaSuccess) return e;
+    perm_l1_kernel<<<grid, 256, 0, st>>>(s1, m1, n, l1);
+    return cudaGetLastError();
+}
+// phase ph: stage 2 of batch ph - 1 (scratch -> rows, caller order) + stage 1 of batch ph (rows, slot order -> the other scratch half)
+__global__ void __launch_bounds__(PERM_NT) permute_staged_kernel(double* rows, const uint32_t* __restrict__ m1, const uint16_t* __restrict__ l1,
+                                                                 const uint16_t* __restrict__ d2, unsigned long long ntraj, unsigned long long nrows,
+                                                                 unsigned long long B, double* scratch, unsigned* barrier) {
+    extern __shared__ double perm_tile[];   // PERM_CH doubles
+    const unsigned long long nb = (nrows + B - 1) / B, nch = (ntraj + PERM_CH - 1) / PERM_CH;
+    unsigned generation = 0;
+    for (unsigned long long ph = 0; ph <= nb; ++ph) {
+        const unsigned long long g_row0 = ph ? (ph - 1) * B : 0, g_nrows = ph ? (ph < nb ? B : nrows - (nb - 1) * B) : 0;
+        const unsigned long long c_row0 = ph * B, c_nrows = ph < nb ? (ph + 1 < nb ? B : nrows - ph * B) : 0;
+        const double* g_scratch = scratch + ((ph + 1) & 1ull) * B * ntraj;
+        double* c_scratch = scratch + (ph & 1ull) * B * ntraj;
+        const unsigned long long g_items = g_nrows * nch, c_items = c_nrows * nch;
+        for (unsigned long long w = blockIdx.x; w < g_items + c_items; w += gridDim.x) {
+            if (w < g_items) {   // stage 2 on the 8 blocks that make up one chunk's worth of columns
+                const unsigned long long q = w / nch, c = w % nch, lo = c * PERM_CH, hi = lo + PERM_CH < ntraj ? lo + PERM_CH : ntraj;
+                const double* s = g_scratch + q * ntraj;
+                double* d = rows + (g_row0 + q) * ntraj;
+#pragma unroll 8
+                for (unsigned long long m = lo + threadIdx.x; m < hi; m += PERM_NT)
+                    perm_tile[((m - lo) & ~(unsigned long long)(PERM_BK - 1)) + d2[m]] = __ldcg(s + m);
+                __syncthreads();
+#pragma unroll 8
+                for (unsigned long long j = lo + threadIdx.x; j < hi; j += PERM_NT) __stcs(d + j, perm_tile[j - lo]);
+                __syncthreads();
+            } else {
+                const unsigned long long ww = w - g_items, q = ww / nch, c = ww % nch, lo = c * PERM_CH, hi = lo + PERM_CH < ntraj ? lo + PERM_CH : ntraj;
+                const double* s = rows + (c_row0 + q) * ntraj;
+                double* d = c_scratch + q * ntraj;
+#pragma unroll 8
+                for (unsigned long long j = lo + threadIdx.x; j < hi; j += PERM_NT) perm_tile[j - lo] = __ldcs(s + j);
+                __syncthreads();
+#pragma unroll 8
+                for (unsigned long long i = lo + threadIdx.x; i < hi; i += PERM_NT) d[m1[i]] = perm_tile[l1[i]];
+                __syncthreads();
+            }
+        }
+        if (ph < nb) grid_barrier(barrier, gridDim.x, generation);
+    }
+}
+// scratch as for launch_permute_rows_inplace: 2 * permute_rows_batch(ntraj) * ntraj doubles + one zeroed barrier word
+cudaError_t launch_permute_rows_staged(double* rows, const void* plan, unsigned long long nrows, unsigned long long ntraj, double* scratch,
+                                       cudaStream_t st) {
+    if (nrows == 0 || ntraj == 0) return cudaSuccess;
+    int dev = 0, sms = 148, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem = PERM_CH * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(permute_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, permute_staged_kernel, PERM_NT, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    if (per_sm > 2) per_sm = 2;   // measured: a third CTA per SM (192 KB of shared memory, little L1 left) halves stage 1's rate
+    const char* q = (const char*)plan;
+    const uint32_t* m1 = (const uint32_t*)q; q += align256(ntraj * 4);
+    const uint16_t* l1 = (const uint16_t*)q; q += align256(ntraj * 2);
+    const uint16_t* d2 = (const uint16_t*)q;
+    const unsigned long long B = permute_rows_batch(ntraj), nch = (ntraj + PERM_CH - 1) / PERM_CH;
+    unsigned* barrier = (unsigned*)(scratch + 2 * B * ntraj);
+    e = cudaMemsetAsync(barrier, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    const unsigned long long cap = (unsigned long long)sms * (unsigned long long)per_sm, want = 2 * B * nch;
+    permute_staged_kernel<<<(unsigned)(want < cap ? want : cap), PERM_NT, smem, st>>>(rows, m1, l1, d2, ntraj, nrows, B, scratch, barrier);
+    return cudaGetLastError();
+}
+
 // DFMA stream: 8 independent accumulator chains per thread, 2 flop per FMA.  The result is written so the loop
 // cannot be removed.  Used to measure the chip's sustained FP64 rate (MEASURED_PEAKS.json has no FP64 figure).
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* sink, int iters) {

@@ -60,6 +60,12 @@ cudaError_t launch_sort_by_h0(const double* h0, unsigned long long n, uint32_t* 
 unsigned long long permute_rows_batch(unsigned long long ntraj);
 cudaError_t launch_permute_rows_inplace(double* rows, const uint32_t* inv, unsigned long long nrows, unsigned long long ntraj, double* scratch,
                                         cudaStream_t st);
+// the same permutation factored into two coalesced stages (kernels_common.cu): plan built once per solve from `order`
+size_t permute_plan_bytes(unsigned long long n);
+size_t permute_plan_scratch_bytes(unsigned long long n);
+cudaError_t launch_permute_plan(const uint32_t* order, unsigned long long n, void* plan, void* scratch, cudaStream_t st);
+cudaError_t launch_permute_rows_staged(double* rows, const void* plan, unsigned long long nrows, unsigned long long ntraj, double* scratch,
+                                       cudaStream_t st);
 cudaError_t launch_test_div(unsigned long long seed, unsigned long long count, unsigned long long* d_out, cudaStream_t st);
 cudaError_t launch_test_pow(const double* x, const double* y, double* out, unsigned long long n, cudaStream_t st);
 cudaError_t launch_test_log10(const double* x, double* out, unsigned long long n, cudaStream_t st);
