@@ -952,7 +952,10 @@ static deq_status solve_host_dense_impl(const deq_rhs* rhs, size_t ntraj, const 
     if (ntspan == 0) return DEQ_OK;   // nothing to solve (problem.rs:211-214)
     deq_options o = o_in;
     o.async = 1;
-    if (o.refill == 2 && o.dense_layout == DEQ_LAYOUT_SOA) o.refill = 0;   // SoA rows: no per-chunk coherence probe (a host round trip); the kernel time hides behind the copies anyway
+    // no per-chunk coherence probe / sorted dispatch (a host round trip on the compute stream): the kernel time hides behind the
+    // copies anyway.  SoA rows: the row-synchronous kernel; trajectory-major: plain lane refill (that layout has no tail compaction,
+    // so refill = 1 is what refill = 2 runs once the probe is out of the way)
+    if (o.refill == 2) o.refill = o.dense_layout == DEQ_LAYOUT_SOA ? 0 : 1;
     const size_t nd = devs.size(), n = (size_t)rhs->n, np = (size_t)rhs->np;
     const bool tm = o.dense_layout == DEQ_LAYOUT_TRAJ_MAJOR && info.adaptive && !sk;
     const bool counts = info.adaptive || sk;
