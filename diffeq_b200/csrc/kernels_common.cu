@@ -298,16 +298,16 @@ cudaError_t launch_permute_rows_inplace(double* rows, const uint32_t* inv, unsig
 // ---- the same in-place permutation with every global access coalesced (ensembles of 2^16 trajectories and more) ------------
 // The gather above moves 8 bytes per 32-byte sector it touches and is bound by the rate of scattered requests.  One permutation
 // serves ALL rows, so it is factored once per solve:  slot s --(stage 1)--> intermediate position m(s) --(stage 2)--> column
-// order[s], where m is the stable rank of s under the key order[s] / 1024.  `order` being a permutation, destination bucket b
-// (columns [1024 b, 1024 b + 1024)) owns exactly the intermediate positions with the same numbers, so
-//   stage 2 is a permutation INSIDE each 1024-element block: read contiguous, shuffle in shared memory, write contiguous;
-//   stage 1 moves a chunk of 8192 consecutive slots (64 KB, staged in shared memory) to ~1024 runs of consecutive intermediate
-//           positions (8 doubles on average at 2^20 trajectories), written in ascending order of m (list M1; L1 = the slot
+// order[s], where m is the stable rank of s under the key order[s] / PERM_BK.  `order` being a permutation, destination bucket b
+// (columns [PERM_BK b, PERM_BK (b + 1))) owns exactly the intermediate positions with the same numbers, so
+//   stage 2 is a permutation INSIDE each PERM_BK-element block: read contiguous, shuffle in shared memory, write contiguous;
+//   stage 1 moves a chunk of 8192 consecutive slots (64 KB, staged in shared memory) to n / PERM_BK runs of consecutive intermediate
+//           positions (32 doubles on average at 2^20 trajectories), written in ascending order of m (list M1; L1 = the slot
 //           inside the chunk that each position takes its value from).
 // Plan: two stable radix sorts and three index kernels, 8 bytes of indices per trajectory (L2-resident while the rows stream
 // through).  Measured in isolation (tools/micro/perm_bench.cu, profiles/r2_microbench_column_permutation.txt): 3.4 ms per 500
 // rows of 2^20 columns against 4.5 ms for the gather form; batching, scratch and barrier as above.
-constexpr int PERM_CH = 8192, PERM_BK = 1024, PERM_NT = 512;
+constexpr int PERM_CH = 8192, PERM_BK = 4096, PERM_NT = 512;   // (bucket size: 1024 / 2048 / 4096 measured 3.48 / 3.33 / 3.27 ms per 500 rows — longer runs in stage 1)
 __global__ void __launch_bounds__(256) perm_keys_a_kernel(const uint32_t* __restrict__ order, unsigned long long n, uint32_t* __restrict__ keys,
                                                           uint32_t* __restrict__ vals) {
     const unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
