@@ -433,6 +433,40 @@ def main():
     if distributed:
         cpu_barrier()
 
+    # ---------------- BASELINE config 4 (quarter size) and dense rows of a sweep handed over in random order, informational ----------------
+    config4 = None
+    dense_permuted = None
+    if rank == 0 and not args.no_config3:
+        n4 = 1 << 22
+        p4 = D.OdeProblem.builder().fun(D.Rhs.builtin(D.System.Pendulum)).params(synth.PENDULUM_PARAMS).init(synth.pendulum_ics(0, n4)).tspan([0.0, 10.0]).build()
+        config4 = {"workload": "configs[3] at 2^22 of its 2^24 trajectories: damped driven pendulum, Ode78 = Fehlberg 7(8) TEXTBOOK coefficients, rtol = atol = 1e-12, "
+                               "tspan [0, 10], final states; PARITY evaluates glibc's sin / cos bit for bit (13 sin + 9 cos per step attempt)"}
+        for name, mode in (("parity", D.Mode.Parity), ("fast", D.Mode.Fast)):
+            o4 = D.OdeOptionMap().insert(D.Reltol(1e-12), D.Abstol(1e-12), mode)
+            p4.solve(D.Ode.Ode78, o4, tableau_set=D.TableauSet.Textbook, fetch=False)
+            s4 = p4.solve(D.Ode.Ode78, o4, tableau_set=D.TableauSet.Textbook, fetch=False)
+            st4 = s4.totals["accepted"] + s4.totals["rejected"]
+            config4[name] = {"kernel_ms": s4.kernel_ms, "step_attempts": st4, "steps_per_s": st4 / (s4.kernel_ms * 1e-3),
+                             "TFLOPs_at_495_flop_per_step": st4 * 495 / (s4.kernel_ms * 1e-3) / 1e12}
+            del s4
+        del p4
+        nd, ntd = 1 << 18, 1000
+        yd, mud = synth.vdp_sweep(0, nd, nd)
+        tsd = D.linspace(0.0, 20.0, ntd)
+        permd = np.random.default_rng(0).permutation(nd)
+        dense_permuted = {"workload": "Van der Pol mu sweep of 2^18 trajectories (a quarter of the probe in profiles/r2_dense_sorted_vs_permuted.jsonl), Ode45fe, rtol 1e-6, "
+                                      "atol 1e-8, 1000 tspan rows per trajectory (4.2 GB) kept on the device; kernel_ms of the second of two solves; "
+                                      "'permuted' = the same sweep in random order (deq_solve sorts the work items by first step size; SoA: + in-place column permutation)"}
+        for order, m in (("sorted", mud), ("permuted", mud[permd].copy())):
+            pd = D.OdeProblem.builder().fun(D.Rhs.builtin(D.System.VanDerPol)).params(m).init(yd).tspan(tsd).build()
+            for lay in (D.DenseLayout.SoA, D.DenseLayout.TrajMajor):
+                od = D.OdeOptionMap().insert(D.Reltol(1e-6), D.Abstol(1e-8), D.Output.Tspan, lay)
+                pd.solve(D.Ode.Ode45fe, od, fetch=False)
+                sd = pd.solve(D.Ode.Ode45fe, od, fetch=False)
+                dense_permuted[order + "_" + lay.name + "_ms"] = sd.kernel_ms
+                del sd
+            del pd
+
     # ---------------- stiff path, informational: ode23s on a Van der Pol stiffness sweep ----------------
     stiff = None
     if rank == 0:
@@ -520,7 +554,7 @@ def main():
                         "exp10 in hinit; DESIGN.md 4.1) — one pow per step instead of two"},
             "mode_check": mode_check,
             "stiff_ode23s": stiff,
-            "config3_e2e": config3_e2e, "strong_scaling": strong, "solve_host_in_library": in_library, "final_gather": final_gather,
+            "config3_e2e": config3_e2e, "config4": config4, "dense_permuted_sweep": dense_permuted, "strong_scaling": strong, "solve_host_in_library": in_library, "final_gather": final_gather,
             "clocks": clocks, "wall_s_timed_region": wall_max,
         }
         if not args.no_cpu_baseline:
