@@ -482,6 +482,8 @@ def main():
             att = r.totals["accepted"] + r.totals["rejected"]
             stiff[name] = {"steps_per_s": att / (r.kernel_ms * 1e-3), "kernel_ms": r.kernel_ms, "step_attempts": att}
         del sp
+    if distributed:
+        cpu_barrier()   # (the other ranks wait here on the CPU, not inside an NCCL kernel, while rank 0 runs the informational sections)
 
     # ---------------- reduce over ranks ----------------
     t = torch.tensor([dev_ms, e2e_s, wall, fast_ms, e2e_fast_s, fold_ms], dtype=torch.float64, device="cuda")
