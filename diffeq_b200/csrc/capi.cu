@@ -601,7 +601,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
                 CKR(cudaStreamSynchronize(st));
                 CKR(cudaMemsetAsync(r->d_scalars + 1, 0, 2 * sizeof(unsigned long long), st));
                 if (hc[1] > 0 && (double)hc[0] <= 0.02 * (double)hc[1]) { if (!probe_tm) mode = (int)deqk::MODE_DENSE; }
-                else if (ntraj >= 64 && ntraj < 0x7fffffffull && !getenv("DEQ_NO_SORTED_DENSE")) {
+                else if (ntraj >= 4096 && ntraj < 0x7fffffffull && !getenv("DEQ_NO_SORTED_DENSE")) {   // (a smaller ensemble is one partial wave: nothing to gain, a sort and a second host round trip to lose)
                     // Not coherent as given.  Sorted by first step size it may be (a parameter sweep handed over in arbitrary order
                     // is): then the lane-refill kernel runs the work items in that order, its row stores coalesce again — columns in
                     // the order of the work items, and an in-place pass through an L2-sized scratch puts the columns back where the
