@@ -118,7 +118,7 @@ def grid(t0, span, npts, allow_dup=True):
 CUR = {}
 for case in range(cases):
     kind = rng.choice(["adapt", "adapt", "adapt", "fixed", "ode23s", "rosen"])
-    n = int(rng.integers(1, 150)) if rng.random() < 0.97 else int(rng.integers(1000, 6000))   # a few multi-CTA ensembles
+    n = int(rng.integers(1, 150)) if rng.random() < 0.97 else int(rng.integers(1000, 12000))   # a few multi-CTA ensembles (from 4096 on: the sorted dense dispatch)
     name, y0, params = system(case, n, stiff=kind in ("ode23s", "rosen"))
     if rng.random() < 0.04:   # special values in the initial state: NaN, infinities, signed zeros, huge and tiny magnitudes
         y0 = y0.copy()
