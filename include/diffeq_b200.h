@@ -157,7 +157,15 @@ size_t deq_abi_options_size(void);
 deq_status deq_rhs_builtin(int system /* deq_system */, deq_rhs** out);
 /* User CUDA source defining
  *     __device__ void rhs(double t, const double* y, double* dy, const double* p);
- * for an n-dimensional state and nparams parameters, compiled with NVRTC for sm_100a. */
+ * for an n-dimensional state (n <= 64) and nparams parameters (<= 8), compiled with NVRTC for sm_100a.  The source may call
+ * deq_sin(x) / deq_cos(x): sin and cos with glibc's bits for every double — what f64::sin / f64::cos of a Rust closure
+ * evaluate to — so that a right-hand side with trigonometric terms stays bit-identical to the reference.  Optional: a source
+ * that also defines
+ *     #define DEQ_USER_NG <count>
+ *     __device__ void forcing(double t, double* g, const double* p);                                 // the time-only terms
+ *     __device__ void rhs_g(double t, const double* y, double* dy, const double* p, const double* g); // rhs, given those terms
+ * with rhs(t, y, dy, p) == rhs_g(t, y, dy, p, g) for g = forcing(t) has its forcing evaluated once per DISTINCT stage time
+ * (rows of a tableau with equal c, the end of an accepted step, the start of the next one): same bits, fewer evaluations. */
 deq_status deq_rhs_from_source(const char* cuda_src, int n, int nparams, deq_rhs** out);
 int deq_rhs_dim(const deq_rhs* rhs);
 int deq_rhs_nparams(const deq_rhs* rhs);
