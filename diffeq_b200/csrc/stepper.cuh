@@ -503,8 +503,30 @@ __device__ __forceinline__ void stage_drain(double* stage, double* out, StageLan
     __syncwarp(am);  // the owners' appends are visible to the helpers
     const unsigned rank = __popc(am & ((1u << lane) - 1u)), m = __popc(am);
     if (!all) {
-        const unsigned pending = __ballot_sync(am, s.cnt >= (unsigned)STAGE_LINE);
+        unsigned pending = __ballot_sync(am, s.cnt >= (unsigned)STAGE_LINE);
         if (pending == 0u) return;
+        if (am == 0xffffffffu && STAGE_LINE == 16) {
+            // the whole warp is here (the steady state of the persistent loop): two pending lanes per iteration, one per half
+            // warp, picked with warp-uniform bit scans — lane e of a half writes element e of its pending lane's line.  (The
+            // general form below finds the n-th pending lane per element with __fns: ~40 instructions per 32 elements, against
+            // ~15 here; ncu on config 3 showed the drain as the larger part of the 500 extra instructions per warp-step of the
+            // trajectory-major layout.)
+            const unsigned all_pending = pending;
+            const unsigned e = lane & 15u;
+            while (pending) {
+                const int src0 = __ffs(pending) - 1;
+                pending &= pending - 1u;
+                const int src1 = pending ? __ffs(pending) - 1 : -1;
+                if (pending) pending &= pending - 1u;
+                const int src = lane < 16u ? src0 : src1;
+                const unsigned h = __shfl_sync(0xffffffffu, s.head, src < 0 ? 0 : src);
+                const unsigned long long g = __shfl_sync(0xffffffffu, s.gpos, src < 0 ? 0 : src);
+                if (src >= 0) out[g + e] = stage_ref(stage, (h + e) & (STAGE_COLS - 1), (unsigned)src);
+            }
+            if ((all_pending >> lane) & 1u) { s.head = (s.head + STAGE_LINE) & (STAGE_COLS - 1); s.cnt -= STAGE_LINE; s.gpos += STAGE_LINE; }
+            __syncwarp(am);
+            return;
+        }
         const unsigned W = (unsigned)STAGE_LINE * __popc(pending);
         for (unsigned base = 0; base < W; base += m) {  // uniform trip count over the participating lanes
             const unsigned i = base + rank;
