@@ -25,3 +25,7 @@ Q="python tests/gpu_quick.py"
 timeout 300 $Q > gpurun_out/quick_$TAG.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -k regex:adapt_kernel_f32 -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_f32 $Q > gpurun_out/ncu_f.log 2>&1
 timeout 600 python tests/gpu_dense_probe.py > gpurun_out/dense_probe_$TAG.jsonl 2>&1; cat gpurun_out/dense_probe_$TAG.jsonl
 head -c 600 gpurun_out/bench_$TAG.json; echo; ls -la gpurun_out | tail -14
+# ---- also run by hand for the round-2 record (profiles/README.md):
+#   differential campaign:  python tests/gpu_fuzz.py 20000 61 ; python tests/gpu_fuzz.py 1500 62 nvrtc ; python tests/gpu_fuzz.py 3000 63 fast   -> profiles/r2_fuzz_campaign.txt
+#   2-GPU bench (gpurun --gpus 2): python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 -> profiles/r2_bench_2gpu.json
+#   column-permutation microbenchmark: nvcc -O3 -std=c++17 [-DPERM_BK=4096] -gencode arch=compute_100a,code=sm_100a tools/micro/perm_bench.cu -o tools/micro/perm_bench ; tools/micro/perm_bench 20 500 -> profiles/r2_microbench_column_permutation.txt
