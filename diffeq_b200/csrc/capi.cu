@@ -614,7 +614,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
                     CKR(dalloc(&order.p, ntraj, st)); CKR(dalloc(&inv.p, ntraj, st)); CKR(dalloc(&hs.p, ntraj, st)); CKR(dalloc(&scratch.p, sb, st));
                     TempBuf<char> plan(st), pscratch(st);
                     const bool staged = !probe_tm && ntraj >= 65536 && !getenv("DEQ_SIMPLE_PERMUTE");   // two coalesced stages (plan: 8 bytes per trajectory, built once)
-                    if (!probe_tm) CKR(dalloc(&rows.p, 2 * deql::permute_rows_batch(ntraj) * ntraj + 1, st));   // + the barrier word of the persistent permutation kernel
+                    if (!probe_tm) CKR(dalloc(&rows.p, 2 * deql::permute_rows_batch(ntraj) * ntraj + 3, st));   // + the barrier word and item counters of the persistent permutation kernel
                     if (staged) { CKR(dalloc(&plan.p, deql::permute_plan_bytes(ntraj), st)); CKR(dalloc(&pscratch.p, deql::permute_plan_scratch_bytes(ntraj), st)); }
                     CKR(cudaEventRecord(r->ev0, st));   // (memory is obtained outside the timed region, like the result arrays)
                     ev0_recorded = true;
