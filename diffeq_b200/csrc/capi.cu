@@ -433,7 +433,7 @@ deq_status deq_solve(deq_ensemble* e, int method, int tableau_set, const deq_opt
     const int n = e->rhs.n;
     const size_t ntraj = e->ntraj, nt = e->nt;
     if (sk) {
-        if (n > 8) return fail(DEQ_ERR_UNSUPPORTED, "the stiff solvers carry systems of dimension <= 8 (Jacobian, W and its inverse are per-thread; see stiff.cuh)");
+        if (n > 32) return fail(DEQ_ERR_UNSUPPORTED, "the stiff solvers carry systems of dimension <= 32 (Jacobian, W and its inverse are per-thread; see stiff.cuh)");
         if (o.precision != DEQ_PRECISION_F64) return fail(DEQ_ERR_UNSUPPORTED, "the stiff solvers are f64 only");
         if (o.output == DEQ_OUT_TSPAN && o.dense_layout != DEQ_LAYOUT_SOA) return fail(DEQ_ERR_UNSUPPORTED, "the stiff solvers write tspan rows in the SoA layout");
         if (o.points != DEQ_POINTS_ALL && o.points != DEQ_POINTS_SPECIFIED) return fail(DEQ_ERR_INVALID_ARG, "unknown points kind");

@@ -6,7 +6,8 @@
 //
 // Same parity contract as stepper.cuh: IEEE f64, -fmad=false, the reference's operation order.  The n x n linear
 // algebra of the reference goes through nalgebra 0.20 (DMatrix operators, lu(), try_inverse()); it is restated here for
-// n <= 8 with every matrix in registers or thread-local memory (all indices are compile-time after unrolling):
+// n <= 32, every matrix per thread: in registers up to n = 8 (loops fully unrolled, all indices compile-time), in thread-local
+// memory beyond (`#pragma unroll (N <= 8 ? N : 1)`: the loops stay rolled, like the explicit path does beyond n = 16):
 //   * M * v             column-ordered accumulation  y = M[:,0] v0;  y = M[:,j] v_j + y
 //   * lu()              partial pivoting on the first largest |.|, multipliers a_ji * (1 / pivot), exactly-zero pivot
 //                       columns skipped; only the packed factors survive (`lu_internal()`), the permutation is dropped
@@ -22,40 +23,40 @@ namespace deqk {
 
 template <int N>
 __device__ __forceinline__ void na_gemv(const double (&m)[N][N], const double (&v)[N], double (&y)[N]) {
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
     for (int r = 0; r < N; ++r) y[r] = m[r][0] * v[0];
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
     for (int j = 1; j < N; ++j) {
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
         for (int r = 0; r < N; ++r) y[r] = m[r][j] * v[j] + y[r];
     }
 }
 
 template <int N>
 __device__ __forceinline__ void na_lu_packed(double (&m)[N][N]) {
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
     for (int i = 0; i < N; ++i) {
         int piv = i;
         double best = fabs(m[i][i]);
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
         for (int r = i + 1; r < N; ++r) { const double v = fabs(m[r][i]); if (v > best) { best = v; piv = r; } }
         // swap rows i and piv (all columns: the ones left of i by swap_rows, the rest inside gauss_step_swap)
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
         for (int r = i + 1; r < N; ++r) {
             if (piv == r) {
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                 for (int c = 0; c < N; ++c) { const double tmp = m[i][c]; m[i][c] = m[r][c]; m[r][c] = tmp; }
             }
         }
         const double diag = m[i][i];
         if (diag != 0.0) {
             const double inv = 1.0 / diag;
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
             for (int r = i + 1; r < N; ++r) m[r][i] = m[r][i] * inv;
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
             for (int k = i + 1; k < N; ++k) {
                 const double a = -m[i][k];
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                 for (int r = i + 1; r < N; ++r) m[r][k] = a * m[r][i] + m[r][k];
             }
         }
@@ -68,7 +69,7 @@ __device__ __forceinline__ bool na_try_inverse(const double (&m)[N][N], double (
 // FAST arithmetic only: the same adjugate formulas with ONE reciprocal of the determinant instead of n^2 IEEE divisions.
 template <int N>
 __device__ __forceinline__ bool inverse_fast(const double (&m)[N][N], double (&o)[N][N]) {
-    static_assert(N >= 1 && N <= 8, "the stiff path carries n <= 8");
+    static_assert(N >= 1 && N <= 32, "the stiff path carries n <= 32");
     if constexpr (N >= 4) {
         return na_try_inverse<N>(m, o);   // same routines, contracted by the FAST translation unit's -fmad=true
     } else
@@ -95,7 +96,7 @@ __device__ __forceinline__ bool inverse_fast(const double (&m)[N][N], double (&o
 
 template <int N>
 __device__ __forceinline__ bool na_try_inverse(const double (&m)[N][N], double (&o)[N][N]) {
-    static_assert(N >= 1 && N <= 8, "the stiff path carries n <= 8");
+    static_assert(N >= 1 && N <= 32, "the stiff path carries n <= 32");
     if constexpr (N == 4) {
         // `do_inverse4` (nalgebra 0.20 linalg/inverse.rs; MESA's gluInvertMatrix cofactor expansion) on the column-major slice
         // f[k] = M[k % 4][k / 4]: products and sums left to right, det from the first row of cofactors, then every cofactor is
@@ -128,17 +129,17 @@ __device__ __forceinline__ bool na_try_inverse(const double (&m)[N][N], double (
         // the row swaps applied to an identity `o`; then o <- L^-1 o (unit diagonal, forward, column by column) and o <- U^-1 o
         // (backward: coeff = b_i / u_ii, b_j = (-coeff) u_ji + b_j for j < i)
         double a[N][N];
-        _Pragma("unroll") for (int r = 0; r < N; ++r) {
-        _Pragma("unroll")     for (int cc = 0; cc < N; ++cc) { a[r][cc] = m[r][cc]; o[r][cc] = r == cc ? 1.0 : 0.0; }
+        _Pragma("unroll (N <= 8 ? N : 1)") for (int r = 0; r < N; ++r) {
+        _Pragma("unroll (N <= 8 ? N : 1)")     for (int cc = 0; cc < N; ++cc) { a[r][cc] = m[r][cc]; o[r][cc] = r == cc ? 1.0 : 0.0; }
         }
         bool ok = true;
-        _Pragma("unroll") for (int i = 0; i < N; ++i) {
+        _Pragma("unroll (N <= 8 ? N : 1)") for (int i = 0; i < N; ++i) {
             int piv = i;
             double best = fabs(a[i][i]);
-        _Pragma("unroll")     for (int r = i + 1; r < N; ++r) { const double v = fabs(a[r][i]); if (v > best) { best = v; piv = r; } }
-        _Pragma("unroll")     for (int r = i + 1; r < N; ++r) {
+        _Pragma("unroll (N <= 8 ? N : 1)")     for (int r = i + 1; r < N; ++r) { const double v = fabs(a[r][i]); if (v > best) { best = v; piv = r; } }
+        _Pragma("unroll (N <= 8 ? N : 1)")     for (int r = i + 1; r < N; ++r) {
                 if (piv == r) {
-        _Pragma("unroll")             for (int cc = 0; cc < N; ++cc) {
+        _Pragma("unroll (N <= 8 ? N : 1)")             for (int cc = 0; cc < N; ++cc) {
                         double tmp = a[i][cc]; a[i][cc] = a[r][cc]; a[r][cc] = tmp;
                         tmp = o[i][cc]; o[i][cc] = o[r][cc]; o[r][cc] = tmp;
                     }
@@ -147,26 +148,26 @@ __device__ __forceinline__ bool na_try_inverse(const double (&m)[N][N], double (
             const double diag = a[i][i];
             if (diag == 0.0) ok = false;
             const double inv = 1.0 / diag;
-        _Pragma("unroll")     for (int r = i + 1; r < N; ++r) a[r][i] = a[r][i] * inv;
-        _Pragma("unroll")     for (int k = i + 1; k < N; ++k) {
+        _Pragma("unroll (N <= 8 ? N : 1)")     for (int r = i + 1; r < N; ++r) a[r][i] = a[r][i] * inv;
+        _Pragma("unroll (N <= 8 ? N : 1)")     for (int k = i + 1; k < N; ++k) {
                 const double p = -a[i][k];
-        _Pragma("unroll")         for (int r = i + 1; r < N; ++r) a[r][k] = p * a[r][i] + a[r][k];
+        _Pragma("unroll (N <= 8 ? N : 1)")         for (int r = i + 1; r < N; ++r) a[r][k] = p * a[r][i] + a[r][k];
             }
         }
         if (!ok) return false;   // (the reference returns at the first zero pivot; nothing computed after it is used)
-        _Pragma("unroll") for (int k = 0; k < N; ++k) {
-        _Pragma("unroll")     for (int i = 0; i + 1 < N; ++i) {
+        _Pragma("unroll (N <= 8 ? N : 1)") for (int k = 0; k < N; ++k) {
+        _Pragma("unroll (N <= 8 ? N : 1)")     for (int i = 0; i + 1 < N; ++i) {
                 const double coeff = o[i][k] / 1.0;
-        _Pragma("unroll")         for (int r = i + 1; r < N; ++r) o[r][k] = (-coeff) * a[r][i] + o[r][k];
+        _Pragma("unroll (N <= 8 ? N : 1)")         for (int r = i + 1; r < N; ++r) o[r][k] = (-coeff) * a[r][i] + o[r][k];
             }
         }
-        _Pragma("unroll") for (int k = 0; k < N; ++k) {
-        _Pragma("unroll")     for (int i = N - 1; i >= 0; --i) {
+        _Pragma("unroll (N <= 8 ? N : 1)") for (int k = 0; k < N; ++k) {
+        _Pragma("unroll (N <= 8 ? N : 1)")     for (int i = N - 1; i >= 0; --i) {
                 const double diag = a[i][i];
                 if (diag == 0.0) ok = false;
                 const double coeff = o[i][k] / diag;
                 o[i][k] = coeff;
-        _Pragma("unroll")         for (int r = 0; r < i; ++r) o[r][k] = (-coeff) * a[r][i] + o[r][k];
+        _Pragma("unroll (N <= 8 ? N : 1)")         for (int r = 0; r < i; ++r) o[r][k] = (-coeff) * a[r][i] + o[r][k];
             }
         }
         if (!ok) return false;
@@ -201,22 +202,22 @@ template <class F, bool FAST = false>
 __device__ __forceinline__ void fdjacobian(double t, const double (&x)[F::N], const double (&ftx)[F::N], const double* prm,
                                            double (&J)[F::N][F::N]) {
     constexpr int N = F::N;
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
     for (int c = 0; c < N; ++c) {
         double xj = x[c];
         if (xj == 0.0) xj += 1.0;
         const double dxj = xj * 0.01;
         double tmp[N], yj[N];
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
         for (int d = 0; d < N; ++d) tmp[d] = x[d];
         tmp[c] += dxj;
         F::eval(t, tmp, yj, prm);
         if (FAST) {
             const double rdx = 1.0 / dxj;
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
             for (int r = 0; r < N; ++r) J[r][c] = (yj[r] - ftx[r]) * rdx;
         } else {
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
             for (int r = 0; r < N; ++r) J[r][c] = (yj[r] - ftx[r]) / dxj;
         }
     }
@@ -226,7 +227,7 @@ __device__ __forceinline__ void fdjacobian(double t, const double (&x)[F::N], co
 template <int N>
 __device__ __forceinline__ double norm2_fast(const double (&v)[N]) {
     double s = 0.0;
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
     for (int d = 0; d < N; ++d) s = __fma_rn(v[d], v[d], s);
     return sqrt(s);
 }
@@ -234,7 +235,7 @@ __device__ __forceinline__ double norm2_fast(const double (&v)[N]) {
 template <int N, class TT>
 __device__ __forceinline__ double pnorm2(const double (&v)[N], int libm_folded, const TT& T) {   // types.rs:109-115, P(2)
     double s = 0.0;
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
     for (int d = 0; d < N; ++d) { const double a = fabs(v[d]); s = s + a * a; }
     return libm_folded ? sqrt(s) : deqm::pow_glibc(s, 0.5, T);
 }
@@ -276,20 +277,20 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
     double y[N], f0[N], jac[N][N], prm[F::NP ? F::NP : 1];
     uint32_t acc = 0, rej = 0, attempts = 0, nv = 1;
     unsigned long long tot_acc = 0, tot_rej = 0, tot_nfe = 0;
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
     for (int d = 0; d < N; ++d) {
         y[d] = 0.0; f0[d] = 0.0;
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
         for (int c = 0; c < N; ++c) jac[d][c] = 0.0;
     }
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
     for (int j = 0; j < (F::NP ? F::NP : 1); ++j) prm[j] = 0.0;
 
     auto emit = [&](double tq, const double (&v)[N]) {   // one REC row
         if (P.rec_mode == REC_WRITE) {
             double* row = P.rec_rows + (P.rec_offsets[traj] + wpos) * (unsigned long long)(N + 1);
             row[0] = tq;
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
             for (int d = 0; d < N; ++d) row[1 + d] = v[d];
         }
         ++wpos;
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
                     traj = my;
                     active = true;
                     load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                     for (int d = 0; d < N; ++d) {
                         y[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
                         f0[d] = P.f0[(unsigned long long)d * P.ntraj + traj];   // init.f0 (:435-441)
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
                     h = tdir * fmin(fabs(hh), P.maxstep);                      // :443
                     acc = 0; rej = 0; attempts = 0; it = 1; wpos = 0; nv = 1; tlast = t; disorder = false;
                     if (SOA) {
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                         for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt) * P.ntraj + traj] = y[d];
                     }
                     if (REC) emit(t, y);
@@ -344,40 +345,40 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
                 if (rem < fabs(h)) h = tfinal - t;
                 const double hd = h * D;
                 double w[N][N];
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                 for (int r = 0; r < N; ++r) {
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                     for (int c = 0; c < N; ++c) w[r][c] = (r == c ? 1.0 : 0.0) - jac[r][c] * hd;
                 }
                 if (N != 1 && !P.true_inverse) na_lu_packed<N>(w);
                 double fdt[N];
                 F::eval(t + h / 100., y, fdt, prm);
                 const double sc = hd / (h / 100.);
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                 for (int i = 0; i < N; ++i) fdt[i] = (fdt[i] - f0[i]) * sc;
                 double winv[N][N];
                 if (!(FAST ? inverse_fast<N>(w, winv) : na_try_inverse<N>(w, winv))) {
                     fin = ST_INVALID_MATRIX; invalid = true;
                 } else {
                     double rhs[N], k1[N], k2[N], k3[N], f1[N], f2[N], ynew[N];
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                     for (int i = 0; i < N; ++i) rhs[i] = f0[i] + fdt[i];
                     na_gemv<N>(winv, rhs, k1);
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                     for (int i = 0; i < N; ++i) rhs[i] = y[i] + (k1[i] * 0.5) * h;
                     F::eval(t + 0.5 * h, rhs, f1, prm);
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                     for (int i = 0; i < N; ++i) rhs[i] = f1[i] - k1[i];
                     na_gemv<N>(winv, rhs, k2);
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                     for (int i = 0; i < N; ++i) { k2[i] = k2[i] + k1[i]; ynew[i] = y[i] + k2[i] * h; }
                     const double tn = t + h;
                     F::eval(tn, ynew, f2, prm);
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                     for (int i = 0; i < N; ++i) rhs[i] = ((f2[i] - (k2[i] - f1[i]) * E32) - (k1[i] - f0[i]) * 2.) + fdt[i];
                     na_gemv<N>(winv, rhs, k3);
                     double kerr[N];
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                     for (int i = 0; i < N; ++i) kerr[i] = (k1[i] - k2[i] * 2.) + k3[i];
                     const double err = (FAST ? norm2_fast<N>(kerr) : pnorm2<N>(kerr, P.libm_folded, T)) * (fabs(h) / 6.);
                     const double delta = FAST ? fmax(fmax(norm2_fast<N>(y), norm2_fast<N>(ynew)) * reltol, abstol)
@@ -400,10 +401,10 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
                                     const double c1 = (s * (1. - s)) / (1. - 2. * D);
                                     const double c2 = (s * (s - 2. * D)) / (1. - 2. * D);
                                     double ytmp[N];
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                                     for (int i = 0; i < N; ++i) ytmp[i] = y[i] + (k1[i] * c1 + k2[i] * c2) * h;
                                     if (SOA) {
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                                         for (int d = 0; d < N; ++d) P.dense[((unsigned long long)d * P.nt + q) * P.ntraj + traj] = ytmp[d];
                                         nv = (uint32_t)q + 1u;
                                     }
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
                             if (REC && !P.points_specified && fabs(tlast - tn) > DBL_EPSILON) { emit(tn, ynew); tlast = tn; }   // :536-542
                         }
                         t = tn;
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                         for (int i = 0; i < N; ++i) { y[i] = ynew[i]; f0[i] = f2[i]; }
                         fdjacobian<F, FAST>(t, y, f0, prm, jac);                 // :549
                     } else {
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
             if (fin != 0xff) {
                 // evaluations the reference performs: hinit 2 (1 with an explicit initstep), N+1 per Jacobian, 3 per attempt
                 const uint32_t nfe = (P.use_initstep ? 1u : 2u) + (uint32_t)(N + 1) * (1u + acc) + 3u * (attempts - (invalid ? 1u : 0u)) + (invalid ? 1u : 0u);
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                 for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = y[d];
                 P.accepted[traj] = acc; P.rejected[traj] = rej; P.nfe[traj] = nfe; P.status[traj] = fin; P.t_reached[traj] = t;
                 if (ROWS) P.nvalid[traj] = SOA ? nv : (uint32_t)it;
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(BLOCK) ode23s_kernel(const AdaptParams P) {
             }
         }
     }
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
     for (int o = 16; o > 0; o >>= 1) {
         tot_acc += __shfl_down_sync(0xffffffffu, tot_acc, o);
         tot_rej += __shfl_down_sync(0xffffffffu, tot_rej, o);
@@ -489,10 +490,10 @@ __global__ void __launch_bounds__(BLOCK) rosenbrock_kernel(const FixedParams P) 
         double prm[F::NP ? F::NP : 1];
         load_params<F, PT>(prm, P.params, P.shared, traj, P.ntraj);
         double x[N];
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
         for (int d = 0; d < N; ++d) x[d] = P.y0[(unsigned long long)d * P.ntraj + traj];
         if (ALL) {
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
             for (int d = 0; d < N; ++d) P.yall[((unsigned long long)d * P.nt) * P.ntraj + traj] = x[d];
         }
         uint8_t st = ST_DONE;
@@ -505,51 +506,51 @@ __global__ void __launch_bounds__(BLOCK) rosenbrock_kernel(const FixedParams P) 
             fdjacobian<F>(ts, x, ftx, prm, dfdx);
             nfe += N + 1;
             const double dg = 1. / (co.gamma * hs);
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
             for (int r = 0; r < N; ++r) {
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                 for (int c = 0; c < N; ++c) jac[r][c] = (r == c ? dg : 0.0) - dfdx[r][c];
             }
             if (!na_try_inverse<N>(jac, jinv)) { st = ST_INVALID_MATRIX; break; }
             double g[4][N], fx[N], nx[N];
             F::eval(ts + co.b[0] * hs, x, fx, prm);
             na_gemv<N>(jinv, fx, g[0]);
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
             for (int d = 0; d < N; ++d) nx[d] = x[d] + g[0][d] * co.b[0];
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
             for (int s = 1; s < 4; ++s) {
                 double dx[N], df[N], xa[N];
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                 for (int d = 0; d < N; ++d) { dx[d] = 0.0; df[d] = 0.0; }
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                 for (int j = 0; j < s - 1; ++j) {
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                     for (int d = 0; d < N; ++d) { dx[d] = dx[d] + g[j][d] * co.a[s][j]; df[d] = df[d] + g[j][d] * co.c[s][j]; }
                 }
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                 for (int d = 0; d < N; ++d) xa[d] = x[d] + dx[d];
                 F::eval(ts + co.b[s] * hs, xa, fx, prm);
                 na_gemv<N>(jinv, fx, g[s]);
                 const double ih = 1. / hs;
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                 for (int d = 0; d < N; ++d) { g[s][d] = g[s][d] + df[d] * ih; nx[d] = nx[d] + g[s][d] * co.b[s]; }
             }
             nfe += 4;
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
             for (int d = 0; d < N; ++d) x[d] = nx[d];
             if (ALL) {
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
                 for (int d = 0; d < N; ++d) P.yall[((unsigned long long)d * P.nt + (i + 1)) * P.ntraj + traj] = x[d];
             }
             ++steps;
             ts = tnext;
         }
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
         for (int d = 0; d < N; ++d) P.yfinal[(unsigned long long)d * P.ntraj + traj] = x[d];
         P.accepted[traj] = (uint32_t)steps; P.rejected[traj] = 0u; P.nfe[traj] = (uint32_t)nfe; P.status[traj] = st;
         P.t_reached[traj] = ts; P.nvalid[traj] = (uint32_t)(P.nt ? steps + 1 : 0);
     }
-#pragma unroll
+#pragma unroll (N <= 8 ? N : 1)
     for (int o = 16; o > 0; o >>= 1) {
         steps += __shfl_down_sync(0xffffffffu, steps, o);
         nfe += __shfl_down_sync(0xffffffffu, nfe, o);

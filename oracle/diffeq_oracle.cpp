@@ -171,7 +171,7 @@ bool make_tableau(int method, int set, Tableau& t) {
 // ------------------------------------------------------------------------------------------
 // Built-in right-hand sides (the reference takes a closure F: Fn(f64,&Y)->Y, problem.rs:32-36).
 // ------------------------------------------------------------------------------------------
-enum Rhs { LORENZ = 0, VANDERPOL = 1, PENDULUM = 2, RING8 = 3, RING16 = 4, RING32 = 5, RING64 = 6, CVDP2 = 7, CVDP3 = 8 };
+enum Rhs { LORENZ = 0, VANDERPOL = 1, PENDULUM = 2, RING8 = 3, RING16 = 4, RING32 = 5, RING64 = 6, CVDP2 = 7, CVDP3 = 8, CVDP6 = 9, CVDP12 = 10 };
 
 struct LorenzF {  // problem.rs:989-1000: params = {sigma, rho, beta}
     static constexpr int N = 3;
@@ -905,6 +905,8 @@ int dispatch_rhs(int rhs, Fn&& fn) {
         case RING64: return fn(RingF<64>());
         case CVDP2: return fn(CoupledVdpF<2>());
         case CVDP3: return fn(CoupledVdpF<3>());
+        case CVDP6: return fn(CoupledVdpF<6>());
+        case CVDP12: return fn(CoupledVdpF<12>());
         default: return ERR_UNSUPPORTED;
     }
 }
@@ -925,8 +927,8 @@ struct oracle_opts {
     int libm_folded;
 };
 
-int oracle_rhs_dim(int rhs) { return rhs == LORENZ ? 3 : (rhs == VANDERPOL || rhs == PENDULUM) ? 2 : rhs == RING8 ? 8 : rhs == RING16 ? 16 : rhs == RING32 ? 32 : rhs == RING64 ? 64 : rhs == CVDP2 ? 4 : rhs == CVDP3 ? 6 : -1; }
-int oracle_rhs_nparams(int rhs) { return rhs == LORENZ ? 3 : rhs == VANDERPOL ? 1 : rhs == PENDULUM ? 3 : (rhs >= RING8 && rhs <= CVDP3) ? 2 : -1; }
+int oracle_rhs_dim(int rhs) { return rhs == LORENZ ? 3 : (rhs == VANDERPOL || rhs == PENDULUM) ? 2 : rhs == RING8 ? 8 : rhs == RING16 ? 16 : rhs == RING32 ? 32 : rhs == RING64 ? 64 : rhs == CVDP2 ? 4 : rhs == CVDP3 ? 6 : rhs == CVDP6 ? 12 : rhs == CVDP12 ? 24 : -1; }
+int oracle_rhs_nparams(int rhs) { return rhs == LORENZ ? 3 : rhs == VANDERPOL ? 1 : rhs == PENDULUM ? 3 : (rhs >= RING8 && rhs <= CVDP12) ? 2 : -1; }
 
 // itertools_num::linspace as recalled (unpinned third-party): a + ((b-a)/(n-1))*i
 void oracle_linspace(double a, double b, size_t n, double* out) {
@@ -1109,7 +1111,7 @@ int oracle_solve_ode23s(int set, int rhs, const double* params, const double* y0
     Opts op{o->reltol, o->abstol, o->has_minstep, o->minstep, o->has_maxstep, o->maxstep, o->initstep, o->points, o->max_steps, o->libm_folded};
     return dispatch_rhs(rhs, [&](auto f) {
         using F = decltype(f);
-        if constexpr (F::N > 8) return (int)ERR_UNSUPPORTED; else {
+        if constexpr (F::N > 32) return (int)ERR_UNSUPPORTED; else {
         Sink sink; sink.tout = tout; sink.yout = yout; sink.cap = cap; sink.N = F::N;
         Counters c;
         int rc = solve_ode23s<F::N, F>(y0, tspan, nt, params, op, set == 1, sink, c, yfinal);
@@ -1132,7 +1134,7 @@ int oracle_ensemble_ode23s(int set, int rhs, size_t ntraj, const double* y0, con
     return dispatch_rhs(rhs, [&](auto f) {
         using F = decltype(f);
         constexpr int N = F::N;
-        if constexpr (N > 8) return (int)ERR_UNSUPPORTED; else {
+        if constexpr (N > 32) return (int)ERR_UNSUPPORTED; else {
 #ifdef _OPENMP
         if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -1163,7 +1165,7 @@ int oracle_solve_rosenbrock(int which, int rhs, const double* params, const doub
     const RosenbrockCoeffs co = rosenbrock_coeffs(which);
     return dispatch_rhs(rhs, [&](auto f) {
         using F = decltype(f);
-        if constexpr (F::N > 8) return (int)ERR_UNSUPPORTED; else
+        if constexpr (F::N > 32) return (int)ERR_UNSUPPORTED; else
         return solve_rosenbrock<F::N, F>(co, y0, tspan, nt, params, yout, yfinal, status, nfe, rows);
     });
 }
@@ -1177,7 +1179,7 @@ int oracle_ensemble_rosenbrock(int which, int rhs, size_t ntraj, const double* y
     return dispatch_rhs(rhs, [&](auto f) {
         using F = decltype(f);
         constexpr int N = F::N;
-        if constexpr (N > 8) return (int)ERR_UNSUPPORTED; else {
+        if constexpr (N > 32) return (int)ERR_UNSUPPORTED; else {
 #ifdef _OPENMP
         if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif

@@ -20,6 +20,7 @@ _LIB = None
 FEULER, HEUN, MIDPOINT, ODE23, ODE23S, ODE4, ODE45, ODE45FE, ODE4SKR, ODE4SS, ODE78, ODE21 = range(12)
 LORENZ, VANDERPOL, PENDULUM = 0, 1, 2
 CVDP2, CVDP3 = 7, 8   # 2 / 3 Van der Pol oscillators in a ring (dimension 4 / 6): the stiff path beyond the closed-form inverses
+CVDP6, CVDP12 = 9, 10  # 6 / 12 oscillators (dimension 12 / 24): the stiff path with its matrices in thread-local memory
 RING8, RING16, RING32, RING64 = 3, 4, 5, 6   # test systems of dimension 8 .. 64 (ring of coupled logistic cells) for the generic-dimension path
 REFERENCE, TEXTBOOK = 0, 1
 POINTS_ALL, POINTS_SPECIFIED = 0, 1

@@ -74,8 +74,8 @@ def test_stiff_goldens_through_the_cuda_path(deq):
     ran = 0
     for c in STIFF["cases"]:
         ts = _tspan(deq, c["tspan"])
-        if c["system"].startswith("Cvdp"):   # dimension 4 / 6: user source through NVRTC (the built-in systems have n <= 3)
-            prob = deq.OdeProblem.builder().fun(deq.Rhs.from_source(USER_CVDP, 2 * int(c["system"][-1]), 2)).params(fh(c["params"])) \
+        if c["system"].startswith("Cvdp"):   # dimension 4 / 6 / 12 / 24: user source through NVRTC (the built-in systems have n <= 3)
+            prob = deq.OdeProblem.builder().fun(deq.Rhs.from_source(USER_CVDP, 2 * int(c["system"][4:]), 2)).params(fh(c["params"])) \
                 .init(fh(c["y0"])).tspan(ts).build()
         else:
             prob = _problem(deq, getattr(deq.System, c["system"]), fh(c["params"]), fh(c["y0"]), ts)
@@ -296,14 +296,15 @@ __device__ void rhs(double t, const double* v, double* d, const double* p) {
 '''
 
 
-@pytest.mark.parametrize("n", [4, 6])
+@pytest.mark.parametrize("n", [4, 6, 12, 24])
 def test_stiff_beyond_closed_form_inverses(deq, oracle, n):
-    """n = 4 goes through nalgebra's 4x4 cofactor inverse (`do_inverse4`), n = 6 through its LU-based `try_inverse`
-    (problem.rs:481,588 on a DMatrix of any size): ode23s in both W-inverse variants (final states, counters, dense rows) and
-    both Rosenbrock coefficient sets against the oracle, bit for bit; the committed pyref goldens pin the oracle."""
-    osys = oracle.CVDP2 if n == 4 else oracle.CVDP3
+    """n = 4 goes through nalgebra's 4x4 cofactor inverse (`do_inverse4`), n >= 5 through its LU-based `try_inverse`
+    (problem.rs:481,588 on a DMatrix of any size; n = 12 and 24 with the matrices in thread-local memory on the device): ode23s in
+    both W-inverse variants (final states, counters, dense rows) and both Rosenbrock coefficient sets against the oracle, bit for
+    bit; the committed pyref goldens pin the oracle."""
+    osys = {4: oracle.CVDP2, 6: oracle.CVDP3, 12: oracle.CVDP6, 24: oracle.CVDP12}[n]
     rng = np.random.default_rng(n)
-    m = 150
+    m = 150 if n <= 6 else 60
     y0 = rng.uniform(-2.0, 2.0, (m, n))
     prm = np.column_stack([np.geomspace(0.5, 300.0, m), rng.uniform(0.0, 2.0, m)])
     rhs = deq.Rhs.from_source(USER_CVDP, n, 2)
@@ -328,8 +329,8 @@ def test_stiff_beyond_closed_form_inverses(deq, oracle, n):
 
 
 def test_stiff_argument_checks(deq):
-    src = "__device__ void rhs(double t, const double* y, double* dy, const double* p) { for (int i = 0; i < 9; ++i) dy[i] = -y[i]; }"
-    p4 = deq.OdeProblem.builder().fun(deq.Rhs.from_source(src, 9, 0)).init([[1.0] * 9]).tspan([0.0, 1.0]).build()   # the stiff path carries n <= 8
+    src = "__device__ void rhs(double t, const double* y, double* dy, const double* p) { for (int i = 0; i < 33; ++i) dy[i] = -y[i]; }"
+    p4 = deq.OdeProblem.builder().fun(deq.Rhs.from_source(src, 33, 0)).init([[1.0] * 33]).tspan([0.0, 1.0]).build()   # the stiff path carries n <= 32
     for m in (deq.Ode.Ode23s, deq.Ode.Ode4skr, deq.Ode.Ode4ss):
         with pytest.raises(deq.OdeError) as e:
             p4.solve(m)

@@ -118,7 +118,8 @@ def linspace(a, b, n):
 METHOD_TAB = {"Feuler": "feuler", "Heun": "heun", "Midpoint": "midpoint", "Ode4": "rk4", "Ode21": "rk21", "Ode23": "rk23",
               "Ode45": "dopri5", "Ode45fe": "rk45", "Ode78": "feh78"}
 SYS = {"Lorenz": pyref.lorenz, "VanDerPol": pyref.vanderpol, "Pendulum": pyref.pendulum,
-       "Cvdp2": lambda p: pyref.coupled_vdp(p, 2), "Cvdp3": lambda p: pyref.coupled_vdp(p, 3)}
+       "Cvdp2": lambda p: pyref.coupled_vdp(p, 2), "Cvdp3": lambda p: pyref.coupled_vdp(p, 3),
+       "Cvdp6": lambda p: pyref.coupled_vdp(p, 6), "Cvdp12": lambda p: pyref.coupled_vdp(p, 12)}
 
 
 def main():
@@ -280,6 +281,12 @@ def main_stiff():
     ode23s("ode23s_textbook_cvdp3_stiff_dense", "Cvdp3", [200.0, 1.5], Y6, ["linspace", 0.0, 100.0, 51], linspace(0.0, 100.0, 51), tset="textbook",
            reltol=1e-6, abstol=1e-8)
     ode23s("ode23s_cvdp2_singular_w", "Cvdp2", [0.0, 0.0], [0.0, 0.0, 0.0, 0.0], ["list", 0.0, 1.0], [0.0, 1.0], tset="textbook", max_steps=200)
+    # n = 12 and n = 24 (matrices in thread-local memory on the device): the same LU-based try_inverse on larger systems
+    Y12 = [2.0, 0.0, -1.5, 0.5, 0.3, -1.0, 1.1, 0.2, -0.4, 0.9, 1.7, -0.6]
+    Y24 = Y12 + [0.25 * ((7 * i) % 11) - 1.25 for i in range(12)]
+    for tset in ("reference", "textbook"):
+        ode23s(f"ode23s_{tset}_cvdp6_mu5", "Cvdp6", [5.0, 0.7], Y12, ["list", 0.0, 4.0], [0.0, 4.0], tset=tset, max_steps=3000)
+        ode23s(f"ode23s_{tset}_cvdp12_mu3", "Cvdp12", [3.0, 0.4], Y24, ["list", 0.0, 2.0], [0.0, 2.0], tset=tset, max_steps=2000)
     for which in ("kr4", "s4"):
         rosen(f"{which}_vdp", which, "VanDerPol", [5.0], [2.0, 0.0], ["linspace", 0.0, 0.39, 40], linspace(0.0, 0.39, 40))
         rosen(f"{which}_lorenz", which, "Lorenz", LOR, [0.1, 0.0, 0.0], ["linspace", 0.0, 0.05, 51], linspace(0.0, 0.05, 51))
@@ -289,6 +296,7 @@ def main_stiff():
         rosen(f"{which}_single_point", which, "Lorenz", LOR, [0.1, 0.0, 0.0], ["list", 0.0], [0.0])
         rosen(f"{which}_cvdp2", which, "Cvdp2", [5.0, 0.7], Y4, ["linspace", 0.0, 0.2, 21], linspace(0.0, 0.2, 21))
         rosen(f"{which}_cvdp3", which, "Cvdp3", [5.0, 0.7], Y6, ["linspace", 0.0, 0.2, 21], linspace(0.0, 0.2, 21))
+        rosen(f"{which}_cvdp6", which, "Cvdp6", [5.0, 0.7], Y12, ["linspace", 0.0, 0.1, 11], linspace(0.0, 0.1, 11))
     json.dump({"rosenbrock_coeffs": {k: dict(gamma=hx(v["gamma"]), a=hx(v["a"]), b=hx(v["b"]), c=hx(v["c"])) for k, v in ros.items()},
                "cases": cases}, open(os.path.join(OUT, "stiff_cases.json"), "w"), indent=0)
     print(f"wrote {len(cases)} stiff cases to {OUT}")
