@@ -1042,7 +1042,7 @@ def test_generic_dimension_user_systems_bit_exact(deq, oracle, n):
     assert np.array_equal(fx.final, rfx, equal_nan=True) and np.isfinite(rfx).all(axis=1).mean() > 0.5
     for i in (3, 7):
         assert np.array_equal(fx.yout[i], oracle.solve_fixed(oracle.ODE4, osys, prm[i], y0[i], ts)["yout"], equal_nan=True)
-    if n > 8:
-        with pytest.raises(deq.OdeError) as e:       # the stiff path carries n <= 8
+    if n > 32:
+        with pytest.raises(deq.OdeError) as e:       # the stiff path carries n <= 32
             prob.solve(deq.Ode.Ode23s)
         assert e.value.kind == "Unsupported"
