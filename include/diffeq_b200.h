@@ -36,7 +36,7 @@ typedef enum deq_status {
                                       stops with DEQ_TRAJ_INVALID_MATRIX and deq_solve itself succeeds */
     DEQ_ERR_CUDA = 7,
     DEQ_ERR_NVRTC = 8,
-    DEQ_ERR_UNSUPPORTED = 9,       /* a combination this build does not carry (e.g. stiff methods with n > 8) */
+    DEQ_ERR_UNSUPPORTED = 9,       /* a combination this build does not carry (e.g. stiff methods with n > 32) */
     DEQ_ERR_INVALID_ARG = 10
 } deq_status;
 
