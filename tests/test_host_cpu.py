@@ -276,3 +276,40 @@ def test_rust_sys_crate_matches_the_header():
     import re
     for used in set(re.findall(r"sys::(deq_\w+)\(", wrapper)):
         assert used in hfuncs, used
+
+
+def test_two_stage_column_permutation_plan_logic():
+    """The factorisation behind `permute_staged_kernel` (kernels_common.cu), restated in numpy: with m(s) the stable rank of slot s
+    under the key order[s] // BK, destination bucket b owns exactly the intermediate positions [BK b, BK (b + 1)), so stage 2 is a
+    shuffle inside each BK-block, and stage 1 writes, per chunk of CH consecutive slots, runs of consecutive intermediate
+    positions in ascending order.  Checked on ragged sizes (last chunk and last bucket partial), with the library's CH / BK."""
+    CH, BK = 8192, 4096
+    rng = np.random.default_rng(3)
+    for n in (1, 5, 4096, 8192, 8193, 70001):
+        order = rng.permutation(n).astype(np.uint32)                       # slot s -> destination column
+        s1 = np.argsort(order // BK, kind="stable").astype(np.uint32)      # intermediate position m -> slot
+        d2 = (order[s1] % BK).astype(np.uint16)                            # stage 2: position inside the block
+        m1 = np.argsort(s1 // CH, kind="stable").astype(np.uint32)         # stage-1 list: positions grouped by source chunk, ascending
+        l1 = (s1[m1] % CH).astype(np.uint16)                               # ... and the slot inside the chunk each one reads
+        # bucket property: position m lies in the block of its destination
+        assert np.array_equal(np.arange(n) // BK, order[s1] // BK)
+        # the stage-1 list of chunk c covers exactly the slots of chunk c, positions ascending
+        for c in range((n + CH - 1) // CH):
+            lo, hi = c * CH, min(n, (c + 1) * CH)
+            assert np.array_equal(np.sort(l1[lo:hi].astype(np.int64)), np.arange(hi - lo))
+            assert np.all(np.diff(m1[lo:hi].astype(np.int64)) > 0)
+        row = rng.standard_normal(n)                                       # one row in slot order
+        mid = np.empty(n)
+        for c in range((n + CH - 1) // CH):                                # stage 1, chunk by chunk through a "tile"
+            lo, hi = c * CH, min(n, (c + 1) * CH)
+            tile = row[lo:hi]
+            mid[m1[lo:hi]] = tile[l1[lo:hi]]
+        out = np.empty(n)
+        for b in range((n + BK - 1) // BK):                                # stage 2, block by block
+            lo, hi = b * BK, min(n, (b + 1) * BK)
+            tile = np.empty(hi - lo)
+            tile[d2[lo:hi]] = mid[lo:hi]
+            out[lo:hi] = tile
+        want = np.empty(n)
+        want[order] = row                                                  # column order[s] <- slot s
+        assert np.array_equal(out, want)
